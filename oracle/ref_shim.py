@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Makes the *unmodified* reference tree (/root/reference, read-only) importable and runnable on CPU in the
+build container so that (a) the oracle restatement in ``oracle/robir_oracle.py`` can be validated against
+the real thing and (b) golden vectors under ``tests/golden/`` can be generated (``tests/golden/make_golden.py``).
+
+/root/reference does not exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or
+``bench.py`` may import this module.  Recipe: SURVEY.md Appendix B.
+
+What it does (nothing under /root/reference is edited):
+  * stub modules for the reference's missing third-party imports (gin, imageio, torch_scatter, pyhocon, ...);
+    ``torch_scatter.scatter_min`` (utils/octree.py:591) is restated as a segment-amin;
+  * ``.cuda()`` becomes a no-op and ``device='cuda'`` kwargs are rewritten to CPU;
+  * registers /root/reference/datasets under the name ``datasets`` (HF ``datasets`` shadows it).
+"""
+import os
+import sys
+import tempfile
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("ROBIR_REFERENCE", "/root/reference")
+_installed = False
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "model"))
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _passthrough_decorator(*a, **k):
+    if len(a) == 1 and callable(a[0]) and not k:
+        return a[0]
+    return lambda f: f
+
+
+def _scatter_min(src, index):
+    # torch_scatter.scatter_min semantic used at utils/octree.py:591: per-segment minimum of src.
+    if index.numel() == 0:
+        return src.new_zeros((0,)), None
+    out = torch.full((int(index.max()) + 1,), torch.iinfo(src.dtype).max, dtype=src.dtype)
+    return out.scatter_reduce(0, index, src, "amin", include_self=True), None
+
+
+def install():
+    """Idempotently install the shim and put the reference on sys.path."""
+    global _installed
+    if _installed:
+        return
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    gin = _mod("gin", configurable=_passthrough_decorator, register=_passthrough_decorator,
+               add_config_file_search_path=lambda *a, **k: None)
+    gin.config = _mod("gin.config", external_configurable=lambda *a, **k: None)
+    io = _mod("imageio", imread=None, imwrite=None)
+    io.plugins = _mod("imageio.plugins")
+    io.plugins.freeimage = _mod("imageio.plugins.freeimage", download=lambda: None)
+    _mod("torch_scatter", scatter_min=_scatter_min)
+    for n in ["matplotlib", "matplotlib.pyplot", "trimesh", "xatlas", "glfw", "OpenGL"]:
+        _mod(n)
+    _mod("OpenGL.GL", GL_TRIANGLES=4)
+    _mod("OpenGL.GL.shaders", compileShader=None, compileProgram=None)
+    _mod("pyhocon", ConfigFactory=None)
+    _mod("tensorboardX", SummaryWriter=None)
+
+    def _nan_guard():
+        raise RuntimeError("reference NaN guard (ipdb.set_trace) hit")
+
+    _mod("ipdb", set_trace=_nan_guard)
+    ds = types.ModuleType("datasets")
+    ds.__path__ = [os.path.join(REF_ROOT, "datasets")]
+    sys.modules["datasets"] = ds
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    from torch import storage as _storage
+    _storage._StorageBase.cuda = lambda self, *a, **k: self
+    torch.UntypedStorage.cuda = lambda self, *a, **k: self
+
+    from torch.overrides import TorchFunctionMode
+
+    class _CpuDevice(TorchFunctionMode):
+        def __torch_function__(self, func, types_, args=(), kwargs=None):
+            kwargs = kwargs or {}
+            dev = kwargs.get("device")
+            if dev is not None and "cuda" in str(dev):
+                kwargs["device"] = "cpu"
+            return func(*args, **kwargs)
+
+    _CpuDevice().__enter__()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import utils.octree as uo
+
+    def _octree_cuda(self):
+        self.device = "cpu"
+        return self
+
+    uo.Octree.cuda = _octree_cuda
+    _installed = True
+
+
+class DictConf(dict):
+    """Stand-in for the pyhocon ConfigTree the reference constructors expect."""
+
+    def _get(self, key):
+        node = self
+        for part in key.split("."):
+            node = node[part]
+        return node
+
+    def get_bool(self, k):
+        return bool(self._get(k))
+
+    def get_int(self, k):
+        return int(self._get(k))
+
+    def get_float(self, k):
+        return float(self._get(k))
+
+    def get_config(self, k):
+        return DictConf(self._get(k))
+
+
+def hotdog_model_conf(num_lgt_sgs=128, use_octree=True, n_steps=100):
+    """The model{} block of confs_sg/hotdog.conf:65-123 as a dict (values restated, not parsed)."""
+    return DictConf(
+        gamma=1.0, hdr_mode=0, use_neus=True, use_octree=use_octree, feature_vector_size=256,
+        implicit_network=dict(d_in=3, d_out=1, dims=[512] * 8, geometric_init=True, bias=0.6, skip_in=[4],
+                              weight_norm=True, multires=6),
+        rendering_network=dict(mode="idr", d_in=9, d_out=3, dims=[512] * 4, weight_norm=True, multires_view=4),
+        indirect_illum_network=dict(multires=10, dims=[512] * 4, num_lgt_sgs=24),
+        visibility_network=dict(points_multires=10, dirs_multires=10, dims=[256] * 4),
+        envmap_material_network=dict(multires=10, brdf_encoder_dims=[512] * 4, brdf_decoder_dims=[128, 128],
+                                     num_lgt_sgs=num_lgt_sgs, upper_hemi=False, specular_albedo=0.05, latent_dim=32),
+        ray_tracer=dict(object_bounding_sphere=1.0, sdf_threshold=5.0e-5, line_search_step=0.5, line_step_iters=3,
+                        sphere_tracing_iters=10, n_steps=n_steps, n_rootfind_steps=32),
+    )
+
+
+def build_reference_model(neus_state_dict, num_lgt_sgs=128, use_octree=True, n_steps=100, seed=0):
+    """Construct the reference IDRNetwork on CPU from a stage-1 NeuS state dict (our synthetic checkpoint)."""
+    install()
+    import confs_sg.env_path as env_path
+    tmp = tempfile.mkdtemp(prefix="robir_neus_")
+    torch.save({"global_step": 0, "model": neus_state_dict}, os.path.join(tmp, "000000.tar"))
+    env_path.set_path(tmp, 0)
+    from model.implicit_differentiable_renderer import IDRNetwork
+    torch.manual_seed(seed)
+    return IDRNetwork(hotdog_model_conf(num_lgt_sgs, use_octree, n_steps))
+
+
+def reference_neus_state_dict(seed=0):
+    install()
+    from model.neus_model import NeuSModel
+    torch.manual_seed(seed)
+    return NeuSModel(mode="idr", hashing=False, embed="PE").state_dict()
+
+
+def bind_pbr_runner(model, no_normal=True, is_training=True):
+    """A bare PBRTrainRunner carrying only what get_sg_render (training/train_pbr.py:348-396) reads."""
+    install()
+    from training.train_pbr import PBRTrainRunner
+    runner = PBRTrainRunner.__new__(PBRTrainRunner)
+    runner.model = model
+    runner.train_spec = True
+    runner.is_training = is_training
+    runner.no_normal = no_normal
+    model.get_sg_render = runner.get_sg_render
+    return runner
+
+
+class ReplayRandom:
+    """Context manager: record (mode='record') or replay (mode='replay') torch.rand / torch.randn /
+    Tensor.uniform_ draws, in call order, so reference and oracle/product see identical randoms."""
+
+    def __init__(self, tape=None):
+        self.tape = [] if tape is None else list(tape)
+        self.replay = tape is not None
+        self._pos = 0
+
+    def _wrap(self, name, orig):
+        def f(*a, **k):
+            if self.replay:
+                out = self.tape[self._pos][1].clone()
+                self._pos += 1
+                return out
+            out = orig(*a, **k)
+            self.tape.append((name, out.clone()))
+            return out
+        return f
+
+    def __enter__(self):
+        self._orig = (torch.rand, torch.randn)
+        torch.rand = self._wrap("rand", self._orig[0])
+        torch.randn = self._wrap("randn", self._orig[1])
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._orig
+        return False

@@ -1,0 +1,168 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference through oracle/ref_shim.py) on
+seeded synthetic weights (robir_b200.synthetic).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The files hold inputs (incl. every random draw) and the reference's outputs; weights are re-created from the seed by
+``synthetic_state_dict`` so the fixtures stay small.  tests/test_golden.py checks the oracle against them on any
+machine; the -m gpu tests check the CUDA product against them on the B200.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_shim  # noqa: E402
+from robir_b200 import synthetic  # noqa: E402
+
+M = 16
+SEED = 0
+
+
+def npy(d):
+    return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+def build(use_octree=True, n_steps=100, perturb=0.0):
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M, perturb=perturb)
+    model = ref_shim.build_reference_model(synthetic.neus_checkpoint_from(sd), num_lgt_sgs=M, use_octree=use_octree,
+                                           n_steps=n_steps)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    ref_shim.bind_pbr_runner(model)
+    return sd, model
+
+
+def main():
+    torch.set_num_threads(8)
+    sd, model = build()
+    sdf_fn = lambda x: model.implicit_network(x)[:, 0]
+    model.ray_tracer.generate(sdf_fn, None)
+    model.octree_ray_tracer.generate(sdf_fn, None)
+    oc = model.ray_tracer.sdf_octree
+    fp = dict(n_nodes=oc.octree.boxes.shape[0], links_sum=int(oc.octree.links.sum()),
+              non_leaf_sum=int(oc.octree.non_leaf.sum()), hit_sum=int(oc.hit_ptr.sum()),
+              sdf_val_sum=float(oc.sdf_val.double().sum()), min_step=oc.min_step)
+    print("octree fingerprint", fp)
+
+    # ---------------- 1. small nets on 96 points near the surface
+    g = torch.Generator().manual_seed(1)
+    dirs = torch.nn.functional.normalize(torch.randn(96, 3, generator=g), dim=-1)
+    pts = dirs * (0.33 + 0.01 * torch.randn(96, 1, generator=g))
+    vdirs = torch.nn.functional.normalize(torch.randn(96, 3, generator=g), dim=-1)
+    hs = torch.rand(96, 1, generator=g)
+    noise = dict(indir=torch.randn(96, 64, generator=g), brdf=torch.randn(96, 32, generator=g),
+                 nrm=torch.randn(96, 60, generator=g))
+    with torch.no_grad():
+        f = model.implicit_network(pts)
+    grad = model.implicit_network.gradient(pts.clone())[:, 0].detach()
+    with ref_shim.ReplayRandom(tape=[("randn", noise["indir"])]):
+        sgs, env = model.indirect_illum_network(pts, hs)
+    with ref_shim.ReplayRandom(tape=[("randn", noise["brdf"]), ("randn", noise["nrm"])]):
+        mat = model.envmap_material_network(pts, train_spec=True)
+    vis_logits = model.visibility_network(pts, vdirs)
+    with torch.no_grad():
+        col = model.implicit_network.batch_borrow_color(pts, vdirs)
+    np.savez_compressed(os.path.join(HERE, "nets.npz"), **npy(dict(
+        pts=pts, vdirs=vdirs, hdr_shift=hs, noise_indir=noise["indir"], noise_brdf=noise["brdf"],
+        noise_nrm=noise["nrm"], sdf_feat_head=f[:, :8], sdf_feat_sum=f.sum(-1), grad=grad, indir_sgs=sgs,
+        indir_env=env, roughness=mat["sg_roughness"], albedo=mat["sg_diffuse_albedo"], metallic=mat["sg_metallic"],
+        normal_map=mat["sg_normal_map"], xi_roughness=mat["random_xi_roughness"],
+        xi_albedo=mat["random_xi_diffuse_albedo"], vis_logits=vis_logits, borrow_color=col)))
+
+    # ---------------- 2. octree casts (primary max_iter=-1, secondary max_iter=32)
+    pix = synthetic.training_pixels(0, n=512, crop=420)
+    inp = synthetic.camera_inputs(pix)
+    from utils import rend_util
+    rd, cl = rend_util.get_camera_params(inp["uv"], inp["pose"], inp["intrinsics"])
+    with torch.no_grad():
+        p1, m1, t1 = model.ray_tracer(sdf=sdf_fn, cam_loc=cl, object_mask=inp["object_mask"].reshape(-1),
+                                      ray_directions=rd)
+        so = pts[:64] + 0.005 * torch.nn.functional.normalize(pts[:64], dim=-1)
+        sdir = torch.nn.functional.normalize(torch.randn(64, 8, 3, generator=g), dim=-1)
+        p2, m2, t2 = model.octree_ray_tracer(sdf=sdf_fn, cam_loc=so, object_mask=None, ray_directions=sdir)
+        # NaN edge case: axis-aligned ray starting on a grid plane
+        eo = torch.tensor([[0.0, 0.0, 2.0], [0.05, 0.1, 2.0]])
+        ed = torch.tensor([[[0.0, 0.0, -1.0]], [[0.0, 0.0, -1.0]]])
+        p3, m3, t3 = model.ray_tracer(sdf=sdf_fn, cam_loc=eo, object_mask=None, ray_directions=ed)
+    np.savez_compressed(os.path.join(HERE, "octree.npz"), **npy(dict(
+        pix=pix, ray_dirs=rd, cam_loc=cl, prim_points=p1, prim_mask=m1, prim_t=t1, sec_o=so, sec_d=sdir,
+        sec_points=p2, sec_mask=m2, sec_t=t2, edge_o=eo, edge_d=ed, edge_mask=m3, edge_t=t3,
+        **{"fp_" + k: v for k, v in fp.items()})))
+    print("octree: prim hits", int(m1.sum()), "/ 512; sec hits", int(m2.sum()), "/ 512; edge", m3.tolist(), t3.tolist())
+
+    # ---------------- 3. PBR forward + loss + backward (N=160 rays), octree tracer
+    pix = synthetic.training_pixels(1, n=160, crop=400)
+    inp = synthetic.camera_inputs(pix)
+    gt = torch.rand(1, 160, 3, generator=g)
+    from model.loss import InvLoss
+    model.get_sg_render.__self__.loss = InvLoss(1.0, 0.1, 100.0, 50.0, 1.0, 1.0, 1.0)
+    runner = model.get_sg_render.__self__
+    torch.manual_seed(1234)
+    with ref_shim.ReplayRandom() as rec:
+        i2 = dict(inp)
+        i2["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(160, 1)
+        out = model(i2, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = runner.pbr_step(out, {"rgb": gt})
+    model.zero_grad()
+    loss.backward()
+    mat = model.envmap_material_network
+    dec = mat.spec_brdf_encoder_layer.brdf_decoder_layer
+    enc = mat.spec_brdf_encoder_layer.brdf_encoder_layer
+    keep = ["points", "network_object_mask", "sg_rgb", "indir_rgb", "sg_diffuse_rgb", "sg_specular_rgb",
+            "indir_diffuse_rgb", "indir_specular_rgb", "normals", "diffuse_albedo", "roughness", "metallic",
+            "normal_map", "vis_shadow", "random_xi_roughness", "random_xi_diffuse_albedo", "sdf_output"]
+    d = {"out_" + k: out[k] for k in keep}
+    d.update({"rnd_%d" % i: t for i, (_, t) in enumerate(rec.tape)})
+    d.update(pix=pix, gt=gt, loss=loss, g_lgtSGs=mat.lgtSGs.grad, g_spec=mat.specular_reflectance.grad,
+             g_adapt=model.gamma.hdr_shift.adapt_illum.grad, g_dec4_bias=dec[4].bias.grad,
+             g_dec4_weight=dec[4].weight.grad, g_enc0_bias=enc[0].bias.grad, g_enc8_weight_sum=enc[8].weight.grad.sum(0))
+    np.savez_compressed(os.path.join(HERE, "pbr_step.npz"), **npy(d))
+    print("pbr: hits", int(out["network_object_mask"].sum()), "loss", float(loss))
+
+    # ---------------- 4. Illum forward + trace_radiance (N=48, nsamp=16)
+    model.zero_grad()
+    pix = synthetic.training_pixels(2, n=48, crop=360)
+    inp = synthetic.camera_inputs(pix)
+    torch.manual_seed(99)
+    with ref_shim.ReplayRandom() as rec2:
+        i2 = dict(inp)
+        i2["hdr_shift"] = torch.rand(48, 1)
+        o_ill = model(i2, trainstage="Illum")
+        tr = model.trace_radiance(o_ill, nsamp=16)
+    d = {"rnd_%d" % i: t for i, (_, t) in enumerate(rec2.tape)}
+    d.update(pix=pix, indirect_sgs=o_ill["indirect_sgs"], indir_integral=o_ill["indir_integral"],
+             normals=o_ill["normals"], points=o_ill["points"], mask=o_ill["network_object_mask"])
+    d.update({"tr_" + k: v for k, v in tr.items()})
+    np.savez_compressed(os.path.join(HERE, "vis_stage.npz"), **npy(d))
+    print("vis stage: hits", int(o_ill["network_object_mask"].sum()), "sec hits", int(tr["gt_vis"].sum()))
+
+    # ---------------- 5. IDR sphere tracer (use_octree=False), eval and training
+    sd2, model2 = build(use_octree=False, n_steps=32)
+    sdf2 = lambda x: model2.implicit_network(x)[:, 0]
+    pix = synthetic.training_pixels(3, n=256, crop=420)
+    inp = synthetic.camera_inputs(pix)
+    rd, cl = rend_util.get_camera_params(inp["uv"], inp["pose"], inp["intrinsics"])
+    om = torch.rand(256, generator=g) > 0.3
+    d = dict(pix=pix, object_mask=om)
+    for training in (False, True):
+        model2.ray_tracer.train(training)
+        torch.manual_seed(5)
+        uni = torch.empty(32).uniform_(0.0, 1.0)
+        torch.manual_seed(5)
+        with torch.no_grad():
+            p, m, t = model2.ray_tracer(sdf=sdf2, cam_loc=cl, object_mask=om, ray_directions=rd)
+        tag = "train" if training else "eval"
+        d.update({tag + "_points": p, tag + "_mask": m, tag + "_t": t, "uniform": uni})
+        print("raytracing", tag, "hits", int(m.sum()))
+    np.savez_compressed(os.path.join(HERE, "raytracing.npz"), **npy(d))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""Oracle (CPU restatement) vs. the golden vectors generated from the unmodified reference
+(tests/golden/make_golden.py).  Runs anywhere; no GPU, no /root/reference."""
+import torch
+
+import pipeline as P
+import robir_oracle as O
+import tracers as T
+from robir_b200 import synthetic
+
+TOL = 2e-5  # fp32 CPU GEMM blocking differs between reference module calls and the functional restatement
+
+
+def close(a, b, tol=TOL):
+    return (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+
+
+def test_small_networks(golden, synth_sd16):
+    g, sd = golden("nets"), synth_sd16
+    pts = g["pts"]
+    f = O.implicit_forward(sd, pts)
+    assert close(f[:, :8], g["sdf_feat_head"]) and close(f.sum(-1), g["sdf_feat_sum"], 1e-4)
+    assert close(O.implicit_gradient(sd, pts)[:, 0], g["grad"])
+    sgs, env = O.indirect_illum(sd, pts, g["hdr_shift"], g["noise_indir"])
+    assert close(sgs, g["indir_sgs"]) and close(env, g["indir_env"])
+    mat = O.envmap_material(sd, pts, g["noise_brdf"], g["noise_nrm"])
+    for a, b in [("sg_roughness", "roughness"), ("sg_diffuse_albedo", "albedo"), ("sg_metallic", "metallic"),
+                 ("sg_normal_map", "normal_map"), ("random_xi_roughness", "xi_roughness"),
+                 ("random_xi_diffuse_albedo", "xi_albedo")]:
+        assert close(mat[a], g[b]), a
+    assert close(O.vis_network(sd, pts, g["vdirs"]), g["vis_logits"])
+    assert close(O.batch_borrow_color(sd, pts, g["vdirs"]), g["borrow_color"])
+
+
+def test_octree_build_and_cast(golden, oracle_octrees):
+    g = golden("octree")
+    prim, sec = oracle_octrees
+    assert prim.boxes.shape[0] == int(g["fp_n_nodes"])
+    assert int(prim.links.sum()) == int(g["fp_links_sum"])
+    assert int(prim.non_leaf.sum()) == int(g["fp_non_leaf_sum"])
+    assert abs(int(prim.hit_ptr.sum()) - int(g["fp_hit_sum"])) <= 2  # 1e-4 threshold on fp32 sdf values
+    p, m, t = prim.trace(g["cam_loc"], g["ray_dirs"])
+    assert torch.equal(m, g["prim_mask"])
+    assert close(t[m], g["prim_t"][m]) and close(p[m], g["prim_points"][m])
+    p, m, t = sec.trace(g["sec_o"], g["sec_d"])
+    assert torch.equal(m, g["sec_mask"])
+    assert close(t, g["sec_t"])
+    # NaN edge case: zero direction components from an origin on a grid plane
+    p, m, t = prim.trace(g["edge_o"], g["edge_d"])
+    assert m.tolist() == g["edge_mask"].tolist() == [False, True]
+    assert torch.isnan(t[0]) and torch.isnan(g["edge_t"][0]) and close(t[1:], g["edge_t"][1:])
+
+
+def _pbr_inputs(g, sd):
+    pix = g["pix"]
+    inp = synthetic.camera_inputs(pix)
+    inp["hdr_shift"] = O.hdr_shift_as_input(sd).expand(pix.shape[0], 1)
+    rnd = P.tape_to_rnd([("r", g["rnd_%d" % i]) for i in range(9)])
+    return inp, rnd
+
+
+def test_pbr_step_forward_backward(golden, synth_sd16, oracle_octrees):
+    g = golden("pbr_step")
+    sd = {k: v.clone() for k, v in synth_sd16.items()}
+    train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    inp, rnd = _pbr_inputs(g, sd)
+    prim, _ = oracle_octrees
+    out = P.idr_forward(sd, inp, lambda c, m, d: prim.trace(c, d), rnd)
+    assert torch.equal(out["network_object_mask"], g["out_network_object_mask"])
+    for k in [k[4:] for k in g if k.startswith("out_") and k != "out_network_object_mask"]:
+        assert close(out[k], g["out_" + k]), k
+    loss, _ = O.pbr_loss(sd, out, g["gt"])
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    loss.backward()
+    pre = "envmap_material_network."
+    dec = pre + "spec_brdf_encoder_layer.brdf_decoder_layer."
+    enc = pre + "spec_brdf_encoder_layer.brdf_encoder_layer."
+    assert close(sd[pre + "lgtSGs"].grad, g["g_lgtSGs"], 1e-4)
+    assert close(sd[pre + "specular_reflectance"].grad, g["g_spec"], 1e-4)
+    assert close(sd["gamma.hdr_shift.adapt_illum"].grad, g["g_adapt"], 1e-4)
+    assert close(sd[dec + "4.bias"].grad, g["g_dec4_bias"], 1e-4)
+    assert close(sd[dec + "4.weight"].grad, g["g_dec4_weight"], 1e-4)
+    assert close(sd[enc + "0.bias"].grad, g["g_enc0_bias"], 1e-4)
+    assert close(sd[enc + "8.weight"].grad.sum(0), g["g_enc8_weight_sum"], 1e-4)
+
+
+def test_vis_stage(golden, synth_sd16, oracle_octrees):
+    g, sd = golden("vis_stage"), synth_sd16
+    prim, sec = oracle_octrees
+    pix = g["pix"]
+    inp = synthetic.camera_inputs(pix)
+    inp["hdr_shift"] = g["rnd_0"]
+    rnd = dict(indir_noise=g["rnd_1"], normal_noise=g["rnd_2"])
+    out = P.idr_forward(sd, inp, lambda c, m, d: prim.trace(c, d), rnd, trainstage="Illum")
+    assert torch.equal(out["network_object_mask"], g["mask"])
+    for k in ["indirect_sgs", "indir_integral", "normals", "points"]:
+        assert close(out[k], g[k]), k
+    tr = P.trace_radiance(sd, out, lambda c, m, d: sec.trace(c, d), g["rnd_3"], g["rnd_4"], 16)
+    for k in ["gt_vis", "indir_mask"]:
+        assert torch.equal(tr[k], g["tr_" + k]), k
+    for k in ["trace_radiance", "sample_dirs", "pred_vis", "gt_integral"]:
+        assert close(tr[k], g["tr_" + k]), k
+
+
+def test_sphere_tracer(golden, synth_sd16):
+    g, sd = golden("raytracing"), synth_sd16
+    inp = synthetic.camera_inputs(g["pix"])
+    rd, cl = O.camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
+    sdf = lambda x: O.implicit_forward(sd, x)[:, 0]
+    for tag, training in (("eval", False), ("train", True)):
+        with torch.no_grad():
+            p, m, t = T.ray_tracing(sdf, cl, g["object_mask"], rd, n_steps=32, training=training,
+                                    uniform_steps=g["uniform"])
+        assert torch.equal(m, g[tag + "_mask"])
+        assert close(t, g[tag + "_t"]) and close(p, g[tag + "_points"])

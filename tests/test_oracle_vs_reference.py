@@ -1,0 +1,95 @@
+"""Oracle vs. the UNMODIFIED reference executed through oracle/ref_shim.py (build container only; skipped where
+/root/reference is absent, e.g. on the GPU box).  This is the pin that makes the oracle trustworthy; the golden
+fixtures are its portable shadow."""
+import numpy as np
+import pytest
+import torch
+
+import pipeline as P
+import ref_shim
+import robir_oracle as O
+import tracers as T
+from robir_b200 import synthetic
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref_model():
+    """Reference IDRNetwork with ITS OWN default initialisation (torch seed 0) and a fitted envmap as lights."""
+    sdn = ref_shim.reference_neus_state_dict(0)
+    model = ref_shim.build_reference_model(sdn, num_lgt_sgs=16)
+    lgt = torch.from_numpy(np.load(ref_shim.REF_ROOT + "/envmaps/envmap6/sg_128.npy"))[:16].float()
+    model.envmap_material_network.lgtSGs.data = lgt.clone()
+    runner = ref_shim.bind_pbr_runner(model)
+    model.train()
+    sdf = lambda x: model.implicit_network(x)[:, 0]
+    model.ray_tracer.generate(sdf, None)
+    from model.loss import InvLoss
+    runner.loss = InvLoss(1.0, 0.1, 100.0, 50.0, 1.0, 1.0, 1.0)
+    return model, runner
+
+
+def test_pbr_step_matches_reference(ref_model):
+    model, runner = ref_model
+    N = 96
+    inp = synthetic.camera_inputs(synthetic.training_pixels(5, n=N, crop=300))
+    gt = {"rgb": torch.full((1, N, 3), 0.4)}
+    torch.manual_seed(1234)
+    with ref_shim.ReplayRandom() as rec:
+        i2 = dict(inp)
+        i2["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+        out_ref = model(i2, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss_ref, _ = runner.pbr_step(out_ref, gt)
+    model.zero_grad()
+    loss_ref.backward()
+    gref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    octree = T.OctreeOracle(lambda x: O.implicit_forward(sd, x)[:, 0], lambda x: O.implicit_gradient(sd, x)[:, 0, :])
+    ro = model.ray_tracer.sdf_octree
+    assert torch.equal(ro.octree.boxes, octree.boxes) and torch.equal(ro.octree.links, octree.links)
+    assert torch.equal(ro.octree.non_leaf[:, 0], octree.non_leaf)
+    i3 = dict(inp)
+    i3["hdr_shift"] = O.hdr_shift_as_input(sd).expand(N, 1)
+    out = P.idr_forward(sd, i3, lambda c, m, d: octree.trace(c, d), P.tape_to_rnd(rec.tape))
+    assert set(out.keys()) == set(out_ref.keys())
+    for k, a in out_ref.items():
+        if a.dtype == torch.bool:
+            assert torch.equal(a, out[k]), k
+        else:
+            assert a.shape == out[k].shape, k
+            assert (a - out[k]).abs().max().item() < 2e-5, k
+    loss, _ = O.pbr_loss(sd, out, gt["rgb"])
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    loss.backward()
+    checked = 0
+    for k in train:
+        if k in gref:
+            assert (gref[k] - sd[k].grad).abs().max().item() < 1e-5 * max(1.0, gref[k].abs().max().item()), k
+            checked += 1
+    assert checked >= 19  # lgtSGs, specular_reflectance, spec-BRDF AE (16), adapt_illum
+
+
+def test_sphere_tracer_matches_reference():
+    sdn = ref_shim.reference_neus_state_dict(0)
+    model = ref_shim.build_reference_model(sdn, num_lgt_sgs=16, use_octree=False, n_steps=32)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    inp = synthetic.camera_inputs(synthetic.training_pixels(6, n=256, crop=400))
+    rd, cl = O.camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
+    om = torch.rand(256, generator=torch.Generator().manual_seed(1)) > 0.3
+    for training in (False, True):
+        model.ray_tracer.train(training)
+        torch.manual_seed(5)
+        uni = torch.empty(32).uniform_(0.0, 1.0)
+        torch.manual_seed(5)
+        with torch.no_grad():
+            p, m, d = model.ray_tracer(sdf=lambda x: model.implicit_network(x)[:, 0], cam_loc=cl, object_mask=om,
+                                       ray_directions=rd)
+            p2, m2, d2 = T.ray_tracing(lambda x: O.implicit_forward(sd, x)[:, 0], cl, om, rd, n_steps=32,
+                                       training=training, uniform_steps=uni)
+        assert torch.equal(m, m2)
+        assert (p - p2).abs().max().item() < 2e-5 and (d - d2).abs().max().item() < 2e-5
