@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s (fwd+bwd) of the PBR-stage hot path on the synthetic hotdog-800x800 workload (BASELINE.json
+configs[1]): each step = one training iteration of the reference (1024 random pixels of one 800x800 view, M=128 light
+SGs, S=32 samples/lobe): camera rays -> octree trace -> SDF normals -> material/indirect nets -> fused visibility MLP
+-> SG render -> loss -> backward -> Adam step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun for N>1), weak scaling: every rank renders its own 1024-ray batch and the gradient of the
+trained parameters is all-reduced over NCCL each step.  Rank 0 prints ONE JSON line.  ``--impl reference`` times the
+CPU oracle port of the reference's path (the reference itself is Python and cannot travel to the GPU box) on the host
+cores, on a bounded ray sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from robir_b200 import synthetic  # noqa: E402
+
+METRIC = "rays/sec (fwd+bwd) PBR stage, hotdog 800x800"
+N_RAYS, M_LOBES, SDF_RADIUS, SEED = 1024, 128, 0.87, 0
+FLOP_PER_QUERY = 458752.0  # 2 * (126*256 + 3*256^2 + 256*2)
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "hotdog-synthetic 800x800 PBR stage: 1024 random pixels/step, M=128 light SGs, S=32, 24 indirect "
+                       "SGs, octree tracer, geometric-init NeuS SDF (stage-2 radius ~0.6), fwd+loss+bwd+Adam",
+           "rays_per_step_per_gpu": N_RAYS, "num_lgt_sgs": M_LOBES, "image": "800x800", "tracer": "octree",
+           "l2": "per-step working set (ReLU masks + pair lists ~0.6 GB) exceeds the 126 MB L2; no explicit flush"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_setup(sd, tree_arrays=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pipeline as P
+    import robir_oracle as O
+    import tracers as T
+    if tree_arrays is None:
+        cache = "/tmp/robir_oracle_octree_r%.2f_s%d.pt" % (SDF_RADIUS, SEED)
+        if os.path.exists(cache):
+            tree = torch.load(cache, weights_only=False)
+        else:
+            tree = T.OctreeOracle(lambda x: O.implicit_forward(sd, x)[:, 0],
+                                  lambda x: O.implicit_gradient(sd, x)[:, 0, :])
+            try:
+                torch.save(tree, cache)
+            except Exception:
+                pass
+    else:
+        tree = T.OctreeOracle.__new__(T.OctreeOracle)
+        for k, v in tree_arrays.items():
+            setattr(tree, k, v)
+        tree.max_iter = -1
+    return O, P, tree
+
+
+def oracle_step(O, P, tree, sd, step, n_rays, gen):
+    """One reference-equivalent training iteration on the CPU: forward + loss + backward (+ SGD-free: the optimizer
+    step is excluded on both arms' CPU leg; it is < 0.1 % of the CPU time)."""
+    pix = synthetic.training_pixels(step, n=N_RAYS)[:n_rays]
+    inp = synthetic.camera_inputs(pix)
+    train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+        sd[k].grad = None
+    inp["hdr_shift"] = O.hdr_shift_as_input(sd).expand(n_rays, 1)
+    gt = torch.full((1, n_rays, 3), 0.5)
+    out = P.idr_forward(sd, inp, lambda c, m, d: tree.trace(c, d), lambda n: P.draw_rnd(n, M_LOBES, gen))
+    loss, _ = O.pbr_loss(sd, out, gt)
+    loss.backward()
+    return int(out["network_object_mask"].sum())
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only, host cores only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M_LOBES, sdf_radius=SDF_RADIUS)
+    O, P, tree = oracle_setup(sd)
+    gen = torch.Generator().manual_seed(1234)
+    # size the per-step ray sample so that (warmup + steps) fits in ~150 s
+    t0 = time.time()
+    oracle_step(O, P, tree, sd, 0, 32, gen)
+    probe = (time.time() - t0) / 32
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_rays = int(max(16, min(N_RAYS, budget / max(probe, 1e-6))))
+    for s in range(args.warmup):
+        oracle_step(O, P, tree, sd, s, n_rays, gen)
+    t0 = time.time()
+    for s in range(args.steps):
+        oracle_step(O, P, tree, sd, 100 + s, n_rays, gen)
+    dt = time.time() - t0
+    value = n_rays * args.steps / dt
+    sample = "%d of the %d rays of each step (random pixels of the 800x800 view), %d steps" % (n_rays, N_RAYS, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config({"rays_per_step_sample": n_rays}),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="robir_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default=None, help="visibility-MLP engine: ffma | tc")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import robir_b200
+    from robir_b200 import _lib, dist as rdist, ops, rng
+    from robir_b200.loss import InvLoss, pbr_step_loss
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.engine:
+        ops.ENGINE["vis"] = args.engine
+    rng.set_mode("device")   # randoms are drawn on the GPU (the reference draws on the CPU and copies; same math)
+
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M_LOBES, sdf_radius=SDF_RADIUS)
+    model = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=M_LOBES)))
+    model.load_state_dict(sd, strict=True)
+    model.to(dev).train()
+    model.generate()                                   # octree build: excluded from the metric
+    loss_fn = InvLoss()
+    params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters())
+    opt = torch.optim.Adam(params, lr=5e-4)           # training/train_pbr.py:104-105, hotdog.conf:25
+    reducer = rdist.GradAllReducer(params)
+    pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
+
+    def host_batch(step):
+        pix = synthetic.training_pixels(step * world + rank, n=N_RAYS)
+        uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None].pin_memory()
+        gt = torch.full((1, N_RAYS, 3), 0.5).pin_memory()
+        om = torch.ones(1, N_RAYS, dtype=torch.bool).pin_memory()
+        return uv, om, gt
+
+    def train_step(uv, om, gt):
+        inp = {"uv": uv, "object_mask": om, "pose": pose, "intrinsics": K,
+               "hdr_shift": model.gamma.hdr_shift.as_input().expand(N_RAYS, 1)}
+        out = model(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = pbr_step_loss(model, loss_fn, out, {"rgb": gt})
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer()
+        opt.step()
+        return loss, out["network_object_mask"]
+
+    total = args.warmup + args.steps
+    batches = [host_batch(s) for s in range(total)]
+    dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for s in range(args.warmup):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.warmup, total):
+            fn(s)
+        e1.record()
+        barrier()
+        return rdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+
+    # ---- (1) device-resident inputs: the headline `value`
+    hits = []
+    clocks = ClockSampler(local)
+    ops.Stats.reset()
+    _lib.launch_count = 0
+    launches_before = None
+
+    def step_resident(s):
+        nonlocal launches_before
+        if s == args.warmup:
+            launches_before = _lib.launch_count
+            ops.Stats.reset()
+        loss, m = train_step(*dev_batches[s])
+        if s >= args.warmup:
+            hits.append(m.sum())
+
+    clocks.start()
+    t_res = timed(step_resident)
+    clk = clocks.stop()
+    launches = _lib.launch_count - launches_before
+    pairs_total = int(ops.Stats.n_pairs.item())
+    n_hits = int(torch.stack(hits).sum().item())
+    value = rdist.sum_over_ranks(N_RAYS * args.steps, dev) / t_res
+
+    # ---- (2) end to end through the public API with host buffers: H2D of the batch + D2H of the loss inside the region
+    h2d = sum(t.numel() * t.element_size() for t in batches[0])
+    losses = []
+
+    def step_e2e(s):
+        uv, om, gt = (t.to(dev, non_blocking=True) for t in batches[s])
+        loss, _ = train_step(uv, om, gt)
+        losses.append(float(loss.item()))          # device -> host read of the step's result
+
+    t_e2e = timed(step_e2e)
+    e2e = rdist.sum_over_ranks(N_RAYS * args.steps, dev) / t_e2e
+
+    # ---- (3) dominant kernel, timed live with CUDA events on the launching stream
+    ops.PROFILE = []
+    ops.Stats.reset()
+    prof_steps = min(args.steps, 5)
+    for s in range(args.warmup, args.warmup + prof_steps):
+        train_step(*dev_batches[s])
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    pairs_prof = int(ops.Stats.n_pairs.item())
+    t_fwd = sum(a.elapsed_time(b) for n, a, b, _ in prof if n == "vis_mlp_fwd") * 1e-3
+    t_bwd = sum(a.elapsed_time(b) for n, a, b, _ in prof if n == "vis_mlp_bwd") * 1e-3
+    n_fwd = sum(1 for n, *_ in prof if n == "vis_mlp_fwd")
+    peaks, peak_kind = measured_peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    achieved = FLOP_PER_QUERY * pairs_prof / max(t_fwd, 1e-9) / 1e12
+    roofline = {"bound": "tensor", "kernel": "vis_mlp_fwd (%s engine)" % ops.ENGINE["vis"], "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peak_kind,
+                "algorithmic_flop_per_launch": FLOP_PER_QUERY * pairs_prof / max(n_fwd, 1),
+                "avg_launch_ms": 1e3 * t_fwd / max(n_fwd, 1), "launches_timed": n_fwd,
+                "bwd_kernel": {"achieved": FLOP_PER_QUERY * pairs_prof / max(t_bwd, 1e-9) / 1e12,
+                               "share_of_step": t_bwd / prof_steps / (t_res / args.steps)},
+                "share_of_step": t_fwd / prof_steps / (t_res / args.steps)}
+
+    # ---- (4) CPU baseline: the oracle port on the host cores, rank 0, bounded sample of the same workload
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        tree = model.ray_tracer.sdf_octree
+        O, P, otree = oracle_setup(sd, tree.host_arrays())
+        gen = torch.Generator().manual_seed(1234)
+        n_s = 128
+        oracle_step(O, P, otree, {k: v.clone() for k, v in sd.items()}, 0, 16, gen)   # warm-up
+        sd_cpu = {k: v.clone() for k, v in sd.items()}
+        t0 = time.time()
+        oracle_step(O, P, otree, sd_cpu, args.warmup, n_s, gen)
+        dt = time.time() - t0
+        cpu = {"value": n_s / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": "first %d of the %d rays of one step, fwd+loss+bwd, octree arrays copied from the GPU build"
+                         % (n_s, N_RAYS)}
+    if world > 1:
+        torch.distributed.barrier()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config({"parallelism": "rays x%d (+ NCCL grad all-reduce)" % world,
+                                       "hit_fraction": n_hits / float(N_RAYS * args.steps),
+                                       "vis_queries_per_step": pairs_total / float(args.steps),
+                                       "vis_engine": ops.ENGINE["vis"], "rng": "device"}),
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "final_loss": losses[-1] if losses else None}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+/* robir_b200 C ABI -- the drop-in boundary of the B200-native RobIR hot path.
+ *
+ * The reference (ingra14m/RobIR) is pure Python/PyTorch and has no FFI; its seams are Python attributes
+ * (SURVEY.md section 8b).  This library is what a binding for those seams calls: plain device pointers, sizes and
+ * scalars, a CUDA stream, an int status (0 = ok; otherwise robir_last_error() describes the failure).  No allocation,
+ * no host synchronisation and no C++ exceptions cross the boundary; all buffers (including workspaces) are owned by
+ * the caller.  Every pointer is a device pointer to contiguous fp32 data unless stated otherwise.
+ * "file:line" citations are into the reference tree.
+ */
+#ifndef ROBIR_B200_H_
+#define ROBIR_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plumbing ---------------------------------------------------------------------------------------------------- */
+const char* robir_last_error(void);
+int robir_abi_version(void);
+int robir_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- weight packing (torch Linear weight [N][K] row-major) ------------------------------------------------------- */
+/* Wt[Kpad][Npad] = scale * W[:, k_begin : k_begin+k_count]^T, zero padded. */
+int robir_pack_transpose(const float* W, int N, int K, int k_begin, int k_count, float* Wt, int Kpad, int Npad,
+                         float scale, void* stream);
+/* out[Npad][Kpad] = W[:, k_begin : k_begin+k_count], zero padded. */
+int robir_pack_window(const float* W, int N, int K, int k_begin, int k_count, float* out, int Npad, int Kpad,
+                      void* stream);
+/* nn.utils.weight_norm folding (model/neus_model.py:378-379): Wt[k][n] = g[n] v[n][k] / ||v[n]||, rows
+ * [n_begin, n_begin+n_count) of v, transposed and zero padded to [Kpad][Npad]. */
+int robir_pack_wn_transpose(const float* v, const float* g, int N, int K, int n_begin, int n_count, float* Wt,
+                            int Kpad, int Npad, void* stream);
+int robir_pack_wn_row(const float* v, const float* g, int K, int n, float* out, void* stream);
+
+/* ---- a5: NeuS SDF network, value + normal + feature in one launch --------------------------------------------------
+ * replaces ImplicitNetworkMy.forward / .gradient (model/neus_model.py:785-818) over SDFNetwork.forward (:385-417). */
+typedef struct {
+  const float* pts; int n;          /* [n][3] */
+  float in_scale;                   /* 2.0: stage-2 points (normalize(), :785-786); 1.0: NeuS coordinates */
+  float sdf_scale, feat_scale;      /* 0.5 / 0.5 for ImplicitNetworkMy.forward (:788-792) */
+  const float* Wt[8];               /* folded, transposed layers 0..7: [64|256][256] */
+  const float* bias[8];             /* [256] zero padded */
+  const float* w8_sdf;              /* [256] folded row 0 of layer 8 */
+  const float* b8;                  /* [257] */
+  const float* Wt8_feat;            /* [256][256] folded rows 1..256 of layer 8, transposed (NULL if feat == NULL) */
+  float* sdf;                       /* [n] */
+  float* grad;                      /* [n][3] or NULL  (d sdf / d p, forward-mode) */
+  float* feat;                      /* [n][256] or NULL */
+} robir_sdf_params;
+int robir_sdf_eval(const robir_sdf_params* p, int sm_count, void* stream);
+
+/* ---- a2: camera rays: rend_util.get_camera_params + lift (utils/rend_util.py:51-97), one 4x4 pose ----------------- */
+int robir_camera_rays(int N, const float* uv /*[N][2]*/, const float* pose /*[4][4]*/, const float* K /*[3][3]*/,
+                      float* dirs /*[N][3]*/, void* stream);
+
+/* ---- a4: octree surface tracer: OctreeSDF.cast (utils/octree.py:421-438) over multi_step_cast (:493-585) and
+ * fast_volume_render (:459-471), + OctreeTracing.forward (model/octree_tracing.py:43-60) --------------------------- */
+typedef struct {
+  const void* nodes;                /* [n_nodes] 32-byte records {min.xyz, size.xyz, child_base(int), sdf_val} */
+  const int* grid;                  /* [gx][gy][gz] base cell -> node (Octree.cache_index, :143) */
+  int gx, gy, gz, n_nodes;
+  float rminx, rminy, rminz, rsizex, rsizey, rsizez;   /* root box (Octree.whole_box) */
+} robir_octree_view;
+typedef struct {
+  robir_octree_view view;
+  const float* sdf_grad;            /* [n_nodes][3] unit gradients at node centres (:392-397) */
+  const float* rays_o;              /* [K / o_div][3] */
+  const float* rays_d;              /* [K][3] */
+  int K, o_div;                     /* ray r starts at origin r / o_div */
+  int max_iter;                     /* -1 primary; 32 secondary (origin bias 0.005, iteration cap; :504-505, :526) */
+  float eps;                        /* 1e-3 */
+  float refine_limit;               /* fp32(10 * min_step) (:433) */
+  float last_node_sdf;              /* sdf_val[-1]: what an out-of-box micro-march sample reads */
+  float* state_t; int* state_ptr;   /* [K] workspaces */
+  float* out_t; float* out_x;       /* [K], [K][3] */
+  unsigned char* out_hit;           /* [K] */
+  unsigned* counters;               /* [robir_octree_counters_len()] zero-initialised: live rays per lock-step
+                                       iteration, then {node visits, micro-march samples, iterations} */
+} robir_octree_cast_params;
+int robir_octree_counters_len(void);
+int robir_octree_cast(const robir_octree_cast_params* p, int sm_count, void* stream);
+
+/* ---- a10/a11: visibility sample directions (model/sg_render.py:123-146 and :204-240) ------------------------------ */
+int robir_sample_dirs_fwd(int K, int S, const float* axis_f, const float* axis_w, const float* sharp,
+                          const float* lam_w, const float* sg_range /*[1]*/, const float* u_theta /*[K][S]*/,
+                          const float* u_phi, int renorm_axis, float* dirs /*[K*S][3]*/, float* w /*[K*S]*/,
+                          void* stream);
+int robir_sample_dirs_bwd(int K, int S, const float* axis_f, const float* axis_w, const float* sharp,
+                          const float* lam_w, const float* sg_range, const float* u_theta, const float* u_phi,
+                          int renorm_axis, const float* g_dirs, const float* g_w, float* g_axis_f, float* g_axis_w,
+                          float* g_sharp, float* g_lam_w, float* g_sg_range /*[1], zero-initialised*/, void* stream);
+
+/* ---- a12: VisNetwork layer 0, factorised: tab[n][256] = PE10(x[n][3]) . Wt[64][256] (+ bias) ---------------------- */
+int robir_pe_linear(const float* x, int n, const float* Wt, const float* bias, float* tab, void* stream);
+
+/* ---- a10: (point, direction) pair lists.  live(i,j) = n_i . dir_j > 1e-6 (model/sg_render.py:155, :246) ----------- */
+int robir_diffuse_rows(int n, int M, int S, const float* normals, const float* dirs, uint32_t* bits /*[n][M]*/,
+                       int* lobe_off /*[n][M+1]*/, int* start /*[n]*/, int* rowA, int* rowB /*[n*roundup(M*S,64)]*/,
+                       int* n_tiles /*[1]*/, long long* n_pairs /*[1], accumulated*/, void* stream);
+int robir_spec_rows(int n, int S, int rows_padded, const float* normals, const float* dirs, int* rowA, int* rowB,
+                    int* n_tiles, long long* n_pairs, void* stream);
+
+/* ---- a10-a12: fused visibility MLP over a pair list: relu(tabA[a]+tabB[b]) -> 3 x (256x256, ReLU) -> sigmoid(z1-z0)
+ * replaces the 2M-row VisModel batches of get_diffuse_visibility (model/sg_render.py:157-173) and
+ * get_specular_visibility (:259-278).  mask: [rows][4][8] uint32 ReLU sign bits for the backward, or NULL. */
+int robir_vis_mlp_fwd(const float* tabA, const float* tabB, const int* rowA, const int* rowB, const int* n_tiles,
+                      int max_tiles, const float* Wt1, const float* Wt2, const float* Wt3, const float* b1,
+                      const float* b2, const float* b3, const float* wd, const float* bd, float* vis, uint32_t* mask,
+                      int sm_count, void* stream);
+/* input-gradient of the same MLP w.r.t. the direction (through PE): g_dirs [nB][3] accumulated (zero-initialised). */
+int robir_vis_mlp_bwd(const int* rowB, const int* n_tiles, int max_tiles, const float* W1, const float* W2,
+                      const float* W3, const float* W0d /*[256][256]: W0[:,63:126] zero padded*/, const float* wd,
+                      const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
+                      int sm_count, void* stream);
+
+/* ---- a10/a11: weighted per-lobe / per-point means (model/sg_render.py:180-183, :283-294) -------------------------- */
+int robir_diffuse_reduce_fwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,
+                             const float* vis, const float* w, float* light_vis /*[n][M]*/, void* stream);
+int robir_diffuse_reduce_bwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,
+                             const float* vis, const float* w, const float* light_vis, const float* g_lv, float* g_vis,
+                             float* g_w /*[M*S], zero-initialised*/, void* stream);
+int robir_spec_reduce_fwd(int n, int S, int inv, int testing, const int* rowB, const float* vis, const float* w,
+                          float* out /*[n]*/, void* stream);
+int robir_spec_reduce_bwd(int n, int S, int inv, const int* rowB, const float* vis, const float* w, const float* out,
+                          const float* g_out, float* g_vis, float* g_w, void* stream);
+
+/* ---- a9: SG render: render_with_all_sg / render_with_sg (model/sg_render.py:304-565), forward and backward -------- */
+typedef struct {
+  int n, M, Mi, lin_diff;
+  const float *normal, *view, *rough, *albedo, *spec_refl, *lgt, *ind_lgt, *light_vis, *bv_dir, *bv_ind, *ind_integral;
+  float *sg_rgb, *sg_spec, *sg_diff, *vis_shadow, *ind_rgb, *ind_spec, *ind_diff, *pre /*[n][9]*/;
+  const float *g_sg_rgb, *g_sg_spec, *g_sg_diff, *g_ind_rgb, *g_ind_spec, *g_ind_diff;   /* NULL = zero */
+  float *g_lgt /*[M][7] zero-init*/, *g_ind_lgt, *g_light_vis, *g_bv_dir, *g_bv_ind, *g_rough, *g_albedo,
+      *g_spec_refl /*[1] zero-init*/, *g_ind_integral;
+} robir_sg_params;
+int robir_sg_render_fwd(const robir_sg_params* p, void* stream);
+int robir_sg_render_bwd(const robir_sg_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBIR_B200_H_ */

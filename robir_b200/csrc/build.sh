@@ -1,0 +1,22 @@
+#!/bin/bash
+# Builds librobir_b200.so in-tree (sm_100a only).  Called by __graft_entry__.build().
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --expt-relaxed-constexpr"
+mkdir -p build
+obj() { # src out extra
+  if [ ! -f "$2" ] || [ "$1" -nt "$2" ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$2")" ]; then
+    echo "nvcc $1"
+    $NVCC $ARCH $COMMON $3 -c "$1" -o "$2"
+  fi
+}
+obj capi.cu build/capi.o "" &
+obj vis.cu build/vis.o "-Xptxas -v" &
+obj sg.cu build/sg.o "" &
+obj sdf.cu build/sdf.o "" &
+obj trace.cu build/trace.o "-fmad=false" &
+wait
+$NVCC $ARCH -shared -o ../librobir_b200.so build/capi.o build/vis.o build/sg.o build/sdf.o build/trace.o -lcudart_static -lpthread -ldl -lrt
+echo "built $(cd .. && pwd)/librobir_b200.so"

@@ -1,0 +1,240 @@
+// Fused spherical-Gaussian render at the hit points: direct lights (M shared lobes, diffuse +
+// specular, with per-lobe light visibility and per-point BRDF visibility) and indirect lights (Mi per-point lobes,
+// specular only; diffuse = indir_integral * albedo / pi), forward and backward in one launch each.
+// Reference: model/sg_render.py:304-337 (render_with_all_sg), :343-565 (render_with_sg), single view, metallic=None,
+// fun_spec=False, diffuse_vis=None.  Math lives in sg_math.h; the backward uses forward-mode duals per (point, lobe).
+#include "common.cuh"
+#include "sg_math.h"
+
+namespace robir {
+
+struct SgParams {
+  int n, M, Mi;
+  int lin_diff;
+  const float* normal;        // [n][3]
+  const float* view;          // [n][3] unit, towards camera
+  const float* rough;         // [n]
+  const float* albedo;        // [n][3]
+  const float* spec_refl;     // [1]  (already abs()'ed by the caller, train_pbr.py:377)
+  const float* lgt;           // [M][7] raw direct SGs
+  const float* ind_lgt;       // [n][Mi][7] raw indirect SGs (may be null when Mi == 0)
+  const float* light_vis;     // [n][M]
+  const float* bv_dir;        // [n]
+  const float* bv_ind;        // [n]
+  const float* ind_integral;  // [n][3] (already * 2 pi, train_pbr.py:365)
+  // forward outputs
+  float* sg_rgb; float* sg_spec; float* sg_diff; float* vis_shadow;
+  float* ind_rgb; float* ind_spec; float* ind_diff;
+  float* pre;                 // [n][9] pre-clamp sums: direct spec(3), direct diff(3), indirect spec(3)
+  // backward inputs (null = zero)
+  const float* g_sg_rgb; const float* g_sg_spec; const float* g_sg_diff;
+  const float* g_ind_rgb; const float* g_ind_spec; const float* g_ind_diff;
+  // backward outputs
+  float* g_lgt;               // [M][7] atomically accumulated (zero-init by caller)
+  float* g_ind_lgt;           // [n][Mi][7]
+  float* g_light_vis;         // [n][M]
+  float* g_bv_dir; float* g_bv_ind; float* g_rough;   // [n]
+  float* g_albedo;            // [n][3]
+  float* g_spec_refl;         // [1] atomically accumulated
+  float* g_ind_integral;      // [n][3]
+};
+
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* sh /* [NV][4] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = warp_sum(v[i]);
+    if (lane == 0) sh[i * 4 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = (sh[i * 4] + sh[i * 4 + 1]) + (sh[i * 4 + 2] + sh[i * 4 + 3]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) sg_render_fwd_kernel(SgParams p) {
+  __shared__ float sh[16 * 4];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const V3<float> nrm = {p.normal[3 * i], p.normal[3 * i + 1], p.normal[3 * i + 2]};
+  const V3<float> view = {p.view[3 * i], p.view[3 * i + 1], p.view[3 * i + 2]};
+  const float rough = p.rough[i];
+  const float alb[3] = {p.albedo[3 * i], p.albedo[3 * i + 1], p.albedo[3 * i + 2]};
+  const float sr = p.spec_refl[0];
+  const SpecPoint<float> sp = spec_point<float>(nrm, view, rough);
+  const float F = fresnel<float>(sr, sp.v_dot_h);
+  const float bvd = p.bv_dir[i], bvi = p.bv_ind[i];
+  // v[0..2] spec, v[3..5] diff, v[6..8] sum(lv*mu), v[9..11] sum(mu), v[12..14] indirect spec
+  float v[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) v[k] = 0.f;
+  for (int m = tid; m < p.M; m += blockDim.x) {
+    const LightSG<float> l = decode_light<float>(p.lgt + 7 * m);
+    const float lv = p.light_vis[(size_t)i * p.M + m];
+    const float Ks = spec_lobe_kernel<float>(nrm, sp, l.lobe, l.lam);
+    const float Kd = diffuse_lobe_kernel<float>(nrm, l.lobe, l.lam);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] += l.mu[c] * bvd * F * Ks;
+      const float fm = p.lin_diff ? l.mu[c] * lv : l.mu[c] * lv * (alb[c] / kPi);
+      v[3 + c] += fm * Kd;
+      v[6 + c] += lv * l.mu[c];
+      v[9 + c] += l.mu[c];
+    }
+  }
+  for (int m = tid; m < p.Mi; m += blockDim.x) {
+    const LightSG<float> l = decode_light<float>(p.ind_lgt + ((size_t)i * p.Mi + m) * 7);
+    const float Ks = spec_lobe_kernel<float>(nrm, sp, l.lobe, l.lam);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[12 + c] += l.mu[c] * bvi * F * Ks;
+  }
+  block_sum<15>(v, sh);
+  if (tid < 3) {
+    const int c = tid;
+    const float spec = fmaxf(v[c], 0.f), diff = fmaxf(v[3 + c], 0.f);
+    p.pre[9 * i + c] = v[c];
+    p.pre[9 * i + 3 + c] = v[3 + c];
+    p.pre[9 * i + 6 + c] = v[12 + c];
+    p.sg_spec[3 * i + c] = spec;
+    p.sg_diff[3 * i + c] = diff;
+    p.sg_rgb[3 * i + c] = spec + diff;
+    p.vis_shadow[3 * i + c] = v[6 + c] / fmaxf(v[9 + c], 1e-4f);
+    const float ispec = p.Mi > 0 ? fmaxf(v[12 + c], 0.f) : 0.f;
+    float idiff = 0.f;
+    if (p.Mi > 0) idiff = p.lin_diff ? p.ind_integral[3 * i + c] : p.ind_integral[3 * i + c] * (alb[c] / kPi);
+    p.ind_spec[3 * i + c] = ispec;
+    p.ind_diff[3 * i + c] = idiff;
+    p.ind_rgb[3 * i + c] = ispec + idiff;
+  }
+}
+
+// dual layout, specular: 0-6 raw SG, 7 rough, 8 spec_refl, 9 brdf_vis;  diffuse: 0-6 raw SG, 7 light_vis
+__global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
+  __shared__ float sh[8 * 4];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const V3<float> nrm = {p.normal[3 * i], p.normal[3 * i + 1], p.normal[3 * i + 2]};
+  const V3<float> view = {p.view[3 * i], p.view[3 * i + 1], p.view[3 * i + 2]};
+  const float rough = p.rough[i];
+  const float alb[3] = {p.albedo[3 * i], p.albedo[3 * i + 1], p.albedo[3 * i + 2]};
+  const float sr = p.spec_refl[0];
+  auto ld = [&](const float* g, int c) { return g ? g[3 * i + c] : 0.f; };
+  float gs[3], gd[3], gis[3], gid[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // torch.clamp(x, min=0) passes the gradient where x >= 0
+    gs[c] = p.pre[9 * i + c] >= 0.f ? ld(p.g_sg_rgb, c) + ld(p.g_sg_spec, c) : 0.f;
+    gd[c] = p.pre[9 * i + 3 + c] >= 0.f ? ld(p.g_sg_rgb, c) + ld(p.g_sg_diff, c) : 0.f;
+    gis[c] = (p.Mi > 0 && p.pre[9 * i + 6 + c] >= 0.f) ? ld(p.g_ind_rgb, c) + ld(p.g_ind_spec, c) : 0.f;
+    gid[c] = p.Mi > 0 ? ld(p.g_ind_rgb, c) + ld(p.g_ind_diff, c) : 0.f;
+  }
+  typedef Dual<10> DS;
+  typedef Dual<8> DD;
+  const V3<DS> nS = lift3<DS>(nrm), vS = lift3<DS>(view);
+  const SpecPoint<DS> sp = spec_point<DS>(nS, vS, DS::seed(rough, 7));
+  const DS F = fresnel<DS>(DS::seed(sr, 8), sp.v_dot_h);
+  const V3<DD> nD = lift3<DD>(nrm);
+  // per-point accumulators: 0 rough, 1 spec_refl, 2 bv_dir, 3 bv_ind, 4-6 albedo
+  float acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+
+  auto spec_lobe = [&](const float* raw, float bv, const float (&g)[3], float* g_raw, int bv_slot) {
+    DS r[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r[k] = DS::seed(raw[k], k);
+    const LightSG<DS> l = decode_light<DS>(r);
+    const DS Ks = spec_lobe_kernel<DS>(nS, sp, l.lobe, l.lam);
+    const DS common = DS::seed(bv, 9) * F * Ks;
+    DS tot(0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tot = tot + (l.mu[c] * common) * g[c];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) g_raw[k] = tot.d[k];
+    acc[0] += tot.d[7];
+    acc[1] += tot.d[8];
+    acc[bv_slot] += tot.d[9];
+  };
+
+  const bool any_dir = (gs[0] != 0.f) | (gs[1] != 0.f) | (gs[2] != 0.f) | (gd[0] != 0.f) | (gd[1] != 0.f) | (gd[2] != 0.f);
+  for (int m = tid; m < p.M; m += blockDim.x) {
+    float g_raw[7] = {0, 0, 0, 0, 0, 0, 0};
+    float g_lv = 0.f;
+    if (any_dir) {
+      spec_lobe(p.lgt + 7 * m, p.bv_dir[i], gs, g_raw, 2);
+      // diffuse
+      DD r[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) r[k] = DD::seed(p.lgt[7 * m + k], k);
+      const LightSG<DD> l = decode_light<DD>(r);
+      const DD lv = DD::seed(p.light_vis[(size_t)i * p.M + m], 7);
+      const DD Kd = diffuse_lobe_kernel<DD>(nD, l.lobe, l.lam);
+      DD tot(0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a = p.lin_diff ? 1.f : alb[c] / kPi;
+        const DD base = l.mu[c] * lv * Kd;
+        tot = tot + base * (a * gd[c]);
+        if (!p.lin_diff) acc[4 + c] += base.v * gd[c] / kPi;
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) g_raw[k] += tot.d[k];
+      g_lv = tot.d[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        if (g_raw[k] != 0.f) atomicAdd(p.g_lgt + 7 * m + k, g_raw[k]);
+    }
+    p.g_light_vis[(size_t)i * p.M + m] = g_lv;
+  }
+  for (int m = tid; m < p.Mi; m += blockDim.x) {
+    float g_raw[7] = {0, 0, 0, 0, 0, 0, 0};
+    spec_lobe(p.ind_lgt + ((size_t)i * p.Mi + m) * 7, p.bv_ind[i], gis, g_raw, 3);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) p.g_ind_lgt[((size_t)i * p.Mi + m) * 7 + k] = g_raw[k];
+  }
+  block_sum<7>(acc, sh);
+  if (tid == 0) {
+    p.g_rough[i] = acc[0];
+    if (acc[1] != 0.f) atomicAdd(p.g_spec_refl, acc[1]);
+    p.g_bv_dir[i] = acc[2];
+    p.g_bv_ind[i] = acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float ga = acc[4 + c];
+      float gi = 0.f;
+      if (p.Mi > 0) {
+        if (p.lin_diff) {
+          gi = gid[c];
+        } else {
+          gi = gid[c] * (alb[c] / kPi);
+          ga += gid[c] * p.ind_integral[3 * i + c] / kPi;
+        }
+      }
+      p.g_albedo[3 * i + c] = ga;
+      p.g_ind_integral[3 * i + c] = gi;
+    }
+  }
+}
+
+}  // namespace robir
+
+using namespace robir;
+
+extern "C" {
+
+// Argument block mirrors SgParams field for field (plain pointers and ints; see include/robir_b200.h).
+int robir_sg_render_fwd(const SgParams* p, void* stream) {
+  if (p->n == 0) return 0;
+  RB_REQUIRE(p->M >= 0 && p->Mi >= 0, "sg_render_fwd: bad lobe counts");
+  sg_render_fwd_kernel<<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int robir_sg_render_bwd(const SgParams* p, void* stream) {
+  if (p->n == 0) return 0;
+  sg_render_bwd_kernel<<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

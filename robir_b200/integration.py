@@ -1,0 +1,57 @@
+"""``install(model)``: re-bind the hot path on a LIVE reference ``IDRNetwork`` (built by the reference's own code)
+without editing reference files.  Seams used:
+
+  1. ``model.ray_tracer`` / ``model.octree_ray_tracer``  -> robir_b200.tracing.OctreeTracing (same call signature,
+     ``generate(sdf_fn, tex_sampler)`` discovered via hasattr by the runners, training/train_pbr.py:403-407);
+  2. ``model.implicit_network.forward / gradient``       -> fused CUDA value / normal kernel reading the module's own
+     weight_g / weight_v / bias parameters (state_dict untouched);
+  3. ``model.sg_render.render_with_all_sg`` (imported inside the runners' get_sg_render at call time,
+     training/train_pbr.py:350) and the module-level name in model.implicit_differentiable_renderer -> ours;
+  4. ``torch.rand/randn(...).cuda()`` draws stay where the reference makes them (CPU generator), so seeds reproduce.
+"""
+import sys
+import types
+
+import torch
+
+from . import ops, sg_render, tracing
+from ._lib import RobirError
+
+
+def install(model, patch_modules=True):
+    if not hasattr(model, "visibility_network") or not hasattr(model, "implicit_network"):
+        raise RobirError("install() expects a reference IDRNetwork")
+    rt_kwargs = {}
+    for name in ("ray_tracer", "octree_ray_tracer"):
+        old = getattr(model, name, None)
+        if old is None or not hasattr(old, "max_iter"):
+            continue                      # use_octree=False keeps the reference RayTracing (sphere tracer row a3)
+        new = tracing.OctreeTracing(max_iter=old.max_iter)
+        setattr(model, name, new)
+    net = model.implicit_network
+    sdfw = ops.SdfWeights(net.neus_model.sdf_network)
+
+    def forward(self, points, compute_grad=False):
+        if points.numel() == 0:
+            return torch.ones_like(points)
+        sdf, _, feat = ops.sdf_eval(sdfw, points, want_feat=True)
+        return torch.cat([sdf[:, None], feat], -1)
+
+    def gradient(self, x):
+        if x.numel() == 0:
+            return torch.ones_like(x)
+        return ops.sdf_eval(sdfw, x, want_grad=True)[1].unsqueeze(1)
+
+    net.forward = types.MethodType(forward, net)
+    net.gradient = types.MethodType(gradient, net)
+    net.sdf = types.MethodType(lambda self, p: ops.sdf_eval(sdfw, p)[0], net)
+    net.sdf_and_normal = types.MethodType(lambda self, p: ops.sdf_eval(sdfw, p, want_grad=True)[:2], net)
+    if patch_modules:
+        for modname in ("model.sg_render", "model.implicit_differentiable_renderer"):
+            mod = sys.modules.get(modname)
+            if mod is not None:
+                mod.render_with_all_sg = sg_render.render_with_all_sg
+                if modname == "model.sg_render":
+                    mod.get_diffuse_visibility = sg_render.get_diffuse_visibility
+                    mod.get_specular_visibility = sg_render.get_specular_visibility
+    return model

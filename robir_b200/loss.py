@@ -1,0 +1,53 @@
+"""PBR-stage loss, the consumer of the hot path's outputs (model/loss.py:7-125 InvLoss, training/train_pbr.py:313-346
+pbr_step / white_loss).  Elementwise torch glue; fusing it into the render epilogue is a 'next' row."""
+import torch
+import torch.nn as nn
+
+from .networks import positional_encoding
+
+
+class InvLoss(nn.Module):
+    def __init__(self, idr_rgb_weight=1.0, eikonal_weight=0.1, mask_weight=100.0, alpha=50.0, sg_rgb_weight=1.0,
+                 kl_weight=1.0, latent_smooth_weight=1.0, brdf_multires=10, loss_type='L1'):
+        super().__init__()
+        self.sg_rgb_weight, self.kl_weight, self.latent_smooth_weight = sg_rgb_weight, kl_weight, latent_smooth_weight
+        self.l2 = loss_type == 'L2'
+
+    @staticmethod
+    def kl_divergence(rho, latent):
+        rho_hat = torch.mean(torch.sigmoid(latent), 0)
+        rho = torch.full_like(rho_hat, rho)
+        return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4))
+                          + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
+
+    def forward(self, model_outputs, ground_truth, mat_model=None, train_idr=False, train_spec=False, hdr_fn=None):
+        rgb_gt = ground_truth['rgb'].to(model_outputs['sg_rgb'].device)
+        nm = model_outputs['network_object_mask'] & model_outputs['object_mask']
+        pred = model_outputs['sg_rgb'] + model_outputs['indir_rgb']
+        pred = hdr_fn(pred) if hdr_fn is not None else pred / (pred + 1)
+        diff = pred - rgb_gt.reshape(-1, 3)
+        per = (diff * diff if self.l2 else diff.abs()) * nm[:, None]
+        sg_rgb_loss = per.sum() / float(model_outputs['object_mask'].shape[0])
+        smooth = (model_outputs['diffuse_albedo'] - model_outputs['random_xi_diffuse_albedo']).abs().mean() + \
+            (model_outputs['roughness'][..., 0] - model_outputs['random_xi_roughness'][..., 0]).abs().mean() * 0.2
+        pts = model_outputs['points'][model_outputs['network_object_mask']]
+        enc = mat_model.spec_brdf_encoder_layer if train_spec else mat_model.brdf_encoder_layer
+        kl = self.kl_divergence(0.05, enc.encode(positional_encoding(pts, 10)))
+        sm = model_outputs['surface_mask']
+        normal_loss = ((model_outputs['normal_map'][sm] - model_outputs['normals'][sm]) ** 2).mean()
+        return {'sg_rgb_loss': sg_rgb_loss, 'kl_loss': self.kl_weight * kl,
+                'latent_smooth_loss': self.latent_smooth_weight * smooth, 'normal_loss': normal_loss,
+                'loss': self.sg_rgb_weight * sg_rgb_loss}
+
+
+def white_loss(lgtSGs):
+    lgt = torch.abs(lgtSGs[..., -3:])
+    mu = lgt.norm(dim=-1, keepdim=True) + 1e-4
+    return (lgt / mu).var(-1).mean() * 0.01
+
+
+def pbr_step_loss(model, loss_fn, model_outputs, ground_truth, train_spec=True):
+    out = loss_fn(model_outputs, ground_truth, mat_model=model.envmap_material_network, train_idr=False,
+                  train_spec=train_spec, hdr_fn=model.gamma.hdr_shift.hdr2ldr)
+    loss = out['loss'] + out['kl_loss'] * 1.0 + out['latent_smooth_loss'] * 0.1
+    return loss + white_loss(model.envmap_material_network.lgtSGs), out

@@ -1,0 +1,278 @@
+"""Parameter containers with the reference's module tree / state_dict keys (134 tensors), so
+that reference checkpoints load here and vice versa.  The heavy evaluation paths go through the CUDA operators in
+``ops``; the small material / indirect networks (<2 % of the step's FLOPs) are plain library GEMMs.
+
+Reference classes mirrored: SDFNetwork / RenderingNetwork / SingleVarianceNetwork / NeuSModel / ImplicitNetworkMy
+(model/neus_model.py:312-438,489-560,644-650,682-884), SparseAE / EnvmapMaterialNetwork
+(model/sg_envmap_material.py:40-275), IndirctIllumNetwork / VisNetwork (model/implicit_differentiable_renderer.py:
+170-258), GammaCorrect / ACESToneMapping (model/color_correction.py:7-137).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, rng
+
+
+def positional_encoding(x, n_freq):
+    out = [x]
+    for l in range(n_freq):
+        f = float(2 ** l)
+        out += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(out, -1)
+
+
+def integrated_positional_encoding(x, n_deg=10, var=1e-5):
+    scales = torch.tensor([2.0 ** i for i in range(n_deg)], device=x.device)
+    y = (x[:, None, :] * scales[:, None]).reshape(x.shape[0], -1)            # [n, 3*n_deg], degree-major
+    y_var = (var * scales ** 2)[:, None].expand(n_deg, x.shape[1]).reshape(1, -1)
+    yy = torch.cat([y, y + 0.5 * math.pi], -1)
+    vv = torch.cat([y_var, y_var], -1)
+    lim = 100 * math.pi
+    safe = torch.where(yy.abs() < lim, yy, yy % lim)
+    return torch.exp(-0.5 * vv) * torch.sin(safe)
+
+
+class _WNLinear(nn.Module):
+    """weight_norm(dim=0)-parametrised linear layer holding weight_g / weight_v / bias like torch's legacy hook."""
+
+    def __init__(self, in_f, out_f):
+        super().__init__()
+        w = torch.empty(out_f, in_f).uniform_(-1, 1) / math.sqrt(in_f)
+        self.weight_g = nn.Parameter(w.norm(dim=1, keepdim=True))
+        self.weight_v = nn.Parameter(w)
+        self.bias = nn.Parameter(torch.zeros(out_f))
+
+    def folded(self):
+        return self.weight_g * self.weight_v / self.weight_v.norm(dim=1, keepdim=True)
+
+
+class SDFNetwork(nn.Module):
+    def __init__(self):
+        super().__init__()
+        dims = [63] + [256] * 8 + [257]
+        for l in range(9):
+            setattr(self, "lin%d" % l, _WNLinear(dims[l], dims[l + 1] - 63 if l + 1 == 4 else dims[l + 1]))
+
+
+class RenderingNetwork(nn.Module):
+    def __init__(self):
+        super().__init__()
+        dims = [289, 256, 256, 256, 256, 3]
+        for l in range(5):
+            setattr(self, "lin%d" % l, _WNLinear(dims[l], dims[l + 1]))
+
+    def forward(self, points, normals, view_dirs, feats):
+        x = torch.cat([points, positional_encoding(view_dirs, 4), normals, feats], -1)
+        for l in range(5):
+            lin = getattr(self, "lin%d" % l)
+            x = F.linear(x, lin.folded(), lin.bias)
+            if l < 4:
+                x = torch.relu(x)
+        return torch.sigmoid(x)
+
+
+class SingleVarianceNetwork(nn.Module):
+    def __init__(self, init_val=0.3):
+        super().__init__()
+        self.variance = nn.Parameter(torch.tensor(init_val))
+
+
+class NeuSModel(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.color_network = RenderingNetwork()
+        self.sdf_network = SDFNetwork()
+        self.deviation_network = SingleVarianceNetwork(0.3)
+
+
+class ImplicitNetworkMy(nn.Module):
+    """f(p) = SDFNetwork(2p) / 2; value, gradient and features come from the fused CUDA kernel (ops.sdf_eval)."""
+
+    def __init__(self):
+        super().__init__()
+        self.neus_model = NeuSModel()
+        self._w = ops.SdfWeights(self.neus_model.sdf_network)
+
+    def forward(self, points):
+        """[k,3] -> [k,257] (sdf, features), all halved like the reference (neus_model.py:788-792)."""
+        if points.numel() == 0:
+            return torch.ones_like(points)
+        sdf, _, feat = ops.sdf_eval(self._w, points, want_feat=True)
+        return torch.cat([sdf[:, None], feat], -1)
+
+    def sdf(self, points):
+        """[k,3] -> [k]: what every tracer calls (``lambda x: implicit_network(x)[:, 0]``) without the feature GEMM."""
+        return ops.sdf_eval(self._w, points)[0]
+
+    def gradient(self, points):
+        """[k,3] -> [k,1,3]; graph-free (hard part 6)."""
+        if points.numel() == 0:
+            return torch.ones_like(points)
+        return ops.sdf_eval(self._w, points, want_grad=True)[1].unsqueeze(1)
+
+    def sdf_and_normal(self, points):
+        sdf, grad, _ = ops.sdf_eval(self._w, points, want_grad=True)
+        return sdf, grad
+
+
+def _mlp(dims, act):
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(act)
+    return nn.Sequential(*layers)
+
+
+class SparseAE(nn.Module):
+    """Encoder in->512x4->32, latent activation, decoder 32->128x2->out; noisy twin output (random_xi)."""
+
+    def __init__(self, in_dim, out_dim, smooth_on_latent=True, out_act=torch.sigmoid, latent_dim=32, high_lr=False):
+        super().__init__()
+        self.actv_fn = nn.LeakyReLU(0.2)
+        self.brdf_encoder_layer = _mlp([in_dim, 512, 512, 512, 512, latent_dim], self.actv_fn)
+        self.brdf_decoder_layer = _mlp([latent_dim, 128, 128, out_dim], self.actv_fn)
+        self.smooth_on_latent = smooth_on_latent
+        self.out_act = out_act
+        self.lc_act = torch.sigmoid
+        self.latent_dim = latent_dim
+        self.var = None  # CESR latent dropout (train_cesr.py:639-641); zeros in the PBR stage
+
+    def encode(self, x):
+        z = self.brdf_encoder_layer(x)
+        if self.var is not None:
+            z = z * (1 - self.var.to(z.device))
+        return z
+
+    def forward(self, x):
+        lc = self.lc_act(self.encode(x))
+        y = self.brdf_decoder_layer(lc)
+        if self.smooth_on_latent:
+            lc_r = lc + rng.randn(lc.shape, lc.device) * 0.01
+        else:
+            lc_r = self.lc_act(self.encode(x + rng.randn(x.shape, x.device) * 0.02))
+        y_r = self.brdf_decoder_layer(lc_r)
+        if self.out_act is not None:
+            y, y_r = self.out_act(y), self.out_act(y_r)
+        return y, y_r
+
+
+class EnvmapMaterialNetwork(nn.Module):
+    def __init__(self, multires=10, brdf_encoder_dims=None, brdf_decoder_dims=None, num_lgt_sgs=128, upper_hemi=False,
+                 specular_albedo=0.05, latent_dim=32):
+        super().__init__()
+        assert multires == 10, "the shipped configs use multires = 10 (confs_sg/*.conf)"
+        self.numLgtSGs = num_lgt_sgs
+        self.envmap = None
+        self.upper_hemi = upper_hemi
+        self.brdf_encoder_layer = SparseAE(63, 5, out_act=None)
+        self.spec_brdf_encoder_layer = SparseAE(63, 5, high_lr=True)
+        self.normal_decoder_layer = SparseAE(60, 3, out_act=None, smooth_on_latent=False)
+        self.specular_reflectance = nn.Parameter(torch.full((1, 1), float(specular_albedo)))
+        from .synthetic import synthetic_light_sgs
+        self.lgtSGs = nn.Parameter(synthetic_light_sgs(torch.Generator().manual_seed(0), num_lgt_sgs))
+
+    def forward(self, points, train_spec=False, train_norm=False):
+        pts_ipe = integrated_positional_encoding(points, 10, 1e-5)
+        emb = positional_encoding(points, 10)
+        ret = {}
+        if not train_norm:
+            brdf, brdf_r = self.spec_brdf_encoder_layer(emb)
+            if train_spec is False:
+                brdf, brdf_r = brdf.detach(), brdf_r.detach()
+            ret.update(sg_roughness=brdf[..., 3:4] * 0.9 + 0.09, sg_metallic=brdf[..., 4:5] * 0.99 + 0.01,
+                       sg_diffuse_albedo=brdf[..., :3], random_xi_roughness=brdf_r[..., 3:4] * 0.9 + 0.09,
+                       random_xi_diffuse_albedo=brdf_r[..., :3], random_xi_metallic=brdf_r[..., 4:5])
+        nm, nm_r = self.normal_decoder_layer(pts_ipe)
+        ret["sg_normal_map"] = nm / torch.clamp(nm.norm(dim=-1, keepdim=True), 1e-4)
+        ret["random_xi_normal"] = nm_r / torch.clamp(nm_r.norm(dim=-1, keepdim=True), 1e-4)
+        if train_norm:
+            return dict(sg_normal_map=ret["sg_normal_map"], random_xi_normal=ret["random_xi_normal"])
+        lgt = self.lgtSGs
+        if self.upper_hemi:
+            lgt = torch.cat((lgt[..., :1], torch.abs(lgt[..., 1:2]), lgt[..., 2:]), dim=-1)
+        ret["sg_lgtSGs"] = lgt
+        ret["sg_specular_reflectance"] = self.specular_reflectance
+        return ret
+
+
+class IndirctIllumNetwork(nn.Module):
+    def __init__(self, multires=10, dims=(512, 512, 512, 512), num_lgt_sgs=24, no_hdr=False):
+        super().__init__()
+        assert multires == 10 and not no_hdr
+        self.num_lgt_sgs = num_lgt_sgs
+        self.lobe_layer = _mlp([64] + list(dims) + [num_lgt_sgs * 6], nn.ReLU())
+        self.integral_layer = SparseAE(64, 3, out_act=None, smooth_on_latent=False)
+        self.integral_layer.lc_act = F.softplus
+
+    def forward(self, points, hdr_shift):
+        x = torch.cat([positional_encoding(points, 10), hdr_shift], -1)
+        out = self.lobe_layer(x).reshape(x.shape[0], self.num_lgt_sgs, 6)
+        ang = torch.sigmoid(out[..., :2])
+        theta, phi = ang[..., :1] * 2 * np.pi, ang[..., 1:2] * np.pi
+        lobes = torch.cat([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], -1)
+        sgs = torch.cat([lobes, torch.sigmoid(out[..., 2:3]) * 30 + 0.1, torch.relu(out[..., 3:])], -1)
+        env_int = torch.abs(self.integral_layer(x)[1])
+        return sgs, env_int
+
+
+class VisNetwork(nn.Module):
+    def __init__(self, points_multires=10, dirs_multires=10, dims=(256, 256, 256, 256)):
+        super().__init__()
+        assert points_multires == 10 and dirs_multires == 10 and tuple(dims) == (256,) * 4
+        self.vis_layer = _mlp([126] + list(dims) + [2], nn.ReLU())
+
+    def forward(self, points, view_dirs):
+        """Plain logits [k,2] (used where the reference calls the network directly, e.g. trace_radiance :632-634)."""
+        return self.vis_layer(torch.cat([positional_encoding(points, 10), positional_encoding(view_dirs, 10)], -1))
+
+
+def aces(x):
+    return x * (2.51 * x + 0.03) / (x * (2.43 * x + 0.59) + 0.14)
+
+
+def aces_inverse(x):
+    return ((0.59 * x - 0.03) + torch.sqrt((0.59 * x - 0.03) ** 2 + 4 * (2.51 - 2.43 * x) * 0.14 * x)) / (
+        2 * (2.51 - 2.43 * x))
+
+
+class ACESToneMapping(nn.Module):
+    def __init__(self, hdr_mode=0):
+        super().__init__()
+        assert hdr_mode == 0, "shipped configs use hdr_mode = 0 (confs_sg/*.conf:67)"
+        self.adapt_illum = nn.Parameter(torch.tensor(0.0))
+
+    def as_input(self):
+        return torch.clamp(self.adapt_illum * 10 + 0.5, 0, 1).view(1, 1)
+
+    def make_shift(self, shift):
+        if shift is None:
+            shift = self.as_input()
+        if not isinstance(shift, torch.Tensor):
+            shift = torch.tensor(shift, device=self.adapt_illum.device)
+        if shift.dim() == 0:
+            shift = shift[None]
+        return torch.clamp(shift, 1e-4, 1)
+
+    def hdr2ldr(self, x, raw_shift=None):
+        return aces(x) / self.make_shift(raw_shift) ** 0.2
+
+    def ldr2hdr(self, x, raw_shift=None):
+        return aces_inverse(x * self.make_shift(raw_shift) ** 0.2)
+
+
+class GammaCorrect(nn.Module):
+    def __init__(self, gamma=1.0, hdr_mode=0):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.tensor(float(gamma)))
+        self.indir_coef = nn.Parameter(torch.tensor(1.0))
+        self.dir_coef = nn.Parameter(torch.tensor(2.0))
+        self.coef = nn.Parameter(torch.tensor(1.0))
+        self.hdr_shift = ACESToneMapping(hdr_mode)
+
+    def forward(self, x):
+        return torch.pow(x, 1 / self.gamma)

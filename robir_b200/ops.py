@@ -1,0 +1,494 @@
+"""Python-side operators over the C ABI: tensor allocation, weight packing caches and torch.autograd.Function
+wrappers whose forward/backward are the hand-written CUDA kernels.  PyTorch only owns memory, streams and the
+autograd graph between operators."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import OctCastParams, OctreeView, SdfParams, SgParams, check, f32, lib, ptr, sm_count, stream
+
+TINY = 1e-6
+
+
+def _empty(*shape, dtype=torch.float32, like=None):
+    return torch.empty(*shape, dtype=dtype, device=like.device)
+
+
+def _zeros(*shape, dtype=torch.float32, like=None):
+    return torch.zeros(*shape, dtype=dtype, device=like.device)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# weight packing (cached on parameter versions; weights that are being trained are re-packed when they change)
+# ----------------------------------------------------------------------------------------------------------------------
+class _PackCache:
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, tensors, build):
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        if key != self.key:
+            self.val = build()
+            self.key = key
+        return self.val
+
+
+def pack_transpose(W, k_begin, k_count, Kpad, Npad, scale=1.0):
+    W = f32(W)
+    N, K = W.shape
+    out = _empty(Kpad, Npad, like=W)
+    check(lib().robir_pack_transpose(ptr(W), N, K, k_begin, k_count, ptr(out), Kpad, Npad, scale, stream()))
+    return out
+
+
+def pack_window(W, k_begin, k_count, Npad, Kpad):
+    W = f32(W)
+    N, K = W.shape
+    out = _empty(Npad, Kpad, like=W)
+    check(lib().robir_pack_window(ptr(W), N, K, k_begin, k_count, ptr(out), Npad, Kpad, stream()))
+    return out
+
+
+def pack_wn_transpose(v, g, n_begin, n_count, Kpad, Npad):
+    v, g = f32(v), f32(g)
+    N, K = v.shape
+    out = _empty(Kpad, Npad, like=v)
+    check(lib().robir_pack_wn_transpose(ptr(v), ptr(g), N, K, n_begin, n_count, ptr(out), Kpad, Npad, stream()))
+    return out
+
+
+class VisWeights:
+    """Packed VisNetwork weights (implicit_differentiable_renderer.py:225-258: 126 -> 256 x4 -> 2, ReLU)."""
+
+    def __init__(self, vis_layer):
+        self.layers = [vis_layer[i] for i in (0, 2, 4, 6, 8)]
+        self.cache = _PackCache()
+
+    def get(self):
+        L = self.layers
+        tensors = [t for l in L for t in (l.weight, l.bias)]
+
+        def build():
+            W0 = L[0].weight
+            if tuple(W0.shape) != (256, 126) or any(tuple(L[i].weight.shape) != (256, 256) for i in (1, 2, 3)) \
+                    or tuple(L[4].weight.shape) != (2, 256):
+                raise _lib.RobirError("VisNetwork must be 126->256->256->256->256->2 (points/dirs multires 10)")
+            d = {}
+            d["Wt0p"] = pack_transpose(W0, 0, 63, 64, 256)
+            d["Wt0d"] = pack_transpose(W0, 63, 63, 64, 256)
+            d["W0d"] = pack_window(W0, 63, 63, 256, 256)
+            d["b0"] = f32(L[0].bias)
+            for i in (1, 2, 3):
+                d["Wt%d" % i] = pack_transpose(L[i].weight, 0, 256, 256, 256)
+                d["W%d" % i] = f32(L[i].weight)
+                d["b%d" % i] = f32(L[i].bias)
+            W4, b4 = f32(L[4].weight), f32(L[4].bias)
+            d["wd"] = (W4[1] - W4[0]).contiguous()
+            d["bd"] = (b4[1] - b4[0]).reshape(1).contiguous()
+            return d
+        return self.cache.get(tensors, build)
+
+
+def pe_linear(x, Wt, bias):
+    x = f32(x)
+    n = x.shape[0]
+    out = _empty(n, 256, like=x)
+    check(lib().robir_pe_linear(ptr(x), n, ptr(Wt), ptr(bias), ptr(out), stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# sample directions
+# ----------------------------------------------------------------------------------------------------------------------
+class _SampleDirs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi, renorm):
+        K, S = u_theta.shape
+        axis_f, axis_w, sharp, lam_w, sg_range = map(f32, (axis_f, axis_w, sharp, lam_w, sg_range))
+        u_theta, u_phi = f32(u_theta), f32(u_phi)
+        dirs = _empty(K * S, 3, like=axis_f)
+        w = _empty(K * S, like=axis_f)
+        check(lib().robir_sample_dirs_fwd(K, S, ptr(axis_f), ptr(axis_w), ptr(sharp), ptr(lam_w), ptr(sg_range),
+                                          ptr(u_theta), ptr(u_phi), int(renorm), ptr(dirs), ptr(w), stream()))
+        ctx.save_for_backward(axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi)
+        ctx.renorm = int(renorm)
+        return dirs, w
+
+    @staticmethod
+    def backward(ctx, g_dirs, g_w):
+        axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi = ctx.saved_tensors
+        K, S = u_theta.shape
+        g_dirs = f32(g_dirs) if g_dirs is not None else _zeros(K * S, 3, like=axis_f)
+        g_w = f32(g_w) if g_w is not None else _zeros(K * S, like=axis_f)
+        g_af = _empty(K, 3, like=axis_f)
+        g_aw = _zeros(K, 3, like=axis_f)
+        g_sharp = _empty(K, like=axis_f)
+        g_lam = _empty(K, like=axis_f)
+        g_rng = _zeros(1, like=axis_f)
+        check(lib().robir_sample_dirs_bwd(K, S, ptr(axis_f), ptr(axis_w), ptr(sharp), ptr(lam_w), ptr(sg_range),
+                                          ptr(u_theta), ptr(u_phi), ctx.renorm, ptr(g_dirs), ptr(g_w), ptr(g_af),
+                                          None if ctx.renorm else ptr(g_aw), ptr(g_sharp), ptr(g_lam), ptr(g_rng),
+                                          stream()))
+        return g_af, g_aw, g_sharp, g_lam, g_rng.reshape(sg_range.shape), None, None, None
+
+
+def sample_dirs(axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi, renorm):
+    return _SampleDirs.apply(axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi, renorm)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused visibility queries
+# ----------------------------------------------------------------------------------------------------------------------
+class Stats:
+    """Device-side counters of executed work (for the algorithmic-FLOP roofline)."""
+    n_pairs = None  # int64 device tensor, accumulated over calls
+
+    @classmethod
+    def pairs_tensor(cls, like):
+        if cls.n_pairs is None or cls.n_pairs.device != like.device:
+            cls.n_pairs = torch.zeros(1, dtype=torch.int64, device=like.device)
+        return cls.n_pairs
+
+    @classmethod
+    def reset(cls):
+        if cls.n_pairs is not None:
+            cls.n_pairs.zero_()
+
+
+ENGINE = {"vis": "ffma"}   # "ffma" (exact fp32) | "tc" (tcgen05 bf16x3), set by robir_b200.set_engine
+PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
+
+
+class _Timed:
+    def __init__(self, name, max_tiles):
+        self.name, self.max_tiles = name, max_tiles
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.name, self.s, self.e, self.max_tiles))
+        return False
+
+
+def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
+    rows = max_tiles * 64
+    vis = _empty(rows, like=tabA)
+    mask = _empty(rows, 4, 8, dtype=torch.int32, like=tabA) if need_mask else None
+    with _Timed("vis_mlp_fwd", max_tiles):
+        check(lib().robir_vis_mlp_fwd(ptr(tabA), ptr(tabB), ptr(rowA), ptr(rowB), ptr(n_tiles), max_tiles,
+                                      ptr(W["Wt1"]), ptr(W["Wt2"]), ptr(W["Wt3"]), ptr(W["b1"]), ptr(W["b2"]),
+                                      ptr(W["b3"]), ptr(W["wd"]), ptr(W["bd"]), ptr(vis), ptr(mask), sm_count(),
+                                      stream()))
+    return vis, mask
+
+
+def _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs):
+    g_dirs = _zeros(dirs.shape[0], 3, like=dirs)
+    with _Timed("vis_mlp_bwd", max_tiles):
+        check(lib().robir_vis_mlp_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["W1"]), ptr(W["W2"]), ptr(W["W3"]),
+                                      ptr(W["W0d"]), ptr(W["wd"]), ptr(vis), ptr(g_vis), ptr(mask), ptr(dirs),
+                                      ptr(g_dirs), sm_count(), stream()))
+    return g_dirs
+
+
+class _DiffuseVis(torch.autograd.Function):
+    """light_vis[n, M] = per-lobe weighted mean of the visibility MLP over the S sample directions of each lobe
+    (model/sg_render.py:148-195).  Differentiable w.r.t. dirs and w only."""
+
+    @staticmethod
+    def forward(ctx, points, normals, dirs, w, M, S, weights, need_grad):
+        W = weights.get()
+        points, normals, dirs, w = map(f32, (points, normals, dirs, w))
+        n = points.shape[0]
+        cap = ((M * S + 63) // 64) * 64
+        dev = points
+        bits = _empty(n, M, dtype=torch.int32, like=dev)
+        lobe_off = _empty(n, M + 1, dtype=torch.int32, like=dev)
+        start = _empty(n, dtype=torch.int32, like=dev)
+        rowA = _empty(n * cap, dtype=torch.int32, like=dev)
+        rowB = _empty(n * cap, dtype=torch.int32, like=dev)
+        n_tiles = _zeros(1, dtype=torch.int32, like=dev)
+        check(lib().robir_diffuse_rows(n, M, S, ptr(normals), ptr(dirs), ptr(bits), ptr(lobe_off), ptr(start),
+                                       ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
+        tabA = pe_linear(points, W["Wt0p"], W["b0"])
+        tabB = pe_linear(dirs, W["Wt0d"], None)
+        max_tiles = n * cap // 64
+        vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_grad)
+        lv = _empty(n, M, like=dev)
+        check(lib().robir_diffuse_reduce_fwd(n, M, S, ptr(bits), ptr(lobe_off), ptr(start), ptr(vis), ptr(w), ptr(lv),
+                                             stream()))
+        if need_grad:
+            ctx.save_for_backward(dirs, w, bits, lobe_off, start, rowB, n_tiles, vis, mask, lv)
+            ctx.meta = (n, M, S, max_tiles, weights)
+        return lv
+
+    @staticmethod
+    def backward(ctx, g_lv):
+        dirs, w, bits, lobe_off, start, rowB, n_tiles, vis, mask, lv = ctx.saved_tensors
+        n, M, S, max_tiles, weights = ctx.meta
+        W = weights.get()
+        g_lv = f32(g_lv)
+        g_vis = _zeros(vis.shape[0], like=vis)
+        g_w = _zeros(M * S, like=vis)
+        check(lib().robir_diffuse_reduce_bwd(n, M, S, ptr(bits), ptr(lobe_off), ptr(start), ptr(vis), ptr(w), ptr(lv),
+                                             ptr(g_lv), ptr(g_vis), ptr(g_w), stream()))
+        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs)
+        return None, None, g_dirs, g_w, None, None, None, None
+
+
+class _SpecVis(torch.autograd.Function):
+    """brdf_vis[n] = weighted mean of the visibility MLP over S per-point sample directions
+    (model/sg_render.py:242-301, single view)."""
+
+    @staticmethod
+    def forward(ctx, points, normals, dirs, w, S, inv, testing, weights, need_grad):
+        W = weights.get()
+        points, normals, dirs, w = map(f32, (points, normals, dirs, w))
+        n = points.shape[0]
+        rows = ((n * S + 63) // 64) * 64
+        dev = points
+        rowA = _empty(rows, dtype=torch.int32, like=dev)
+        rowB = _empty(rows, dtype=torch.int32, like=dev)
+        n_tiles = _zeros(1, dtype=torch.int32, like=dev)
+        check(lib().robir_spec_rows(n, S, rows, ptr(normals), ptr(dirs), ptr(rowA), ptr(rowB), ptr(n_tiles),
+                                    ptr(Stats.pairs_tensor(dev)), stream()))
+        tabA = pe_linear(points, W["Wt0p"], W["b0"])
+        tabB = pe_linear(dirs, W["Wt0d"], None)
+        vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, rows // 64, need_grad)
+        out = _empty(n, like=dev)
+        check(lib().robir_spec_reduce_fwd(n, S, int(inv), int(testing), ptr(rowB), ptr(vis), ptr(w), ptr(out),
+                                          stream()))
+        if need_grad:
+            ctx.save_for_backward(dirs, w, rowB, n_tiles, vis, mask, out)
+            ctx.meta = (n, S, int(inv), rows, weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        dirs, w, rowB, n_tiles, vis, mask, out = ctx.saved_tensors
+        n, S, inv, rows, weights = ctx.meta
+        W = weights.get()
+        g_out = f32(g_out)
+        g_vis = _zeros(rows, like=vis)
+        g_w = _empty(n * S, like=vis)
+        check(lib().robir_spec_reduce_bwd(n, S, inv, ptr(rowB), ptr(vis), ptr(w), ptr(out), ptr(g_out), ptr(g_vis),
+                                          ptr(g_w), stream()))
+        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, rows // 64, vis, g_vis, mask, dirs)
+        return None, None, g_dirs, g_w, None, None, None, None, None
+
+
+def diffuse_vis(points, normals, dirs, w, M, S, weights, need_grad):
+    return _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad)
+
+
+def spec_vis(points, normals, dirs, w, S, inv, testing, weights, need_grad):
+    return _SpecVis.apply(points, normals, dirs, w, S, inv, testing, weights, need_grad)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SG render
+# ----------------------------------------------------------------------------------------------------------------------
+class _SgRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, bv_dir, bv_ind, ind_integral,
+                lin_diff):
+        normal, view, rough, albedo, spec_refl, lgt, light_vis, bv_dir = map(
+            f32, (normal, view, rough, albedo, spec_refl, lgt, light_vis, bv_dir))
+        n, M = normal.shape[0], lgt.shape[0]
+        has_ind = ind_lgt is not None
+        Mi = ind_lgt.shape[1] if has_ind else 0
+        if has_ind:
+            ind_lgt, bv_ind, ind_integral = f32(ind_lgt), f32(bv_ind), f32(ind_integral)
+        outs = [_empty(n, 3, like=normal) for _ in range(7)]
+        pre = _empty(n, 9, like=normal)
+        p = SgParams()
+        p.n, p.M, p.Mi, p.lin_diff = n, M, Mi, int(lin_diff)
+        for k, t in dict(normal=normal, view=view, rough=rough, albedo=albedo, spec_refl=spec_refl, lgt=lgt,
+                         ind_lgt=ind_lgt if has_ind else None, light_vis=light_vis, bv_dir=bv_dir,
+                         bv_ind=bv_ind if has_ind else bv_dir, ind_integral=ind_integral if has_ind else None,
+                         sg_rgb=outs[0], sg_spec=outs[1], sg_diff=outs[2], vis_shadow=outs[3], ind_rgb=outs[4],
+                         ind_spec=outs[5], ind_diff=outs[6], pre=pre).items():
+            setattr(p, k, ptr(t))
+        check(lib().robir_sg_render_fwd(ctypes.byref(p), stream()))
+        ctx.save_for_backward(normal, view, rough, albedo, spec_refl, lgt, ind_lgt if has_ind else None, light_vis,
+                              bv_dir, bv_ind if has_ind else None, ind_integral if has_ind else None, pre)
+        ctx.meta = (n, M, Mi, int(lin_diff), tuple(rough.shape))
+        ctx.mark_non_differentiable(outs[3])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_spec, g_diff, _g_shadow, g_irgb, g_ispec, g_idiff):
+        normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, bv_dir, bv_ind, ind_integral, pre = \
+            ctx.saved_tensors
+        n, M, Mi, lin_diff, rough_shape = ctx.meta
+        has_ind = Mi > 0
+        z = lambda *s: _zeros(*s, like=normal)
+        g_lgt, g_ind_lgt, g_lv = z(M, 7), (z(n, Mi, 7) if has_ind else None), z(n, M)
+        g_bvd, g_bvi, g_rough, g_alb, g_sr, g_int = z(n), z(n), z(n), z(n, 3), z(1), z(n, 3)
+        p = SgParams()
+        p.n, p.M, p.Mi, p.lin_diff = n, M, Mi, lin_diff
+        fz = lambda g: f32(g) if g is not None else None
+        for k, t in dict(normal=normal, view=view, rough=rough, albedo=albedo, spec_refl=spec_refl, lgt=lgt,
+                         ind_lgt=ind_lgt, light_vis=light_vis, bv_dir=bv_dir, bv_ind=bv_ind if has_ind else bv_dir,
+                         ind_integral=ind_integral, pre=pre, g_sg_rgb=fz(g_rgb), g_sg_spec=fz(g_spec),
+                         g_sg_diff=fz(g_diff), g_ind_rgb=fz(g_irgb), g_ind_spec=fz(g_ispec), g_ind_diff=fz(g_idiff),
+                         g_lgt=g_lgt, g_ind_lgt=g_ind_lgt, g_light_vis=g_lv, g_bv_dir=g_bvd, g_bv_ind=g_bvi,
+                         g_rough=g_rough, g_albedo=g_alb, g_spec_refl=g_sr, g_ind_integral=g_int).items():
+            setattr(p, k, ptr(t))
+        check(lib().robir_sg_render_bwd(ctypes.byref(p), stream()))
+        return (None, None, g_rough.reshape(rough_shape), g_alb, g_sr.reshape(spec_refl.shape), g_lgt, g_ind_lgt, g_lv,
+                g_bvd, g_bvi if has_ind else None, g_int if has_ind else None, None)
+
+
+def sg_render(normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, bv_dir, bv_ind, ind_integral,
+              lin_diff=False):
+    return _SgRender.apply(normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, bv_dir, bv_ind,
+                           ind_integral, lin_diff)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SDF network
+# ----------------------------------------------------------------------------------------------------------------------
+class SdfWeights:
+    """Folded + packed SDFNetwork weights (model/neus_model.py:312-438)."""
+
+    def __init__(self, sdf_network):
+        self.net = sdf_network
+        self.cache = _PackCache()
+
+    def get(self):
+        net = self.net
+        lins = [getattr(net, "lin%d" % l) for l in range(9)]
+        tensors = [t for l in lins for t in (l.weight_v, l.weight_g, l.bias)]
+
+        def build():
+            d = {}
+            for l in range(8):
+                v, g = lins[l].weight_v, lins[l].weight_g
+                N, K = v.shape
+                exp = (256, 63) if l == 0 else ((193, 256) if l == 3 else (256, 256))
+                if (N, K) != exp:
+                    raise _lib.RobirError("SDFNetwork layer %d has shape %s, expected %s" % (l, (N, K), exp))
+                d["Wt%d" % l] = pack_wn_transpose(v, g, 0, N, 64 if l == 0 else 256, 256)
+                b = torch.zeros(256, device=v.device)
+                b[:N] = f32(lins[l].bias)
+                d["b%d" % l] = b
+            v8, g8 = lins[8].weight_v, lins[8].weight_g
+            if tuple(v8.shape) != (257, 256):
+                raise _lib.RobirError("SDFNetwork last layer must be 256 -> 257")
+            d["Wt8_feat"] = pack_wn_transpose(v8, g8, 1, 256, 256, 256)
+            w8 = _empty(256, like=f32(v8))
+            check(lib().robir_pack_wn_row(ptr(f32(v8)), ptr(f32(g8)), 256, 0, ptr(w8), stream()))
+            d["w8_sdf"] = w8
+            d["b8"] = f32(lins[8].bias)
+            return d
+        return self.cache.get(tensors, build)
+
+
+def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_grad=False, want_feat=False):
+    """-> sdf [n], grad [n,3] | None, feat [n,256] | None   (no autograd: the SDF network is frozen in stage 2)."""
+    W = weights.get()
+    pts = f32(pts)
+    n = pts.shape[0]
+    sdf = _empty(n, like=pts)
+    grad = _empty(n, 3, like=pts) if want_grad else None
+    feat = _empty(n, 256, like=pts) if want_feat else None
+    p = SdfParams()
+    p.pts, p.n, p.in_scale, p.sdf_scale, p.feat_scale = ptr(pts), n, in_scale, sdf_scale, feat_scale
+    for l in range(8):
+        p.Wt[l] = W["Wt%d" % l].data_ptr()
+        p.bias[l] = W["b%d" % l].data_ptr()
+    p.w8_sdf, p.b8, p.Wt8_feat = ptr(W["w8_sdf"]), ptr(W["b8"]), ptr(W["Wt8_feat"])
+    p.sdf, p.grad, p.feat = ptr(sdf), ptr(grad), ptr(feat)
+    check(lib().robir_sdf_eval(ctypes.byref(p), sm_count(), stream()))
+    return sdf, grad, feat
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# camera rays / octree
+# ----------------------------------------------------------------------------------------------------------------------
+def camera_rays(uv, pose, intrinsics):
+    """uv [1,N,2], pose [1,4,4], intrinsics [1,3,3] -> ray_dirs [1,N,3], cam_loc [1,3]  (utils/rend_util.py:51-97)."""
+    if uv.shape[0] != 1 or pose.shape[1:] != (4, 4):
+        raise _lib.RobirError("camera_rays supports one 4x4 pose per call (the reference's training/eval usage)")
+    uv, pose, K = f32(uv), f32(pose), f32(intrinsics)
+    N = uv.shape[1]
+    dirs = _empty(1, N, 3, like=uv)
+    check(lib().robir_camera_rays(N, ptr(uv), ptr(pose), ptr(K), ptr(dirs), stream()))
+    return dirs, pose[:, :3, 3].contiguous()
+
+
+class PackedOctree:
+    """Device copy of the cached-SDF octree in the 32-byte node layout of csrc/octree_walk.h."""
+
+    def __init__(self, root, boxes, non_leaf, links, grid, sdf_val, sdf_grad, min_step, device):
+        n = boxes.shape[0]
+        nodes = torch.empty(n, 8, dtype=torch.float32)
+        nodes[:, :6] = boxes.float().cpu()
+        child = torch.where(non_leaf.cpu().reshape(-1) != 0, links.cpu()[:, 0], torch.full((n,), -1, dtype=torch.long))
+        nodes[:, 6] = child.to(torch.int32).view(torch.float32)
+        nodes[:, 7] = sdf_val.float().cpu()
+        self.nodes = nodes.to(device).contiguous()
+        self.grid = grid.to(torch.int32).to(device).contiguous()
+        self.sdf_grad = sdf_grad.float().to(device).contiguous()
+        self.root = [float(v) for v in root.float().cpu()]
+        self.n_nodes = n
+        self.last_sdf = float(sdf_val.float().cpu()[-1])
+        self.min_step = float(min_step)
+        # torch.clamp(x, -min_step*10, min_step*10): python-double product, then cast to fp32 (utils/octree.py:433)
+        self.refine_limit = float(torch.tensor(self.min_step * 10, dtype=torch.float32))
+        self.node_bytes = self.nodes.numel() * 4 + self.grid.numel() * 4 + self.sdf_grad.numel() * 4
+
+    def host_arrays(self):
+        """Unpack to the plain-tensor layout of the reference / oracle octree (CPU), e.g. for bench.py's CPU leg."""
+        nodes = self.nodes.cpu()
+        boxes = nodes[:, :6].contiguous()
+        child = nodes[:, 6].contiguous().view(torch.int32).long()
+        non_leaf = (child >= 0).long()
+        links = torch.where(child[:, None] >= 0, child[:, None] + torch.arange(8)[None, :], torch.zeros(1, dtype=torch.long))
+        sdf_val = nodes[:, 7].contiguous()
+        return dict(root=torch.tensor(self.root), boxes=boxes, non_leaf=non_leaf, links=links,
+                    grid=self.grid.cpu().long(), sdf_val=sdf_val, sdf_grad=self.sdf_grad.cpu(),
+                    centers=boxes[:, :3] + boxes[:, 3:] * 0.5, hit_ptr=torch.relu(sdf_val) <= 1e-4,
+                    min_step=self.min_step)
+
+    def view(self):
+        v = OctreeView()
+        v.nodes, v.grid = ptr(self.nodes), ptr(self.grid)
+        v.gx, v.gy, v.gz = self.grid.shape
+        v.n_nodes = self.n_nodes
+        v.rminx, v.rminy, v.rminz, v.rsizex, v.rsizey, v.rsizez = self.root
+        return v
+
+
+def octree_cast(tree, rays_o, rays_d, max_iter=-1, o_div=1, return_stats=False):
+    """OctreeSDF.cast + OctreeTracing.forward (utils/octree.py:421-438, model/octree_tracing.py:43-60).
+    rays_o [K/o_div, 3], rays_d [K,3] -> hit_x [K,3], is_hit [K] bool, hit_t [K]."""
+    rays_o, rays_d = f32(rays_o), f32(rays_d)
+    K = rays_d.shape[0]
+    dev = rays_d
+    out_t, out_x = _empty(K, like=dev), _empty(K, 3, like=dev)
+    out_hit = _empty(K, dtype=torch.uint8, like=dev)
+    if K == 0:
+        return out_x, out_hit.bool(), out_t
+    st_t, st_p = _empty(K, like=dev), _empty(K, dtype=torch.int32, like=dev)
+    counters = _zeros(lib().robir_octree_counters_len(), dtype=torch.int32, like=dev)
+    p = OctCastParams()
+    p.view = tree.view()
+    p.sdf_grad, p.rays_o, p.rays_d = ptr(tree.sdf_grad), ptr(rays_o), ptr(rays_d)
+    p.K, p.o_div, p.max_iter, p.eps = K, o_div, max_iter, 1e-3
+    p.refine_limit, p.last_node_sdf = tree.refine_limit, tree.last_sdf
+    p.state_t, p.state_ptr, p.out_t, p.out_x, p.out_hit, p.counters = map(ptr, (st_t, st_p, out_t, out_x, out_hit,
+                                                                                counters))
+    check(lib().robir_octree_cast(ctypes.byref(p), sm_count(), stream()))
+    if return_stats:
+        return out_x, out_hit.bool(), out_t, counters
+    return out_x, out_hit.bool(), out_t

@@ -1,0 +1,188 @@
+"""Model facade with the reference's surface: ``IDRNetwork.forward(input, trainstage, fun_spec, lin_diff, train_spec)``
+and ``IDRNetwork.trace_radiance(input, nsamp, test_dir)`` return the same dict keys / shapes / dtypes
+(model/implicit_differentiable_renderer.py:261-650), ``get_sg_render`` is the re-bindable hook (:400-409, :499-529) and
+``pbr_get_sg_render`` is the PBR runner's version of it (training/train_pbr.py:348-396)."""
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import networks, ops, rng, sg_render, tracing
+from ._lib import RobirError
+
+
+def _cfg(conf, key, default=None):
+    if conf is None:
+        return default
+    node = conf
+    try:
+        for part in key.split("."):
+            node = node[part]
+        return node
+    except (KeyError, TypeError):
+        return default
+
+
+class IDRNetwork(nn.Module):
+    def __init__(self, conf=None):
+        super().__init__()
+        if not _cfg(conf, "use_neus", True) or not _cfg(conf, "use_octree", True):
+            if not _cfg(conf, "use_neus", True):
+                raise RobirError("only use_neus=True models are supported (all shipped configs)")
+        rt = dict(_cfg(conf, "ray_tracer", {}) or {})
+        self.feature_vector_size = int(_cfg(conf, "feature_vector_size", 256))
+        self.octree_ray_tracer = tracing.OctreeTracing(**rt, max_iter=32)
+        if _cfg(conf, "use_octree", True):
+            self.ray_tracer = tracing.OctreeTracing(**rt)
+        else:
+            from .sphere_tracing import RayTracing
+            self.ray_tracer = RayTracing(**rt)
+        self.object_bounding_sphere = float(rt.get("object_bounding_sphere", 1.0))
+        self.implicit_network = networks.ImplicitNetworkMy()
+        self.indirect_illum_network = networks.IndirctIllumNetwork(
+            num_lgt_sgs=int(_cfg(conf, "indirect_illum_network.num_lgt_sgs", 24)))
+        self.visibility_network = networks.VisNetwork()
+        self.envmap_material_network = networks.EnvmapMaterialNetwork(
+            num_lgt_sgs=int(_cfg(conf, "envmap_material_network.num_lgt_sgs", 128)),
+            upper_hemi=bool(_cfg(conf, "envmap_material_network.upper_hemi", False)),
+            specular_albedo=float(_cfg(conf, "envmap_material_network.specular_albedo", 0.05)))
+        self.gamma = networks.GammaCorrect(float(_cfg(conf, "gamma", 1.0)), int(_cfg(conf, "hdr_mode", 0)))
+        # PBR-runner state read by pbr_get_sg_render (training/train_pbr.py:414-415, 131-159)
+        self.no_normal = True
+        self.is_training = True
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def generate(self):
+        """What every runner does before its loop (train_pbr.py:403-407)."""
+        sdf_fn = lambda x: self.implicit_network(x)[:, 0]
+        self.ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
+        if isinstance(self.ray_tracer, tracing.OctreeTracing):
+            self.octree_ray_tracer.sdf_octree = self.ray_tracer.sdf_octree   # same tree, different max_iter
+        else:
+            self.octree_ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
+
+    def _trace(self, tracer, cam_loc, object_mask, ray_dirs):
+        return tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc, object_mask=object_mask,
+                      ray_directions=ray_dirs)
+
+    def forward(self, input, trainstage='IDR', fun_spec=False, lin_diff=False, train_spec=False):
+        if fun_spec:
+            raise RobirError("fun_spec=True is not on the accelerated path")
+        if "intrinsics" in input:
+            object_mask = input["object_mask"].reshape(-1)
+            ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
+            batch_size, num_pixels, _ = ray_dirs.shape
+            with torch.no_grad():
+                points, network_object_mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+        else:
+            cam_loc = input["points"].reshape(-1, 3)
+            ray_dirs = input["dirs"].reshape(-1, 1, 3)
+            object_mask = input["object_mask"].reshape(-1) if "object_mask" in input else \
+                torch.ones_like(ray_dirs[..., 0, 0], dtype=torch.bool)
+            batch_size, num_pixels, _ = ray_dirs.shape
+            points = torch.zeros_like(cam_loc)
+            network_object_mask = torch.zeros_like(object_mask)
+            dists = torch.zeros_like(cam_loc[..., 0])
+            with torch.no_grad():
+                p, m, d = self._trace(self.ray_tracer, cam_loc[object_mask], object_mask[object_mask],
+                                      ray_dirs[object_mask])
+                points[object_mask], network_object_mask[object_mask], dists[object_mask] = p, m, d
+        points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
+        sdf_output = self.implicit_network.sdf(points)[:, None]
+        ray_dirs = ray_dirs.reshape(-1, 3)
+        ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': network_object_mask,
+               'object_mask': object_mask, 'ray_dirs': ray_dirs}
+        surface_mask = network_object_mask
+        hit_idx = surface_mask.nonzero()[:, 0]          # one host sync per call, like the reference's boolean indexing
+        n_hit = hit_idx.shape[0]
+        total = points.shape[0]
+        dev = points.device
+        hit_points = points[hit_idx]
+        n_ind = self.indirect_illum_network.num_lgt_sgs
+        indirect_sgs = torch.ones(total, n_ind, 7, device=dev)
+        indirect_sgs[:, :, -3:] = 0
+        indirect_integral = torch.ones(total, 3, device=dev)
+        hit_sgs = hit_int = None
+        if 'hdr_shift' in input:
+            if n_hit > 0:
+                hit_sgs, hit_int = self.indirect_illum_network(hit_points, input['hdr_shift'][hit_idx])
+                indirect_sgs = indirect_sgs.index_copy(0, hit_idx, hit_sgs)
+                indirect_integral = indirect_integral.index_copy(0, hit_idx, hit_int)
+            ret['hdr_shift'] = input['hdr_shift']
+        if trainstage == 'Illum':
+            ret.update({'indirect_sgs': indirect_sgs, 'indir_integral': indirect_integral})
+            normals = torch.ones_like(points)
+            if n_hit > 0:
+                mat = self.envmap_material_network(hit_points, train_spec=False, train_norm=True)
+                normals = normals.index_copy(0, hit_idx, mat["sg_normal_map"])
+            ret['normals'] = normals
+            return ret
+
+        ones3 = lambda: torch.ones(total, 3, device=dev)
+        ones1 = lambda: torch.ones(total, 1, device=dev)
+        buf = {k: ones3() for k in ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
+                                    'indir_specular_rgb', 'normals', 'diffuse_albedo', 'roughness', 'normal_map',
+                                    'vis_shadow', 'random_xi_diffuse_albedo', 'random_xi_roughness')}
+        buf['metallic'] = ones1()
+        buf['random_xi_metallic'] = ones1()
+        if n_hit > 0:
+            if hit_sgs is None:
+                hit_sgs, hit_int = indirect_sgs[hit_idx], indirect_integral[hit_idx]
+            r = self.get_sg_render(hit_points, -ray_dirs[hit_idx], hit_sgs,
+                                   albedo_ratio=input.get('albedo_ratio'), fun_spec=fun_spec, lin_diff=lin_diff,
+                                   train_spec=train_spec, indir_integral=hit_int,
+                                   tex_uv=None, hdr_shift=input['hdr_shift'][hit_idx] if 'hdr_shift' in input else None)
+            for k in buf:
+                if k not in r:
+                    continue
+                v = r[k]
+                if k in ('roughness', 'random_xi_roughness'):
+                    v = v.expand(-1, 3)
+                buf[k] = buf[k].index_copy(0, hit_idx, v)
+        ret.update({'final_t': ones1(), 'gradient_error': torch.tensor(0.0, device=dev), 'acc': ones1(),
+                    'bg_rgb': ones3(), 'surface_mask': surface_mask})
+        ret.update(buf)
+        return ret
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def get_idr_render(self, points, view_dirs=None, normal_only=False):
+        if not normal_only:
+            raise RobirError("get_idr_render(normal_only=False) is not on the accelerated path")
+        return self.implicit_network.gradient(points)[:, 0, :]
+
+    def get_sg_render(self, points, view_dirs, indir_lgtSGs, albedo_ratio=None, fun_spec=False, lin_diff=False,
+                      train_spec=False, **kwargs):
+        """Default hook = the PBR runner's (the runners re-bind this attribute: train_pbr.py:413)."""
+        return pbr_get_sg_render(self, points, view_dirs, indir_lgtSGs, albedo_ratio=albedo_ratio, fun_spec=fun_spec,
+                                 lin_diff=lin_diff, train_spec=train_spec, **kwargs)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def trace_radiance(self, input, nsamp=16, test_dir=None):
+        from .vis_stage import trace_radiance
+        return trace_radiance(self, input, nsamp=nsamp, test_dir=test_dir)
+
+
+def pbr_get_sg_render(model, points, view_dirs, indir_lgtSGs, albedo_ratio=None, fun_spec=False, lin_diff=False,
+                      train_spec=False, indir_integral=None, **kwargs):
+    """training/train_pbr.py:348-396 (model.no_normal / model.is_training play the runner's attributes)."""
+    view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
+    normals = model.get_idr_render(points, view_dirs, normal_only=True)
+    normals = normals / torch.clamp(torch.norm(normals, dim=-1, keepdim=True), 1e-4)
+    ret = {'normals': normals}
+    mat = model.envmap_material_network(points, train_spec=train_spec)
+    indir_integral = indir_integral * 2 * np.pi
+    normal_map = mat['sg_normal_map']
+    sg = sg_render.render_with_all_sg(points=points.detach(),
+                                      normal=normals.detach() if model.no_normal else normal_map.detach(),
+                                      viewdirs=view_dirs, lgtSGs=mat['sg_lgtSGs'], indir_integral=indir_integral,
+                                      specular_reflectance=mat['sg_specular_reflectance'].abs(),
+                                      roughness=mat['sg_roughness'], diffuse_albedo=mat['sg_diffuse_albedo'],
+                                      indir_lgtSGs=indir_lgtSGs, VisModel=model.visibility_network, fun_spec=False,
+                                      lin_diff=False, testing=not model.is_training, metallic=None)
+    ret.update(sg)
+    ret.update({'diffuse_albedo': mat['sg_diffuse_albedo'], 'roughness': mat['sg_roughness'],
+                'metallic': mat['sg_metallic'], 'normal_map': normal_map,
+                'random_xi_roughness': mat['random_xi_roughness'], 'random_xi_metallic': mat['random_xi_metallic'],
+                'random_xi_diffuse_albedo': mat['random_xi_diffuse_albedo']})
+    return ret

@@ -1,0 +1,66 @@
+"""Random draws of the hot path.  The reference draws every hot-path random tensor on the CPU generator and copies it
+to the GPU (model/sg_render.py:135-136,224-225; model/sg_envmap_material.py:81,83).  Modes:
+
+  "cpu"     (default) identical call order / shapes on torch's CPU generator -> same numbers as the reference under the
+            same ``torch.manual_seed``; costs a host draw + H2D copy per call, like the reference;
+  "device"  draw on the CUDA generator (no host round trip; different numbers);
+  "replay"  pop tensors from a tape (parity tests feed the reference's recorded randoms).
+"""
+import contextlib
+
+import torch
+
+_mode = "cpu"
+_tape = None
+_record = None
+
+
+def set_mode(mode):
+    global _mode
+    assert mode in ("cpu", "device", "replay")
+    _mode = mode
+
+
+@contextlib.contextmanager
+def replay(tensors):
+    """Feed the given list of tensors, in order, to the next draws."""
+    global _mode, _tape
+    old = (_mode, _tape)
+    _mode, _tape = "replay", list(tensors)
+    try:
+        yield
+    finally:
+        _mode, _tape = old
+
+
+@contextlib.contextmanager
+def record():
+    global _record
+    _record = []
+    try:
+        yield _record
+    finally:
+        _record = None
+
+
+def _draw(fn, shape, device):
+    shape = tuple(int(s) for s in shape)
+    if _mode == "replay":
+        t = _tape.pop(0)
+        assert tuple(t.shape) == shape, "replayed random tensor has shape %s, expected %s" % (tuple(t.shape), shape)
+        out = t.to(device=device, dtype=torch.float32)
+    elif _mode == "device":
+        out = fn(shape, device=device)
+    else:
+        out = fn(shape).to(device, non_blocking=True)
+    if _record is not None:
+        _record.append(out.detach().cpu().clone())
+    return out
+
+
+def rand(shape, device):
+    return _draw(torch.rand, shape, device)
+
+
+def randn(shape, device):
+    return _draw(torch.randn, shape, device)

@@ -1,0 +1,116 @@
+"""Drop-in replacements for model/sg_render.py's public functions with the reference signatures
+(get_diffuse_visibility :111, get_specular_visibility :198, render_with_all_sg :304, render_with_sg :343), backed by
+the fused CUDA operators.  ``VisModel`` must expose the reference VisNetwork layout (a ``vis_layer`` nn.Sequential of
+five Linear layers, 126->256x4->2); an arbitrary callable (e.g. the reference's OctreeVisModel) is rejected loudly.
+"""
+import numpy as np
+import torch
+
+from . import ops, rng
+from ._lib import RobirError
+
+TINY_NUMBER = 1e-6
+
+
+def _weights_of(VisModel):
+    w = getattr(VisModel, "_robir_vis_weights", None)
+    if w is None:
+        if not hasattr(VisModel, "vis_layer"):
+            raise RobirError("robir_b200 needs a VisNetwork-like VisModel (with .vis_layer); got %r" % type(VisModel))
+        w = ops.VisWeights(VisModel.vis_layer)
+        try:
+            VisModel._robir_vis_weights = w
+        except Exception:
+            pass
+    return w
+
+
+def _norm_axis(x):
+    return x / (torch.norm(x, dim=-1, keepdim=True) + TINY_NUMBER)
+
+
+def get_diffuse_visibility(points, normals, VisModel, lgtSGLobes, lgtSGLambdas, nsamp=8, testing=False, thr=1.0,
+                           bounding=False, argmax_vis=False):
+    """[n,3], [n,3], VisModel, lobes [M,3], lambdas [M,1] -> vis [M, n]."""
+    if bounding or argmax_vis:
+        raise RobirError("bounding / argmax_vis variants are not on the accelerated path")
+    M = lgtSGLobes.shape[0]
+    n = points.shape[0]
+    dev = points.device
+    sharp = torch.clamp(lgtSGLambdas[:, 0], min=1e-4)
+    sg_range = torch.clamp(sharp.min(), max=thr).reshape(1)
+    u_theta = rng.rand((M, nsamp), dev)
+    u_phi = rng.rand((M, nsamp), dev)
+    dirs, w = ops.sample_dirs(lgtSGLobes, lgtSGLobes, sharp, lgtSGLambdas[:, 0], sg_range, u_theta, u_phi, True)
+    need_grad = torch.is_grad_enabled() and not testing and (dirs.requires_grad or w.requires_grad)
+    if testing:
+        dirs_q, w_q = dirs.detach(), w   # the reference runs VisModel under no_grad but keeps the weights' graph
+    else:
+        dirs_q, w_q = dirs, w
+    lv = ops.diffuse_vis(points.detach(), normals.detach(), dirs_q, w_q, M, nsamp, _weights_of(VisModel), need_grad)
+    return lv.permute(1, 0)
+
+
+def _spec_frame(normals, viewdirs):
+    ndv = torch.clamp(torch.sum(normals * viewdirs, dim=-1, keepdim=True), min=0.)
+    return -viewdirs + 2 * ndv * normals
+
+
+def get_specular_visibility(points, normals, viewdirs, VisModel, lgtSGLobes, lgtSGLambdas, nsamp=24, multi_view=False,
+                            testing=False, inv=False, argmax_vis=False):
+    """[n,3] x3, VisModel, lobes [n,3], lambdas [n,1] -> vis [n]."""
+    if multi_view or argmax_vis:
+        raise RobirError("multi_view / argmax_vis variants are not on the accelerated path")
+    n = points.shape[0]
+    dev = points.device
+    ref_dir = _spec_frame(normals, viewdirs)
+    sharp = torch.clip(lgtSGLambdas[:, 0], min=0.1, max=50)
+    sg_range = torch.clamp(sharp.min(), max=1).reshape(1)
+    u_theta = rng.rand((n, nsamp), dev)
+    u_phi = rng.rand((n, nsamp), dev)
+    dirs, w = ops.sample_dirs(ref_dir, lgtSGLobes, sharp, sharp, sg_range, u_theta, u_phi, False)
+    need_grad = torch.is_grad_enabled() and not testing and (dirs.requires_grad or w.requires_grad)
+    dirs_q = dirs.detach() if testing else dirs
+    return ops.spec_vis(points.detach(), normals.detach(), dirs_q, w, nsamp, inv, testing, _weights_of(VisModel),
+                        need_grad)
+
+
+def _spec_warp(normal, viewdirs, roughness):
+    """Per-point warped BRDF lobe / sharpness (sg_render.py:417-428), needed as sampling input."""
+    inv_r4 = 2. / (roughness * roughness * roughness * roughness)
+    vdl = torch.clamp(torch.sum(normal * viewdirs, dim=-1, keepdim=True), min=0.)
+    wl = 2 * vdl * normal - viewdirs
+    wl = wl / (torch.norm(wl, dim=-1, keepdim=True) + TINY_NUMBER)
+    return wl, inv_r4 / (4 * vdl + TINY_NUMBER)
+
+
+def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
+                       indir_integral=None, indir_lgtSGs=None, VisModel=None, fun_spec=False, lin_diff=False,
+                       testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False):
+    """model/sg_render.py:304-337 for the PBR-stage configuration (fun_spec=False, metallic=None, diffuse_vis=None)."""
+    if fun_spec or metallic is not None or diffuse_vis is not None or argmax_vis or viewdirs.dim() != 2:
+        raise RobirError("render_with_all_sg: fun_spec / metallic / diffuse_vis / argmax_vis / multi-view variants are "
+                         "not on the accelerated path (CESR extras are a later row, SURVEY.md section 8f)")
+    if lgtSGs.dim() != 2:
+        raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
+    n = normal.shape[0]
+    M = lgtSGs.shape[0]
+    viewdirs = viewdirs.detach()
+    # ---- direct light visibility per lobe (sg_render.py:364-366, 388-391)
+    lobes = lgtSGs[:, :3] / (torch.norm(lgtSGs[:, :3], dim=-1, keepdim=True) + TINY_NUMBER)
+    lambdas = torch.abs(lgtSGs[:, 3:4])
+    light_vis = get_diffuse_visibility(points, normal.detach(), VisModel, lobes, lambdas, nsamp=32,
+                                       testing=testing).permute(1, 0)
+    # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
+    wl, wlam = _spec_warp(normal, viewdirs, roughness)
+    bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing, inv=False)
+    bv_ind = None
+    if indir_lgtSGs is not None:
+        bv_ind = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
+                                         inv=True)
+    outs = ops.sg_render(normal.detach(), viewdirs, roughness, diffuse_albedo, specular_reflectance.reshape(1), lgtSGs,
+                         indir_lgtSGs, light_vis.contiguous(), bv_dir, bv_ind, indir_integral, lin_diff)
+    sg_rgb, sg_spec, sg_diff, vis_shadow, ind_rgb, ind_spec, ind_diff = outs
+    return {'sg_rgb': sg_rgb, 'sg_specular_rgb': sg_spec, 'sg_diffuse_rgb': sg_diff, 'vis_shadow': vis_shadow,
+            'supervise': torch.tensor(0.0, device=points.device), 'indir_rgb': ind_rgb,
+            'indir_diffuse_rgb': ind_diff, 'indir_specular_rgb': ind_spec}
