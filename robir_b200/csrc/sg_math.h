@@ -42,6 +42,10 @@ RB_HD float val(float x) { return x; }
 template <int N>
 RB_HD float val(const Dual<N>& x) { return x.v; }
 
+// derivative propagation that treats "no dependence" (tangent exactly 0) as 0 even when the local slope is inf/nan,
+// like reverse-mode autograd, which never visits a path without gradient (e.g. sqrt'(0) * 0 at a detached input).
+RB_HD float dmul(float slope, float tangent) { return tangent == 0.f ? 0.f : slope * tangent; }
+
 #define RB_DUAL_UNARY(name, fv, dfdx)                 \
   template <int N>                                    \
   RB_HD Dual<N> name(const Dual<N>& a) {              \
@@ -50,7 +54,7 @@ RB_HD float val(const Dual<N>& x) { return x.v; }
     const float f = (fv);                             \
     const float g = (dfdx);                           \
     r.v = f;                                          \
-    _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = g * a.d[i]; \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = dmul(g, a.d[i]); \
     return r;                                         \
   }
 
@@ -98,7 +102,7 @@ RB_HD Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
   Dual<N> r;
   r.v = a.v * b.v;
 #pragma unroll
-  for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+  for (int i = 0; i < N; ++i) r.d[i] = dmul(b.v, a.d[i]) + dmul(a.v, b.d[i]);
   return r;
 }
 template <int N>
@@ -107,7 +111,7 @@ RB_HD Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
   const float inv = 1.f / b.v;
   r.v = a.v / b.v;
 #pragma unroll
-  for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+  for (int i = 0; i < N; ++i) r.d[i] = dmul(inv, a.d[i]) - dmul(r.v * inv, b.d[i]);
   return r;
 }
 template <int N>
@@ -123,7 +127,7 @@ RB_HD Dual<N> operator*(const Dual<N>& a, float b) {
   Dual<N> r;
   r.v = a.v * b;
 #pragma unroll
-  for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b;
+  for (int i = 0; i < N; ++i) r.d[i] = dmul(b, a.d[i]);
   return r;
 }
 template <int N>

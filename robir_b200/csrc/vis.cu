@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256, 2) vis_mlp_bwd_kernel(VisBwdParams p) {
     }
     // ---- through the direction half of layer 0: dPE [64] (only columns 0..63 of the pass are non-zero)
     zero_acc<R>(acc);
-    tile_gemm_pass<R>(Xs, 256, p.W0d, 64, 0, Wbuf, acc);   // reads [256][64]; see note in launch code (ld = 64)
+    tile_gemm_pass<R>(Xs, 256, p.W0d, 256, 0, Wbuf, acc);   // W0d is zero padded to [256][256]
     store_acc<R>(Xs, 0, 64, acc);
     __syncthreads();
     // ---- PE jacobian: d dir_i = dPE[i] + sum_f 2^f (cos(2^f x_i) dPE[3+6f+i] - sin(2^f x_i) dPE[6+6f+i])

@@ -77,7 +77,10 @@ def _rand_scene(n, M, Mi, seed=0):
     gen = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=gen)
     nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
-    view = torch.nn.functional.normalize(nrm + 0.8 * torch.randn(n, 3, generator=gen), dim=-1)
+    raw = nrm + 0.8 * torch.randn(n, 3, generator=gen)
+    raw[::7] = -raw[::7]                                   # some back-facing hits (n.v < 0)
+    view = raw / (raw.norm(dim=-1, keepdim=True) + 1e-6)   # the runner's normalisation (train_pbr.py:351): with it
+    # ||v|| + 1e-6 == 1 and the half vector of a back-facing point is exactly 0 -> sqrt'(0) must not leak NaN
     from robir_b200.synthetic import synthetic_light_sgs
     lgt = synthetic_light_sgs(gen, M)
     lgt[:, 4:] *= torch.sign(torch.randn(M, 3, generator=gen))      # exercise abs()
