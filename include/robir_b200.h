@@ -95,11 +95,13 @@ int robir_sample_dirs_bwd(int K, int S, const float* axis_f, const float* axis_w
 int robir_pe_linear(const float* x, int n, const float* Wt, const float* bias, float* tab, void* stream);
 
 /* ---- a10: (point, direction) pair lists.  live(i,j) = n_i . dir_j > 1e-6 (model/sg_render.py:155, :246) ----------- */
-int robir_diffuse_rows(int n, int M, int S, const float* normals, const float* dirs, uint32_t* bits /*[n][M]*/,
-                       int* lobe_off /*[n][M+1]*/, int* start /*[n]*/, int* rowA, int* rowB /*[n*roundup(M*S,64)]*/,
-                       int* n_tiles /*[1]*/, long long* n_pairs /*[1], accumulated*/, void* stream);
-int robir_spec_rows(int n, int S, int rows_padded, const float* normals, const float* dirs, int* rowA, int* rowB,
-                    int* n_tiles, long long* n_pairs, void* stream);
+/* tile_rows = 64 (FFMA engine) or 128 (tensor-core engine): every point's rows are padded to that multiple. */
+int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals, const float* dirs,
+                       uint32_t* bits /*[n][M]*/, int* lobe_off /*[n][M+1]*/, int* start /*[n]*/, int* rowA,
+                       int* rowB /*[n*roundup(M*S,tile_rows)]*/, int* n_tiles /*[1]*/,
+                       long long* n_pairs /*[1], accumulated*/, void* stream);
+int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, const float* normals, const float* dirs, int* rowA,
+                    int* rowB, int* n_tiles, long long* n_pairs, void* stream);
 
 /* ---- a10-a12: fused visibility MLP over a pair list: relu(tabA[a]+tabB[b]) -> 3 x (256x256, ReLU) -> sigmoid(z1-z0)
  * replaces the 2M-row VisModel batches of get_diffuse_visibility (model/sg_render.py:157-173) and
@@ -113,6 +115,21 @@ int robir_vis_mlp_bwd(const int* rowB, const int* n_tiles, int max_tiles, const 
                       const float* W3, const float* W0d /*[256][256]: W0[:,63:126] zero padded*/, const float* wd,
                       const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
                       int sm_count, void* stream);
+
+/* ---- a10-a12, tensor-core engine (tcgen05 + TMEM, bf16 hi/lo 3-term split = fp32 parity): same contract as
+ * robir_vis_mlp_fwd/bwd over 128-row tiles.  Weight images are built once per weight version with
+ * robir_tc_pack_layer: forward = W1, W2, W3 (transpose=0); backward = W3^T, W2^T, W1^T (transpose=1) followed by the
+ * 64-row image of W0[:, 63:126]^T.  mask words: [rows][4][8], word w bit i = sign of hidden unit 32 w + i. */
+int robir_tc_pack_layer(const float* W, int ldw, int N, int K, int transpose, int n_halves, void* img, void* stream);
+int robir_tc_image_bytes(int n_layers256, int n_layers64);
+int robir_vis_tc_fwd(const float* tabA, const float* tabB, const int* rowA, const int* rowB, const int* n_tiles,
+                     int max_tiles, const void* img, const float* bias3x256, const float* wd, const float* bd,
+                     float* vis, uint32_t* mask, int sm_count, void* stream);
+int robir_vis_tc_bwd(const int* rowB, const int* n_tiles, int max_tiles, const void* img, const float* wd,
+                     const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
+                     int sm_count, void* stream);
+/* unit-test hook: D[128][256] = A[128][256] . W[256][256]^T through the same pipeline (one layer image) */
+int robir_tc_selftest(const float* A, const void* img, float* D, void* stream);
 
 /* ---- a10/a11: weighted per-lobe / per-point means (model/sg_render.py:180-183, :283-294) -------------------------- */
 int robir_diffuse_reduce_fwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,

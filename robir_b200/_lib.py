@@ -56,8 +56,13 @@ _SIGNATURES = {
     "robir_pe_linear": [_P, _I, _P, _P, _P, _P],
     "robir_sample_dirs_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "robir_sample_dirs_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
-    "robir_diffuse_rows": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "robir_spec_rows": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "robir_diffuse_rows": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "robir_spec_rows": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "robir_tc_pack_layer": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "robir_tc_image_bytes": [_I, _I],
+    "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P],
+    "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "robir_tc_selftest": [_P, _P, _P, _P],
     "robir_vis_mlp_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_vis_mlp_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_diffuse_reduce_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -78,6 +83,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ["robir_last_error"])
 
 # kernels launched per C call (for bench.py's gpu_launches claim); everything not listed launches exactly one
 _KERNELS_PER_CALL = {"robir_diffuse_rows": 3, "robir_octree_counters_len": 0, "robir_device_info": 0,
+                     "robir_tc_image_bytes": 0,
                      "robir_abi_version": 0, "robir_last_error": 0}
 launch_count = 0
 

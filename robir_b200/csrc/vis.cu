@@ -193,7 +193,7 @@ __global__ void diffuse_count_kernel(int n, int M, int S, const float* __restric
 }
 
 // exclusive scan of 64-padded per-point counts; writes start[i] (row offset) and counters: n_tiles, n_pairs
-__global__ void diffuse_scan_kernel(int n, int M, const int* __restrict__ lobe_off, int* __restrict__ start,
+__global__ void diffuse_scan_kernel(int n, int M, int pad, const int* __restrict__ lobe_off, int* __restrict__ start,
                                     int* __restrict__ n_tiles, long long* __restrict__ n_pairs) {
   __shared__ int s_part[1024];
   __shared__ long long s_pairs[1024];
@@ -205,7 +205,7 @@ __global__ void diffuse_scan_kernel(int n, int M, const int* __restrict__ lobe_o
     const int i = t * per + q;
     if (i < n) {
       const int c = lobe_off[(size_t)i * (M + 1) + M];
-      sum += (c + 63) & ~63;
+      sum += ((c + pad - 1) / pad) * pad;
       pairs += c;
     }
   }
@@ -221,7 +221,7 @@ __global__ void diffuse_scan_kernel(int n, int M, const int* __restrict__ lobe_o
       run += v;
       p += s_pairs[q];
     }
-    *n_tiles = run / 64;
+    *n_tiles = run / pad;
     *n_pairs += p;
   }
   __syncthreads();
@@ -230,12 +230,12 @@ __global__ void diffuse_scan_kernel(int n, int M, const int* __restrict__ lobe_o
     const int i = t * per + q;
     if (i < n) {
       start[i] = run;
-      run += (lobe_off[(size_t)i * (M + 1) + M] + 63) & ~63;
+      run += ((lobe_off[(size_t)i * (M + 1) + M] + pad - 1) / pad) * pad;
     }
   }
 }
 
-__global__ void diffuse_fill_kernel(int n, int M, int S, const uint32_t* __restrict__ bits,
+__global__ void diffuse_fill_kernel(int n, int M, int S, int pad, const uint32_t* __restrict__ bits,
                                     const int* __restrict__ lobe_off, const int* __restrict__ start,
                                     int* __restrict__ rowA, int* __restrict__ rowB) {
   const int i = blockIdx.x;
@@ -250,7 +250,7 @@ __global__ void diffuse_fill_kernel(int n, int M, int S, const uint32_t* __restr
     }
   }
   const int cnt = lobe_off[(size_t)i * (M + 1) + M];
-  const int padded = (cnt + 63) & ~63;
+  const int padded = ((cnt + pad - 1) / pad) * pad;
   for (int q = cnt + threadIdx.x; q < padded; q += blockDim.x) {
     rowA[base + q] = i;
     rowB[base + q] = -1;
@@ -530,11 +530,11 @@ __global__ void spec_reduce_bwd_kernel(int n, int S, int inv, const int* __restr
 }
 
 // specular row list: rowB[q] = q if n_i . dir_q > 1e-6 else -1; rows beyond n*S (tile padding) = -1
-__global__ void spec_rows_kernel(int n, int S, int rows_padded, const float* __restrict__ normals,
+__global__ void spec_rows_kernel(int n, int S, int rows_padded, int pad, const float* __restrict__ normals,
                                  const float* __restrict__ dirs, int* __restrict__ rowA, int* __restrict__ rowB,
                                  int* __restrict__ n_tiles, long long* __restrict__ n_pairs) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q == 0) *n_tiles = rows_padded / 64;
+  if (q == 0) *n_tiles = rows_padded / pad;
   if (q >= rows_padded) return;
   int a = 0, b = -1;
   if (q < n * S) {
@@ -613,32 +613,36 @@ int robir_sample_dirs_bwd(int K, int S, const float* axis_f, const float* axis_w
   return 0;
 }
 
-// Builds the diffuse row list.  Workspace (caller-owned, int32 unless noted): bits [n*M] (u32), lobe_off [n*(M+1)],
-// start [n], rowA/rowB [n * roundup(M*S,64)], counters: n_tiles [1] (int), n_pairs [1] (int64, accumulated).
-int robir_diffuse_rows(int n, int M, int S, const float* normals, const float* dirs, uint32_t* bits, int* lobe_off,
-                       int* start, int* rowA, int* rowB, int* n_tiles, long long* n_pairs, void* stream) {
+// Builds the diffuse row list, every point padded to a multiple of tile_rows (64: FFMA engine, 128: tensor-core
+// engine).  Workspace (caller-owned, int32 unless noted): bits [n*M] (u32), lobe_off [n*(M+1)], start [n],
+// rowA/rowB [n * roundup(M*S, tile_rows)], counters: n_tiles [1] (int), n_pairs [1] (int64, accumulated).
+int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals, const float* dirs, uint32_t* bits,
+                       int* lobe_off, int* start, int* rowA, int* rowB, int* n_tiles, long long* n_pairs,
+                       void* stream) {
   RB_REQUIRE(S >= 1 && S <= 32, "diffuse_rows: S must be in [1,32]");
+  RB_REQUIRE(tile_rows == 64 || tile_rows == 128, "diffuse_rows: tile_rows must be 64 or 128");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     RB_CHECK_CUDA(cudaMemsetAsync(n_tiles, 0, sizeof(int), st));
     return 0;
   }
   diffuse_count_kernel<<<n, 256, M * sizeof(int), st>>>(n, M, S, normals, dirs, bits, lobe_off);
-  diffuse_scan_kernel<<<1, 1024, 0, st>>>(n, M, lobe_off, start, n_tiles, n_pairs);
-  diffuse_fill_kernel<<<n, 256, 0, st>>>(n, M, S, bits, lobe_off, start, rowA, rowB);
+  diffuse_scan_kernel<<<1, 1024, 0, st>>>(n, M, tile_rows, lobe_off, start, n_tiles, n_pairs);
+  diffuse_fill_kernel<<<n, 256, 0, st>>>(n, M, S, tile_rows, bits, lobe_off, start, rowA, rowB);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int robir_spec_rows(int n, int S, int rows_padded, const float* normals, const float* dirs, int* rowA, int* rowB,
-                    int* n_tiles, long long* n_pairs, void* stream) {
-  RB_REQUIRE(rows_padded % 64 == 0 && rows_padded >= n * S, "spec_rows: rows_padded must be a multiple of 64");
+int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, const float* normals, const float* dirs, int* rowA,
+                    int* rowB, int* n_tiles, long long* n_pairs, void* stream) {
+  RB_REQUIRE((tile_rows == 64 || tile_rows == 128) && rows_padded % tile_rows == 0 && rows_padded >= n * S,
+             "spec_rows: rows_padded must be a multiple of tile_rows (64 or 128)");
   if (rows_padded == 0) {
     RB_CHECK_CUDA(cudaMemsetAsync(n_tiles, 0, sizeof(int), (cudaStream_t)stream));
     return 0;
   }
-  spec_rows_kernel<<<cdiv(rows_padded, 256), 256, 0, (cudaStream_t)stream>>>(n, S, rows_padded, normals, dirs, rowA,
-                                                                             rowB, n_tiles, n_pairs);
+  spec_rows_kernel<<<cdiv(rows_padded, 256), 256, 0, (cudaStream_t)stream>>>(n, S, rows_padded, tile_rows, normals,
+                                                                             dirs, rowA, rowB, n_tiles, n_pairs);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -88,8 +88,34 @@ class VisWeights:
             W4, b4 = f32(L[4].weight), f32(L[4].bias)
             d["wd"] = (W4[1] - W4[0]).contiguous()
             d["bd"] = (b4[1] - b4[0]).reshape(1).contiguous()
+            # tensor-core engine: pre-swizzled bf16 hi/lo weight images (csrc/vis_tc.cu)
+            stage = 32768
+            fwd = torch.empty(3 * 8 * stage, dtype=torch.uint8, device=W0.device)
+            bwd = torch.zeros(4 * 8 * stage, dtype=torch.uint8, device=W0.device)
+            for j, i in enumerate((1, 2, 3)):
+                tc_pack_layer(d["W%d" % i], 256, 256, 256, False, 2, fwd[j * 8 * stage:])
+            for j, i in enumerate((3, 2, 1)):
+                tc_pack_layer(d["W%d" % i], 256, 256, 256, True, 2, bwd[j * 8 * stage:])
+            W0c = f32(W0)
+            tc_pack_layer(W0c.reshape(-1)[63:], 126, 63, 256, True, 1, bwd[3 * 8 * stage:])
+            d["tc_fwd"], d["tc_bwd"] = fwd, bwd
+            d["bias3"] = torch.stack([d["b1"], d["b2"], d["b3"]]).contiguous()
             return d
         return self.cache.get(tensors, build)
+
+
+def tc_pack_layer(W, ldw, N, K, transpose, n_halves, out):
+    check(lib().robir_tc_pack_layer(ptr(W), ldw, N, K, int(transpose), n_halves, ptr(out), stream()))
+
+
+def tc_selftest(A, W):
+    """D[128,256] = A[128,256] @ W[256,256]^T through the tcgen05 machinery (bf16x3 split) -- unit test hook."""
+    A, W = f32(A), f32(W)
+    img = torch.empty(8 * 32768, dtype=torch.uint8, device=A.device)
+    tc_pack_layer(W, 256, 256, 256, False, 2, img)
+    D = torch.zeros(128, 256, device=A.device)
+    check(lib().robir_tc_selftest(ptr(A), ptr(img), ptr(D), stream()))
+    return D
 
 
 def pe_linear(x, Wt, bias):
@@ -158,7 +184,7 @@ class Stats:
             cls.n_pairs.zero_()
 
 
-ENGINE = {"vis": "ffma"}   # "ffma" (exact fp32) | "tc" (tcgen05 bf16x3), set by robir_b200.set_engine
+ENGINE = {"vis": "tc"}     # "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
 
 
@@ -178,10 +204,20 @@ class _Timed:
         return False
 
 
+def tile_rows():
+    return 128 if ENGINE["vis"] == "tc" else 64
+
+
 def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
-    rows = max_tiles * 64
+    rows = max_tiles * tile_rows()
     vis = _empty(rows, like=tabA)
     mask = _empty(rows, 4, 8, dtype=torch.int32, like=tabA) if need_mask else None
+    if ENGINE["vis"] == "tc":
+        with _Timed("vis_mlp_fwd", max_tiles):
+            check(lib().robir_vis_tc_fwd(ptr(tabA), ptr(tabB), ptr(rowA), ptr(rowB), ptr(n_tiles), max_tiles,
+                                         ptr(W["tc_fwd"]), ptr(W["bias3"]), ptr(W["wd"]), ptr(W["bd"]), ptr(vis),
+                                         ptr(mask), sm_count(), stream()))
+        return vis, mask
     with _Timed("vis_mlp_fwd", max_tiles):
         check(lib().robir_vis_mlp_fwd(ptr(tabA), ptr(tabB), ptr(rowA), ptr(rowB), ptr(n_tiles), max_tiles,
                                       ptr(W["Wt1"]), ptr(W["Wt2"]), ptr(W["Wt3"]), ptr(W["b1"]), ptr(W["b2"]),
@@ -190,8 +226,13 @@ def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
     return vis, mask
 
 
-def _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs):
+def _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs, engine):
     g_dirs = _zeros(dirs.shape[0], 3, like=dirs)
+    if engine == "tc":
+        with _Timed("vis_mlp_bwd", max_tiles):
+            check(lib().robir_vis_tc_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["tc_bwd"]), ptr(W["wd"]), ptr(vis),
+                                         ptr(g_vis), ptr(mask), ptr(dirs), ptr(g_dirs), sm_count(), stream()))
+        return g_dirs
     with _Timed("vis_mlp_bwd", max_tiles):
         check(lib().robir_vis_mlp_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["W1"]), ptr(W["W2"]), ptr(W["W3"]),
                                       ptr(W["W0d"]), ptr(W["wd"]), ptr(vis), ptr(g_vis), ptr(mask), ptr(dirs),
@@ -208,7 +249,8 @@ class _DiffuseVis(torch.autograd.Function):
         W = weights.get()
         points, normals, dirs, w = map(f32, (points, normals, dirs, w))
         n = points.shape[0]
-        cap = ((M * S + 63) // 64) * 64
+        T = tile_rows()
+        cap = ((M * S + T - 1) // T) * T
         dev = points
         bits = _empty(n, M, dtype=torch.int32, like=dev)
         lobe_off = _empty(n, M + 1, dtype=torch.int32, like=dev)
@@ -216,31 +258,31 @@ class _DiffuseVis(torch.autograd.Function):
         rowA = _empty(n * cap, dtype=torch.int32, like=dev)
         rowB = _empty(n * cap, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
-        check(lib().robir_diffuse_rows(n, M, S, ptr(normals), ptr(dirs), ptr(bits), ptr(lobe_off), ptr(start),
+        check(lib().robir_diffuse_rows(n, M, S, T, ptr(normals), ptr(dirs), ptr(bits), ptr(lobe_off), ptr(start),
                                        ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
         tabA = pe_linear(points, W["Wt0p"], W["b0"])
         tabB = pe_linear(dirs, W["Wt0d"], None)
-        max_tiles = n * cap // 64
+        max_tiles = n * cap // T
         vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_grad)
         lv = _empty(n, M, like=dev)
         check(lib().robir_diffuse_reduce_fwd(n, M, S, ptr(bits), ptr(lobe_off), ptr(start), ptr(vis), ptr(w), ptr(lv),
                                              stream()))
         if need_grad:
             ctx.save_for_backward(dirs, w, bits, lobe_off, start, rowB, n_tiles, vis, mask, lv)
-            ctx.meta = (n, M, S, max_tiles, weights)
+            ctx.meta = (n, M, S, max_tiles, weights, ENGINE["vis"])
         return lv
 
     @staticmethod
     def backward(ctx, g_lv):
         dirs, w, bits, lobe_off, start, rowB, n_tiles, vis, mask, lv = ctx.saved_tensors
-        n, M, S, max_tiles, weights = ctx.meta
+        n, M, S, max_tiles, weights, engine = ctx.meta
         W = weights.get()
         g_lv = f32(g_lv)
         g_vis = _zeros(vis.shape[0], like=vis)
         g_w = _zeros(M * S, like=vis)
         check(lib().robir_diffuse_reduce_bwd(n, M, S, ptr(bits), ptr(lobe_off), ptr(start), ptr(vis), ptr(w), ptr(lv),
                                              ptr(g_lv), ptr(g_vis), ptr(g_w), stream()))
-        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs)
+        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs, engine)
         return None, None, g_dirs, g_w, None, None, None, None
 
 
@@ -253,35 +295,36 @@ class _SpecVis(torch.autograd.Function):
         W = weights.get()
         points, normals, dirs, w = map(f32, (points, normals, dirs, w))
         n = points.shape[0]
-        rows = ((n * S + 63) // 64) * 64
+        T = tile_rows()
+        rows = ((n * S + T - 1) // T) * T
         dev = points
         rowA = _empty(rows, dtype=torch.int32, like=dev)
         rowB = _empty(rows, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
-        check(lib().robir_spec_rows(n, S, rows, ptr(normals), ptr(dirs), ptr(rowA), ptr(rowB), ptr(n_tiles),
+        check(lib().robir_spec_rows(n, S, rows, T, ptr(normals), ptr(dirs), ptr(rowA), ptr(rowB), ptr(n_tiles),
                                     ptr(Stats.pairs_tensor(dev)), stream()))
         tabA = pe_linear(points, W["Wt0p"], W["b0"])
         tabB = pe_linear(dirs, W["Wt0d"], None)
-        vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, rows // 64, need_grad)
+        vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, rows // T, need_grad)
         out = _empty(n, like=dev)
         check(lib().robir_spec_reduce_fwd(n, S, int(inv), int(testing), ptr(rowB), ptr(vis), ptr(w), ptr(out),
                                           stream()))
         if need_grad:
             ctx.save_for_backward(dirs, w, rowB, n_tiles, vis, mask, out)
-            ctx.meta = (n, S, int(inv), rows, weights)
+            ctx.meta = (n, S, int(inv), rows, weights, T, ENGINE["vis"])
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         dirs, w, rowB, n_tiles, vis, mask, out = ctx.saved_tensors
-        n, S, inv, rows, weights = ctx.meta
+        n, S, inv, rows, weights, T, engine = ctx.meta
         W = weights.get()
         g_out = f32(g_out)
         g_vis = _zeros(rows, like=vis)
         g_w = _empty(n * S, like=vis)
         check(lib().robir_spec_reduce_bwd(n, S, inv, ptr(rowB), ptr(vis), ptr(w), ptr(out), ptr(g_out), ptr(g_vis),
                                           ptr(g_w), stream()))
-        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, rows // 64, vis, g_vis, mask, dirs)
+        g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, rows // T, vis, g_vis, mask, dirs, engine)
         return None, None, g_dirs, g_w, None, None, None, None, None
 
 

@@ -20,11 +20,15 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
 
 
-def grad_close(a, b, l2=3e-3, linf=3e-2):
+def grad_close(a, b, l2=3e-3, linf=3e-2, engine="ffma"):
     """Gradients that pass through the ReLU visibility MLP are only piecewise continuous: a hidden unit whose
     pre-activation is ~0 can take a different sign on the GPU than in the CPU oracle (fp32 rounding), which changes a
     few entries by O(weight x upstream) while everything else agrees to ~1e-6 (the fp32-vs-fp64 oracle shows the same
-    effect).  Hence: tight relative L2, looser relative max."""
+    effect).  Hence: tight relative L2, looser relative max.  The tensor-core engine represents every operand with 16
+    mantissa bits (bf16 hi+lo), so its pre-activations differ from fp32 by ~1e-5 relative instead of ~1e-7 and
+    proportionally more borderline units flip: its gradient bounds are 4x wider (forward outputs stay < 1e-4)."""
+    if engine == "tc":
+        l2, linf = 4 * l2, 4 * linf
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     scale = max(b.abs().max().item(), 1e-12)
     e2 = (a - b).norm().item() / max(b.norm().item(), 1e-12)
@@ -46,6 +50,28 @@ def test_extension_is_loaded():
     from robir_b200 import _lib
     assert _lib.lib().robir_abi_version() == 1
     assert _lib.sm_count() >= 100
+
+
+@pytest.fixture(params=["ffma", "tc"])
+def engine(request):
+    """Both visibility-MLP engines: exact-fp32 FFMA and tcgen05 bf16x3 (the fp32-parity tensor-core mode)."""
+    from robir_b200 import ops
+    old = ops.ENGINE["vis"]
+    ops.ENGINE["vis"] = request.param
+    yield request.param
+    ops.ENGINE["vis"] = old
+
+
+def test_tc_gemm_selftest():
+    """tcgen05 machinery in isolation: TMEM-resident A (bf16 hi/lo), swizzled weight ring, 3-term split."""
+    from robir_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    A = torch.randn(128, 256, generator=gen)
+    W = torch.randn(256, 256, generator=gen) / 16
+    D = ops.tc_selftest(A.cuda(), W.cuda()).cpu()
+    ref = (A.double() @ W.double().t()).float()
+    err = (D - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-5, "tcgen05 GEMM self-test: max rel err %.3e" % err
 
 
 def test_sdf_network(golden, synth_sd16, model16):
@@ -71,7 +97,7 @@ def _vis_fn(sd):
     return lambda p, d: O.vis_network(sd, p, d)
 
 
-def test_vis_mlp_backward_stagewise(synth_sd16, model16):
+def test_vis_mlp_backward_stagewise(synth_sd16, model16, engine):
     """Hot-kernel backward in isolation: d out / d sample_dir and d out / d weight against the oracle's autograd."""
     from robir_b200 import ops, sg_render
     sd = synth_sd16
@@ -93,11 +119,11 @@ def test_vis_mlp_backward_stagewise(synth_sd16, model16):
     out = ops.diffuse_vis(pts.cuda(), nrm.cuda(), d2, w2, M, S, sg_render._weights_of(model16.visibility_network), True)
     assert rel_err(out, ref) < REL
     (out * gup.cuda()).sum().backward()
-    grad_close(w2.grad, w1.grad, 1e-4, 1e-3)
-    grad_close(d2.grad, d1.grad)
+    grad_close(w2.grad, w1.grad, 1e-4, 1e-3, engine)
+    grad_close(d2.grad, d1.grad, engine=engine)
 
 
-def test_diffuse_visibility_fwd_bwd(synth_sd16, model16):
+def test_diffuse_visibility_fwd_bwd(synth_sd16, model16, engine):
     from robir_b200 import rng, sg_render
     sd = synth_sd16
     gen = torch.Generator().manual_seed(3)
@@ -117,8 +143,8 @@ def test_diffuse_visibility_fwd_bwd(synth_sd16, model16):
     (out * gup.cuda()).sum().backward()
     assert out.shape == ref.shape == (M, n)
     assert rel_err(out, ref) < REL
-    grad_close(lo2.grad, lo.grad)
-    grad_close(la2.grad, la.grad)
+    grad_close(lo2.grad, lo.grad, engine=engine)
+    grad_close(la2.grad, la.grad, engine=engine)
     # testing mode (no_grad VisModel) gives the same values
     with rng.replay([ut, up]), torch.no_grad():
         out_t = sg_render.get_diffuse_visibility(pts.cuda(), nrm.cuda(), model16.visibility_network, lobes.cuda(),
@@ -126,7 +152,7 @@ def test_diffuse_visibility_fwd_bwd(synth_sd16, model16):
     assert rel_err(out_t, ref) < REL
 
 
-def test_specular_visibility_fwd_bwd(synth_sd16, model16):
+def test_specular_visibility_fwd_bwd(synth_sd16, model16, engine):
     from robir_b200 import rng, sg_render
     sd = synth_sd16
     gen = torch.Generator().manual_seed(4)
@@ -149,7 +175,7 @@ def test_specular_visibility_fwd_bwd(synth_sd16, model16):
                                                     wl2, wlam2, nsamp=S, inv=inv)
         (out * gup.cuda()).sum().backward()
         assert rel_err(out, ref) < REL
-        grad_close(r2.grad, r1.grad)
+        grad_close(r2.grad, r1.grad, engine=engine)
 
 
 def test_octree_cast_on_oracle_tree(golden, oracle_octrees):
@@ -219,7 +245,7 @@ def test_sg_render_kernel(synth_sd16):
         assert (got - ref).abs().max().item() <= tol * max(1e-6, ref.abs().max().item()), k
 
 
-def test_pbr_step_vs_golden(golden, synth_sd16, model16):
+def test_pbr_step_vs_golden(golden, synth_sd16, model16, engine):
     """Full IDRNetwork.forward('Material') + loss + backward against the reference's golden outputs and gradients."""
     from robir_b200 import rng
     from robir_b200.loss import InvLoss, pbr_step_loss
@@ -246,7 +272,7 @@ def test_pbr_step_vs_golden(golden, synth_sd16, model16):
               (dec[4].weight.grad, g["g_dec4_weight"]), (enc[0].bias.grad, g["g_enc0_bias"]),
               (enc[8].weight.grad.sum(0), g["g_enc8_weight_sum"])]
     for a, b in checks:
-        grad_close(a, b, 5e-3, 3e-2)
+        grad_close(a, b, 5e-3, 3e-2, engine)
 
 
 def test_pbr_forward_properties_full_size(model16, synth_sd16):
