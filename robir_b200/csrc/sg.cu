@@ -127,6 +127,14 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
     gis[c] = (p.Mi > 0 && p.pre[9 * i + 6 + c] >= 0.f) ? ld(p.g_ind_rgb, c) + ld(p.g_ind_spec, c) : 0.f;
     gid[c] = p.Mi > 0 ? ld(p.g_ind_rgb, c) + ld(p.g_ind_diff, c) : 0.f;
   }
+  {
+    // rows without any upstream gradient (e.g. masked-out rays of the static-shape mode) contribute nothing;
+    // every output was zero-initialised by the caller
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) any |= (gs[c] != 0.f) | (gd[c] != 0.f) | (gis[c] != 0.f) | (gid[c] != 0.f);
+    if (!any) return;
+  }
   typedef Dual<10> DS;
   typedef Dual<8> DD;
   const V3<DS> nS = lift3<DS>(nrm), vS = lift3<DS>(view);

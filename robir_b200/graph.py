@@ -1,0 +1,73 @@
+"""Whole-step CUDA graph for the PBR stage: camera rays -> octree trace -> nets -> fused visibility MLP -> SG render ->
+loss -> backward (-> Adam) captured once and replayed, so the ~1000 small launches and all Python overhead of a step
+collapse into one graph launch.  Needs ``model.static_shapes = True`` (no data-dependent shapes / host syncs) and
+device-side random numbers."""
+import torch
+
+from . import rng
+from .loss import pbr_step_loss
+
+
+class GraphedPBRStep:
+    """step(uv [1,N,2], object_mask [1,N] bool, rgb_gt [1,N,3]) -> loss (0-d device tensor, valid until the next call).
+
+    With ``reducer`` (multi-GPU gradient all-reduce) the step is split into two graphs -- forward+backward and the
+    optimizer update -- with the NCCL collective issued eagerly in between."""
+
+    def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3):
+        if rng._mode != "device":
+            raise RuntimeError("GraphedPBRStep needs robir_b200.rng.set_mode('device')")
+        model.static_shapes = True
+        loss_fn.static_shapes = True
+        dev = pose.device
+        self.model, self.loss_fn, self.opt, self.reducer = model, loss_fn, optimizer, reducer
+        self.uv = torch.zeros(1, n_rays, 2, device=dev)
+        self.om = torch.ones(1, n_rays, dtype=torch.bool, device=dev)
+        self.gt = torch.zeros(1, n_rays, 3, device=dev)
+        self.pose, self.K, self.n = pose, intrinsics, n_rays
+        self.hits = None
+        split = reducer is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                if split:
+                    reducer()
+                self.opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        self.g1 = torch.cuda.CUDAGraph()
+        self.g2 = None
+        before = _lib.launch_count
+        with torch.cuda.graph(self.g1):
+            self.loss = self._fwd_bwd()
+            if not split:
+                self.opt.step()
+        self.launches_per_step = _lib.launch_count - before    # kernels of the C-ABI library inside one replay
+        if split:
+            self.g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g2):
+                self.opt.step()
+
+    def _fwd_bwd(self):
+        m = self.model
+        inp = {"uv": self.uv, "object_mask": self.om, "pose": self.pose, "intrinsics": self.K,
+               "hdr_shift": m.gamma.hdr_shift.as_input().expand(self.n, 1)}
+        out = m(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = pbr_step_loss(m, self.loss_fn, out, {"rgb": self.gt})
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.hits = out["network_object_mask"].sum()
+        return loss.detach()
+
+    def __call__(self, uv, object_mask, rgb_gt):
+        self.uv.copy_(uv, non_blocking=True)
+        self.om.copy_(object_mask, non_blocking=True)
+        self.gt.copy_(rgb_gt, non_blocking=True)
+        self.g1.replay()
+        if self.g2 is not None:
+            self.reducer()
+            self.g2.replay()
+        return self.loss

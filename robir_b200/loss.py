@@ -12,6 +12,7 @@ class InvLoss(nn.Module):
         super().__init__()
         self.sg_rgb_weight, self.kl_weight, self.latent_smooth_weight = sg_rgb_weight, kl_weight, latent_smooth_weight
         self.l2 = loss_type == 'L2'
+        self.static_shapes = False
 
     @staticmethod
     def kl_divergence(rho, latent):
@@ -30,11 +31,22 @@ class InvLoss(nn.Module):
         sg_rgb_loss = per.sum() / float(model_outputs['object_mask'].shape[0])
         smooth = (model_outputs['diffuse_albedo'] - model_outputs['random_xi_diffuse_albedo']).abs().mean() + \
             (model_outputs['roughness'][..., 0] - model_outputs['random_xi_roughness'][..., 0]).abs().mean() * 0.2
-        pts = model_outputs['points'][model_outputs['network_object_mask']]
         enc = mat_model.spec_brdf_encoder_layer if train_spec else mat_model.brdf_encoder_layer
-        kl = self.kl_divergence(0.05, enc.encode(positional_encoding(pts, 10)))
         sm = model_outputs['surface_mask']
-        normal_loss = ((model_outputs['normal_map'][sm] - model_outputs['normals'][sm]) ** 2).mean()
+        if self.static_shapes:
+            # same statistics without data-dependent shapes (CUDA-graph capturable): masked batch mean of the latent
+            hit = model_outputs['network_object_mask']
+            pts = torch.where(hit[:, None], model_outputs['points'], torch.zeros_like(model_outputs['points']))
+            lat = torch.sigmoid(enc.encode(positional_encoding(pts, 10)))
+            rho_hat = (lat * hit[:, None]).sum(0) / hit.sum().clamp(min=1)
+            rho = torch.full_like(rho_hat, 0.05)
+            kl = torch.mean(rho * torch.log(rho / (rho_hat + 1e-4))
+                            + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
+            normal_loss = torch.zeros((), device=pts.device)     # reported only, never part of the loss (loss.py:114-123)
+        else:
+            pts = model_outputs['points'][model_outputs['network_object_mask']]
+            kl = self.kl_divergence(0.05, enc.encode(positional_encoding(pts, 10)))
+            normal_loss = ((model_outputs['normal_map'][sm] - model_outputs['normals'][sm]) ** 2).mean()
         return {'sg_rgb_loss': sg_rgb_loss, 'kl_loss': self.kl_weight * kl,
                 'latent_smooth_loss': self.latent_smooth_weight * smooth, 'normal_loss': normal_loss,
                 'loss': self.sg_rgb_weight * sg_rgb_loss}

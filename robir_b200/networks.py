@@ -26,7 +26,7 @@ def positional_encoding(x, n_freq):
 
 
 def integrated_positional_encoding(x, n_deg=10, var=1e-5):
-    scales = torch.tensor([2.0 ** i for i in range(n_deg)], device=x.device)
+    scales = torch.exp2(torch.arange(n_deg, device=x.device, dtype=x.dtype))   # no H2D copy: CUDA-graph capturable
     y = (x[:, None, :] * scales[:, None]).reshape(x.shape[0], -1)            # [n, 3*n_deg], degree-major
     y_var = (var * scales ** 2)[:, None].expand(n_deg, x.shape[1]).reshape(1, -1)
     yy = torch.cat([y, y + 0.5 * math.pi], -1)

@@ -51,6 +51,10 @@ class IDRNetwork(nn.Module):
         # PBR-runner state read by pbr_get_sg_render (training/train_pbr.py:414-415, 131-159)
         self.no_normal = True
         self.is_training = True
+        # static_shapes=True: no hit compaction (no host sync, no data-dependent shapes) -- every ray is carried through
+        # the per-hit stages with a validity mask, which makes the whole training step capturable in one CUDA graph
+        # (robir_b200.graph.GraphedPBRStep).  Hit rows get bit-identical results; random draws have shape [N, .].
+        self.static_shapes = False
 
     # ------------------------------------------------------------------------------------------------------------------
     def generate(self):
@@ -69,6 +73,8 @@ class IDRNetwork(nn.Module):
     def forward(self, input, trainstage='IDR', fun_spec=False, lin_diff=False, train_spec=False):
         if fun_spec:
             raise RobirError("fun_spec=True is not on the accelerated path")
+        if self.static_shapes and trainstage != 'Illum' and "intrinsics" in input and 'hdr_shift' in input:
+            return self._forward_static(input, lin_diff=lin_diff, train_spec=train_spec)
         if "intrinsics" in input:
             object_mask = input["object_mask"].reshape(-1)
             ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
@@ -145,6 +151,35 @@ class IDRNetwork(nn.Module):
         ret.update(buf)
         return ret
 
+    def _forward_static(self, input, lin_diff=False, train_spec=False):
+        object_mask = input["object_mask"].reshape(-1)
+        ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
+        batch_size, num_pixels, _ = ray_dirs.shape
+        with torch.no_grad():
+            _, mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+        points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
+        sdf_output = self.implicit_network.sdf(points)[:, None]
+        ray_dirs = ray_dirs.reshape(-1, 3)
+        m1 = mask[:, None]
+        pts = torch.where(m1, points, torch.zeros_like(points))      # finite inputs for the rows that are masked out
+        sgs, integ = self.indirect_illum_network(pts, input['hdr_shift'])
+        ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
+               'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
+        r = pbr_get_sg_render(self, pts, -ray_dirs, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
+                              valid=mask)
+        one = lambda v: torch.where(m1, v, torch.ones_like(v))
+        for k in ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
+                  'indir_specular_rgb', 'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow',
+                  'random_xi_diffuse_albedo', 'metallic', 'random_xi_metallic'):
+            ret[k] = one(r[k])
+        ret['roughness'] = one(r['roughness'].expand(-1, 3))
+        ret['random_xi_roughness'] = one(r['random_xi_roughness'].expand(-1, 3))
+        total, dev = points.shape[0], points.device
+        ret.update({'final_t': torch.ones(total, 1, device=dev), 'gradient_error': torch.zeros((), device=dev),
+                    'acc': torch.ones(total, 1, device=dev), 'bg_rgb': torch.ones(total, 3, device=dev),
+                    'surface_mask': mask})
+        return ret
+
     # ------------------------------------------------------------------------------------------------------------------
     def get_idr_render(self, points, view_dirs=None, normal_only=False):
         if not normal_only:
@@ -164,22 +199,28 @@ class IDRNetwork(nn.Module):
 
 
 def pbr_get_sg_render(model, points, view_dirs, indir_lgtSGs, albedo_ratio=None, fun_spec=False, lin_diff=False,
-                      train_spec=False, indir_integral=None, **kwargs):
-    """training/train_pbr.py:348-396 (model.no_normal / model.is_training play the runner's attributes)."""
+                      train_spec=False, indir_integral=None, valid=None, **kwargs):
+    """training/train_pbr.py:348-396 (model.no_normal / model.is_training play the runner's attributes).
+    valid: optional [n] bool mask of the static-shape mode (rows that are not surface hits are carried along with a
+    zero normal, which culls all of their visibility queries)."""
     view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
     normals = model.get_idr_render(points, view_dirs, normal_only=True)
     normals = normals / torch.clamp(torch.norm(normals, dim=-1, keepdim=True), 1e-4)
+    if valid is not None:
+        normals = torch.where(valid[:, None], normals, torch.zeros_like(normals))
     ret = {'normals': normals}
     mat = model.envmap_material_network(points, train_spec=train_spec)
     indir_integral = indir_integral * 2 * np.pi
     normal_map = mat['sg_normal_map']
     sg = sg_render.render_with_all_sg(points=points.detach(),
-                                      normal=normals.detach() if model.no_normal else normal_map.detach(),
+                                      normal=normals.detach() if model.no_normal else (
+                                          normal_map.detach() if valid is None else
+                                          torch.where(valid[:, None], normal_map.detach(), torch.zeros_like(normal_map))),
                                       viewdirs=view_dirs, lgtSGs=mat['sg_lgtSGs'], indir_integral=indir_integral,
                                       specular_reflectance=mat['sg_specular_reflectance'].abs(),
                                       roughness=mat['sg_roughness'], diffuse_albedo=mat['sg_diffuse_albedo'],
                                       indir_lgtSGs=indir_lgtSGs, VisModel=model.visibility_network, fun_spec=False,
-                                      lin_diff=False, testing=not model.is_training, metallic=None)
+                                      lin_diff=False, testing=not model.is_training, metallic=None, valid=valid)
     ret.update(sg)
     ret.update({'diffuse_albedo': mat['sg_diffuse_albedo'], 'roughness': mat['sg_roughness'],
                 'metallic': mat['sg_metallic'], 'normal_map': normal_map,

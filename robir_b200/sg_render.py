@@ -57,15 +57,17 @@ def _spec_frame(normals, viewdirs):
 
 
 def get_specular_visibility(points, normals, viewdirs, VisModel, lgtSGLobes, lgtSGLambdas, nsamp=24, multi_view=False,
-                            testing=False, inv=False, argmax_vis=False):
-    """[n,3] x3, VisModel, lobes [n,3], lambdas [n,1] -> vis [n]."""
+                            testing=False, inv=False, argmax_vis=False, valid=None):
+    """[n,3] x3, VisModel, lobes [n,3], lambdas [n,1] -> vis [n].  valid (static-shape mode): rows excluded from the
+    batch-global sharpness minimum (model/sg_render.py:220-222)."""
     if multi_view or argmax_vis:
         raise RobirError("multi_view / argmax_vis variants are not on the accelerated path")
     n = points.shape[0]
     dev = points.device
     ref_dir = _spec_frame(normals, viewdirs)
     sharp = torch.clip(lgtSGLambdas[:, 0], min=0.1, max=50)
-    sg_range = torch.clamp(sharp.min(), max=1).reshape(1)
+    sharp_for_min = sharp if valid is None else torch.where(valid, sharp, torch.full_like(sharp, float("inf")))
+    sg_range = torch.clamp(sharp_for_min.min(), max=1).reshape(1)
     u_theta = rng.rand((n, nsamp), dev)
     u_phi = rng.rand((n, nsamp), dev)
     dirs, w = ops.sample_dirs(ref_dir, lgtSGLobes, sharp, sharp, sg_range, u_theta, u_phi, False)
@@ -86,7 +88,7 @@ def _spec_warp(normal, viewdirs, roughness):
 
 def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
                        indir_integral=None, indir_lgtSGs=None, VisModel=None, fun_spec=False, lin_diff=False,
-                       testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False):
+                       testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False, valid=None):
     """model/sg_render.py:304-337 for the PBR-stage configuration (fun_spec=False, metallic=None, diffuse_vis=None)."""
     if fun_spec or metallic is not None or diffuse_vis is not None or argmax_vis or viewdirs.dim() != 2:
         raise RobirError("render_with_all_sg: fun_spec / metallic / diffuse_vis / argmax_vis / multi-view variants are "
@@ -103,14 +105,17 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
                                        testing=testing).permute(1, 0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
     wl, wlam = _spec_warp(normal, viewdirs, roughness)
-    bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing, inv=False)
+    bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing, inv=False,
+                                     valid=valid)
     bv_ind = None
     if indir_lgtSGs is not None:
+        if indir_integral is None:
+            raise RobirError("render_with_all_sg: indirect SGs need indir_integral (PBR-stage configuration)")
         bv_ind = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
-                                         inv=True)
+                                         inv=True, valid=valid)
     outs = ops.sg_render(normal.detach(), viewdirs, roughness, diffuse_albedo, specular_reflectance.reshape(1), lgtSGs,
                          indir_lgtSGs, light_vis.contiguous(), bv_dir, bv_ind, indir_integral, lin_diff)
     sg_rgb, sg_spec, sg_diff, vis_shadow, ind_rgb, ind_spec, ind_diff = outs
     return {'sg_rgb': sg_rgb, 'sg_specular_rgb': sg_spec, 'sg_diffuse_rgb': sg_diff, 'vis_shadow': vis_shadow,
-            'supervise': torch.tensor(0.0, device=points.device), 'indir_rgb': ind_rgb,
+            'supervise': torch.zeros((), device=points.device), 'indir_rgb': ind_rgb,
             'indir_diffuse_rgb': ind_diff, 'indir_specular_rgb': ind_spec}

@@ -295,3 +295,63 @@ def test_pbr_forward_properties_full_size(model16, synth_sd16):
         assert torch.all(a[k][~m] == 1.0), k
         assert torch.isfinite(a[k]).all(), k
     assert (a["sg_rgb"][m] >= 0).all()
+
+
+def test_static_shape_mode_matches_compacted_mode(model16):
+    """static_shapes=True (no hit compaction; what the CUDA-graph step uses) vs. the reference-shaped path."""
+    from robir_b200 import rng
+    model16.generate()
+    N = 512
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(12, n=N, crop=460)).items()}
+    inp["hdr_shift"] = torch.full((N, 1), 0.5).cuda()
+    with rng.record() as tape, torch.no_grad():
+        a = model16(inp, trainstage="Material", train_spec=True)
+    m = a["network_object_mask"].cpu()
+    assert 0 < int(m.sum()) < N
+    tape_static = []
+    for t in tape:
+        if t.shape[0] == int(m.sum()) and t.shape[0] != 16:      # per-hit draws -> scattered to [N, .]
+            full = torch.zeros(N, *t.shape[1:])
+            full[m] = t
+            tape_static.append(full)
+        else:
+            tape_static.append(t)
+    model16.static_shapes = True
+    try:
+        with rng.replay(tape_static), torch.no_grad():
+            b = model16(inp, trainstage="Material", train_spec=True)
+    finally:
+        model16.static_shapes = False
+    assert set(a.keys()) == set(b.keys())
+    for k in a:
+        if a[k].dtype == torch.bool:
+            assert torch.equal(a[k], b[k]), k
+        elif k != "points":
+            assert a[k].shape == b[k].shape, k
+            assert rel_err(b[k], a[k]) < 1e-5, (k, rel_err(b[k], a[k]))
+
+
+def test_graphed_step_runs_and_trains(synth_sd16):
+    """CUDA-graph capture of the whole PBR training step: replays are deterministic functions of the inputs and the
+    loss goes down."""
+    import robir_b200
+    from robir_b200 import graph, rng
+    from robir_b200.loss import InvLoss
+    m = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=16)))
+    m.load_state_dict(synth_sd16, strict=True)
+    m.cuda().train()
+    m.generate()
+    params = list(m.gamma.parameters()) + list(m.envmap_material_network.parameters())
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=True)
+    rng.set_mode("device")
+    try:
+        N = 256
+        step = graph.GraphedPBRStep(m, InvLoss(), opt, N, synthetic.camera_pose().cuda(),
+                                    synthetic.camera_intrinsics().cuda())
+        inp = synthetic.camera_inputs(synthetic.training_pixels(3, n=N, crop=400))
+        gt = torch.full((1, N, 3), 0.3).cuda()
+        losses = [float(step(inp["uv"].cuda(), inp["object_mask"].cuda(), gt)) for _ in range(25)]
+        assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+        assert step.launches_per_step > 20
+    finally:
+        rng.set_mode("cpu")
