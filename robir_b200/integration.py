@@ -18,6 +18,21 @@ from . import ops, sg_render, tracing
 from ._lib import RobirError
 
 
+_saved_module_attrs = []
+
+
+def uninstall_modules():
+    """Undo the module-level re-bindings of install() (the per-model attribute changes stay with the model object)."""
+    while _saved_module_attrs:
+        mod, name, old = _saved_module_attrs.pop()
+        setattr(mod, name, old)
+
+
+def _patch(mod, name, new):
+    _saved_module_attrs.append((mod, name, getattr(mod, name)))
+    setattr(mod, name, new)
+
+
 def install(model, patch_modules=True):
     if not hasattr(model, "visibility_network") or not hasattr(model, "implicit_network"):
         raise RobirError("install() expects a reference IDRNetwork")
@@ -50,8 +65,8 @@ def install(model, patch_modules=True):
         for modname in ("model.sg_render", "model.implicit_differentiable_renderer"):
             mod = sys.modules.get(modname)
             if mod is not None:
-                mod.render_with_all_sg = sg_render.render_with_all_sg
+                _patch(mod, "render_with_all_sg", sg_render.render_with_all_sg)
                 if modname == "model.sg_render":
-                    mod.get_diffuse_visibility = sg_render.get_diffuse_visibility
-                    mod.get_specular_visibility = sg_render.get_specular_visibility
+                    _patch(mod, "get_diffuse_visibility", sg_render.get_diffuse_visibility)
+                    _patch(mod, "get_specular_visibility", sg_render.get_specular_visibility)
     return model

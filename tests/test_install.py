@@ -16,7 +16,19 @@ def test_install_rebinds_reference_seams(synth_sd16):
     model = ref_shim.build_reference_model(synthetic.neus_checkpoint_from(synth_sd16), num_lgt_sgs=16)
     model.load_state_dict(synth_sd16, strict=True)
     keys_before = list(model.state_dict().keys())
+    from robir_b200 import integration
     robir_b200.install(model)
+    try:
+        _check(model, keys_before, synth_sd16)
+    finally:
+        integration.uninstall_modules()
+    assert sys.modules["model.sg_render"].render_with_all_sg is not ours.render_with_all_sg
+
+
+def _check(model, keys_before, synth_sd16):
+    import robir_b200
+    from robir_b200 import tracing
+    from robir_b200 import sg_render as ours
     assert isinstance(model.ray_tracer, tracing.OctreeTracing) and model.ray_tracer.max_iter == -1
     assert isinstance(model.octree_ray_tracer, tracing.OctreeTracing) and model.octree_ray_tracer.max_iter == 32
     assert sys.modules["model.sg_render"].render_with_all_sg is ours.render_with_all_sg
