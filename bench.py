@@ -225,6 +225,9 @@ def main():
         return loss, out["network_object_mask"]
 
     graphed = None
+    if args.mode == "eager-static":
+        model.static_shapes = True
+        loss_fn.static_shapes = True
     if args.mode == "graph":
         from robir_b200.graph import GraphedPBRStep
         graphed = GraphedPBRStep(model, loss_fn, opt, N_RAYS, pose, K, reducer=reducer if world > 1 else None)

@@ -33,6 +33,18 @@ class SdfParams(Structure):
                 ("b8", c_void_p), ("Wt8_feat", c_void_p), ("sdf", c_void_p), ("grad", c_void_p), ("feat", c_void_p)]
 
 
+class MlpLayer(Structure):
+    _fields_ = [("Wt", c_void_p), ("Wb", c_void_p), ("bias", c_void_p), ("K", c_int), ("N", c_int), ("Kpad", c_int),
+                ("Npad", c_int), ("act", c_int), ("save", c_void_p), ("G", c_void_p)]
+
+
+class MlpParams(Structure):
+    _fields_ = [("n", c_int), ("n_layers", c_int), ("in_mode", c_int), ("in_dim", c_int), ("in_pad", c_int),
+                ("x", c_void_p), ("extra", c_void_p), ("noise", c_void_p), ("noise_scale", c_float),
+                ("x0_save", c_void_p), ("L", MlpLayer * 8), ("out", c_void_p), ("ldo", c_int), ("g_out", c_void_p),
+                ("g_x", c_void_p)]
+
+
 class OctreeView(Structure):
     _fields_ = [("nodes", c_void_p), ("grid", c_void_p), ("gx", c_int), ("gy", c_int), ("gz", c_int),
                 ("n_nodes", c_int), ("rminx", c_float), ("rminy", c_float), ("rminz", c_float), ("rsizex", c_float),
@@ -63,6 +75,9 @@ _SIGNATURES = {
     "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_tc_selftest": [_P, _P, _P, _P],
+    "robir_pack_pad": [_P, _I, _I, _P, _I, _I, _P],
+    "robir_mlp_fwd": [POINTER(MlpParams), _I, _P],
+    "robir_mlp_bwd": [POINTER(MlpParams), _I, _P],
     "robir_vis_mlp_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_vis_mlp_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "robir_diffuse_reduce_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],

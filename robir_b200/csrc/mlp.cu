@@ -1,0 +1,336 @@
+// Fused small-MLP kernels: the SparseAE encoders / decoders of the material network
+// (model/sg_envmap_material.py:40-99) and the indirect-illumination lobe network
+// (model/implicit_differentiable_renderer.py:170-222) run as ONE launch per chain instead of ~40 library kernels:
+// input encoding (PE10 / PE10+hdr / IPE, optional additive noise in embedding space) -> up to 8 Linear(+ReLU|LeakyReLU)
+// layers on 16-row tiles held in shared memory (fp32 FFMA, column-per-lane mapping, cp.async weight ring).  The backward kernel runs the
+// input-gradient chain and emits the per-layer pre-activation gradients G_l; weight gradients are then plain GEMMs
+// G_l^T A_{l-1} (library calls on the host side).
+#include "mlp_engine.cuh"
+
+namespace robir {
+
+constexpr int kMlpMaxLayers = 8;
+constexpr int kMlpR = 16;
+constexpr int kMlpKMax = 512;
+
+enum InMode { IN_RAW = 0, IN_PE10 = 1, IN_PE10_EXTRA = 2, IN_IPE10 = 3 };
+
+struct MlpLayer {
+  const float* Wt;    // forward: [Kpad][Npad] (transposed, zero padded, Npad % 256 == 0, Kpad % 16 == 0)
+  const float* Wb;    // backward: [Npad16][Kpad256] row-major copy of W (zero padded)
+  const float* bias;  // [Npad]
+  int K, N, Kpad, Npad;
+  int act;            // Act of common.cuh applied to this layer's output
+  float* save;        // forward: post-activation output [n][Npad] or null;  backward: same buffer (input)
+  float* G;           // backward: pre-activation gradient of this layer [n][Npad] or null
+};
+
+struct MlpParams {
+  int n, n_layers, in_mode, in_dim, in_pad;   // in_dim = K of layer 0; in_pad = Kpad of layer 0
+  const float* x;       // IN_RAW: [n][in_dim]; else points [n][3]
+  const float* extra;   // IN_PE10_EXTRA: [n] appended as column 63
+  const float* noise;   // optional [n][in_dim], added as 0.02 * noise in embedding space (sg_envmap_material.py:83)
+  float noise_scale;
+  float* x0_save;       // embedded input [n][in_pad] (forward: written if non-null; backward: unused)
+  MlpLayer L[kMlpMaxLayers];
+  float* out;           // [n][ldo] first N_last columns written
+  int ldo;
+  const float* g_out;   // backward: [n][ldo]
+  float* g_x;           // backward: gradient w.r.t. the embedded input [n][in_pad] or null
+};
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
+  return x;
+}
+// derivative from the post-activation value (sign is preserved by ReLU / LeakyReLU)
+__device__ __forceinline__ float act_bwd(float y, int act) {
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ACT_LEAKY02) return y > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// safe_trig_helper of model/neus_model.py:15-16: arguments with |a| >= 100 pi are wrapped with python-style %
+__device__ __forceinline__ float safe_arg(float a) {
+  const float T = 314.15927f;   // float32(100 * pi)
+  if (fabsf(a) < T) return a;
+  float m = fmodf(a, T);
+  if (m != 0.f && m < 0.f) m += T;
+  return m;
+}
+
+__device__ __forceinline__ void encode_row(float* Xs, int RP, int r, const MlpParams& p, int row, bool valid) {
+  const int K = p.in_dim;
+  if (p.in_mode == IN_RAW) {
+    for (int k = 0; k < K; ++k) Xs[k * RP + r] = valid ? p.x[(size_t)row * K + k] : 0.f;
+  } else {
+    float v[3] = {0.f, 0.f, 0.f};
+    if (valid) { v[0] = p.x[3 * row]; v[1] = p.x[3 * row + 1]; v[2] = p.x[3 * row + 2]; }
+    if (p.in_mode == IN_IPE10) {
+      // integrated PE, isotropic var 1e-5: [exp(-var 4^l / 2) sin(2^l x)] (30) then the same with +pi/2 (30)
+      float f = 1.f;
+      for (int l = 0; l < 10; ++l) {
+        const float damp = expf(-0.5f * (1e-5f * f * f));
+        for (int i = 0; i < 3; ++i) {
+          const float y = v[i] * f;
+          Xs[(3 * l + i) * RP + r] = valid ? damp * sinf(safe_arg(y)) : 0.f;
+          Xs[(30 + 3 * l + i) * RP + r] = valid ? damp * sinf(safe_arg(y + 1.57079632679489661923f)) : 0.f;
+        }
+        f *= 2.f;
+      }
+    } else {
+      for (int i = 0; i < 3; ++i) Xs[i * RP + r] = v[i];
+      float f = 1.f;
+      for (int l = 0; l < 10; ++l) {
+        for (int i = 0; i < 3; ++i) {
+          Xs[(3 + 6 * l + i) * RP + r] = valid ? sinf(v[i] * f) : 0.f;
+          Xs[(6 + 6 * l + i) * RP + r] = valid ? cosf(v[i] * f) : 0.f;
+        }
+        f *= 2.f;
+      }
+      if (p.in_mode == IN_PE10_EXTRA) Xs[63 * RP + r] = valid ? p.extra[row] : 0.f;
+    }
+  }
+  if (p.noise != nullptr && valid)
+    for (int k = 0; k < K; ++k) Xs[k * RP + r] += p.noise_scale * p.noise[(size_t)row * K + k];
+  for (int k = K; k < p.in_pad; ++k) Xs[k * RP + r] = 0.f;
+  if (p.x0_save != nullptr && valid)
+    for (int k = 0; k < p.in_pad; ++k) p.x0_save[(size_t)row * p.in_pad + k] = Xs[k * RP + r];
+}
+
+// Column-per-lane tile GEMM for narrow row tiles: warp w / lane l own output column 32 w + l of the current 256-column
+// pass and all R rows of the tile (R accumulators in registers); per k one conflict-free LDS.32 of the weight row and
+// R/4 broadcast LDS.128 of the activations -> FFMA-issue bound even at R = 16, which lets 1024 rows spread over 64 CTAs.
+template <int R>
+__device__ __forceinline__ void col_gemm_pass(const float* __restrict__ Xs, int K, const float* __restrict__ Wt,
+                                              int ldw, int col0, float* __restrict__ Wbuf, float (&acc)[R]) {
+  constexpr int RP = R + 4;
+  const int tid = threadIdx.x;
+  auto load_chunk = [&](int buf, int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int row = idx >> 6, c4 = idx & 63;
+      cp_async16(Wbuf + buf * (kChunkK * kPassCols) + row * kPassCols + c4 * 4,
+                 Wt + (size_t)(k0 + row) * ldw + col0 + c4 * 4);
+    }
+    cp_async_commit();
+  };
+  const int nchunk = K / kChunkK;
+  load_chunk(0, 0);
+  for (int c = 0; c < nchunk; ++c) {
+    if (c + 1 < nchunk) {
+      load_chunk((c + 1) & 1, (c + 1) * kChunkK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = Wbuf + (c & 1) * (kChunkK * kPassCols) + tid;
+    const float* xb = Xs + (size_t)(c * kChunkK) * RP;
+#pragma unroll
+    for (int kk = 0; kk < kChunkK; ++kk) {
+      const float w = wb[kk * kPassCols];
+#pragma unroll
+      for (int r = 0; r < R; r += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(xb + kk * RP + r);
+        acc[r] = fmaf(x.x, w, acc[r]);
+        acc[r + 1] = fmaf(x.y, w, acc[r + 1]);
+        acc[r + 2] = fmaf(x.z, w, acc[r + 2]);
+        acc[r + 3] = fmaf(x.w, w, acc[r + 3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void col_store(float* __restrict__ Xs, int col, const float (&v)[R]) {
+  float* dst = Xs + (size_t)col * (R + 4);
+#pragma unroll
+  for (int r = 0; r < R; r += 4) *reinterpret_cast<float4*>(dst + r) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mlp_fwd_layer(const MlpParams& p, int l, float* Xs, float* Wbuf, int row0) {
+  constexpr int R = kMlpR;
+  const MlpLayer& L = p.L[l];
+  const bool last = l == p.n_layers - 1;
+  float acc[NPASS][R];
+#pragma unroll
+  for (int ps = 0; ps < NPASS; ++ps) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[ps][r] = 0.f;
+    col_gemm_pass<R>(Xs, L.Kpad, L.Wt, L.Npad, ps * kPassCols, Wbuf, acc[ps]);
+  }
+#pragma unroll
+  for (int ps = 0; ps < NPASS; ++ps) {
+    const int col = ps * kPassCols + threadIdx.x;
+    const bool live = col < L.N;
+    const float b = live ? __ldg(L.bias + col) : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float y = live ? act_fwd(acc[ps][r] + b, L.act) : 0.f;
+      acc[ps][r] = y;
+      const int row = row0 + r;
+      if (row < p.n) {
+        if (L.save != nullptr) L.save[(size_t)row * L.Npad + col] = y;
+        if (last && live) p.out[(size_t)row * p.ldo + col] = y;
+      }
+    }
+    if (!last) col_store<R>(Xs, col, acc[ps]);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) mlp_fwd_kernel(MlpParams p) {
+  constexpr int R = kMlpR, RP = R + 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;                        // [kMlpKMax][RP]
+  float* Wbuf = Xs + kMlpKMax * RP;
+  const int tid = threadIdx.x;
+  const int ntile = (p.n + R - 1) / R;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int row0 = tile * R;
+    __syncthreads();
+    if (tid < R) encode_row(Xs, RP, tid, p, row0 + tid, row0 + tid < p.n);
+    __syncthreads();
+    for (int l = 0; l < p.n_layers; ++l) {
+      if (p.L[l].Npad == kPassCols) mlp_fwd_layer<1>(p, l, Xs, Wbuf, row0);
+      else mlp_fwd_layer<2>(p, l, Xs, Wbuf, row0);
+    }
+  }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mlp_bwd_layer(const MlpParams& p, int l, float* Xs, float* Wbuf, int row0) {
+  constexpr int R = kMlpR;
+  const MlpLayer& L = p.L[l];
+  const int kin = (L.N + 15) & ~15;                 // contraction length (rows of Wb)
+  const int outp = NPASS * kPassCols;
+  float acc[NPASS][R];
+#pragma unroll
+  for (int ps = 0; ps < NPASS; ++ps) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[ps][r] = 0.f;
+    col_gemm_pass<R>(Xs, kin, L.Wb, outp, ps * kPassCols, Wbuf, acc[ps]);
+  }
+#pragma unroll
+  for (int ps = 0; ps < NPASS; ++ps) {
+    const int col = ps * kPassCols + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      float g = (col < L.K) ? acc[ps][r] : 0.f;
+      if (l > 0) {
+        const MlpLayer& P = p.L[l - 1];
+        if (row < p.n && col < P.N) {
+          g *= act_bwd(P.save[(size_t)row * P.Npad + col], P.act);
+          if (P.G != nullptr) P.G[(size_t)row * P.Npad + col] = g;
+        } else {
+          g = 0.f;
+        }
+      } else if (p.g_x != nullptr && row < p.n && col < p.in_pad) {
+        p.g_x[(size_t)row * p.in_pad + col] = g;
+      }
+      acc[ps][r] = g;
+    }
+    if (l > 0) col_store<R>(Xs, col, acc[ps]);
+  }
+  __syncthreads();
+}
+
+// backward: G_L = g_out; for l = L-1..0: emit G_l, dA = G_l . W_l, G_{l-1} = dA * act'(A_{l-1})
+__global__ void __launch_bounds__(256, 2) mlp_bwd_kernel(MlpParams p) {
+  constexpr int R = kMlpR, RP = R + 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;
+  float* Wbuf = Xs + kMlpKMax * RP;
+  const int tid = threadIdx.x;
+  const int ntile = (p.n + R - 1) / R;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int row0 = tile * R;
+    __syncthreads();
+    {
+      // G of the last layer (its act is applied by the caller or is NONE): tile rows <- g_out, zero padded to Npad16
+      const MlpLayer& L = p.L[p.n_layers - 1];
+      const int kp = (L.N + 15) & ~15;
+      for (int idx = tid; idx < kp * R; idx += 256) {
+        const int k = idx / R, r = idx % R, row = row0 + r;
+        float g = 0.f;
+        if (row < p.n && k < L.N) {
+          g = p.g_out[(size_t)row * p.ldo + k];
+          if (L.act != ACT_NONE) g *= act_bwd(L.save[(size_t)row * L.Npad + k], L.act);
+        }
+        Xs[k * RP + r] = g;
+        if (L.G != nullptr && row < p.n && k < L.N) L.G[(size_t)row * L.Npad + k] = g;
+      }
+    }
+    __syncthreads();
+    for (int l = p.n_layers - 1; l >= 0; --l) {
+      if (p.L[l].K <= kPassCols) mlp_bwd_layer<1>(p, l, Xs, Wbuf, row0);
+      else mlp_bwd_layer<2>(p, l, Xs, Wbuf, row0);
+    }
+  }
+}
+
+// W [N][K] -> Wb [Npad16][Kpad256] (zero padded row-major copy for the backward chain)
+__global__ void pack_pad_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out, int Np, int Kp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Np * Kp) return;
+  const int n = idx / Kp, k = idx % Kp;
+  out[idx] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+}
+
+}  // namespace robir
+
+using namespace robir;
+
+extern "C" {
+
+int robir_pack_pad(const float* W, int N, int K, float* out, int Np, int Kp, void* stream) {
+  RB_REQUIRE(Np >= N && Kp >= K, "pack_pad: padded shape too small");
+  pack_pad_kernel<<<(Np * Kp + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, N, K, out, Np, Kp);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int mlp_check(const MlpParams* p) {
+  RB_REQUIRE(p->n_layers >= 1 && p->n_layers <= kMlpMaxLayers, "mlp: 1..8 layers");
+  for (int l = 0; l < p->n_layers; ++l) {
+    const MlpLayer& L = p->L[l];
+    RB_REQUIRE(L.Kpad % 16 == 0 && L.Kpad <= kMlpKMax && L.Npad % 256 == 0 && L.Npad <= 512 && L.K <= L.Kpad &&
+                   L.N <= L.Npad,
+               "mlp: layer shape outside the supported envelope (K <= 512, N <= 512)");
+    if (l > 0) RB_REQUIRE(L.Kpad == p->L[l - 1].Npad || L.K == p->L[l - 1].N, "mlp: layer chain mismatch");
+  }
+  RB_REQUIRE(p->in_pad == p->L[0].Kpad && p->in_dim == p->L[0].K, "mlp: input width mismatch");
+  return 0;
+}
+
+int robir_mlp_fwd(const MlpParams* p, int sm_count, void* stream) {
+  if (p->n == 0) return 0;
+  if (int e = mlp_check(p)) return e;
+  const int smem = (kMlpKMax * (kMlpR + 4) + kWbufFloats) * 4;
+  RB_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int tiles = (p->n + kMlpR - 1) / kMlpR;
+  mlp_fwd_kernel<<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int robir_mlp_bwd(const MlpParams* p, int sm_count, void* stream) {
+  if (p->n == 0) return 0;
+  if (int e = mlp_check(p)) return e;
+  for (int l = 0; l < p->n_layers - 1; ++l)
+    RB_REQUIRE(p->L[l].save != nullptr, "mlp_bwd: hidden activations must have been saved by the forward");
+  const int smem = (kMlpKMax * (kMlpR + 4) + kWbufFloats) * 4;
+  RB_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int tiles = (p->n + kMlpR - 1) / kMlpR;
+  mlp_bwd_kernel<<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -33,11 +33,22 @@ class InvLoss(nn.Module):
             (model_outputs['roughness'][..., 0] - model_outputs['random_xi_roughness'][..., 0]).abs().mean() * 0.2
         enc = mat_model.spec_brdf_encoder_layer if train_spec else mat_model.brdf_encoder_layer
         sm = model_outputs['surface_mask']
+
+        def latent_of(pts):
+            # the reference re-encodes the hit points (loss.py:86-88); the forward already did exactly that, so the
+            # fused path reuses its latent (identical values, gradients add up in the same graph node)
+            z = getattr(mat_model, "_last_spec_latent", None) if train_spec else None
+            if z is not None and z.shape[0] == pts.shape[0] and z.requires_grad == torch.is_grad_enabled():
+                return z
+            if pts.is_cuda and hasattr(enc, "encode_points"):
+                return enc.encode_points(pts, "pe10")
+            return enc.encode(positional_encoding(pts, 10))
+
         if self.static_shapes:
             # same statistics without data-dependent shapes (CUDA-graph capturable): masked batch mean of the latent
             hit = model_outputs['network_object_mask']
             pts = torch.where(hit[:, None], model_outputs['points'], torch.zeros_like(model_outputs['points']))
-            lat = torch.sigmoid(enc.encode(positional_encoding(pts, 10)))
+            lat = torch.sigmoid(latent_of(pts))
             rho_hat = (lat * hit[:, None]).sum(0) / hit.sum().clamp(min=1)
             rho = torch.full_like(rho_hat, 0.05)
             kl = torch.mean(rho * torch.log(rho / (rho_hat + 1e-4))
@@ -45,7 +56,7 @@ class InvLoss(nn.Module):
             normal_loss = torch.zeros((), device=pts.device)     # reported only, never part of the loss (loss.py:114-123)
         else:
             pts = model_outputs['points'][model_outputs['network_object_mask']]
-            kl = self.kl_divergence(0.05, enc.encode(positional_encoding(pts, 10)))
+            kl = self.kl_divergence(0.05, latent_of(pts))
             normal_loss = ((model_outputs['normal_map'][sm] - model_outputs['normals'][sm]) ** 2).mean()
         return {'sg_rgb_loss': sg_rgb_loss, 'kl_loss': self.kl_weight * kl,
                 'latent_smooth_loss': self.latent_smooth_weight * smooth, 'normal_loss': normal_loss,

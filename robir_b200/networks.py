@@ -16,6 +16,8 @@ import torch.nn.functional as F
 
 from . import ops, rng
 
+FUSED_MLP = True   # CUDA tensors take the fused-kernel path (csrc/mlp.cu); False = plain library GEMMs (debug)
+
 
 def positional_encoding(x, n_freq):
     out = [x]
@@ -148,6 +150,59 @@ class SparseAE(nn.Module):
             z = z * (1 - self.var.to(z.device))
         return z
 
+    # ---- fused CUDA path: the encoding + every Linear/LeakyReLU chain is one kernel launch (csrc/mlp.cu) -------------
+    def _chain(self, which, in_mode):
+        key = "_robir_%s_%s" % (which, in_mode)
+        ch = self.__dict__.get(key)
+        if ch is None:
+            seq = self.brdf_encoder_layer if which == "enc" else self.brdf_decoder_layer
+            ch = ops.MlpChain.from_sequential(seq, "leaky", in_mode)
+            self.__dict__[key] = ch
+        return ch
+
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def encode_points(self, points, in_mode="pe10", extra=None, noise=None, train=None):
+        """encoder(embed(points) (+ 0.02 noise)) -> latent pre-activation [n, 32]"""
+        train = self._wants_grad() if train is None else train
+        z = ops.fused_mlp(self._chain("enc", in_mode), points, extra=extra, noise=noise, noise_scale=0.02,
+                          want_param_grad=train)
+        if self.var is not None:
+            z = z * (1 - self.var.to(z.device))
+        return z
+
+    def forward_points(self, points, in_mode="pe10", extra=None, train=None, noisy_only=False):
+        """SparseAE.forward on raw points (model/sg_envmap_material.py:74-94) -> (y, y_noisy, z_clean)."""
+        train = self._wants_grad() if train is None else train
+        n = points.shape[0]
+        dec = self._chain("dec", "raw")
+        if self.smooth_on_latent:
+            z = self.encode_points(points, in_mode, extra, None, train)
+            lc = self.lc_act(z)
+            lc_r = lc + rng.randn(lc.shape, lc.device) * 0.01
+            y2 = ops.fused_mlp(dec, torch.cat([lc, lc_r], 0), want_param_grad=train)
+            y, y_r = y2[:n], y2[n:]
+        else:
+            in_dim = self.brdf_encoder_layer[0].in_features
+            noise = rng.randn((n, in_dim), points.device)
+            if noisy_only:
+                z = None
+                lc_r = self.lc_act(self.encode_points(points, in_mode, extra, noise, train))
+                y = None
+                y_r = ops.fused_mlp(dec, lc_r, want_param_grad=train)
+            else:
+                pts2 = torch.cat([points, points], 0)
+                ex2 = torch.cat([extra, extra], 0) if extra is not None else None
+                z2 = self.encode_points(pts2, in_mode, ex2, torch.cat([torch.zeros_like(noise), noise], 0), train)
+                z = z2[:n]
+                y2 = ops.fused_mlp(dec, self.lc_act(z2), want_param_grad=train)
+                y, y_r = y2[:n], y2[n:]
+        if self.out_act is not None:
+            y = self.out_act(y) if y is not None else None
+            y_r = self.out_act(y_r)
+        return y, y_r, z
+
     def forward(self, x):
         lc = self.lc_act(self.encode(x))
         y = self.brdf_decoder_layer(lc)
@@ -177,17 +232,27 @@ class EnvmapMaterialNetwork(nn.Module):
         self.lgtSGs = nn.Parameter(synthetic_light_sgs(torch.Generator().manual_seed(0), num_lgt_sgs))
 
     def forward(self, points, train_spec=False, train_norm=False):
-        pts_ipe = integrated_positional_encoding(points, 10, 1e-5)
-        emb = positional_encoding(points, 10)
+        fused = points.is_cuda and FUSED_MLP
         ret = {}
+        if not fused:
+            pts_ipe = integrated_positional_encoding(points, 10, 1e-5)
+            emb = positional_encoding(points, 10)
         if not train_norm:
-            brdf, brdf_r = self.spec_brdf_encoder_layer(emb)
+            if fused:
+                brdf, brdf_r, z = self.spec_brdf_encoder_layer.forward_points(points.detach(), "pe10",
+                                                                              train=None if train_spec else False)
+                self._last_spec_latent = z          # reused by the KL term of the loss (same points, same encoder)
+            else:
+                brdf, brdf_r = self.spec_brdf_encoder_layer(emb)
             if train_spec is False:
                 brdf, brdf_r = brdf.detach(), brdf_r.detach()
             ret.update(sg_roughness=brdf[..., 3:4] * 0.9 + 0.09, sg_metallic=brdf[..., 4:5] * 0.99 + 0.01,
                        sg_diffuse_albedo=brdf[..., :3], random_xi_roughness=brdf_r[..., 3:4] * 0.9 + 0.09,
                        random_xi_diffuse_albedo=brdf_r[..., :3], random_xi_metallic=brdf_r[..., 4:5])
-        nm, nm_r = self.normal_decoder_layer(pts_ipe)
+        if fused:
+            nm, nm_r, _ = self.normal_decoder_layer.forward_points(points.detach(), "ipe10")
+        else:
+            nm, nm_r = self.normal_decoder_layer(pts_ipe)
         ret["sg_normal_map"] = nm / torch.clamp(nm.norm(dim=-1, keepdim=True), 1e-4)
         ret["random_xi_normal"] = nm_r / torch.clamp(nm_r.norm(dim=-1, keepdim=True), 1e-4)
         if train_norm:
@@ -208,16 +273,33 @@ class IndirctIllumNetwork(nn.Module):
         self.lobe_layer = _mlp([64] + list(dims) + [num_lgt_sgs * 6], nn.ReLU())
         self.integral_layer = SparseAE(64, 3, out_act=None, smooth_on_latent=False)
         self.integral_layer.lc_act = F.softplus
+        self._lobe_chain = None
+        # PBR stage: these weights are not optimised (train_pbr.py:104-105) -> only the input gradient (hdr_shift)
+        # is propagated; the Vis stage sets train_weights = True
+        self.train_weights = False
 
     def forward(self, points, hdr_shift):
+        if points.is_cuda and FUSED_MLP:
+            if self._lobe_chain is None:
+                self._lobe_chain = ops.MlpChain.from_sequential(self.lobe_layer, "relu", "pe10_extra")
+            train = self.train_weights and torch.is_grad_enabled()
+            pts = points.detach()
+            out = ops.fused_mlp(self._lobe_chain, pts, extra=hdr_shift, want_param_grad=train)
+            out = out.reshape(pts.shape[0], self.num_lgt_sgs, 6)
+            _, env_r, _ = self.integral_layer.forward_points(pts, "pe10_extra", extra=hdr_shift, train=train,
+                                                             noisy_only=True)
+            return self._decode_lobes(out), torch.abs(env_r)
         x = torch.cat([positional_encoding(points, 10), hdr_shift], -1)
         out = self.lobe_layer(x).reshape(x.shape[0], self.num_lgt_sgs, 6)
+        env_int = torch.abs(self.integral_layer(x)[1])
+        return self._decode_lobes(out), env_int
+
+    @staticmethod
+    def _decode_lobes(out):
         ang = torch.sigmoid(out[..., :2])
         theta, phi = ang[..., :1] * 2 * np.pi, ang[..., 1:2] * np.pi
         lobes = torch.cat([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], -1)
-        sgs = torch.cat([lobes, torch.sigmoid(out[..., 2:3]) * 30 + 0.1, torch.relu(out[..., 3:])], -1)
-        env_int = torch.abs(self.integral_layer(x)[1])
-        return sgs, env_int
+        return torch.cat([lobes, torch.sigmoid(out[..., 2:3]) * 30 + 0.1, torch.relu(out[..., 3:])], -1)
 
 
 class VisNetwork(nn.Module):

@@ -7,7 +7,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import OctCastParams, OctreeView, SdfParams, SgParams, check, f32, lib, ptr, sm_count, stream
+from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, check, f32, lib, ptr, sm_count,
+                   stream)
 
 TINY = 1e-6
 
@@ -535,3 +536,170 @@ def octree_cast(tree, rays_o, rays_d, max_iter=-1, o_div=1, return_stats=False):
     if return_stats:
         return out_x, out_hit.bool(), out_t, counters
     return out_x, out_hit.bool(), out_t
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused small MLP chains (material / indirect networks)
+# ----------------------------------------------------------------------------------------------------------------------
+ACT = {"none": 0, "relu": 1, "leaky": 2}
+IN_MODE = {"raw": 0, "pe10": 1, "pe10_extra": 2, "ipe10": 3}
+
+
+def _up(x, m):
+    return (x + m - 1) // m * m
+
+
+class MlpChain:
+    """A chain of nn.Linear layers (an nn.Sequential of the reference modules) evaluated by one fused kernel.
+    Packed copies (transposed for the forward, padded for the backward) are cached per parameter version."""
+
+    def __init__(self, linears, acts, in_mode):
+        self.linears, self.acts, self.in_mode = list(linears), [ACT[a] for a in acts], IN_MODE[in_mode]
+        assert len(self.linears) == len(self.acts) <= 8
+        self.cache = _PackCache()
+
+    @classmethod
+    def from_sequential(cls, seq, hidden_act, in_mode):
+        lins = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        return cls(lins, [hidden_act] * (len(lins) - 1) + ["none"], in_mode)
+
+    def params(self):
+        return [t for l in self.linears for t in (l.weight, l.bias)]
+
+    def packed(self):
+        def build():
+            out = []
+            for lin in self.linears:
+                W, b = f32(lin.weight), f32(lin.bias)
+                N, K = W.shape
+                Kp, Np = _up(K, 16), _up(N, 256)
+                Wt = pack_transpose(W, 0, K, Kp, Np)
+                Wb = _empty(_up(N, 16), _up(K, 256), like=W)
+                check(lib().robir_pack_pad(ptr(W), N, K, ptr(Wb), _up(N, 16), _up(K, 256), stream()))
+                bp = torch.zeros(Np, device=W.device)
+                bp[:N] = b
+                out.append(dict(Wt=Wt, Wb=Wb, bias=bp, K=K, N=N, Kpad=Kp, Npad=Np))
+            return out
+        return self.cache.get(self.params(), build)
+
+
+def _mlp_params(chain, packed, n, x, extra, noise, noise_scale):
+    p = MlpParams()
+    p.n, p.n_layers, p.in_mode = n, len(packed), chain.in_mode
+    p.in_dim, p.in_pad = packed[0]["K"], packed[0]["Kpad"]
+    p.x, p.extra, p.noise, p.noise_scale = ptr(x), ptr(extra), ptr(noise), float(noise_scale)
+    for l, d in enumerate(packed):
+        L = p.L[l]
+        L.Wt, L.Wb, L.bias = d["Wt"].data_ptr(), d["Wb"].data_ptr(), d["bias"].data_ptr()
+        L.K, L.N, L.Kpad, L.Npad, L.act = d["K"], d["N"], d["Kpad"], d["Npad"], chain.acts[l]
+    return p
+
+
+class _FusedMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, chain, x, extra, noise, noise_scale, want_param_grad, *params):
+        packed = chain.packed()
+        need_bwd = want_param_grad or (extra is not None and extra.requires_grad) or x.requires_grad
+        ctx.extra_shape = tuple(extra.shape) if extra is not None else None
+        x = f32(x)
+        n = x.shape[0]
+        extra = f32(extra).reshape(-1) if extra is not None else None
+        noise = f32(noise) if noise is not None else None
+        n_out = packed[-1]["N"]
+        out = _empty(n, n_out, like=x)
+        p = _mlp_params(chain, packed, n, x, extra, noise, noise_scale)
+        saves, x0 = [], None
+        if need_bwd:
+            for l, d in enumerate(packed[:-1]):
+                sv = _empty(n, d["Npad"], like=x)
+                saves.append(sv)
+                p.L[l].save = sv.data_ptr()
+            if want_param_grad:
+                x0 = _empty(n, packed[0]["Kpad"], like=x)
+                p.x0_save = x0.data_ptr()
+        p.out, p.ldo = ptr(out), n_out
+        check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
+        ctx.chain, ctx.n, ctx.want_param_grad = chain, n, want_param_grad
+        ctx.has_extra = extra is not None
+        ctx.save_for_backward(x, extra, noise, x0, *saves)
+        ctx.noise_scale = noise_scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        chain, n = ctx.chain, ctx.n
+        x, extra, noise, x0, *saves = ctx.saved_tensors
+        packed = chain.packed()
+        g_out = f32(g_out)
+        p = _mlp_params(chain, packed, n, x, extra, noise, ctx.noise_scale)
+        for l, sv in enumerate(saves):
+            p.L[l].save = sv.data_ptr()
+        Gs = []
+        if ctx.want_param_grad:
+            for l, d in enumerate(packed):
+                G = _zeros(n, d["Npad"], like=x)
+                Gs.append(G)
+                p.L[l].G = G.data_ptr()
+        g_x = _empty(n, packed[0]["Kpad"], like=x)
+        p.g_out, p.ldo, p.g_x = ptr(g_out), packed[-1]["N"], ptr(g_x)
+        check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
+        grads = []
+        if ctx.want_param_grad:
+            prev = x0
+            for l, d in enumerate(packed):
+                G = Gs[l][:, :d["N"]]
+                grads.append(G.t() @ prev[:, :d["K"]])     # plain library GEMM: dW = G^T A
+                grads.append(G.sum(0))
+                prev = saves[l] if l < len(saves) else None
+        gx = g_x[:, :packed[0]["K"]] if chain.in_mode == 0 else None
+        g_extra = g_x[:, 63].reshape(ctx.extra_shape) if ctx.has_extra else None
+        return (None, gx, g_extra, None, None, None, *grads)
+
+
+def fused_mlp(chain, x, extra=None, noise=None, noise_scale=0.02, want_param_grad=False):
+    """x: [n,K] (raw mode) or points [n,3]; extra: [n,1] appended column (pe10_extra); noise: [n,K] in embedding space."""
+    params = chain.params() if want_param_grad else []
+    return _FusedMLP.apply(chain, x, extra, noise, noise_scale, want_param_grad, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fork / join of independent sub-graphs on side streams (captured as parallel branches of the step's CUDA graph)
+# ----------------------------------------------------------------------------------------------------------------------
+_side_streams = []
+
+
+def _tensors_in(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _tensors_in(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _tensors_in(v)
+
+
+def fork_join(fns):
+    """Run the callables concurrently: fns[0] on the current stream, the others on pooled side streams that fork from
+    and join back into it.  Host-side call order (hence the order of random draws) stays sequential."""
+    main = torch.cuda.current_stream()
+    while len(_side_streams) < len(fns) - 1:
+        _side_streams.append(torch.cuda.Stream())
+    results = [None] * len(fns)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    for i, fn in enumerate(fns):              # host order = list order (keeps the random-draw order of the reference)
+        if i == 0:
+            results[0] = fn()
+            continue
+        side = _side_streams[i - 1]
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            results[i] = fn()
+    for i in range(len(fns) - 1):
+        main.wait_stream(_side_streams[i])
+    if not torch.cuda.is_current_stream_capturing():
+        for r in results[1:]:
+            for t in _tensors_in(r):
+                t.record_stream(main)
+    return results

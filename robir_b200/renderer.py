@@ -162,11 +162,16 @@ class IDRNetwork(nn.Module):
         ray_dirs = ray_dirs.reshape(-1, 3)
         m1 = mask[:, None]
         pts = torch.where(m1, points, torch.zeros_like(points))      # finite inputs for the rows that are masked out
-        sgs, integ = self.indirect_illum_network(pts, input['hdr_shift'])
+        # the indirect-illumination net, the material net and the SDF normal are independent given the hit points:
+        # three parallel branches (random draws keep the reference order: indirect, BRDF latent, normal input)
+        (sgs, integ), mat, nrm = ops.fork_join([
+            lambda: self.indirect_illum_network(pts, input['hdr_shift']),
+            lambda: self.envmap_material_network(pts, train_spec=train_spec),
+            lambda: self.get_idr_render(pts, None, normal_only=True)])
         ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
         r = pbr_get_sg_render(self, pts, -ray_dirs, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
-                              valid=mask)
+                              valid=mask, precomputed=(nrm, mat))
         one = lambda v: torch.where(m1, v, torch.ones_like(v))
         for k in ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
                   'indir_specular_rgb', 'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow',
@@ -199,17 +204,17 @@ class IDRNetwork(nn.Module):
 
 
 def pbr_get_sg_render(model, points, view_dirs, indir_lgtSGs, albedo_ratio=None, fun_spec=False, lin_diff=False,
-                      train_spec=False, indir_integral=None, valid=None, **kwargs):
+                      train_spec=False, indir_integral=None, valid=None, precomputed=None, **kwargs):
     """training/train_pbr.py:348-396 (model.no_normal / model.is_training play the runner's attributes).
     valid: optional [n] bool mask of the static-shape mode (rows that are not surface hits are carried along with a
     zero normal, which culls all of their visibility queries)."""
     view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
-    normals = model.get_idr_render(points, view_dirs, normal_only=True)
+    normals = precomputed[0] if precomputed is not None else model.get_idr_render(points, view_dirs, normal_only=True)
     normals = normals / torch.clamp(torch.norm(normals, dim=-1, keepdim=True), 1e-4)
     if valid is not None:
         normals = torch.where(valid[:, None], normals, torch.zeros_like(normals))
     ret = {'normals': normals}
-    mat = model.envmap_material_network(points, train_spec=train_spec)
+    mat = precomputed[1] if precomputed is not None else model.envmap_material_network(points, train_spec=train_spec)
     indir_integral = indir_integral * 2 * np.pi
     normal_map = mat['sg_normal_map']
     sg = sg_render.render_with_all_sg(points=points.detach(),

@@ -355,3 +355,49 @@ def test_graphed_step_runs_and_trains(synth_sd16):
         assert step.launches_per_step > 20
     finally:
         rng.set_mode("cpu")
+
+
+def test_fused_small_networks_vs_golden_and_library(golden, model16):
+    """Rows a6/a7: fused MLP kernels (csrc/mlp.cu) vs the reference goldens (forward) and vs the plain library-GEMM
+    evaluation of the same modules on the GPU (forward + all gradients)."""
+    from robir_b200 import networks, rng
+    g = golden("nets")
+    pts, hs = g["pts"].cuda(), g["hdr_shift"].cuda()
+    with rng.replay([g["noise_indir"]]):
+        sgs, env = model16.indirect_illum_network(pts, hs)
+    assert rel_err(sgs, g["indir_sgs"]) < REL and rel_err(env, g["indir_env"]) < REL
+    with rng.replay([g["noise_brdf"], g["noise_nrm"]]):
+        mat = model16.envmap_material_network(pts, train_spec=True)
+    for a, b in [("sg_roughness", "roughness"), ("sg_diffuse_albedo", "albedo"), ("sg_metallic", "metallic"),
+                 ("sg_normal_map", "normal_map"), ("random_xi_roughness", "xi_roughness"),
+                 ("random_xi_diffuse_albedo", "xi_albedo")]:
+        assert rel_err(mat[a], g[b]) < REL, a
+
+    def run(fused):
+        networks.FUSED_MLP = fused
+        model16.zero_grad()
+        h = hs.clone().requires_grad_(True)
+        model16.indirect_illum_network.train_weights = True
+        try:
+            with rng.replay([g["noise_indir"], g["noise_brdf"], g["noise_nrm"]]):
+                s, e = model16.indirect_illum_network(pts, h)
+                m = model16.envmap_material_network(pts, train_spec=True)
+            gen = torch.Generator().manual_seed(8)
+            w = [torch.randn(t.shape, generator=gen).cuda() for t in (s, e, m["sg_roughness"], m["sg_diffuse_albedo"],
+                                                                      m["random_xi_roughness"])]
+            loss = sum((t * wi).sum() for t, wi in zip((s, e, m["sg_roughness"], m["sg_diffuse_albedo"],
+                                                         m["random_xi_roughness"]), w))
+            loss.backward()
+        finally:
+            networks.FUSED_MLP = True
+            model16.indirect_illum_network.train_weights = False
+        grads = {k: p.grad.clone() for k, p in model16.named_parameters() if p.grad is not None}
+        return float(loss), h.grad.clone(), grads
+
+    l1, gh1, g1 = run(True)
+    l0, gh0, g0 = run(False)
+    assert abs(l1 - l0) < 1e-4 * max(1.0, abs(l0))
+    grad_close(gh1, gh0, 1e-4, 1e-3)
+    assert set(g1) == set(g0) and len(g0) >= 40
+    for k in g0:
+        grad_close(g1[k], g0[k], 2e-4, 2e-3)
