@@ -154,6 +154,39 @@ typedef struct {
 int robir_sg_render_fwd(const robir_sg_params* p, void* stream);
 int robir_sg_render_bwd(const robir_sg_params* p, void* stream);
 
+/* ---- a6/a7/a12/a13: fused small-MLP chains: input encoding + up to 8 Linear(+ReLU|LeakyReLU 0.2) layers in one launch.
+ * Replaces the nn.Sequential stacks of SparseAE (model/sg_envmap_material.py:40-99), IndirctIllumNetwork
+ * (model/implicit_differentiable_renderer.py:170-222), VisNetwork.forward (:225-258) and the NeuS colour network
+ * (model/neus_model.py:489-560).  in_mode: 0 raw rows [n][in_dim]; 1 PE10(x[n][3]); 2 PE10(x) ++ extra[n];
+ * 3 IPE10(x, var 1e-5) (model/neus_model.py:25-94); 4 PE10(x[:, :3]) ++ PE10(x[:, 3:]) from x[n][6].
+ * Backward: input-gradient chain; per-layer pre-activation gradients are written to L[l].G (weight gradients are
+ * G_l^T A_{l-1}, formed by the caller). */
+typedef struct {
+  const float* Wt;   /* forward  [Kpad][Npad] transposed, zero padded (robir_pack_transpose) */
+  const float* Wb;   /* backward [Npad16][Kpad256] row-major, zero padded (robir_pack_pad) */
+  const float* bias; /* [Npad] */
+  int K, N, Kpad, Npad;
+  int act;           /* 0 none, 1 ReLU, 2 LeakyReLU(0.2): applied to this layer's output */
+  float* save;       /* post-activation output [n][Npad] (forward: written when non-NULL; backward: read) */
+  float* G;          /* backward: pre-activation gradient [n][Npad] or NULL */
+} robir_mlp_layer;
+typedef struct {
+  int n, n_layers, in_mode, in_dim, in_pad;
+  const float* x;
+  const float* extra;
+  const float* noise; /* optional [n][in_dim], added as noise_scale * noise in embedding space (sg_envmap_material.py:83) */
+  float noise_scale;
+  float* x0_save;     /* embedded input [n][in_pad] or NULL */
+  robir_mlp_layer L[8];
+  float* out;         /* [n][ldo] */
+  int ldo;
+  const float* g_out; /* backward: [n][ldo] */
+  float* g_x;         /* backward: gradient w.r.t. the embedded input [n][in_pad] or NULL */
+} robir_mlp_params;
+int robir_pack_pad(const float* W, int N, int K, float* out /*[Np][Kp]*/, int Np, int Kp, void* stream);
+int robir_mlp_fwd(const robir_mlp_params* p, int sm_count, void* stream);
+int robir_mlp_bwd(const robir_mlp_params* p, int sm_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -550,3 +550,20 @@ def pbr_loss(sd, out, rgb_gt, sg_rgb_weight=1.0, kl_weight=1.0, latent_smooth_we
     white = (lgt / (lgt.norm(dim=-1, keepdim=True) + 1e-4)).var(-1).mean() * 0.01
     loss = sg_rgb_weight * rgb_loss + kl_weight * kl * 1.0 + latent_smooth_weight * smooth * 0.1 + white
     return loss, dict(rgb_loss=rgb_loss, kl=kl, smooth=smooth, white=white)
+
+
+def illum_loss(out, tr, anneal_t=0.0):
+    """IllumLoss.forward + query_indir_illum (model/loss.py:128-179, L1): -> (radiance_loss, visibility_loss)."""
+    indir_mask, pm = tr["indir_mask"], out["network_object_mask"]
+    sgs = out["indirect_sgs"][pm]
+    n, S = tr["sample_dirs"].shape[:2]
+    M = sgs.shape[1]
+    sg = sgs.unsqueeze(-3).expand(-1, S, -1, -1)
+    sdirs = tr["sample_dirs"].unsqueeze(-2).expand(-1, -1, M, -1)
+    lobes = sg[..., :3] / torch.norm(sg[..., :3], dim=-1, keepdim=True)
+    pred = (sg[..., -3:] * torch.exp(sg[..., 3:4] * (torch.sum(sdirs * lobes, dim=-1, keepdim=True) - 1.))).sum(2)
+    gt = tr["trace_radiance"][indir_mask] + anneal_t
+    rad = F.l1_loss(gt, pred[indir_mask[pm]]) + F.l1_loss(tr["gt_integral"][pm], out["indir_integral"][pm])
+    gt_vis = (~tr["gt_vis"][pm]).long().reshape(-1)
+    vis = F.cross_entropy(tr["pred_vis"][pm].reshape(-1, 2), gt_vis)
+    return rad, vis

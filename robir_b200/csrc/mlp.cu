@@ -13,7 +13,7 @@ constexpr int kMlpMaxLayers = 8;
 constexpr int kMlpR = 16;
 constexpr int kMlpKMax = 512;
 
-enum InMode { IN_RAW = 0, IN_PE10 = 1, IN_PE10_EXTRA = 2, IN_IPE10 = 3 };
+enum InMode { IN_RAW = 0, IN_PE10 = 1, IN_PE10_EXTRA = 2, IN_IPE10 = 3, IN_PE10X2 = 4 };
 
 struct MlpLayer {
   const float* Wt;    // forward: [Kpad][Npad] (transposed, zero padded, Npad % 256 == 0, Kpad % 16 == 0)
@@ -64,6 +64,22 @@ __device__ __forceinline__ void encode_row(float* Xs, int RP, int r, const MlpPa
   const int K = p.in_dim;
   if (p.in_mode == IN_RAW) {
     for (int k = 0; k < K; ++k) Xs[k * RP + r] = valid ? p.x[(size_t)row * K + k] : 0.f;
+  } else if (p.in_mode == IN_PE10X2) {
+    // VisNetwork input: [PE10(point) | PE10(direction)] from x = [n][6]  (implicit_differentiable_renderer.py:250-256)
+    for (int h = 0; h < 2; ++h) {
+      float v[3] = {0.f, 0.f, 0.f};
+      if (valid) { v[0] = p.x[6 * row + 3 * h]; v[1] = p.x[6 * row + 3 * h + 1]; v[2] = p.x[6 * row + 3 * h + 2]; }
+      const int o = 63 * h;
+      for (int i = 0; i < 3; ++i) Xs[(o + i) * RP + r] = v[i];
+      float f = 1.f;
+      for (int l = 0; l < 10; ++l) {
+        for (int i = 0; i < 3; ++i) {
+          Xs[(o + 3 + 6 * l + i) * RP + r] = valid ? sinf(v[i] * f) : 0.f;
+          Xs[(o + 6 + 6 * l + i) * RP + r] = valid ? cosf(v[i] * f) : 0.f;
+        }
+        f *= 2.f;
+      }
+    }
   } else {
     float v[3] = {0.f, 0.f, 0.f};
     if (valid) { v[0] = p.x[3 * row]; v[1] = p.x[3 * row + 1]; v[2] = p.x[3 * row + 2]; }

@@ -74,3 +74,34 @@ def pbr_step_loss(model, loss_fn, model_outputs, ground_truth, train_spec=True):
                   train_spec=train_spec, hdr_fn=model.gamma.hdr_shift.hdr2ldr)
     loss = out['loss'] + out['kl_loss'] * 1.0 + out['latent_smooth_loss'] * 0.1
     return loss + white_loss(model.envmap_material_network.lgtSGs), out
+
+
+def query_indir_illum(lgtSGs, sample_dirs):
+    """Radiance of the per-point indirect SG mixture along sample_dirs (model/loss.py:128-141).
+    lgtSGs [n,Mi,7], sample_dirs [n,S,3] -> [n,S,3]."""
+    lobes = lgtSGs[:, None, :, :3] / torch.norm(lgtSGs[:, None, :, :3], dim=-1, keepdim=True)
+    lam, mu = lgtSGs[:, None, :, 3:4], lgtSGs[:, None, :, -3:]
+    cos = torch.sum(sample_dirs[:, :, None, :] * lobes, dim=-1, keepdim=True)
+    return torch.sum(mu * torch.exp(lam * (cos - 1.)), dim=2)
+
+
+class IllumLoss(nn.Module):
+    """Vis-stage losses (model/loss.py:144-179): radiance L1 of the indirect SGs against the traced radiance plus the
+    integral term, and the visibility cross-entropy."""
+
+    def __init__(self, loss_type='L1'):
+        super().__init__()
+        self.rgb_loss = nn.L1Loss(reduction='mean') if loss_type == 'L1' else nn.MSELoss(reduction='mean')
+
+    def forward(self, model_outputs, trace_outputs, anneal_t):
+        indir_mask = trace_outputs["indir_mask"]
+        pm = model_outputs["network_object_mask"]
+        lgtSGs = model_outputs["indirect_sgs"][pm]
+        gt_radiance = trace_outputs['trace_radiance'][indir_mask] + anneal_t
+        pred_radiance = query_indir_illum(lgtSGs, trace_outputs['sample_dirs'])
+        radiance_loss = self.rgb_loss(gt_radiance, pred_radiance[indir_mask[pm]])
+        radiance_loss = radiance_loss + self.rgb_loss(trace_outputs['gt_integral'][pm],
+                                                      model_outputs['indir_integral'][pm])
+        gt_vis = (~trace_outputs['gt_vis'][pm]).long().reshape(-1)
+        pred_vis = trace_outputs['pred_vis'][pm].reshape(-1, 2)
+        return radiance_loss, nn.functional.cross_entropy(pred_vis, gt_vis)

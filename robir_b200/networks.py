@@ -120,6 +120,42 @@ class ImplicitNetworkMy(nn.Module):
         sdf, grad, _ = ops.sdf_eval(self._w, points, want_grad=True)
         return sdf, grad
 
+    # ---- NeuS-coordinate evaluation used by the secondary-ray radiance (neus_model.py:745-752, 828-884) ----------------
+    def neus_forward(self, pts_neus, dirs):
+        """NeuSModel.forward: colour(x, grad sdf(x), dirs, feat) and sdf at NeuS-coordinate points (no autograd)."""
+        sdf, grad, feat = ops.sdf_eval(self._w, pts_neus, in_scale=1.0, sdf_scale=1.0, feat_scale=1.0, want_grad=True,
+                                       want_feat=True)
+        if self.__dict__.get("_color_chain") is None:
+            net = self.neus_model.color_network
+            self.__dict__["_color_chain"] = ops.MlpChain.from_weightnorm([getattr(net, "lin%d" % l) for l in range(5)],
+                                                                          "relu", "raw")
+        x = torch.cat([pts_neus, positional_encoding(dirs, 4), grad, feat], -1)
+        return torch.sigmoid(ops.fused_mlp(self.__dict__["_color_chain"], x)), sdf[:, None]
+
+    def borrow_color(self, points, view_dirs):
+        """16-sample NeuS micro volume render around a surface point (neus_model.py:828-869)."""
+        vd = -view_dirs / torch.norm(view_dirs, dim=-1, keepdim=True)
+        n_samp = 16
+        t = torch.linspace(-0.01, 0.05, n_samp, device=points.device)[:, None]
+        p = points[:, None, :] * 2 + vd[:, None, :] * t
+        d = vd[:, None, :].expand(-1, n_samp, -1)
+        color, sdf = self.neus_forward(p.reshape(-1, 3), d.reshape(-1, 3))
+        color, sdf = color.view(-1, n_samp, 3), sdf.view(-1, n_samp, 1)
+        inv_s = torch.exp(self.neus_model.deviation_network.variance * 10.0).clip(1e-6, 1e6)
+        nxt = torch.cat([sdf[:, 1:], sdf[:, -1:]], 1)
+        prv = torch.cat([sdf[:, :-1], sdf[:, -1:]], 1)
+        prev_cdf, next_cdf = torch.sigmoid(prv * inv_s), torch.sigmoid(nxt * inv_s)
+        alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).reshape(-1, n_samp).clip(0.0, 1.0)
+        trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+        return (color * (alpha * trans)[:, :, None]).sum(1)
+
+    def batch_borrow_color(self, points, view_dirs, batch=8192):
+        if points.shape[0] == 0:
+            return torch.zeros_like(points)
+        with torch.no_grad():
+            return torch.cat([self.borrow_color(points[i:i + batch], view_dirs[i:i + batch])
+                              for i in range(0, points.shape[0], batch)], 0)
+
 
 def _mlp(dims, act):
     layers = []
@@ -310,6 +346,12 @@ class VisNetwork(nn.Module):
 
     def forward(self, points, view_dirs):
         """Plain logits [k,2] (used where the reference calls the network directly, e.g. trace_radiance :632-634)."""
+        if points.is_cuda and FUSED_MLP:
+            if self.__dict__.get("_chain") is None:
+                self.__dict__["_chain"] = ops.MlpChain.from_sequential(self.vis_layer, "relu", "pe10x2")
+            train = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            return ops.fused_mlp(self.__dict__["_chain"], torch.cat([points, view_dirs], -1).detach(),
+                                 want_param_grad=train)
         return self.vis_layer(torch.cat([positional_encoding(points, 10), positional_encoding(view_dirs, 10)], -1))
 
 

@@ -542,7 +542,7 @@ def octree_cast(tree, rays_o, rays_d, max_iter=-1, o_div=1, return_stats=False):
 # fused small MLP chains (material / indirect networks)
 # ----------------------------------------------------------------------------------------------------------------------
 ACT = {"none": 0, "relu": 1, "leaky": 2}
-IN_MODE = {"raw": 0, "pe10": 1, "pe10_extra": 2, "ipe10": 3}
+IN_MODE = {"raw": 0, "pe10": 1, "pe10_extra": 2, "ipe10": 3, "pe10x2": 4}
 
 
 def _up(x, m):
@@ -563,14 +563,30 @@ class MlpChain:
         lins = [m for m in seq if isinstance(m, torch.nn.Linear)]
         return cls(lins, [hidden_act] * (len(lins) - 1) + ["none"], in_mode)
 
+    @classmethod
+    def from_weightnorm(cls, lins, hidden_act, in_mode):
+        """Chain over weight-normed layers (weight_g / weight_v / bias, e.g. the NeuS colour network); forward only."""
+        ch = cls([], [], in_mode)
+        ch.linears, ch.acts, ch.weightnorm = list(lins), [ACT[hidden_act]] * (len(lins) - 1) + [ACT["none"]], True
+        return ch
+
+    weightnorm = False
+
     def params(self):
+        if self.weightnorm:
+            return [t for l in self.linears for t in (l.weight_v, l.weight_g, l.bias)]
         return [t for l in self.linears for t in (l.weight, l.bias)]
 
     def packed(self):
         def build():
             out = []
             for lin in self.linears:
-                W, b = f32(lin.weight), f32(lin.bias)
+                if self.weightnorm:
+                    v, g = f32(lin.weight_v), f32(lin.weight_g)
+                    W = g * v / v.norm(dim=1, keepdim=True)
+                else:
+                    W = f32(lin.weight)
+                b = f32(lin.bias)
                 N, K = W.shape
                 Kp, Np = _up(K, 16), _up(N, 256)
                 Wt = pack_transpose(W, 0, K, Kp, Np)

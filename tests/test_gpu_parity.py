@@ -401,3 +401,113 @@ def test_fused_small_networks_vs_golden_and_library(golden, model16):
     assert set(g1) == set(g0) and len(g0) >= 40
     for k in g0:
         grad_close(g1[k], g0[k], 2e-4, 2e-3)
+
+
+def _with_oracle_tree(model, prim):
+    """Give both tracers of the model the oracle's octree arrays (so that hit masks are comparable bit for bit)."""
+    from robir_b200 import ops
+    a = prim.arrays()
+    tree = ops.PackedOctree(a["root"], a["boxes"], a["non_leaf"], a["links"], a["grid"], a["sdf_val"], a["sdf_grad"],
+                            a["min_step"], "cuda")
+    model.ray_tracer.sdf_octree = tree
+    model.octree_ray_tracer.sdf_octree = tree
+    return tree
+
+
+def test_borrow_color_vs_golden(golden, model16):
+    """Row a13: batch_borrow_color = fused SDF value/normal/feature kernel + fused colour MLP + 16-sample NeuS render."""
+    g = golden("nets")
+    col = model16.implicit_network.batch_borrow_color(g["pts"].cuda(), g["vdirs"].cuda())
+    assert rel_err(col, g["borrow_color"]) < REL
+    assert model16.implicit_network.batch_borrow_color(g["pts"][:0].cuda(), g["vdirs"][:0].cuda()).shape == (0, 3)
+    logits = model16.visibility_network(g["pts"].cuda(), g["vdirs"].cuda())
+    assert rel_err(logits, g["vis_logits"]) < REL
+
+
+def test_vis_stage_vs_golden(golden, synth_sd16, model16, oracle_octrees):
+    """Row a13 / config 3: forward('Illum') + trace_radiance against the reference's golden outputs, then the Vis-stage
+    losses (model/loss.py:144-179) and their gradients w.r.t. the visibility / indirect networks against the oracle."""
+    from robir_b200 import rng
+    from robir_b200.loss import IllumLoss
+    g, sd = golden("vis_stage"), synth_sd16
+    prim, sec = oracle_octrees
+    _with_oracle_tree(model16, prim)
+    model16.zero_grad()
+    model16.indirect_illum_network.train_weights = True
+    try:
+        inp = {k: v.cuda() for k, v in synthetic.camera_inputs(g["pix"]).items()}
+        inp["hdr_shift"] = g["rnd_0"].cuda()
+        with rng.replay([g["rnd_1"], g["rnd_2"]]):
+            out = model16(inp, trainstage="Illum")
+        assert torch.equal(out["network_object_mask"].cpu(), g["mask"])
+        for k in ["indirect_sgs", "indir_integral", "normals", "points"]:
+            assert rel_err(out[k], g[k]) < REL, k
+        with rng.replay([g["rnd_3"], g["rnd_4"]]):
+            tr = model16.trace_radiance(out, nsamp=16)
+        for k in ["gt_vis", "indir_mask"]:
+            assert torch.equal(tr[k].cpu(), g["tr_" + k]), k
+        for k in ["trace_radiance", "sample_dirs", "pred_vis", "gt_integral"]:
+            assert tr[k].shape == g["tr_" + k].shape, k
+            assert rel_err(tr[k], g["tr_" + k]) < REL, (k, rel_err(tr[k], g["tr_" + k]))
+        rad_loss, vis_loss = IllumLoss()(out, tr, 0.0)
+        (rad_loss + vis_loss).backward()
+    finally:
+        model16.indirect_illum_network.train_weights = False
+    # ---- oracle: same losses by autograd over the state dict
+    sdg = {k: v.clone() for k, v in sd.items()}
+    train = [k for k in sdg if k.startswith("visibility_network.") or k.startswith("indirect_illum_network.")]
+    for k in train:
+        sdg[k].requires_grad_(True)
+    inp_o = synthetic.camera_inputs(g["pix"])
+    inp_o["hdr_shift"] = g["rnd_0"]
+    out_o = P.idr_forward(sdg, inp_o, lambda c, m, d: prim.trace(c, d),
+                          dict(indir_noise=g["rnd_1"], normal_noise=g["rnd_2"]), trainstage="Illum")
+    tr_o = P.trace_radiance(sdg, out_o, lambda c, m, d: sec.trace(c, d), g["rnd_3"], g["rnd_4"], 16)
+    rad_o, vis_o = O.illum_loss(out_o, tr_o, 0.0)
+    (rad_o + vis_o).backward()
+    assert abs(float(rad_loss) - float(rad_o)) < 1e-4 * max(1.0, abs(float(rad_o)))
+    assert abs(float(vis_loss) - float(vis_o)) < 1e-4
+    got = dict(model16.named_parameters())
+    n_checked = 0
+    for k in train:
+        if sdg[k].grad is None:
+            continue
+        assert got[k].grad is not None, k
+        grad_close(got[k].grad, sdg[k].grad, 2e-3, 2e-2)
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def test_vis_stage_full_size_properties(model16):
+    """Config-3 sized call (N=256 primary rays, nsamp=512 -> 131 072 secondary rays): shapes, masks and invariants that
+    do not need the oracle: back-facing samples carry no radiance, gt_integral is the cosine-weighted hemisphere mean,
+    rows of non-hit primary rays stay zero, replayed randoms reproduce the result bit for bit."""
+    from robir_b200 import rng
+    model16.generate()
+    N, S = 256, 512
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(5, n=N, crop=420)).items()}
+    inp["hdr_shift"] = torch.rand(N, 1, generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        with rng.record() as tape:
+            out = model16(inp, trainstage="Illum")
+            tr = model16.trace_radiance(out, nsamp=S)
+        with rng.replay(tape):
+            out2 = model16(inp, trainstage="Illum")
+            tr2 = model16.trace_radiance(out2, nsamp=S)
+    m = out["network_object_mask"]
+    n = int(m.sum())
+    assert 0 < n < N
+    assert tr["trace_radiance"].shape == (N, S, 3) and tr["sample_dirs"].shape == (n, S, 3)
+    assert tr["gt_vis"].shape == (N, S, 1) and tr["pred_vis"].shape == (N, S, 2) and tr["indir_mask"].shape == (N, S)
+    for k in tr:
+        assert torch.equal(tr[k], tr2[k]), k
+        assert torch.isfinite(tr[k].float()).all(), k
+    assert not tr["gt_vis"][~m].any() and (tr["trace_radiance"][~m] == 0).all() and (tr["pred_vis"][~m] == 0).all()
+    nrm = out["normals"][m]
+    nrm = nrm / nrm.norm(dim=-1, keepdim=True).clamp_min(1e-4)
+    cosv = (nrm[:, None, :] * tr["sample_dirs"]).sum(-1)
+    assert (tr["trace_radiance"][m][cosv < 0] == 0).all()
+    assert not tr["indir_mask"][m][cosv < 0].any()
+    want = (tr["trace_radiance"][m] * torch.relu(cosv)[..., None]).sum(1) / (cosv >= 0).sum(-1, keepdim=True).clamp_min(1e-4)
+    assert rel_err(tr["gt_integral"][m], want) < 1e-5
+    assert (tr["sample_dirs"].norm(dim=-1) - 1).abs().max() < 1e-5

@@ -93,3 +93,49 @@ def test_sphere_tracer_matches_reference():
                                        training=training, uniform_steps=uni)
         assert torch.equal(m, m2)
         assert (p - p2).abs().max().item() < 2e-5 and (d - d2).abs().max().item() < 2e-5
+
+
+def test_vis_stage_losses_match_reference(ref_model):
+    """forward('Illum') + trace_radiance + IllumLoss (model/loss.py:144-179) of the reference vs the oracle, incl. the
+    gradients that the Vis stage steps (visibility_network.*, indirect_illum_network.*)."""
+    import copy
+    model, _ = ref_model
+    sdf = lambda x: model.implicit_network(x)[:, 0]
+    if model.octree_ray_tracer.sdf_octree is None:
+        model.octree_ray_tracer.generate(sdf, None)
+    from model.loss import IllumLoss
+    N, S = 40, 12
+    inp = synthetic.camera_inputs(synthetic.training_pixels(8, n=N, crop=300))
+    torch.manual_seed(77)
+    with ref_shim.ReplayRandom() as rec:
+        i2 = dict(inp)
+        i2["hdr_shift"] = torch.rand(N, 1)
+        out_ref = model(i2, trainstage="Illum")
+        tr_ref = model.trace_radiance(out_ref, nsamp=S)
+    rad_ref, vis_ref = IllumLoss()(out_ref, tr_ref, 0.0)
+    model.zero_grad()
+    (rad_ref + vis_ref).backward()
+    gref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    rnd = [t for _, t in rec.tape]
+
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    train = [k for k in sd if k.startswith("visibility_network.") or k.startswith("indirect_illum_network.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    prim = T.OctreeOracle(lambda x: O.implicit_forward(sd, x)[:, 0], lambda x: O.implicit_gradient(sd, x)[:, 0, :])
+    sec = copy.copy(prim)
+    sec.max_iter = 32
+    i3 = dict(inp)
+    i3["hdr_shift"] = rnd[0]
+    out = P.idr_forward(sd, i3, lambda c, m, d: prim.trace(c, d), dict(indir_noise=rnd[1], normal_noise=rnd[2]),
+                        trainstage="Illum")
+    tr = P.trace_radiance(sd, out, lambda c, m, d: sec.trace(c, d), rnd[3], rnd[4], S)
+    rad, vis = O.illum_loss(out, tr, 0.0)
+    assert abs(rad.item() - rad_ref.item()) < 1e-5 and abs(vis.item() - vis_ref.item()) < 1e-5
+    (rad + vis).backward()
+    checked = 0
+    for k in train:
+        if k in gref:
+            assert (gref[k] - sd[k].grad).abs().max().item() < 1e-5 * max(1.0, gref[k].abs().max().item()), k
+            checked += 1
+    assert checked >= 20
