@@ -81,6 +81,41 @@ typedef struct {
 int robir_octree_counters_len(void);
 int robir_octree_cast(const robir_octree_cast_params* p, int sm_count, void* stream);
 
+/* ---- a3: IDR sphere tracer: RayTracing.forward / sphere_tracing / ray_sampler / secant / minimal_sdf_points
+ * (model/ray_tracing.py:26-326) with rend_util.get_sphere_intersection (utils/rend_util.py:141-163).  The SDF network
+ * is evaluated inline by persistent march kernels; no host synchronisation.  f(p) = net(in_scale p)[0] * out_scale. */
+typedef struct {
+  const float* Wt[8];   /* folded weight-norm layers 0..7, packed [Kpad][256] (robir_pack_wn_transpose) */
+  const float* bias[8];
+  const float* w8_sdf;  /* [256] folded row 0 of layer 8 (robir_pack_wn_row) */
+  const float* b8;
+} robir_sdf_net;
+typedef struct {
+  robir_sdf_net net;
+  int N, o_div;                      /* rays; rays per origin (cam_loc is [N / o_div][3]) */
+  const float* cam_loc;
+  const float* ray_dirs;             /* [N][3] */
+  const unsigned char* object_mask;  /* [N] or NULL (all true) */
+  float in_scale, out_scale;
+  float radius, sdf_threshold, line_search_step;
+  int line_step_iters, sphere_tracing_iters, n_steps, n_secant_steps, training;
+  const float* uniform_steps;        /* [n_steps]: the uniform_(0,1) draw of minimal_sdf_points (:305), training only */
+  float* points;                     /* out [N][3] */
+  unsigned char* net_mask;           /* out [N] */
+  float* dists;                      /* out [N] */
+  /* caller-owned workspace */
+  float *acc_s, *acc_e, *min_dis, *max_dis; /* [N] each */
+  unsigned char* flags;              /* [N] */
+  int *samp_list, *sec_list;         /* [N] each */
+  float* sec_state;                  /* [N][4] */
+  int* min_list;                     /* [N] */
+  float* vals;                       /* [N * n_steps] */
+  int* counters;                     /* [8] zero-initialised; on return: sampler rays, secant rays, min-sdf rays,
+                                        loop flag, executed SDF queries */
+} robir_sphere_trace_params;
+int robir_sphere_trace(const robir_sphere_trace_params* p, int sm_count, void* stream);
+int robir_sphere_trace_launches(int training);
+
 /* ---- a10/a11: visibility sample directions (model/sg_render.py:123-146 and :204-240) ------------------------------ */
 int robir_sample_dirs_fwd(int K, int S, const float* axis_f, const float* axis_w, const float* sharp,
                           const float* lam_w, const float* sg_range /*[1]*/, const float* u_theta /*[K][S]*/,

@@ -33,6 +33,19 @@ class SdfParams(Structure):
                 ("b8", c_void_p), ("Wt8_feat", c_void_p), ("sdf", c_void_p), ("grad", c_void_p), ("feat", c_void_p)]
 
 
+class SdfNet(Structure):
+    _fields_ = [("Wt", c_void_p * 8), ("bias", c_void_p * 8), ("w8_sdf", c_void_p), ("b8", c_void_p)]
+
+
+class SphereTraceParams(Structure):
+    _fields_ = [("net", SdfNet), ("N", c_int), ("o_div", c_int), ("cam_loc", c_void_p), ("ray_dirs", c_void_p),
+                ("object_mask", c_void_p), ("in_scale", c_float), ("out_scale", c_float), ("radius", c_float),
+                ("sdf_threshold", c_float), ("line_search_step", c_float), ("line_step_iters", c_int),
+                ("sphere_tracing_iters", c_int), ("n_steps", c_int), ("n_secant_steps", c_int), ("training", c_int)] + [
+        (k, c_void_p) for k in ("uniform_steps", "points", "net_mask", "dists", "acc_s", "acc_e", "min_dis", "max_dis",
+                                "flags", "samp_list", "sec_list", "sec_state", "min_list", "vals", "counters")]
+
+
 class MlpLayer(Structure):
     _fields_ = [("Wt", c_void_p), ("Wb", c_void_p), ("bias", c_void_p), ("K", c_int), ("N", c_int), ("Kpad", c_int),
                 ("Npad", c_int), ("act", c_int), ("save", c_void_p), ("G", c_void_p)]
@@ -90,6 +103,8 @@ _SIGNATURES = {
     "robir_camera_rays": [_I, _P, _P, _P, _P, _P],
     "robir_octree_cast": [POINTER(OctCastParams), _I, _P],
     "robir_octree_counters_len": [],
+    "robir_sphere_trace": [POINTER(SphereTraceParams), _I, _P],
+    "robir_sphere_trace_launches": [_I],
     "robir_device_info": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     "robir_abi_version": [],
 }
@@ -97,7 +112,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ["robir_last_error"])
 
 
 # kernels launched per C call (for bench.py's gpu_launches claim); everything not listed launches exactly one
-_KERNELS_PER_CALL = {"robir_diffuse_rows": 3, "robir_octree_counters_len": 0, "robir_device_info": 0,
+_KERNELS_PER_CALL = {"robir_diffuse_rows": 3, "robir_sphere_trace": 7, "robir_sphere_trace_launches": 0, "robir_octree_counters_len": 0, "robir_device_info": 0,
                      "robir_tc_image_bytes": 0,
                      "robir_abi_version": 0, "robir_last_error": 0}
 launch_count = 0

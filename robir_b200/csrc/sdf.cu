@@ -4,7 +4,7 @@
 // The gradient is propagated in forward mode (three tangent rows ride along each value row through the same tile
 // GEMMs), so nothing is stored and no second pass is needed; the reference's autograd double-backward graph is not
 // reproduced (it is never consumed: SURVEY.md section 7, hard part 6).
-#include "mlp_engine.cuh"
+#include "sdf_tile.cuh"
 
 namespace robir {
 
@@ -51,36 +51,6 @@ struct SdfParams {
   float* grad;          // [n][3] or null
   float* feat;          // [n][256] or null
 };
-
-// write PE10 (value row) and its three directional derivatives (tangent rows) into tile rows [k0, k0+63)
-template <bool JET>
-__device__ __forceinline__ void sdf_pe_rows(float* Xs, int RP, int k0, int pt_local, const float* x, bool valid,
-                                            float scale) {
-  const int rbase = JET ? pt_local * 4 : pt_local;
-  for (int i = 0; i < 3; ++i) {
-    Xs[(k0 + i) * RP + rbase] = valid ? x[i] * scale : 0.f;
-    if (JET)
-      for (int j = 0; j < 3; ++j) Xs[(k0 + i) * RP + rbase + 1 + j] = (valid && i == j) ? scale : 0.f;
-  }
-  float f = 1.f;
-  for (int l = 0; l < 10; ++l) {
-    for (int i = 0; i < 3; ++i) {
-      float sn = 0.f, cs = 0.f;
-      if (valid) {
-        sn = sinf(x[i] * f);
-        cs = cosf(x[i] * f);
-      }
-      Xs[(k0 + 3 + 6 * l + i) * RP + rbase] = sn * scale;
-      Xs[(k0 + 6 + 6 * l + i) * RP + rbase] = cs * scale;
-      if (JET)
-        for (int j = 0; j < 3; ++j) {
-          Xs[(k0 + 3 + 6 * l + i) * RP + rbase + 1 + j] = (i == j) ? f * cs * scale : 0.f;
-          Xs[(k0 + 6 + 6 * l + i) * RP + rbase + 1 + j] = (i == j) ? -f * sn * scale : 0.f;
-        }
-    }
-    f *= 2.f;
-  }
-}
 
 template <bool JET>
 __global__ void __launch_bounds__(256, 2) sdf_eval_kernel(SdfParams p) {

@@ -2,7 +2,8 @@
 without editing reference files.  Seams used:
 
   1. ``model.ray_tracer`` / ``model.octree_ray_tracer``  -> robir_b200.tracing.OctreeTracing (same call signature,
-     ``generate(sdf_fn, tex_sampler)`` discovered via hasattr by the runners, training/train_pbr.py:403-407);
+     ``generate(sdf_fn, tex_sampler)`` discovered via hasattr by the runners, training/train_pbr.py:403-407), or
+     robir_b200.sphere_tracing.RayTracing when the model was built with use_octree=False;
   2. ``model.implicit_network.forward / gradient``       -> fused CUDA value / normal kernel reading the module's own
      weight_g / weight_v / bias parameters (state_dict untouched);
   3. ``model.sg_render.render_with_all_sg`` (imported inside the runners' get_sg_render at call time,
@@ -36,14 +37,21 @@ def _patch(mod, name, new):
 def install(model, patch_modules=True):
     if not hasattr(model, "visibility_network") or not hasattr(model, "implicit_network"):
         raise RobirError("install() expects a reference IDRNetwork")
-    rt_kwargs = {}
+    net = model.implicit_network
     for name in ("ray_tracer", "octree_ray_tracer"):
         old = getattr(model, name, None)
-        if old is None or not hasattr(old, "max_iter"):
-            continue                      # use_octree=False keeps the reference RayTracing (sphere tracer row a3)
-        new = tracing.OctreeTracing(max_iter=old.max_iter)
+        if old is None:
+            continue
+        if hasattr(old, "max_iter"):
+            new = tracing.OctreeTracing(max_iter=old.max_iter)
+        else:                             # use_octree=False: the IDR sphere tracer (model/ray_tracing.py, row a3)
+            from .sphere_tracing import RayTracing
+            new = RayTracing(object_bounding_sphere=old.object_bounding_sphere, sdf_threshold=old.sdf_threshold,
+                             line_search_step=old.line_search_step, line_step_iters=old.line_step_iters,
+                             sphere_tracing_iters=old.sphere_tracing_iters, n_steps=old.n_steps,
+                             n_rootfind_steps=old.n_secant_steps).bind(net)
+            new.train(old.training)
         setattr(model, name, new)
-    net = model.implicit_network
     sdfw = ops.SdfWeights(net.neus_model.sdf_network)
 
     def forward(self, points, compute_grad=False):

@@ -7,8 +7,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, check, f32, lib, ptr, sm_count,
-                   stream)
+from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, SphereTraceParams, check, f32, lib, ptr,
+                   sm_count, stream)
 
 TINY = 1e-6
 
@@ -536,6 +536,55 @@ def octree_cast(tree, rays_o, rays_d, max_iter=-1, o_div=1, return_stats=False):
     if return_stats:
         return out_x, out_hit.bool(), out_t, counters
     return out_x, out_hit.bool(), out_t
+
+
+def sphere_trace(weights, cam_loc, ray_dirs, object_mask, radius=1.0, sdf_threshold=5.0e-5, line_search_step=0.5,
+                 line_step_iters=1, sphere_tracing_iters=10, n_steps=100, n_secant_steps=8, training=False,
+                 uniform_steps=None, in_scale=2.0, out_scale=0.5, return_stats=False):
+    """RayTracing.forward (model/ray_tracing.py:26-100).  cam_loc [B,3], ray_dirs [B,N,3], object_mask [B*N] bool|None
+    -> points [B*N,3], network_object_mask [B*N] bool, dists [B*N]  (+ int32 counters [8] with return_stats)."""
+    W = weights.get()
+    B, Np, _ = ray_dirs.shape
+    cam_loc, dirs = f32(cam_loc).reshape(B, 3), f32(ray_dirs).reshape(-1, 3)
+    K = B * Np
+    dev = dirs
+    points, dists = _empty(K, 3, like=dev), _empty(K, like=dev)
+    mask = _empty(K, dtype=torch.uint8, like=dev)
+    counters = _zeros(8, dtype=torch.int32, like=dev)
+    if K == 0:
+        return (points, mask.bool(), dists, counters) if return_stats else (points, mask.bool(), dists)
+    om = object_mask.reshape(-1).to(torch.uint8).contiguous() if object_mask is not None else None
+    fws = _empty(8, K, like=dev)                         # acc_s, acc_e, min_dis, max_dis, sec_state[K][4]
+    iws = _empty(3, K, dtype=torch.int32, like=dev)      # samp_list, sec_list, min_list
+    flags = _empty(K, dtype=torch.uint8, like=dev)
+    vals = _empty(K * n_steps, like=dev)
+    p = SphereTraceParams()
+    for l in range(8):
+        p.net.Wt[l] = W["Wt%d" % l].data_ptr()
+        p.net.bias[l] = W["b%d" % l].data_ptr()
+    p.net.w8_sdf, p.net.b8 = ptr(W["w8_sdf"]), ptr(W["b8"])
+    p.N, p.o_div, p.cam_loc, p.ray_dirs, p.object_mask = K, Np, ptr(cam_loc), ptr(dirs), ptr(om)
+    p.in_scale, p.out_scale, p.radius, p.sdf_threshold = in_scale, out_scale, radius, sdf_threshold
+    p.line_search_step, p.line_step_iters, p.sphere_tracing_iters = line_search_step, line_step_iters, sphere_tracing_iters
+    p.n_steps, p.n_secant_steps, p.training = n_steps, n_secant_steps, int(bool(training))
+    if training:
+        if uniform_steps is None or uniform_steps.numel() != n_steps:
+            raise _lib.RobirError("sphere_trace(training=True) needs uniform_steps[n_steps]")
+        uniform_steps = f32(uniform_steps).to(dev.device)
+        p.uniform_steps = ptr(uniform_steps)
+    p.points, p.net_mask, p.dists = ptr(points), ptr(mask), ptr(dists)
+    p.acc_s, p.acc_e, p.min_dis, p.max_dis = (c_ptr(fws, i * K * 4) for i in range(4))
+    p.sec_state = c_ptr(fws, 4 * K * 4)
+    p.samp_list, p.sec_list, p.min_list = (c_ptr(iws, i * K * 4) for i in range(3))
+    p.flags, p.vals, p.counters = ptr(flags), ptr(vals), ptr(counters)
+    check(lib().robir_sphere_trace(ctypes.byref(p), sm_count(), stream()))
+    if return_stats:
+        return points, mask.bool(), dists, counters
+    return points, mask.bool(), dists
+
+
+def c_ptr(t, byte_offset):
+    return ctypes.c_void_p(t.data_ptr() + byte_offset)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -60,10 +60,11 @@ class IDRNetwork(nn.Module):
     def generate(self):
         """What every runner does before its loop (train_pbr.py:403-407)."""
         sdf_fn = lambda x: self.implicit_network(x)[:, 0]
-        self.ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
         if isinstance(self.ray_tracer, tracing.OctreeTracing):
+            self.ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
             self.octree_ray_tracer.sdf_octree = self.ray_tracer.sdf_octree   # same tree, different max_iter
-        else:
+        else:   # use_octree=False: the IDR sphere tracer has nothing to build (no generate(), like the reference's)
+            self.ray_tracer.bind(self.implicit_network)
             self.octree_ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
 
     def _trace(self, tracer, cam_loc, object_mask, ray_dirs):

@@ -64,3 +64,8 @@ def rand(shape, device):
 
 def randn(shape, device):
     return _draw(torch.randn, shape, device)
+
+
+def uniform(shape, device):
+    """torch.empty(shape).uniform_(0, 1) of the reference (model/ray_tracing.py:305): same generator stream as rand."""
+    return _draw(lambda s, **kw: torch.empty(s, **kw).uniform_(0.0, 1.0), shape, device)

@@ -511,3 +511,99 @@ def test_vis_stage_full_size_properties(model16):
     want = (tr["trace_radiance"][m] * torch.relu(cosv)[..., None]).sum(1) / (cosv >= 0).sum(-1, keepdim=True).clamp_min(1e-4)
     assert rel_err(tr["gt_integral"][m], want) < 1e-5
     assert (tr["sample_dirs"].norm(dim=-1) - 1).abs().max() < 1e-5
+
+
+def _trace_agreement(got, ref, tol=2e-4, frac=0.98):
+    """Sphere-tracer outputs vs the oracle: the march makes threshold decisions on fp32 SDF values (5e-5 convergence
+    test, sign of samples), so a handful of borderline rays may take another branch on the GPU; the rest must agree to
+    fp32 accuracy.  -> fraction of rays with identical mask and |dt|, |dp| < tol."""
+    (p, m, t), (p2, m2, t2) = got, ref
+    p, m, t = p.cpu(), m.cpu(), t.cpu()
+    same = (m == m2) & ((t - t2).abs() < tol) & ((p - p2).abs().max(-1)[0] < tol)
+    agree = same.float().mean().item()
+    assert agree >= frac, "sphere tracer agrees with the oracle on %.1f %% of the rays only" % (100 * agree)
+    return agree
+
+
+def test_sphere_tracer_vs_golden(golden, synth_sd16, model16):
+    """Row a3: persistent march kernels (csrc/sphere_trace.cu) vs the reference's RayTracing outputs (eval and training
+    mode, n_steps = 32, hotdog.conf tracer settings)."""
+    from robir_b200 import ops, rng
+    from robir_b200.sphere_tracing import RayTracing
+    g = golden("raytracing")
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(g["pix"]).items()}
+    rd, cl = ops.camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
+    tracer = RayTracing(line_step_iters=3, n_steps=32, n_rootfind_steps=32).bind(model16.implicit_network).cuda()
+    om = g["object_mask"].cuda()
+    for tag, training in (("eval", False), ("train", True)):
+        tracer.train(training)
+        with rng.replay([g["uniform"]] if training else []):
+            got = tracer(sdf=model16.implicit_network.sdf, cam_loc=cl, object_mask=om, ray_directions=rd)
+        assert got[0].shape == (256, 3) and got[1].dtype == torch.bool and got[2].shape == (256,)
+        _trace_agreement(got, (g[tag + "_points"], g[tag + "_mask"], g[tag + "_t"]))
+        assert int(tracer.last_counters[4]) > 256      # SDF queries executed inline
+    # ragged / empty batches
+    for k in (0, 1, 17):
+        p, m, t = tracer(sdf=model16.implicit_network.sdf, cam_loc=cl, object_mask=om[:k], ray_directions=rd[:, :k])
+        assert p.shape == (k, 3) and m.shape == (k,) and t.shape == (k,)
+
+
+def test_sphere_tracer_vs_oracle_perturbed_and_sampler(synth_sd16):
+    """Row a3 on a perturbed (non-spherical) SDF, 1024 rays, n_steps = 128 (BASELINE config 2), with a tight
+    sphere-tracing budget so that the sampler + secant phases carry most rays; per-origin batches (o_div = 1)."""
+    import robir_b200
+    from robir_b200 import ops
+    from robir_b200.sphere_tracing import RayTracing
+    sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=16, perturb=0.05)
+    model = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=16)))
+    model.load_state_dict(sd, strict=True)
+    model.cuda()
+    sdf_o = lambda x: O.implicit_forward(sd, x)[:, 0]
+    inp = synthetic.camera_inputs(synthetic.training_pixels(4, n=1024, crop=460))
+    rd_o, cl_o = O.camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
+    om = torch.rand(1024, generator=torch.Generator().manual_seed(2)) > 0.2
+    uni = torch.rand(128, generator=torch.Generator().manual_seed(3))
+    for iters, training in ((10, False), (2, False), (2, True)):
+        with torch.no_grad():
+            ref = T.ray_tracing(sdf_o, cl_o, om, rd_o, line_step_iters=3, sphere_tracing_iters=iters, n_steps=128,
+                                n_secant_steps=32, training=training, uniform_steps=uni)
+        got = ops.sphere_trace(model.implicit_network._w, cl_o.cuda(), rd_o.cuda(), om.cuda(), line_step_iters=3,
+                               sphere_tracing_iters=iters, n_steps=128, n_secant_steps=32, training=training,
+                               uniform_steps=uni.cuda(), return_stats=True)
+        _trace_agreement(got[:3], ref, frac=0.97)
+        cnt = got[3].cpu()
+        if iters == 2:
+            assert int(cnt[0]) > 100 and int(cnt[1]) > 50     # sampler and secant rays
+    # secondary-ray style call: one origin per ray
+    o = torch.nn.functional.normalize(torch.randn(300, 3, generator=torch.Generator().manual_seed(5)), dim=-1) * 0.9
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(300, 3, generator=torch.Generator().manual_seed(6)), dim=-1)
+    with torch.no_grad():
+        ref = T.ray_tracing(sdf_o, o, torch.ones(300, dtype=torch.bool), d[:, None, :], line_step_iters=3, n_steps=64,
+                            n_secant_steps=8)
+    got = ops.sphere_trace(model.implicit_network._w, o.cuda(), d[:, None, :].cuda(), None, line_step_iters=3,
+                           n_steps=64, n_secant_steps=8)
+    _trace_agreement(got, ref, frac=0.97)
+
+
+def test_idr_network_with_sphere_tracer(synth_sd16):
+    """use_octree=False model: forward('Material') runs on the sphere tracer and agrees with the octree model on the
+    rays both tracers hit (two different surface finders on the same SDF: points agree to ~1e-3)."""
+    import robir_b200
+    from robir_b200 import rng
+    conf = dict(envmap_material_network=dict(num_lgt_sgs=16), use_octree=False,
+                ray_tracer=dict(line_step_iters=3, n_steps=128, n_rootfind_steps=32))
+    model = robir_b200.IDRNetwork(conf)
+    model.load_state_dict(synth_sd16, strict=True)
+    model.cuda().eval()
+    model.generate()
+    N = 256
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(7, n=N, crop=420)).items()}
+    inp["hdr_shift"] = torch.full((N, 1), 0.5).cuda()
+    with torch.no_grad():
+        out = model(inp, trainstage="Material", train_spec=True)
+    m = out["network_object_mask"]
+    assert 0 < int(m.sum()) < N
+    sdf = model.implicit_network.sdf(out["points"][m])
+    assert sdf.abs().max() < 1e-3                       # hit points lie on the zero level set
+    for k in ("sg_rgb", "indir_rgb", "normals"):
+        assert torch.isfinite(out[k]).all() and (out[k][~m] == 1).all(), k
