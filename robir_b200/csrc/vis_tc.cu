@@ -67,7 +67,8 @@ struct TcParams {
   const float* wd;         // [256]
   const float* bd;         // [1]
   float* vis;              // [rows]
-  uint32_t* mask;          // [rows][4][8]  word w of layer l: bit i = (h_{l+1}[32 w + i] > 0)
+  uint32_t* mask;          // [tiles][4 layers][8 words][128 rows] (a warp stores one 128-byte line); bit i of word
+                           // w of layer l, bit (31 - i) = (pre-activation of h_{l+1}[32 w + i] is not negative)
   // backward
   const float* g_vis; const float* dirs; float* g_dirs;
   // self-test: plain GEMM D = A . W^T through the same machinery
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   __shared__ uint64_t full_bar[kTcStages], empty_bar[kTcStages], a_ready[2], d_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_a[128], s_b[128];
-  __shared__ float s_bias[3 * 256], s_wd[256];
+  __shared__ __align__(16) float s_bias[3 * 256];
+  __shared__ __align__(16) float s_wd[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kLayers = (MODE == 0) ? 3 : (MODE == 1 ? 4 : 1);
@@ -103,41 +105,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
 
   if (warp == 0) {
     // ===================================== weight producer =====================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int layer = 0; layer < kLayers; ++layer) {
-          const int halves = (MODE == 1 && layer == 3) ? 1 : 2;
-          for (int nh = 0; nh < halves; ++nh)
-            for (int kb = 0; kb < 4; ++kb, ++it) {
-              const int st = it % kTcStages;
-              mbar_wait(&empty_bar[st], ((it / kTcStages) & 1) ^ 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int layer = 0; layer < kLayers; ++layer) {
+        const int halves = (MODE == 1 && layer == 3) ? 1 : 2;
+        for (int nh = 0; nh < halves; ++nh)
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            const int st = it % kTcStages;
+            mbar_wait(&empty_bar[st], ((it / kTcStages) & 1) ^ 1);
+            if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_bar[st], kTcStageBytes);
               bulk_g2s(ring + (size_t)st * kTcStageBytes, p.img + (size_t)((layer * 2 + nh) * 4 + kb) * kTcStageBytes,
                        kTcStageBytes, &full_bar[st]);
             }
-        }
+            __syncwarp();
+          }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      uint32_t it = 0, a_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int layer = 0; layer < kLayers; ++layer, ++a_phase) {
-          const uint32_t a_half = tmem_base + ((layer & 1) ? 256u : 0u);
-          const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
-          const bool last64 = (MODE == 1 && layer == 3);
-          const int halves = last64 ? 1 : 2;
-          for (int nh = 0; nh < halves; ++nh) {
-            for (int kb = 0; kb < 4; ++kb, ++it) {
-              if (nh == 0 && (kb == 0 || kb == 2)) {       // A K-half becomes available (epilogue of previous layer)
-                mbar_wait(&a_ready[kb >> 1], a_phase & 1);
-                tc_fence_after();
-              }
-              const int st = it % kTcStages;
-              mbar_wait(&full_bar[st], (it / kTcStages) & 1);
-              tc_fence_after();
+    // The whole warp runs the loop converged and one elected lane issues (elect.sync): tcgen05.mma / commit are
+    // warp-uniform instructions, and inside a divergent `if (lane == 0)` ptxas wraps every one of them in an
+    // ELECT / BRA.U.ANY retry loop (~75 issue cycles per MMA).
+    uint32_t it = 0, a_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int layer = 0; layer < kLayers; ++layer, ++a_phase) {
+        const uint32_t a_half = tmem_base + ((layer & 1) ? 256u : 0u);
+        const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
+        const bool last64 = (MODE == 1 && layer == 3);
+        const int halves = last64 ? 1 : 2;
+        for (int nh = 0; nh < halves; ++nh) {
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            if (nh == 0 && (kb == 0 || kb == 2)) mbar_wait(&a_ready[kb >> 1], a_phase & 1);   // A K-half available
+            const int st = it % kTcStages;
+            mbar_wait(&full_bar[st], (it / kTcStages) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
               const uint8_t* sb = ring + (size_t)st * kTcStageBytes;
               const uint64_t b_hi = smem_desc_sw128(sb), b_lo = smem_desc_sw128(sb + 16384);
               const uint32_t d_addr = d_half + 128u * nh;
@@ -146,83 +149,131 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
               for (int j = 0; j < 4; ++j) {
                 const int s = kb * 4 + j;                   // k16 step 0..15
                 const uint32_t a_hi = a_half + 32u * (s >> 1) + 8u * (s & 1), a_lo = a_hi + 16u;
-                const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-                umma_ts(d_addr, a_hi, b_hi + 2u * j, idesc, first);
-                umma_ts(d_addr, a_lo, b_hi + 2u * j, idesc, 1u);
-                umma_ts(d_addr, a_hi, b_lo + 2u * j, idesc, 1u);
+                if (kb == 0 && j == 0) umma_ts<0>(d_addr, a_hi, b_hi + 2u * j, idesc);
+                else umma_ts<1>(d_addr, a_hi, b_hi + 2u * j, idesc);
+                umma_ts<1>(d_addr, a_lo, b_hi + 2u * j, idesc);
+                umma_ts<1>(d_addr, a_hi, b_lo + 2u * j, idesc);
               }
               umma_commit(&empty_bar[st]);
               if (kb == 3) umma_commit(&d_full[nh]);
             }
+            __syncwarp();
           }
         }
       }
     }
   } else {
     // ===================================== epilogue warps =====================================
+    // Everything this role reads from global memory is requested one step before it is needed (next tile's row
+    // indices and first two gather chunks during the last layer, gather chunk c + 2 while chunk c converts, the
+    // backward's mask words one layer ahead): a single warp per scheduler cannot hide an L2 round trip otherwise.
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t d_phase[2] = {0, 0};
+    // backward: the 8 ReLU-mask words the next consumer (stage 0 / layer epilogue) needs
+    uint32_t mw[8];
+    auto load_mask = [&](int t, int slot) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) mw[w] = __ldg(p.mask + ((size_t)t * 32 + slot * 8 + w) * 128 + row);
+    };
+    auto pick_mask = [&](int w) {      // register file has no dynamic indexing: 8 selects
+      uint32_t v = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v = (i == w) ? mw[i] : v;
+      return v;
+    };
+    // per-tile inputs of this row
+    int a_idx = 0, b_idx = -1;
+    float g0 = 0.f;
+    auto load_row = [&](int t, int& a, int& b, float& g) {
+      a = p.rowA ? p.rowA[t * 128 + row] : 0;
+      b = p.rowB[t * 128 + row];
+      g = 0.f;
+      if (MODE == 1 && b >= 0) {
+        const float v = p.vis[t * 128 + row];
+        g = p.g_vis[t * 128 + row] * v * (1.f - v);
+      }
+    };
+    // forward: gather pipeline of layer-0 pre-activation chunks (32 features of tabA[a] and tabB[b] each)
+    float4 ga[2][8], gb[2][8];
+    auto gather = [&](int c, int slot, int a, int b) {
+      const float4* pa = reinterpret_cast<const float4*>(p.tabA + (size_t)a * 256 + 32 * c);
+      const float4* pb = reinterpret_cast<const float4*>(p.tabB + (size_t)(b >= 0 ? b : 0) * 256 + 32 * c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ga[slot][i] = __ldg(pa + i); gb[slot][i] = __ldg(pb + i); }
+    };
+    if (MODE <= 1 && blockIdx.x < ntiles) {
+      load_row(blockIdx.x, a_idx, b_idx, g0);
+      if (MODE == 1) load_mask(blockIdx.x, 3);
+      if (MODE == 0) { gather(0, 0, a_idx, b_idx); gather(1, 1, a_idx, b_idx); }
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int q0 = tile * 128;
-      int a_idx = 0, b_idx = -1;
-      if (MODE <= 1) { a_idx = p.rowA ? p.rowA[q0 + row] : 0; b_idx = p.rowB[q0 + row]; }
+      const bool valid = b_idx >= 0;
+      const bool has_next = tile + (int)gridDim.x < ntiles;
+      uint32_t* mtile = p.mask ? p.mask + (size_t)tile * (32 * 128) + row : nullptr;
       // ---------------- stage 0: first A operand into TMEM half X (columns 0..255)
-      {
-        float g0 = 0.f;
-        if (MODE == 1 && b_idx >= 0) {
-          const float v = p.vis[q0 + row];
-          g0 = p.g_vis[q0 + row] * v * (1.f - v);
-        }
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float x[32];
-          uint32_t mword = 0;
-          if (MODE == 0) {
-            if (b_idx >= 0) {
-              const float4* pa = reinterpret_cast<const float4*>(p.tabA + (size_t)a_idx * 256 + 32 * c);
-              const float4* pb = reinterpret_cast<const float4*>(p.tabB + (size_t)b_idx * 256 + 32 * c);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 va = __ldg(pa + i), vb = __ldg(pb + i);
-                x[4 * i] = va.x + vb.x; x[4 * i + 1] = va.y + vb.y; x[4 * i + 2] = va.z + vb.z; x[4 * i + 3] = va.w + vb.w;
-              }
-            } else {
+      for (int c = 0; c < 8; ++c) {
+        float x[32];
+        if (MODE == 0) {
+          uint32_t m = 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mword |= (x[i] > 0.f ? 1u : 0u) << i;
-              x[i] = fmaxf(x[i], 0.f);
-            }
-            if (p.mask && b_idx >= 0) p.mask[((size_t)(q0 + row) * 4 + 0) * 8 + c] = mword;
-          } else if (MODE == 1) {
-            mword = b_idx >= 0 ? __ldg(p.mask + ((size_t)(q0 + row) * 4 + 3) * 8 + c) : 0u;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = ((mword >> i) & 1u) ? g0 * s_wd[32 * c + i] : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = p.test_A[(size_t)row * 256 + 32 * c + i];
+          for (int i = 0; i < 8; ++i) {
+            const float4 va = ga[c & 1][i], vb = gb[c & 1][i];
+            const float v0 = va.x + vb.x, v1 = va.y + vb.y, v2 = va.z + vb.z, v3 = va.w + vb.w;
+            m = __funnelshift_l(__float_as_uint(v0), m, 1);
+            m = __funnelshift_l(__float_as_uint(v1), m, 1);
+            m = __funnelshift_l(__float_as_uint(v2), m, 1);
+            m = __funnelshift_l(__float_as_uint(v3), m, 1);
+            x[4 * i] = fmaxf(v0, 0.f); x[4 * i + 1] = fmaxf(v1, 0.f);
+            x[4 * i + 2] = fmaxf(v2, 0.f); x[4 * i + 3] = fmaxf(v3, 0.f);
           }
-          uint32_t hi[16], lo[16];
+          if (c + 2 < 8) gather(c + 2, c & 1, a_idx, b_idx);
+          if (mtile != nullptr && valid) mtile[(0 * 8 + c) * 128] = ~m;
+        } else if (MODE == 1) {
+          const uint32_t mword = valid ? mw[c] : 0u;
+          const float4* wp = reinterpret_cast<const float4*>(s_wd + 32 * c);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_pack(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
-          tmem_st16(tmem_base + lane_addr + 32u * c, hi);
-          tmem_st16(tmem_base + lane_addr + 32u * c + 16u, lo);
+          for (int i = 0; i < 8; ++i) {
+            const float4 w = wp[i];
+            x[4 * i] = ((int)(mword << (4 * i)) < 0) ? g0 * w.x : 0.f;
+            x[4 * i + 1] = ((int)(mword << (4 * i + 1)) < 0) ? g0 * w.y : 0.f;
+            x[4 * i + 2] = ((int)(mword << (4 * i + 2)) < 0) ? g0 * w.z : 0.f;
+            x[4 * i + 3] = ((int)(mword << (4 * i + 3)) < 0) ? g0 * w.w : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = p.test_A[(size_t)row * 256 + 32 * c + i];
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&a_ready[0]);
-        mbar_arrive(&a_ready[1]);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pack(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+        tmem_st16(tmem_base + lane_addr + 32u * c, hi);
+        tmem_st16(tmem_base + lane_addr + 32u * c + 16u, lo);
+        if (c == 3 || c == 7) {                       // K-half c / 4 of the first A operand is complete
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&a_ready[c >> 2]);
+        }
       }
+      if (MODE == 1) load_mask(tile, 2);
+      int a_nxt = 0, b_nxt = -1;
+      float g_nxt = 0.f;
       // ---------------- layers
       float logit = 0.f;
+#pragma unroll 1
       for (int layer = 0; layer < kLayers; ++layer) {
         const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
         const bool last64 = (MODE == 1 && layer == 3);
         const int halves = last64 ? 1 : 2;
+        if (MODE <= 1 && layer == kLayers - 1 && has_next) {       // next tile: rows, first gather chunks / mask words
+          load_row(tile + gridDim.x, a_nxt, b_nxt, g_nxt);
+          if (MODE == 1) load_mask(tile + gridDim.x, 3);
+          if (MODE == 0) { gather(0, 0, a_nxt, b_nxt); gather(1, 1, a_nxt, b_nxt); }
+        }
+#pragma unroll 1
         for (int h = 0; h < halves; ++h) {
           mbar_wait(&d_full[h], d_phase[h] & 1);
           ++d_phase[h];
@@ -233,7 +284,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
             tmem_ld32(d_half + lane_addr, r0);
             tmem_ld32(d_half + lane_addr + 32u, r1);
             tmem_wait_ld();
-            if (b_idx >= 0) {
+            if (valid) {
               float dpe[64];
 #pragma unroll
               for (int i = 0; i < 32; ++i) { dpe[i] = __uint_as_float(r0[i]); dpe[32 + i] = __uint_as_float(r1[i]); }
@@ -260,26 +311,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
               tmem_ld32(taddr, r);
               tmem_wait_ld();
               float x[32];
-              uint32_t mword = 0;
               if (MODE == 0) {
+                const float4* bp = reinterpret_cast<const float4*>(s_bias + layer * 256 + n0);
+                uint32_t m = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float v = __uint_as_float(r[i]) + s_bias[layer * 256 + n0 + i];
-                  mword |= (v > 0.f ? 1u : 0u) << i;
-                  x[i] = fmaxf(v, 0.f);
+                for (int i = 0; i < 8; ++i) {
+                  const float4 bb = bp[i];
+                  const float v0 = __uint_as_float(r[4 * i]) + bb.x, v1 = __uint_as_float(r[4 * i + 1]) + bb.y;
+                  const float v2 = __uint_as_float(r[4 * i + 2]) + bb.z, v3 = __uint_as_float(r[4 * i + 3]) + bb.w;
+                  m = __funnelshift_l(__float_as_uint(v0), m, 1);
+                  m = __funnelshift_l(__float_as_uint(v1), m, 1);
+                  m = __funnelshift_l(__float_as_uint(v2), m, 1);
+                  m = __funnelshift_l(__float_as_uint(v3), m, 1);
+                  x[4 * i] = fmaxf(v0, 0.f); x[4 * i + 1] = fmaxf(v1, 0.f);
+                  x[4 * i + 2] = fmaxf(v2, 0.f); x[4 * i + 3] = fmaxf(v3, 0.f);
                 }
-                if (p.mask && b_idx >= 0) p.mask[((size_t)(q0 + row) * 4 + layer + 1) * 8 + (n0 >> 5)] = mword;
+                if (mtile != nullptr && valid) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
               } else if (MODE == 1) {
-                mword = b_idx >= 0 ? __ldg(p.mask + ((size_t)(q0 + row) * 4 + (2 - layer)) * 8 + (n0 >> 5)) : 0u;
+                const uint32_t mword = valid ? pick_mask(4 * h + c) : 0u;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = ((mword >> i) & 1u) ? __uint_as_float(r[i]) : 0.f;
+                for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) : 0.f;
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) p.test_D[(size_t)row * 256 + n0 + i] = __uint_as_float(r[i]);
               }
               if (MODE == 0 && layer == 2) {
+                const float4* wp = reinterpret_cast<const float4*>(s_wd + n0);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) logit = fmaf(s_wd[n0 + i], x[i], logit);
+                for (int i = 0; i < 8; ++i) {
+                  const float4 w = wp[i];
+                  logit = fmaf(w.x, x[4 * i], logit); logit = fmaf(w.y, x[4 * i + 1], logit);
+                  logit = fmaf(w.z, x[4 * i + 2], logit); logit = fmaf(w.w, x[4 * i + 3], logit);
+                }
               } else if (MODE <= 1) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -295,8 +358,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
             }
           }
         }
+        if (MODE == 1 && layer < 2) load_mask(tile, 1 - layer);     // words of the next layer's epilogue
       }
-      if (MODE == 0) p.vis[q0 + row] = b_idx >= 0 ? 1.f / (1.f + expf(-(logit + p.bd[0]))) : 0.f;
+      if (MODE == 0) p.vis[q0 + row] = valid ? 1.f / (1.f + expf(-(logit + p.bd[0]))) : 0.f;
+      a_idx = a_nxt; b_idx = b_nxt; g0 = g_nxt;
     }
   }
   // ---- teardown
