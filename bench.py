@@ -202,7 +202,7 @@ def main():
     model.generate()                                   # octree build: excluded from the metric
     loss_fn = InvLoss()
     params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters())
-    opt = torch.optim.Adam(params, lr=5e-4, capturable=True)   # training/train_pbr.py:104-105, hotdog.conf:25
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=True)   # training/train_pbr.py:104-105, hotdog.conf:25
     reducer = rdist.GradAllReducer(params)
     pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
 

@@ -47,6 +47,8 @@ typedef struct {
   float* sdf;                       /* [n] */
   float* grad;                      /* [n][3] or NULL  (d sdf / d p, forward-mode) */
   float* feat;                      /* [n][256] or NULL */
+  const int* n_active;              /* optional device scalar: only points [0, min(*n_active, n)) are evaluated (hit rays
+                                       compacted to the front of a fixed-capacity batch); the other outputs are 0 */
 } robir_sdf_params;
 int robir_sdf_eval(const robir_sdf_params* p, int sm_count, void* stream);
 
@@ -217,6 +219,9 @@ typedef struct {
   int ldo;
   const float* g_out; /* backward: [n][ldo] */
   float* g_x;         /* backward: gradient w.r.t. the embedded input [n][in_pad] or NULL */
+  const int* n_active; /* optional device scalar: only rows with (row % seg) < *n_active are evaluated; tiles without
+                          such a row write zeros */
+  int seg;             /* rows per segment when the batch concatenates equally ordered copies; 0 = n */
 } robir_mlp_params;
 int robir_pack_pad(const float* W, int N, int K, float* out /*[Np][Kp]*/, int Np, int Kp, void* stream);
 int robir_mlp_fwd(const robir_mlp_params* p, int sm_count, void* stream);

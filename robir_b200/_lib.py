@@ -30,7 +30,8 @@ class SgParams(Structure):
 class SdfParams(Structure):
     _fields_ = [("pts", c_void_p), ("n", c_int), ("in_scale", c_float), ("sdf_scale", c_float),
                 ("feat_scale", c_float), ("Wt", c_void_p * 8), ("bias", c_void_p * 8), ("w8_sdf", c_void_p),
-                ("b8", c_void_p), ("Wt8_feat", c_void_p), ("sdf", c_void_p), ("grad", c_void_p), ("feat", c_void_p)]
+                ("b8", c_void_p), ("Wt8_feat", c_void_p), ("sdf", c_void_p), ("grad", c_void_p), ("feat", c_void_p),
+                ("n_active", c_void_p)]
 
 
 class SdfNet(Structure):
@@ -55,7 +56,7 @@ class MlpParams(Structure):
     _fields_ = [("n", c_int), ("n_layers", c_int), ("in_mode", c_int), ("in_dim", c_int), ("in_pad", c_int),
                 ("x", c_void_p), ("extra", c_void_p), ("noise", c_void_p), ("noise_scale", c_float),
                 ("x0_save", c_void_p), ("L", MlpLayer * 8), ("out", c_void_p), ("ldo", c_int), ("g_out", c_void_p),
-                ("g_x", c_void_p)]
+                ("g_x", c_void_p), ("n_active", c_void_p), ("seg", c_int)]
 
 
 class OctreeView(Structure):

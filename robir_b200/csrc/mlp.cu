@@ -10,7 +10,7 @@
 namespace robir {
 
 constexpr int kMlpMaxLayers = 8;
-constexpr int kMlpR = 16;
+// rows per CTA tile: 16, or 8 when the batch is small (<= 2048 rows) so that a 1024-ray step still fills 128 SMs
 constexpr int kMlpKMax = 512;
 
 enum InMode { IN_RAW = 0, IN_PE10 = 1, IN_PE10_EXTRA = 2, IN_IPE10 = 3, IN_PE10X2 = 4 };
@@ -37,7 +37,24 @@ struct MlpParams {
   int ldo;
   const float* g_out;   // backward: [n][ldo]
   float* g_x;           // backward: gradient w.r.t. the embedded input [n][in_pad] or null
+  const int* n_active;  // optional device scalar: only rows with (row % seg) < *n_active are evaluated (hit rays
+                        // compacted to the front of a fixed-capacity batch); tiles without such a row write zeros
+  int seg;              // rows per segment (the batch may be a concatenation of equally ordered copies); 0 = n
 };
+
+struct MlpActive { int n_act, seg; };
+__device__ __forceinline__ MlpActive mlp_active(const MlpParams& p) {
+  MlpActive a;
+  a.seg = p.seg > 0 ? p.seg : (p.n > 0 ? p.n : 1);
+  a.n_act = p.n_active ? min(__ldg(p.n_active), a.seg) : a.seg;
+  return a;
+}
+__device__ __forceinline__ bool mlp_row_active(int row, const MlpActive& a) { return (row % a.seg) < a.n_act; }
+// whole tile inside the inactive tail of one segment
+__device__ __forceinline__ bool mlp_tile_inactive(int row0, int R, const MlpActive& a) {
+  const int o = row0 % a.seg;
+  return o >= a.n_act && o + R <= a.seg;
+}
 
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
@@ -168,9 +185,8 @@ __device__ __forceinline__ void col_store(float* __restrict__ Xs, int col, const
   for (int r = 0; r < R; r += 4) *reinterpret_cast<float4*>(dst + r) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
 }
 
-template <int NPASS>
+template <int R, int NPASS>
 __device__ __forceinline__ void mlp_fwd_layer(const MlpParams& p, int l, float* Xs, float* Wbuf, int row0) {
-  constexpr int R = kMlpR;
   const MlpLayer& L = p.L[l];
   const bool last = l == p.n_layers - 1;
   float acc[NPASS][R];
@@ -200,28 +216,39 @@ __device__ __forceinline__ void mlp_fwd_layer(const MlpParams& p, int l, float* 
   __syncthreads();
 }
 
+template <int R>
 __global__ void __launch_bounds__(256, 2) mlp_fwd_kernel(MlpParams p) {
-  constexpr int R = kMlpR, RP = R + 4;
+  constexpr int RP = R + 4;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;                        // [kMlpKMax][RP]
   float* Wbuf = Xs + kMlpKMax * RP;
   const int tid = threadIdx.x;
   const int ntile = (p.n + R - 1) / R;
+  const MlpActive act = mlp_active(p);
   for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int row0 = tile * R;
+    if (mlp_tile_inactive(row0, R, act)) {  // zero every output row, no arithmetic
+      const int rows = min(R, p.n - row0);
+      for (int l = 0; l < p.n_layers; ++l)
+        if (p.L[l].save != nullptr)
+          for (int i = tid; i < rows * p.L[l].Npad; i += 256) p.L[l].save[(size_t)row0 * p.L[l].Npad + i] = 0.f;
+      if (p.x0_save != nullptr)
+        for (int i = tid; i < rows * p.in_pad; i += 256) p.x0_save[(size_t)row0 * p.in_pad + i] = 0.f;
+      for (int i = tid; i < rows * p.ldo; i += 256) p.out[(size_t)row0 * p.ldo + i] = 0.f;
+      continue;
+    }
     __syncthreads();
-    if (tid < R) encode_row(Xs, RP, tid, p, row0 + tid, row0 + tid < p.n);
+    if (tid < R) encode_row(Xs, RP, tid, p, row0 + tid, row0 + tid < p.n && mlp_row_active(row0 + tid, act));
     __syncthreads();
     for (int l = 0; l < p.n_layers; ++l) {
-      if (p.L[l].Npad == kPassCols) mlp_fwd_layer<1>(p, l, Xs, Wbuf, row0);
-      else mlp_fwd_layer<2>(p, l, Xs, Wbuf, row0);
+      if (p.L[l].Npad == kPassCols) mlp_fwd_layer<R, 1>(p, l, Xs, Wbuf, row0);
+      else mlp_fwd_layer<R, 2>(p, l, Xs, Wbuf, row0);
     }
   }
 }
 
-template <int NPASS>
+template <int R, int NPASS>
 __device__ __forceinline__ void mlp_bwd_layer(const MlpParams& p, int l, float* Xs, float* Wbuf, int row0) {
-  constexpr int R = kMlpR;
   const MlpLayer& L = p.L[l];
   const int kin = (L.N + 15) & ~15;                 // contraction length (rows of Wb)
   const int outp = NPASS * kPassCols;
@@ -258,15 +285,26 @@ __device__ __forceinline__ void mlp_bwd_layer(const MlpParams& p, int l, float* 
 }
 
 // backward: G_L = g_out; for l = L-1..0: emit G_l, dA = G_l . W_l, G_{l-1} = dA * act'(A_{l-1})
+template <int R>
 __global__ void __launch_bounds__(256, 2) mlp_bwd_kernel(MlpParams p) {
-  constexpr int R = kMlpR, RP = R + 4;
+  constexpr int RP = R + 4;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;
   float* Wbuf = Xs + kMlpKMax * RP;
   const int tid = threadIdx.x;
   const int ntile = (p.n + R - 1) / R;
+  const MlpActive act = mlp_active(p);
   for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int row0 = tile * R;
+    if (mlp_tile_inactive(row0, R, act)) {  // zero gradients
+      const int rows = min(R, p.n - row0);
+      for (int l = 0; l < p.n_layers; ++l)
+        if (p.L[l].G != nullptr)
+          for (int i = tid; i < rows * p.L[l].Npad; i += 256) p.L[l].G[(size_t)row0 * p.L[l].Npad + i] = 0.f;
+      if (p.g_x != nullptr)
+        for (int i = tid; i < rows * p.in_pad; i += 256) p.g_x[(size_t)row0 * p.in_pad + i] = 0.f;
+      continue;
+    }
     __syncthreads();
     {
       // G of the last layer (its act is applied by the caller or is NONE): tile rows <- g_out, zero padded to Npad16
@@ -285,8 +323,8 @@ __global__ void __launch_bounds__(256, 2) mlp_bwd_kernel(MlpParams p) {
     }
     __syncthreads();
     for (int l = p.n_layers - 1; l >= 0; --l) {
-      if (p.L[l].K <= kPassCols) mlp_bwd_layer<1>(p, l, Xs, Wbuf, row0);
-      else mlp_bwd_layer<2>(p, l, Xs, Wbuf, row0);
+      if (p.L[l].K <= kPassCols) mlp_bwd_layer<R, 1>(p, l, Xs, Wbuf, row0);
+      else mlp_bwd_layer<R, 2>(p, l, Xs, Wbuf, row0);
     }
   }
 }
@@ -303,15 +341,6 @@ __global__ void pack_pad_kernel(const float* __restrict__ W, int N, int K, float
 
 using namespace robir;
 
-extern "C" {
-
-int robir_pack_pad(const float* W, int N, int K, float* out, int Np, int Kp, void* stream) {
-  RB_REQUIRE(Np >= N && Kp >= K, "pack_pad: padded shape too small");
-  pack_pad_kernel<<<(Np * Kp + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, N, K, out, Np, Kp);
-  RB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 static int mlp_check(const MlpParams* p) {
   RB_REQUIRE(p->n_layers >= 1 && p->n_layers <= kMlpMaxLayers, "mlp: 1..8 layers");
   for (int l = 0; l < p->n_layers; ++l) {
@@ -325,15 +354,34 @@ static int mlp_check(const MlpParams* p) {
   return 0;
 }
 
+template <bool FWD, int R>
+static int mlp_launch_r(const MlpParams* p, int sm_count, void* stream) {
+  const int smem = (kMlpKMax * (R + 4) + kWbufFloats) * 4;
+  auto kern = FWD ? mlp_fwd_kernel<R> : mlp_bwd_kernel<R>;
+  RB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int tiles = (p->n + R - 1) / R;
+  kern<<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <bool FWD>
+static int mlp_launch(const MlpParams* p, int sm_count, void* stream) {
+  return p->n <= 2048 ? mlp_launch_r<FWD, 8>(p, sm_count, stream) : mlp_launch_r<FWD, 16>(p, sm_count, stream);
+}
+
+extern "C" {
+
+int robir_pack_pad(const float* W, int N, int K, float* out, int Np, int Kp, void* stream) {
+  RB_REQUIRE(Np >= N && Kp >= K, "pack_pad: padded shape too small");
+  pack_pad_kernel<<<(Np * Kp + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, N, K, out, Np, Kp);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int robir_mlp_fwd(const MlpParams* p, int sm_count, void* stream) {
   if (p->n == 0) return 0;
   if (int e = mlp_check(p)) return e;
-  const int smem = (kMlpKMax * (kMlpR + 4) + kWbufFloats) * 4;
-  RB_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int tiles = (p->n + kMlpR - 1) / kMlpR;
-  mlp_fwd_kernel<<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
-  RB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return mlp_launch<true>(p, sm_count, stream);
 }
 
 int robir_mlp_bwd(const MlpParams* p, int sm_count, void* stream) {
@@ -341,12 +389,7 @@ int robir_mlp_bwd(const MlpParams* p, int sm_count, void* stream) {
   if (int e = mlp_check(p)) return e;
   for (int l = 0; l < p->n_layers - 1; ++l)
     RB_REQUIRE(p->L[l].save != nullptr, "mlp_bwd: hidden activations must have been saved by the forward");
-  const int smem = (kMlpKMax * (kMlpR + 4) + kWbufFloats) * 4;
-  RB_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int tiles = (p->n + kMlpR - 1) / kMlpR;
-  mlp_bwd_kernel<<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
-  RB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return mlp_launch<false>(p, sm_count, stream);
 }
 
 }  // extern "C"

@@ -50,6 +50,7 @@ struct SdfParams {
   float* sdf;           // [n]
   float* grad;          // [n][3] or null
   float* feat;          // [n][256] or null
+  const int* n_active;  // optional device scalar: points at or beyond min(*n_active, n) are not evaluated (outputs = 0)
 };
 
 template <bool JET>
@@ -64,8 +65,16 @@ __global__ void __launch_bounds__(256, 2) sdf_eval_kernel(SdfParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntile = (p.n + PTS - 1) / PTS;
   const float kInvSqrt2 = 0.70710678118654752440f;
+  const int n_act = p.n_active ? min(__ldg(p.n_active), p.n) : p.n;
   for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int p0 = tile * PTS;
+    if (p0 >= n_act) {                     // inactive tile (hit rays are compacted to the front): zero outputs
+      const int pts = min(PTS, p.n - p0);
+      for (int i = tid; i < pts; i += 256) p.sdf[p0 + i] = 0.f;
+      if (p.grad) for (int i = tid; i < pts * 3; i += 256) p.grad[(size_t)p0 * 3 + i] = 0.f;
+      if (p.feat) for (int i = tid; i < pts * 256; i += 256) p.feat[(size_t)p0 * 256 + i] = 0.f;
+      continue;
+    }
     __syncthreads();
     if (tid < PTS) {
       const int i = p0 + tid;

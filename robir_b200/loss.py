@@ -48,7 +48,11 @@ class InvLoss(nn.Module):
             # same statistics without data-dependent shapes (CUDA-graph capturable): masked batch mean of the latent
             hit = model_outputs['network_object_mask']
             pts = torch.where(hit[:, None], model_outputs['points'], torch.zeros_like(model_outputs['points']))
-            lat = torch.sigmoid(latent_of(pts))
+            z = latent_of(pts)
+            if z is getattr(mat_model, "_last_spec_latent", None) and \
+                    getattr(mat_model, "_last_latent_valid", None) is not None:
+                hit = mat_model._last_latent_valid      # the cached latent lives in the renderer's compacted row order
+            lat = torch.sigmoid(z)
             rho_hat = (lat * hit[:, None]).sum(0) / hit.sum().clamp(min=1)
             rho = torch.full_like(rho_hat, 0.05)
             kl = torch.mean(rho * torch.log(rho / (rho_hat + 1e-4))

@@ -199,11 +199,11 @@ class SparseAE(nn.Module):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def encode_points(self, points, in_mode="pe10", extra=None, noise=None, train=None):
+    def encode_points(self, points, in_mode="pe10", extra=None, noise=None, train=None, segments=1):
         """encoder(embed(points) (+ 0.02 noise)) -> latent pre-activation [n, 32]"""
         train = self._wants_grad() if train is None else train
         z = ops.fused_mlp(self._chain("enc", in_mode), points, extra=extra, noise=noise, noise_scale=0.02,
-                          want_param_grad=train)
+                          want_param_grad=train, segments=segments)
         if self.var is not None:
             z = z * (1 - self.var.to(z.device))
         return z
@@ -217,7 +217,7 @@ class SparseAE(nn.Module):
             z = self.encode_points(points, in_mode, extra, None, train)
             lc = self.lc_act(z)
             lc_r = lc + rng.randn(lc.shape, lc.device) * 0.01
-            y2 = ops.fused_mlp(dec, torch.cat([lc, lc_r], 0), want_param_grad=train)
+            y2 = ops.fused_mlp(dec, torch.cat([lc, lc_r], 0), want_param_grad=train, segments=2)
             y, y_r = y2[:n], y2[n:]
         else:
             in_dim = self.brdf_encoder_layer[0].in_features
@@ -230,9 +230,10 @@ class SparseAE(nn.Module):
             else:
                 pts2 = torch.cat([points, points], 0)
                 ex2 = torch.cat([extra, extra], 0) if extra is not None else None
-                z2 = self.encode_points(pts2, in_mode, ex2, torch.cat([torch.zeros_like(noise), noise], 0), train)
+                z2 = self.encode_points(pts2, in_mode, ex2, torch.cat([torch.zeros_like(noise), noise], 0), train,
+                                        segments=2)
                 z = z2[:n]
-                y2 = ops.fused_mlp(dec, self.lc_act(z2), want_param_grad=train)
+                y2 = ops.fused_mlp(dec, self.lc_act(z2), want_param_grad=train, segments=2)
                 y, y_r = y2[:n], y2[n:]
         if self.out_act is not None:
             y = self.out_act(y) if y is not None else None

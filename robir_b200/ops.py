@@ -185,6 +185,23 @@ class Stats:
             cls.n_pairs.zero_()
 
 
+class active_rows:
+    """Context: a device int32 scalar n_act; inside it the per-point networks (fused MLP chains, SDF) evaluate only
+    rows [0, n_act) of their fixed-capacity batch (hit rays compacted to the front) and write zeros for the rest."""
+    current = None
+
+    def __init__(self, n_act):
+        self.n_act = n_act
+
+    def __enter__(self):
+        self.old, active_rows.current = active_rows.current, self.n_act
+        return self
+
+    def __exit__(self, *exc):
+        active_rows.current = self.old
+        return False
+
+
 ENGINE = {"vis": "tc"}     # "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
 
@@ -452,6 +469,7 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
         p.bias[l] = W["b%d" % l].data_ptr()
     p.w8_sdf, p.b8, p.Wt8_feat = ptr(W["w8_sdf"]), ptr(W["b8"]), ptr(W["Wt8_feat"])
     p.sdf, p.grad, p.feat = ptr(sdf), ptr(grad), ptr(feat)
+    p.n_active = ptr(active_rows.current)
     check(lib().robir_sdf_eval(ctypes.byref(p), sm_count(), stream()))
     return sdf, grad, feat
 
@@ -648,11 +666,12 @@ class MlpChain:
         return self.cache.get(self.params(), build)
 
 
-def _mlp_params(chain, packed, n, x, extra, noise, noise_scale):
+def _mlp_params(chain, packed, n, x, extra, noise, noise_scale, n_active=None, segments=1):
     p = MlpParams()
     p.n, p.n_layers, p.in_mode = n, len(packed), chain.in_mode
     p.in_dim, p.in_pad = packed[0]["K"], packed[0]["Kpad"]
     p.x, p.extra, p.noise, p.noise_scale = ptr(x), ptr(extra), ptr(noise), float(noise_scale)
+    p.n_active, p.seg = ptr(n_active), n // segments
     for l, d in enumerate(packed):
         L = p.L[l]
         L.Wt, L.Wb, L.bias = d["Wt"].data_ptr(), d["Wb"].data_ptr(), d["bias"].data_ptr()
@@ -662,7 +681,7 @@ def _mlp_params(chain, packed, n, x, extra, noise, noise_scale):
 
 class _FusedMLP(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, chain, x, extra, noise, noise_scale, want_param_grad, *params):
+    def forward(ctx, chain, x, extra, noise, noise_scale, want_param_grad, segments, *params):
         packed = chain.packed()
         need_bwd = want_param_grad or (extra is not None and extra.requires_grad) or x.requires_grad
         ctx.extra_shape = tuple(extra.shape) if extra is not None else None
@@ -672,7 +691,8 @@ class _FusedMLP(torch.autograd.Function):
         noise = f32(noise) if noise is not None else None
         n_out = packed[-1]["N"]
         out = _empty(n, n_out, like=x)
-        p = _mlp_params(chain, packed, n, x, extra, noise, noise_scale)
+        n_active = active_rows.current
+        p = _mlp_params(chain, packed, n, x, extra, noise, noise_scale, n_active, segments)
         saves, x0 = [], None
         if need_bwd:
             for l, d in enumerate(packed[:-1]):
@@ -686,17 +706,17 @@ class _FusedMLP(torch.autograd.Function):
         check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
         ctx.chain, ctx.n, ctx.want_param_grad = chain, n, want_param_grad
         ctx.has_extra = extra is not None
-        ctx.save_for_backward(x, extra, noise, x0, *saves)
-        ctx.noise_scale = noise_scale
+        ctx.save_for_backward(x, extra, noise, x0, n_active, *saves)
+        ctx.noise_scale, ctx.segments = noise_scale, segments
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         chain, n = ctx.chain, ctx.n
-        x, extra, noise, x0, *saves = ctx.saved_tensors
+        x, extra, noise, x0, n_active, *saves = ctx.saved_tensors
         packed = chain.packed()
         g_out = f32(g_out)
-        p = _mlp_params(chain, packed, n, x, extra, noise, ctx.noise_scale)
+        p = _mlp_params(chain, packed, n, x, extra, noise, ctx.noise_scale, n_active, ctx.segments)
         for l, sv in enumerate(saves):
             p.L[l].save = sv.data_ptr()
         Gs = []
@@ -718,13 +738,14 @@ class _FusedMLP(torch.autograd.Function):
                 prev = saves[l] if l < len(saves) else None
         gx = g_x[:, :packed[0]["K"]] if chain.in_mode == 0 else None
         g_extra = g_x[:, 63].reshape(ctx.extra_shape) if ctx.has_extra else None
-        return (None, gx, g_extra, None, None, None, *grads)
+        return (None, gx, g_extra, None, None, None, None, *grads)
 
 
-def fused_mlp(chain, x, extra=None, noise=None, noise_scale=0.02, want_param_grad=False):
-    """x: [n,K] (raw mode) or points [n,3]; extra: [n,1] appended column (pe10_extra); noise: [n,K] in embedding space."""
+def fused_mlp(chain, x, extra=None, noise=None, noise_scale=0.02, want_param_grad=False, segments=1):
+    """x: [n,K] (raw mode) or points [n,3]; extra: [n,1] appended column (pe10_extra); noise: [n,K] in embedding space;
+    segments: the batch is a concatenation of that many equally ordered copies (matters under ops.active_rows)."""
     params = chain.params() if want_param_grad else []
-    return _FusedMLP.apply(chain, x, extra, noise, noise_scale, want_param_grad, *params)
+    return _FusedMLP.apply(chain, x, extra, noise, noise_scale, want_param_grad, segments, *params)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -159,21 +159,41 @@ class IDRNetwork(nn.Module):
         with torch.no_grad():
             _, mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
-        sdf_output = self.implicit_network.sdf(points)[:, None]
         ray_dirs = ray_dirs.reshape(-1, 3)
-        m1 = mask[:, None]
-        pts = torch.where(m1, points, torch.zeros_like(points))      # finite inputs for the rows that are masked out
-        # the indirect-illumination net, the material net and the SDF normal are independent given the hit points:
-        # three parallel branches (random draws keep the reference order: indirect, BRDF latent, normal input)
-        (sgs, integ), mat, nrm = ops.fork_join([
-            lambda: self.indirect_illum_network(pts, input['hdr_shift']),
-            lambda: self.envmap_material_network(pts, train_spec=train_spec),
-            lambda: self.get_idr_render(pts, None, normal_only=True)])
+        total, dev = points.shape[0], points.device
+        # hit rays are compacted to the front of the fixed-capacity batch (device-side permutation, no host sync); the
+        # per-point networks then evaluate n_act rows instead of N (ops.active_rows), like the reference's boolean
+        # indexing (implicit_differentiable_renderer.py:341-347) but capturable in a CUDA graph
+        hit = mask
+        n_act = hit.sum().to(torch.int32).reshape(1)
+        csum = torch.cumsum(hit, 0)
+        pos = torch.where(hit, csum - 1, n_act.to(torch.int64) + torch.arange(total, device=dev) - csum)
+        order = torch.empty_like(pos).scatter_(0, pos, torch.arange(total, device=dev))
+        valid = torch.arange(total, device=dev) < n_act
+        v1 = valid[:, None]
+        pts = torch.where(v1, points.index_select(0, order), torch.zeros_like(points))   # finite inputs for inactive rows
+        view = -ray_dirs.index_select(0, order)
+        hdr = input['hdr_shift'].index_select(0, order)
+        # the indirect-illumination net, the material net, the SDF normal and the reported sdf_output are independent
+        # given the hit points: parallel branches (random draws keep the reference order: indirect, BRDF latent,
+        # normal input)
+        def act(fn):
+            def run():
+                with ops.active_rows(n_act):
+                    return fn()
+            return run
+        (sgs, integ), mat, nrm, sdf_output = ops.fork_join([
+            act(lambda: self.indirect_illum_network(pts, hdr)),
+            act(lambda: self.envmap_material_network(pts, train_spec=train_spec)),
+            act(lambda: self.get_idr_render(pts, None, normal_only=True)),
+            lambda: self.implicit_network.sdf(points)[:, None]])
+        self.envmap_material_network._last_latent_valid = valid
         ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
-        r = pbr_get_sg_render(self, pts, -ray_dirs, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
-                              valid=mask, precomputed=(nrm, mat))
-        one = lambda v: torch.where(m1, v, torch.ones_like(v))
+        r = pbr_get_sg_render(self, pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
+                              valid=valid, precomputed=(nrm, mat))
+        m1 = mask[:, None]
+        one = lambda v: torch.where(m1, v.index_select(0, pos), torch.ones_like(v))      # back to ray order
         for k in ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
                   'indir_specular_rgb', 'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow',
                   'random_xi_diffuse_albedo', 'metallic', 'random_xi_metallic'):

@@ -298,7 +298,8 @@ def test_pbr_forward_properties_full_size(model16, synth_sd16):
 
 
 def test_static_shape_mode_matches_compacted_mode(model16):
-    """static_shapes=True (no hit compaction; what the CUDA-graph step uses) vs. the reference-shaped path."""
+    """static_shapes=True (fixed-capacity batch, device-side hit compaction; what the CUDA-graph step uses) vs. the
+    reference-shaped path."""
     from robir_b200 import rng
     model16.generate()
     N = 512
@@ -310,9 +311,9 @@ def test_static_shape_mode_matches_compacted_mode(model16):
     assert 0 < int(m.sum()) < N
     tape_static = []
     for t in tape:
-        if t.shape[0] == int(m.sum()) and t.shape[0] != 16:      # per-hit draws -> scattered to [N, .]
-            full = torch.zeros(N, *t.shape[1:])
-            full[m] = t
+        if t.shape[0] == int(m.sum()) and t.shape[0] != 16:      # per-hit draws -> rows [0, n_hit) of [N, .] (the
+            full = torch.zeros(N, *t.shape[1:])                  # static path compacts the hit rays to the front)
+            full[:t.shape[0]] = t
             tape_static.append(full)
         else:
             tape_static.append(t)
