@@ -53,14 +53,15 @@ struct SdfParams {
   const int* n_active;  // optional device scalar: points at or beyond min(*n_active, n) are not evaluated (outputs = 0)
 };
 
-template <bool JET>
+// R = tile rows (64, or 32 for small batches so that a 1024-point call still spreads over ~128 CTAs)
+template <bool JET, int R>
 __global__ void __launch_bounds__(256, 2) sdf_eval_kernel(SdfParams p) {
-  constexpr int R = 64, RP = TileCfg<R>::RP, TR = TileCfg<R>::TR;
-  constexpr int PTS = JET ? 16 : 64;
+  constexpr int RP = TileCfg<R>::RP, TR = TileCfg<R>::TR;
+  constexpr int PTS = JET ? R / 4 : R;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;
   float* Wbuf = Xs + 256 * RP;
-  float* red = Wbuf + kWbufFloats;  // [4][64]
+  float* red = Wbuf + kWbufFloats;  // [256 / R][R]
   __shared__ float s_x[PTS][3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntile = (p.n + PTS - 1) / PTS;
@@ -120,14 +121,22 @@ __global__ void __launch_bounds__(256, 2) sdf_eval_kernel(SdfParams p) {
     }
     // ---- layer 8, column 0 (sdf / gradient components): dot over the 256 activations of every row
     {
-      const int row = tid & 63, part = tid >> 6;
+      constexpr int PARTS = 256 / R, KLEN = 256 / PARTS;
+      const int row = tid % R, part = tid / R;
       float s = 0.f;
-      for (int k = part * 64; k < part * 64 + 64; ++k) s = fmaf(__ldg(p.w8_sdf + k), Xs[k * RP + row], s);
-      red[part * 64 + row] = s;
+      for (int k = part * KLEN; k < part * KLEN + KLEN; ++k) s = fmaf(__ldg(p.w8_sdf + k), Xs[k * RP + row], s);
+      red[part * R + row] = s;
     }
     __syncthreads();
     if (tid < R) {
-      const float d = (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
+      float d;
+      if (R == 64) {
+        d = (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]);
+      } else {
+        d = 0.f;
+#pragma unroll
+        for (int q = 0; q < 256 / R; ++q) d += red[q * R + tid];
+      }
       if (JET) {
         const int i = p0 + (tid >> 2), j = tid & 3;
         if (i < p.n) {
@@ -191,15 +200,14 @@ int robir_sdf_eval(const SdfParams* p, int sm_count, void* stream) {
   const int smem = (256 * 68 + kWbufFloats + 256) * 4;
   const bool jet = p->grad != nullptr;
   RB_REQUIRE(p->feat == nullptr || p->Wt8_feat != nullptr, "sdf_eval: feature output needs Wt8_feat");
-  if (jet) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(sdf_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int tiles = cdiv_i(p->n, 16);
-    sdf_eval_kernel<true><<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
-  } else {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(sdf_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int tiles = cdiv_i(p->n, 64);
-    sdf_eval_kernel<false><<<tiles < 2 * sm_count ? tiles : 2 * sm_count, 256, smem, (cudaStream_t)stream>>>(*p);
-  }
+  const bool small = (long long)p->n * (jet ? 4 : 1) <= 4096;   // 32-row tiles: 1024 points -> 128 (jet) / 32 CTAs
+  const int pts = (small ? 32 : 64) / (jet ? 4 : 1);
+  const int tiles = cdiv_i(p->n, pts);
+  const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
+  void (*kern)(SdfParams) = jet ? (small ? sdf_eval_kernel<true, 32> : sdf_eval_kernel<true, 64>)
+                                : (small ? sdf_eval_kernel<false, 32> : sdf_eval_kernel<false, 64>);
+  RB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 256, smem, (cudaStream_t)stream>>>(*p);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -274,10 +274,15 @@ class EnvmapMaterialNetwork(nn.Module):
         if not fused:
             pts_ipe = integrated_positional_encoding(points, 10, 1e-5)
             emb = positional_encoding(points, 10)
+        nm = None
         if not train_norm:
             if fused:
-                brdf, brdf_r, z = self.spec_brdf_encoder_layer.forward_points(points.detach(), "pe10",
-                                                                              train=None if train_spec else False)
+                # the BRDF and the normal auto-encoders only share the input points: two parallel branches (host call
+                # order = random-draw order of the reference: BRDF latent noise, then normal input noise)
+                (brdf, brdf_r, z), (nm, nm_r, _) = ops.fork_join([
+                    lambda: self.spec_brdf_encoder_layer.forward_points(points.detach(), "pe10",
+                                                                        train=None if train_spec else False),
+                    lambda: self.normal_decoder_layer.forward_points(points.detach(), "ipe10")])
                 self._last_spec_latent = z          # reused by the KL term of the loss (same points, same encoder)
             else:
                 brdf, brdf_r = self.spec_brdf_encoder_layer(emb)
@@ -287,7 +292,8 @@ class EnvmapMaterialNetwork(nn.Module):
                        sg_diffuse_albedo=brdf[..., :3], random_xi_roughness=brdf_r[..., 3:4] * 0.9 + 0.09,
                        random_xi_diffuse_albedo=brdf_r[..., :3], random_xi_metallic=brdf_r[..., 4:5])
         if fused:
-            nm, nm_r, _ = self.normal_decoder_layer.forward_points(points.detach(), "ipe10")
+            if nm is None:
+                nm, nm_r, _ = self.normal_decoder_layer.forward_points(points.detach(), "ipe10")
         else:
             nm, nm_r = self.normal_decoder_layer(pts_ipe)
         ret["sg_normal_map"] = nm / torch.clamp(nm.norm(dim=-1, keepdim=True), 1e-4)
@@ -321,10 +327,12 @@ class IndirctIllumNetwork(nn.Module):
                 self._lobe_chain = ops.MlpChain.from_sequential(self.lobe_layer, "relu", "pe10_extra")
             train = self.train_weights and torch.is_grad_enabled()
             pts = points.detach()
-            out = ops.fused_mlp(self._lobe_chain, pts, extra=hdr_shift, want_param_grad=train)
+            # lobe network and integral auto-encoder are independent: two parallel branches (forward and backward)
+            out, (_, env_r, _) = ops.fork_join([
+                lambda: ops.fused_mlp(self._lobe_chain, pts, extra=hdr_shift, want_param_grad=train),
+                lambda: self.integral_layer.forward_points(pts, "pe10_extra", extra=hdr_shift, train=train,
+                                                           noisy_only=True)])
             out = out.reshape(pts.shape[0], self.num_lgt_sgs, 6)
-            _, env_r, _ = self.integral_layer.forward_points(pts, "pe10_extra", extra=hdr_shift, train=train,
-                                                             noisy_only=True)
             return self._decode_lobes(out), torch.abs(env_r)
         x = torch.cat([positional_encoding(points, 10), hdr_shift], -1)
         out = self.lobe_layer(x).reshape(x.shape[0], self.num_lgt_sgs, 6)

@@ -765,25 +765,39 @@ def _tensors_in(obj):
             yield from _tensors_in(v)
 
 
+_fork_state = {"depth": 0, "next": 0}
+
+
 def fork_join(fns):
     """Run the callables concurrently: fns[0] on the current stream, the others on pooled side streams that fork from
-    and join back into it.  Host-side call order (hence the order of random draws) stays sequential."""
+    and join back into it.  Host-side call order (hence the order of random draws) stays sequential.  Calls nest: every
+    branch of one outermost call gets its own stream, so sibling sub-branches never queue behind each other."""
     main = torch.cuda.current_stream()
-    while len(_side_streams) < len(fns) - 1:
+    st = _fork_state
+    base = st["next"]
+    st["next"] = base + len(fns) - 1
+    st["depth"] += 1
+    while len(_side_streams) < st["next"]:
         _side_streams.append(torch.cuda.Stream())
+    sides = _side_streams[base:base + len(fns) - 1]
     results = [None] * len(fns)
-    fork = torch.cuda.Event()
-    fork.record(main)
-    for i, fn in enumerate(fns):              # host order = list order (keeps the random-draw order of the reference)
-        if i == 0:
-            results[0] = fn()
-            continue
-        side = _side_streams[i - 1]
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
-            results[i] = fn()
-    for i in range(len(fns) - 1):
-        main.wait_stream(_side_streams[i])
+    try:
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for i, fn in enumerate(fns):          # host order = list order (keeps the random-draw order of the reference)
+            if i == 0:
+                results[0] = fn()
+                continue
+            side = sides[i - 1]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                results[i] = fn()
+        for side in sides:
+            main.wait_stream(side)
+    finally:
+        st["depth"] -= 1
+        if st["depth"] == 0:
+            st["next"] = 0
     if not torch.cuda.is_current_stream_capturing():
         for r in results[1:]:
             for t in _tensors_in(r):
