@@ -227,6 +227,31 @@ int robir_pack_pad(const float* W, int N, int K, float* out /*[Np][Kp]*/, int Np
 int robir_mlp_fwd(const robir_mlp_params* p, int sm_count, void* stream);
 int robir_mlp_bwd(const robir_mlp_params* p, int sm_count, void* stream);
 
+/* ---- loss epilogue: model/loss.py:61-125 (InvLoss: masked L1/L2 on the ACES tone-mapped radiance,
+ * latent-smooth L1, KL sparsity of the BRDF latent), model/color_correction.py:31-59 (hdr2ldr with the learnable
+ * exposure shift), training/train_pbr.py:313-346 (white_loss; loss = rgb + kl + 0.1 smooth + white).  One launch
+ * computes the value and every input gradient. ------------------------------------------------------------------- */
+typedef struct {
+  int N, n_lat, M, l2;
+  const float* sg_rgb; const float* indir_rgb;   /* [N][3], row strides ld_sg / ld_ind (floats) */
+  int ld_sg, ld_ind;
+  const float* gt;                                /* [N][3] */
+  const unsigned char* mask;                      /* [N] network_object_mask & object_mask */
+  const float* adapt_illum;                       /* [1] */
+  const float* albedo; const float* albedo_r;     /* [N][3], strides ld_alb / ld_albr */
+  int ld_alb, ld_albr;
+  const float* rough; const float* rough_r;       /* [N] (column 0), strides ld_r / ld_rr */
+  int ld_r, ld_rr;
+  const float* z;                                 /* [n_lat][32] */
+  const unsigned char* z_valid;                   /* [n_lat] or NULL */
+  const float* lgt;                               /* [M][7] */
+  float w_rgb, w_kl, w_smooth, rho;
+  float* losses;                                  /* [5] total, sg_rgb_loss, kl, smooth, white */
+  float* g_pred; float* g_adapt; float* g_albedo; float* g_albedo_r; float* g_rough; float* g_rough_r;
+  float* g_z; float* g_lgt;
+} robir_loss_params;
+int robir_pbr_loss(const robir_loss_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,17 @@ class SphereTraceParams(Structure):
                                 "flags", "samp_list", "sec_list", "sec_state", "min_list", "vals", "counters")]
 
 
+class LossParams(Structure):
+    _fields_ = [("N", c_int), ("n_lat", c_int), ("M", c_int), ("l2", c_int), ("sg_rgb", c_void_p),
+                ("indir_rgb", c_void_p), ("ld_sg", c_int), ("ld_ind", c_int), ("gt", c_void_p), ("mask", c_void_p),
+                ("adapt_illum", c_void_p), ("albedo", c_void_p), ("albedo_r", c_void_p), ("ld_alb", c_int),
+                ("ld_albr", c_int), ("rough", c_void_p), ("rough_r", c_void_p), ("ld_r", c_int), ("ld_rr", c_int),
+                ("z", c_void_p), ("z_valid", c_void_p), ("lgt", c_void_p), ("w_rgb", c_float), ("w_kl", c_float),
+                ("w_smooth", c_float), ("rho", c_float)] + [
+        (k, c_void_p) for k in ("losses", "g_pred", "g_adapt", "g_albedo", "g_albedo_r", "g_rough", "g_rough_r", "g_z",
+                                "g_lgt")]
+
+
 class MlpLayer(Structure):
     _fields_ = [("Wt", c_void_p), ("Wb", c_void_p), ("bias", c_void_p), ("K", c_int), ("N", c_int), ("Kpad", c_int),
                 ("Npad", c_int), ("act", c_int), ("save", c_void_p), ("G", c_void_p)]
@@ -106,6 +117,7 @@ _SIGNATURES = {
     "robir_octree_counters_len": [],
     "robir_sphere_trace": [POINTER(SphereTraceParams), _I, _P],
     "robir_sphere_trace_launches": [_I],
+    "robir_pbr_loss": [POINTER(LossParams), _P],
     "robir_device_info": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     "robir_abi_version": [],
 }

@@ -1,0 +1,196 @@
+// Fused PBR-stage loss: tone map + masked L1/L2 + latent-smooth L1 + KL sparsity + white-light
+// regulariser, forward value AND every input gradient in one launch (the loss is a scalar, so the backward of the
+// autograd node is a multiplication by the upstream gradient).  Replaces ~180 elementwise / reduction launches of
+//   model/loss.py:61-125 (InvLoss.forward: get_rgb_loss, get_latent_smooth_loss, kl_divergence),
+//   model/color_correction.py:31-59,131-133 (ACES hdr2ldr with the learnable exposure shift),
+//   training/train_pbr.py:313-346 (white_loss, loss = rgb + kl + 0.1 smooth + white).
+// One CTA of 1024 threads strides over the rays; sums are reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace robir {
+
+struct LossParams {
+  int N;                 // rays
+  int n_lat;             // rows of the latent (hit points; == N in the fixed-capacity mode)
+  int M;                 // light SGs
+  int l2;                // 0: L1 (hotdog.conf loss_type), 1: L2
+  const float* sg_rgb; const float* indir_rgb;            // [N][3], row strides ld_sg / ld_ind (floats)
+  int ld_sg, ld_ind;
+  const float* gt;                                         // [N][3]
+  const unsigned char* mask;                               // [N] network_object_mask & object_mask
+  const float* adapt_illum;                                // [1] gamma.hdr_shift.adapt_illum
+  const float* albedo; const float* albedo_r;              // [N][3], strides ld_alb / ld_albr
+  int ld_alb, ld_albr;
+  const float* rough; const float* rough_r;                // [N] (column 0), strides ld_r / ld_rr
+  int ld_r, ld_rr;
+  const float* z;                                          // [n_lat][32] latent pre-activation
+  const unsigned char* z_valid;                            // [n_lat] or null (all valid)
+  const float* lgt;                                        // [M][7]
+  float w_rgb, w_kl, w_smooth, rho;
+  float* losses;                                           // [5] total, sg_rgb_loss, kl, smooth, white
+  float* g_pred;                                           // [N][3]  (gradient of sg_rgb and of indir_rgb)
+  float* g_adapt;                                          // [1]
+  float* g_albedo; float* g_albedo_r;                      // [N][3]
+  float* g_rough; float* g_rough_r;                        // [N]
+  float* g_z;                                              // [n_lat][32]
+  float* g_lgt;                                            // [M][7]
+};
+
+constexpr int kLossThreads = 1024;
+constexpr int kLossSums = 40;   // 0 rgb, 1 d rgb / d shift, 2 albedo L1, 3 rough L1, 4 n_valid, 5 white, 8..39 sigmoid(z) columns
+
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p) {
+  __shared__ float s_part[32][kLossSums];
+  __shared__ float s_tot[kLossSums];
+  __shared__ float s_dkl[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float acc[kLossSums];
+#pragma unroll
+  for (int i = 0; i < kLossSums; ++i) acc[i] = 0.f;
+
+  // exposure shift: clamp(clamp(10 a + 0.5, 0, 1), 1e-4, 1) ** 0.2   (color_correction.py:37-45)
+  const float a = __ldg(p.adapt_illum);
+  const float raw = 10.f * a + 0.5f;
+  const float shift = fminf(fmaxf(fminf(fmaxf(raw, 0.f), 1.f), 1e-4f), 1.f);
+  const bool shift_live = raw >= 1e-4f && raw <= 1.f;      // torch.clamp passes the gradient on [min, max] inclusive
+  const float inv_s02 = powf(shift, -0.2f);
+  const float inv_N = 1.f / (float)p.N;
+
+  // ---- pass 1 over rays: rgb term (value + gradient), smooth terms (value + gradient)
+  for (int i = tid; i < p.N; i += kLossThreads) {
+    const float m = p.mask[i] ? 1.f : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = p.sg_rgb[(size_t)i * p.ld_sg + c] + p.indir_rgb[(size_t)i * p.ld_ind + c];
+      const float num = x * (2.51f * x + 0.03f), den = x * (2.43f * x + 0.59f) + 0.14f;
+      const float ac = num / den;
+      const float dac = ((5.02f * x + 0.03f) * den - num * (4.86f * x + 0.59f)) / (den * den);
+      const float diff = ac * inv_s02 - p.gt[(size_t)i * 3 + c];
+      const float dper = (p.l2 ? 2.f * diff : sgnf(diff)) * m;            // d per / d ldr
+      acc[0] += (p.l2 ? diff * diff : fabsf(diff)) * m;
+      acc[1] += dper * ac;                                                // times d (s^-0.2) / d s below
+      p.g_pred[(size_t)i * 3 + c] = p.w_rgb * inv_N * dper * dac * inv_s02;
+      const float da = p.albedo[(size_t)i * p.ld_alb + c] - p.albedo_r[(size_t)i * p.ld_albr + c];
+      acc[2] += fabsf(da);
+      const float ga = p.w_smooth * sgnf(da) * inv_N * (1.f / 3.f);
+      p.g_albedo[(size_t)i * 3 + c] = ga;
+      p.g_albedo_r[(size_t)i * 3 + c] = -ga;
+    }
+    const float dr = p.rough[(size_t)i * p.ld_r] - p.rough_r[(size_t)i * p.ld_rr];
+    acc[3] += fabsf(dr);
+    const float gr = p.w_smooth * 0.2f * sgnf(dr) * inv_N;
+    p.g_rough[i] = gr;
+    p.g_rough_r[i] = -gr;
+  }
+  // ---- latent: column sums of sigmoid(z) over the valid rows
+  for (int i = tid; i < p.n_lat; i += kLossThreads) {
+    if (p.z_valid != nullptr && !p.z_valid[i]) continue;
+    acc[4] += 1.f;
+    const float4* zr = reinterpret_cast<const float4*>(p.z + (size_t)i * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(zr + q);
+      acc[8 + 4 * q] += 1.f / (1.f + expf(-v.x));
+      acc[9 + 4 * q] += 1.f / (1.f + expf(-v.y));
+      acc[10 + 4 * q] += 1.f / (1.f + expf(-v.z));
+      acc[11 + 4 * q] += 1.f / (1.f + expf(-v.w));
+    }
+  }
+  // ---- white-light regulariser: var_c(|mu| / (||mu|| + 1e-4)) averaged over the lobes, * 0.01  (train_pbr.py:313-317)
+  for (int i = tid; i < p.M; i += kLossThreads) {
+    const float* r = p.lgt + (size_t)i * 7;
+    const float x[3] = {r[4], r[5], r[6]};
+    const float c[3] = {fabsf(x[0]), fabsf(x[1]), fabsf(x[2])};
+    const float nrm = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const float mu = nrm + 1e-4f;
+    const float u[3] = {c[0] / mu, c[1] / mu, c[2] / mu};
+    const float ub = (u[0] + u[1] + u[2]) * (1.f / 3.f);
+    const float d[3] = {u[0] - ub, u[1] - ub, u[2] - ub};
+    acc[5] += 0.5f * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);          // unbiased variance over 3 channels
+    // d var / d u_k = d_k;  d u_k / d c_j = delta_kj / mu - c_k c_j / (mu^2 nrm)
+    const float dc = d[0] * c[0] + d[1] * c[1] + d[2] * c[2];
+    const float scale = 0.01f / (float)p.M;
+    float* g = p.g_lgt + (size_t)i * 7;
+    g[0] = g[1] = g[2] = g[3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float gcj = d[j] / mu - (nrm > 0.f ? dc * c[j] / (mu * mu * nrm) : 0.f);
+      g[4 + j] = scale * gcj * sgnf(x[j]);
+    }
+  }
+  // ---- block reduction (fixed order)
+#pragma unroll
+  for (int i = 0; i < kLossSums; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) s_part[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < kLossSums) {
+    float t = 0.f;
+    for (int w = 0; w < kLossThreads / 32; ++w) t += s_part[w][tid];
+    s_tot[tid] = t;
+  }
+  __syncthreads();
+  const float n_valid = fmaxf(s_tot[4], 1.f);
+  if (tid < 32) {
+    const float rh = s_tot[8 + tid] / n_valid;
+    const float term = p.rho * logf(p.rho / (rh + 1e-4f)) + (1.f - p.rho) * logf((1.f - p.rho) / (1.f - rh + 1e-4f));
+    s_part[0][tid] = term;                                                // reuse as scratch (all reads are done)
+    s_dkl[tid] = (-p.rho / (rh + 1e-4f) + (1.f - p.rho) / (1.f - rh + 1e-4f)) * (1.f / 32.f);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float kl = 0.f;
+    for (int j = 0; j < 32; ++j) kl += s_part[0][j];
+    kl *= (1.f / 32.f);
+    const float rgb = s_tot[0] * inv_N;
+    const float smooth = s_tot[2] * inv_N * (1.f / 3.f) + 0.2f * s_tot[3] * inv_N;
+    const float white = 0.01f * s_tot[5] / (float)p.M;
+    p.losses[0] = p.w_rgb * rgb + p.w_kl * kl + p.w_smooth * smooth + white;
+    p.losses[1] = rgb;
+    p.losses[2] = kl;
+    p.losses[3] = smooth;
+    p.losses[4] = white;
+    // d / d adapt_illum through ldr = aces / s^0.2
+    p.g_adapt[0] = shift_live ? p.w_rgb * inv_N * s_tot[1] * (-0.2f) * powf(shift, -1.2f) * 10.f : 0.f;
+  }
+  // ---- pass 2: KL gradient w.r.t. the latent
+  for (int i = tid; i < p.n_lat; i += kLossThreads) {
+    const bool ok = p.z_valid == nullptr || p.z_valid[i];
+    const float4* zr = reinterpret_cast<const float4*>(p.z + (size_t)i * 32);
+    float4* gz = reinterpret_cast<float4*>(p.g_z + (size_t)i * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        const float4 v = __ldg(zr + q);
+        const float k = p.w_kl / n_valid;
+        const float s0 = 1.f / (1.f + expf(-v.x)), s1 = 1.f / (1.f + expf(-v.y));
+        const float s2 = 1.f / (1.f + expf(-v.z)), s3 = 1.f / (1.f + expf(-v.w));
+        o.x = k * s_dkl[4 * q] * s0 * (1.f - s0);
+        o.y = k * s_dkl[4 * q + 1] * s1 * (1.f - s1);
+        o.z = k * s_dkl[4 * q + 2] * s2 * (1.f - s2);
+        o.w = k * s_dkl[4 * q + 3] * s3 * (1.f - s3);
+      }
+      gz[q] = o;
+    }
+  }
+}
+
+}  // namespace robir
+
+using namespace robir;
+
+extern "C" {
+
+// Value + gradients of the PBR-stage training loss.  All buffers are caller-owned; z rows are 32 floats (latent_dim).
+int robir_pbr_loss(const LossParams* p, void* stream) {
+  RB_REQUIRE(p->N > 0 && p->M > 0, "pbr_loss: empty batch");
+  pbr_loss_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,5 +1,7 @@
 """PBR-stage loss, the consumer of the hot path's outputs (model/loss.py:7-125 InvLoss, training/train_pbr.py:313-346
 pbr_step / white_loss).  Elementwise torch glue; fusing it into the render epilogue is a 'next' row."""
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -73,7 +75,107 @@ def white_loss(lgtSGs):
     return (lgt / mu).var(-1).mean() * 0.01
 
 
+class _FusedPBRLoss(torch.autograd.Function):
+    """loss = w_rgb * L(hdr2ldr(sg_rgb + indir_rgb), gt) + kl + 0.1 * smooth + white in one launch (csrc/loss.cu);
+    the kernel also writes every input gradient, so backward is a scaling by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, sg_rgb, indir_rgb, adapt_illum, albedo, albedo_r, rough, rough_r, z, lgt, gt, mask, z_valid, cfg):
+        from . import _lib
+        from ._lib import LossParams, check, lib, ptr, stream
+        w_rgb, w_kl, w_smooth, l2 = cfg
+        N, n_lat, M = sg_rgb.shape[0], z.shape[0], lgt.shape[0]
+        dev = sg_rgb.device
+
+        def rows(t, cols):          # [N, >= cols] view with unit column stride -> (tensor, row stride)
+            t = t.detach()
+            if t.dtype != torch.float32 or t.stride(-1) != 1 or t.dim() != 2:
+                t = t.float().reshape(t.shape[0], -1).contiguous()
+            return t, t.stride(0)
+
+        ts = {}
+        p = LossParams()
+        p.N, p.n_lat, p.M, p.l2 = N, n_lat, M, int(l2)
+        for name, t, ld in (("sg_rgb", sg_rgb, "ld_sg"), ("indir_rgb", indir_rgb, "ld_ind"), ("albedo", albedo, "ld_alb"),
+                            ("albedo_r", albedo_r, "ld_albr"), ("rough", rough, "ld_r"), ("rough_r", rough_r, "ld_rr")):
+            v, st = rows(t, 3)
+            ts[name] = v
+            setattr(p, name, ctypes.c_void_p(v.data_ptr()))       # views: data_ptr() already includes the offset
+            setattr(p, ld, st)
+        gt_c = gt.detach().to(dev).reshape(-1, 3).float().contiguous()
+        mask_c = mask.detach().to(torch.uint8).contiguous()
+        z_c = z.detach().float().contiguous()
+        zv = z_valid.detach().to(torch.uint8).contiguous() if z_valid is not None else None
+        lgt_c = lgt.detach().float().contiguous()
+        a_c = adapt_illum.detach().float().reshape(1).contiguous()
+        p.gt, p.mask, p.adapt_illum, p.z, p.z_valid, p.lgt = ptr(gt_c), ptr(mask_c), ptr(a_c), ptr(z_c), ptr(zv), ptr(lgt_c)
+        p.w_rgb, p.w_kl, p.w_smooth, p.rho = float(w_rgb), float(w_kl), float(w_smooth), 0.05
+        losses = torch.empty(5, device=dev)
+        g = dict(g_pred=torch.empty(N, 3, device=dev), g_adapt=torch.empty(1, device=dev),
+                 g_albedo=torch.empty(N, 3, device=dev), g_albedo_r=torch.empty(N, 3, device=dev),
+                 g_rough=torch.empty(N, device=dev), g_rough_r=torch.empty(N, device=dev),
+                 g_z=torch.empty(n_lat, 32, device=dev), g_lgt=torch.empty(M, 7, device=dev))
+        p.losses = ptr(losses)
+        for k, t in g.items():
+            setattr(p, k, ptr(t))
+        check(lib().robir_pbr_loss(ctypes.byref(p), stream()))
+        ctx.save_for_backward(*g.values())
+        ctx.shapes = (tuple(adapt_illum.shape), tuple(rough.shape), tuple(rough_r.shape))
+        ctx.mark_non_differentiable(losses)
+        return losses[0], losses
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_all):
+        g_pred, g_adapt, g_alb, g_albr, g_r, g_rr, g_z, g_lgt = ctx.saved_tensors
+        sa, sr, srr = ctx.shapes
+
+        def col0(g, shape):         # roughness arrives as [N, 1] or [N, 3] (expanded): the loss reads column 0 only
+            out = torch.zeros(shape, device=g.device)
+            out[:, 0] = g * g_loss
+            return out
+        return (g_pred * g_loss, g_pred * g_loss, (g_adapt * g_loss).reshape(sa), g_alb * g_loss, g_albr * g_loss,
+                col0(g_r, sr), col0(g_rr, srr), g_z * g_loss, g_lgt * g_loss, None, None, None, None)
+
+
+def fused_pbr_loss(model, loss_fn, model_outputs, ground_truth):
+    """pbr_step_loss on the fused kernel; None when its preconditions do not hold (CPU tensors, no cached latent)."""
+    mat = model.envmap_material_network
+    z = getattr(mat, "_last_spec_latent", None)
+    o = model_outputs
+    if z is None or not o['sg_rgb'].is_cuda or z.shape[1] != 32 or not z.requires_grad == torch.is_grad_enabled():
+        return None
+    if loss_fn.static_shapes:
+        z_valid = getattr(mat, "_last_latent_valid", None)
+        if z_valid is None or z.shape[0] != z_valid.shape[0]:
+            return None
+    else:
+        z_valid = None
+        if z.shape[0] != int(o['network_object_mask'].sum()):
+            return None
+    nm = o['network_object_mask'] & o['object_mask']
+    cfg = (loss_fn.sg_rgb_weight, loss_fn.kl_weight * 1.0, loss_fn.latent_smooth_weight * 0.1, loss_fn.l2)
+    loss, parts = _FusedPBRLoss.apply(o['sg_rgb'], o['indir_rgb'], model.gamma.hdr_shift.adapt_illum,
+                                      o['diffuse_albedo'], o['random_xi_diffuse_albedo'], o['roughness'],
+                                      o['random_xi_roughness'], z, mat.lgtSGs, ground_truth['rgb'], nm, z_valid, cfg)
+    if loss_fn.static_shapes:
+        normal_loss = torch.zeros((), device=loss.device)
+    else:
+        with torch.no_grad():
+            sm = o['surface_mask']
+            normal_loss = ((o['normal_map'][sm] - o['normals'][sm]) ** 2).mean()
+    return loss, {'sg_rgb_loss': parts[1], 'kl_loss': loss_fn.kl_weight * parts[2],
+                  'latent_smooth_loss': loss_fn.latent_smooth_weight * parts[3], 'normal_loss': normal_loss,
+                  'loss': loss_fn.sg_rgb_weight * parts[1]}
+
+
+FUSED_LOSS = True
+
+
 def pbr_step_loss(model, loss_fn, model_outputs, ground_truth, train_spec=True):
+    if FUSED_LOSS and train_spec:
+        fused = fused_pbr_loss(model, loss_fn, model_outputs, ground_truth)
+        if fused is not None:
+            return fused
     out = loss_fn(model_outputs, ground_truth, mat_model=model.envmap_material_network, train_idr=False,
                   train_spec=train_spec, hdr_fn=model.gamma.hdr_shift.hdr2ldr)
     loss = out['loss'] + out['kl_loss'] * 1.0 + out['latent_smooth_loss'] * 0.1

@@ -192,14 +192,20 @@ class IDRNetwork(nn.Module):
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
         r = pbr_get_sg_render(self, pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
                               valid=valid, precomputed=(nrm, mat))
-        m1 = mask[:, None]
-        one = lambda v: torch.where(m1, v.index_select(0, pos), torch.ones_like(v))      # back to ray order
-        for k in ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
-                  'indir_specular_rgb', 'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow',
-                  'random_xi_diffuse_albedo', 'metallic', 'random_xi_metallic'):
-            ret[k] = one(r[k])
-        ret['roughness'] = one(r['roughness'].expand(-1, 3))
-        ret['random_xi_roughness'] = one(r['random_xi_roughness'].expand(-1, 3))
+        # back to ray order, 1.0 for the rays that missed (implicit_differentiable_renderer.py:365-385): one gather over
+        # the column-concatenated outputs instead of one per tensor
+        keys = ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb', 'indir_specular_rgb',
+                'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow', 'random_xi_diffuse_albedo', 'metallic',
+                'random_xi_metallic', 'roughness', 'random_xi_roughness')
+        wide = torch.cat([r[k] for k in keys], 1)
+        wide = torch.where(mask[:, None], wide.index_select(0, pos), torch.ones((), device=dev))
+        c = 0
+        for k in keys:
+            w = r[k].shape[1]
+            ret[k] = wide[:, c:c + w]
+            c += w
+        ret['roughness'] = ret['roughness'].expand(-1, 3)
+        ret['random_xi_roughness'] = ret['random_xi_roughness'].expand(-1, 3)
         total, dev = points.shape[0], points.device
         ret.update({'final_t': torch.ones(total, 1, device=dev), 'gradient_error': torch.zeros((), device=dev),
                     'acc': torch.ones(total, 1, device=dev), 'bg_rgb': torch.ones(total, 3, device=dev),

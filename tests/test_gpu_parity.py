@@ -275,6 +275,39 @@ def test_pbr_step_vs_golden(golden, synth_sd16, model16, engine):
         grad_close(a, b, 5e-3, 3e-2, engine)
 
 
+def test_fused_loss_matches_torch_glue(golden, model16):
+    """csrc/loss.cu (value + all gradients in one launch) against the elementwise torch restatement of
+    model/loss.py:61-125 + train_pbr.py:313-346 on the same forward graph, L1 and L2."""
+    from robir_b200 import loss as L, rng
+    g = golden("pbr_step")
+    model16.generate()
+    N = g["pix"].shape[0]
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(g["pix"]).items()}
+    inp["hdr_shift"] = model16.gamma.hdr_shift.as_input().expand(N, 1)
+    with rng.replay([g["rnd_%d" % i] for i in range(9)]):
+        out = model16(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+    mat = model16.envmap_material_network
+    enc = mat.spec_brdf_encoder_layer.brdf_encoder_layer
+    leaves = [mat.lgtSGs, mat.specular_reflectance, model16.gamma.hdr_shift.adapt_illum, enc[0].bias, enc[8].weight]
+    gen = torch.Generator().manual_seed(5)
+    gt = {"rgb": torch.rand(1, N, 3, generator=gen)}
+    for loss_type in ("L1", "L2"):
+        fn = L.InvLoss(loss_type=loss_type)
+        L.FUSED_LOSS = False
+        try:
+            ref, ref_parts = L.pbr_step_loss(model16, fn, out, gt)
+        finally:
+            L.FUSED_LOSS = True
+        got, parts = L.pbr_step_loss(model16, fn, out, gt)
+        assert abs(got.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item())), loss_type
+        for k in ("sg_rgb_loss", "kl_loss", "latent_smooth_loss", "loss"):
+            assert abs(parts[k].item() - ref_parts[k].item()) < 1e-5 * max(1.0, abs(ref_parts[k].item())), k
+        g_ref = torch.autograd.grad(ref, leaves, retain_graph=True)
+        g_got = torch.autograd.grad(got, leaves, retain_graph=True)
+        for a, b in zip(g_got, g_ref):
+            assert (a - b).abs().max().item() <= 2e-4 * max(1e-7, b.abs().max().item()), loss_type
+
+
 def test_pbr_forward_properties_full_size(model16, synth_sd16):
     """BASELINE-size batch (1024 rays): size-independent properties -- determinism under replayed randoms, outputs of
     non-hit rays keep the reference's 1.0 fill, and hit-ray outputs do not depend on which other rays share the batch
