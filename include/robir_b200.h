@@ -137,8 +137,16 @@ int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals,
                        uint32_t* bits /*[n][M]*/, int* lobe_off /*[n][M+1]*/, int* start /*[n]*/, int* rowA,
                        int* rowB /*[n*roundup(M*S,tile_rows)]*/, int* n_tiles /*[1]*/,
                        long long* n_pairs /*[1], accumulated*/, void* stream);
-int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, const float* normals, const float* dirs, int* rowA,
-                    int* rowB, int* n_tiles, long long* n_pairs, void* stream);
+/* a_mod > 0: the n "points" are copies of the same a_mod points (rowA = (q / S) % a_mod, normals [a_mod][3]) */
+int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, int a_mod, const float* normals, const float* dirs,
+                    int* rowA, int* rowB, int* n_tiles, long long* n_pairs, void* stream);
+/* sampling inputs shared by the direct and the indirect get_specular_visibility call (model/sg_render.py:198-225 on the
+ * warp of :417-428), written twice (rows i and n + i): ref / wl [2n][3], sharp [2n], sg_range [1]; wlam [n] and
+ * argmin [1] feed the backward, whose only differentiable input is the roughness */
+int robir_spec_prep_fwd(int n, const float* normal, const float* view, const float* rough, const unsigned char* valid,
+                        float* ref, float* wl, float* sharp, float* sg_range, float* wlam, int* argmin, void* stream);
+int robir_spec_prep_bwd(int n, const float* rough, const float* wlam, const int* argmin, const float* g_sharp,
+                        const float* g_sg_range, float* g_rough, void* stream);
 
 /* ---- a10-a12: fused visibility MLP over a pair list: relu(tabA[a]+tabB[b]) -> 3 x (256x256, ReLU) -> sigmoid(z1-z0)
  * replaces the 2M-row VisModel batches of get_diffuse_visibility (model/sg_render.py:157-173) and

@@ -94,7 +94,9 @@ _SIGNATURES = {
     "robir_sample_dirs_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "robir_sample_dirs_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_diffuse_rows": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "robir_spec_rows": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "robir_spec_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "robir_spec_prep_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "robir_spec_prep_bwd": [_I, _P, _P, _P, _P, _P, _P, _P],
     "robir_tc_pack_layer": [_P, _I, _I, _I, _I, _I, _P, _P],
     "robir_tc_image_bytes": [_I, _I],
     "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P],

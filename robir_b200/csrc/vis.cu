@@ -530,7 +530,8 @@ __global__ void spec_reduce_bwd_kernel(int n, int S, int inv, const int* __restr
 }
 
 // specular row list: rowB[q] = q if n_i . dir_q > 1e-6 else -1; rows beyond n*S (tile padding) = -1
-__global__ void spec_rows_kernel(int n, int S, int rows_padded, int pad, const float* __restrict__ normals,
+// a_mod > 0: the list concatenates copies of the same a_mod points (direct + indirect BRDF-lobe queries in one launch)
+__global__ void spec_rows_kernel(int n, int S, int rows_padded, int pad, int a_mod, const float* __restrict__ normals,
                                  const float* __restrict__ dirs, int* __restrict__ rowA, int* __restrict__ rowB,
                                  int* __restrict__ n_tiles, long long* __restrict__ n_pairs) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,6 +540,7 @@ __global__ void spec_rows_kernel(int n, int S, int rows_padded, int pad, const f
   int a = 0, b = -1;
   if (q < n * S) {
     a = q / S;
+    if (a_mod > 0) a %= a_mod;
     const float* d = dirs + 3 * q;
     const float dp = __fadd_rn(__fadd_rn(__fmul_rn(normals[3 * a], d[0]), __fmul_rn(normals[3 * a + 1], d[1])),
                                __fmul_rn(normals[3 * a + 2], d[2]));
@@ -548,6 +550,75 @@ __global__ void spec_rows_kernel(int n, int S, int rows_padded, int pad, const f
   rowB[q] = b;
   const unsigned live = __ballot_sync(__activemask(), b >= 0);
   if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long*)n_pairs, (unsigned long long)__popc(live));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BRDF-lobe sampling inputs for get_specular_visibility (model/sg_render.py:198-225) from the warp of render_with_sg
+// (:417-428), once for the direct and the indirect call: per point
+//   vdl = clamp(n.v, 0), ref = 2 vdl n - v (reflection axis), wl = ref / (|ref| + 1e-6), wlam = (2 / r^4) / (4 vdl + 1e-6),
+//   sharp = clip(wlam, 0.1, 50);   sg_range = clamp(min over the valid points of sharp, max = 1)  (batch-global, :220-222)
+// Outputs are written twice (rows i and n + i) so that both calls share one launch chain.  One CTA.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) spec_prep_fwd_kernel(int n, const float* __restrict__ normal,
+                                                                const float* __restrict__ view,
+                                                                const float* __restrict__ rough,
+                                                                const unsigned char* __restrict__ valid,
+                                                                float* __restrict__ ref, float* __restrict__ wl,
+                                                                float* __restrict__ sharp, float* __restrict__ sg_range,
+                                                                float* __restrict__ wlam_out, int* __restrict__ argmin) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  float best = INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float nx = normal[3 * i], ny = normal[3 * i + 1], nz = normal[3 * i + 2];
+    const float vx = view[3 * i], vy = view[3 * i + 1], vz = view[3 * i + 2];
+    const float r = rough[i];
+    const float vdl = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(nx, vx), __fmul_rn(ny, vy)), __fmul_rn(nz, vz)), 0.f);
+    const float rx = 2.f * vdl * nx - vx, ry = 2.f * vdl * ny - vy, rz = 2.f * vdl * nz - vz;
+    const float inv = 1.f / (sqrtf(rx * rx + ry * ry + rz * rz) + 1e-6f);
+    const float wlam = (2.f / (r * r * r * r)) / (4.f * vdl + 1e-6f);
+    const float sh = fminf(fmaxf(wlam, 0.1f), 50.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t o = (size_t)h * n + i;
+      ref[3 * o] = rx; ref[3 * o + 1] = ry; ref[3 * o + 2] = rz;
+      wl[3 * o] = rx * inv; wl[3 * o + 1] = ry * inv; wl[3 * o + 2] = rz * inv;
+      sharp[o] = sh;
+    }
+    wlam_out[i] = wlam;
+    if ((valid == nullptr || valid[i]) && (sh < best || (sh == best && i < best_i))) { best = sh; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov < best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_v[w] < best || (s_v[w] == best && s_i[w] < best_i)) { best = s_v[w]; best_i = s_i[w]; }
+    sg_range[0] = fminf(best, 1.f);
+    argmin[0] = (best <= 1.f && best_i != 0x7fffffff) ? best_i : -1;   // row that receives d / d sg_range
+  }
+}
+
+// g_rough[i] = (g_sharp[i] + g_sharp[n + i] + [i == argmin] g_sg_range) * [0.1 <= wlam <= 50] * d wlam / d r
+__global__ void spec_prep_bwd_kernel(int n, const float* __restrict__ rough, const float* __restrict__ wlam,
+                                     const int* __restrict__ argmin, const float* __restrict__ g_sharp,
+                                     const float* __restrict__ g_sg_range, float* __restrict__ g_rough) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float w = wlam[i];
+  float g = 0.f;
+  if (w >= 0.1f && w <= 50.f) {
+    g = g_sharp[i] + g_sharp[n + i];
+    if (argmin[0] == i) g += g_sg_range[0];
+    g *= -4.f * w / rough[i];
+  }
+  g_rough[i] = g;
 }
 
 }  // namespace robir
@@ -633,16 +704,16 @@ int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals,
   return 0;
 }
 
-int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, const float* normals, const float* dirs, int* rowA,
-                    int* rowB, int* n_tiles, long long* n_pairs, void* stream) {
+int robir_spec_rows(int n, int S, int rows_padded, int tile_rows, int a_mod, const float* normals, const float* dirs,
+                    int* rowA, int* rowB, int* n_tiles, long long* n_pairs, void* stream) {
   RB_REQUIRE((tile_rows == 64 || tile_rows == 128) && rows_padded % tile_rows == 0 && rows_padded >= n * S,
              "spec_rows: rows_padded must be a multiple of tile_rows (64 or 128)");
   if (rows_padded == 0) {
     RB_CHECK_CUDA(cudaMemsetAsync(n_tiles, 0, sizeof(int), (cudaStream_t)stream));
     return 0;
   }
-  spec_rows_kernel<<<cdiv(rows_padded, 256), 256, 0, (cudaStream_t)stream>>>(n, S, rows_padded, tile_rows, normals,
-                                                                             dirs, rowA, rowB, n_tiles, n_pairs);
+  spec_rows_kernel<<<cdiv(rows_padded, 256), 256, 0, (cudaStream_t)stream>>>(n, S, rows_padded, tile_rows, a_mod,
+                                                                             normals, dirs, rowA, rowB, n_tiles, n_pairs);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -715,6 +786,26 @@ int robir_spec_reduce_bwd(int n, int S, int inv, const int* rowB, const float* v
   if (n == 0) return 0;
   spec_reduce_bwd_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(n, S, inv, rowB, vis, w, out, g_out, g_vis,
                                                                          g_w);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Shared sampling inputs of the two get_specular_visibility calls of render_with_all_sg (direct + indirect), doubled:
+// ref / wl [2n][3], sharp [2n]; sg_range [1]; wlam [n] and argmin [1] are kept for the backward.
+int robir_spec_prep_fwd(int n, const float* normal, const float* view, const float* rough, const unsigned char* valid,
+                        float* ref, float* wl, float* sharp, float* sg_range, float* wlam, int* argmin, void* stream) {
+  if (n == 0) return 0;
+  spec_prep_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, normal, view, rough, valid, ref, wl, sharp, sg_range, wlam,
+                                                             argmin);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int robir_spec_prep_bwd(int n, const float* rough, const float* wlam, const int* argmin, const float* g_sharp,
+                        const float* g_sg_range, float* g_rough, void* stream) {
+  if (n == 0) return 0;
+  spec_prep_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, rough, wlam, argmin, g_sharp, g_sg_range,
+                                                                       g_rough);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -119,6 +119,32 @@ def tc_selftest(A, W):
     return D
 
 
+_point_tab = {"key": None, "tab": None}
+
+
+class point_table_scope:
+    """Inside the scope the layer-0 point table W0[:, :63] PE(p) + b0 is computed once per (points, weights) and shared
+    by the diffuse and the BRDF-lobe visibility queries of one render_with_all_sg call."""
+
+    def __enter__(self):
+        _point_tab["key"], _point_tab["tab"], self.on = None, None, True
+        _point_tab["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _point_tab["key"], _point_tab["tab"], _point_tab["on"] = None, None, False
+        return False
+
+
+def point_table(W, points):
+    if not _point_tab.get("on"):
+        return pe_linear(points, W["Wt0p"], W["b0"])
+    key = (points.data_ptr(), tuple(points.shape), id(W))
+    if _point_tab["key"] != key:
+        _point_tab["key"], _point_tab["tab"] = key, pe_linear(points, W["Wt0p"], W["b0"])
+    return _point_tab["tab"]
+
+
 def pe_linear(x, Wt, bias):
     x = f32(x)
     n = x.shape[0]
@@ -278,7 +304,7 @@ class _DiffuseVis(torch.autograd.Function):
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
         check(lib().robir_diffuse_rows(n, M, S, T, ptr(normals), ptr(dirs), ptr(bits), ptr(lobe_off), ptr(start),
                                        ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
-        tabA = pe_linear(points, W["Wt0p"], W["b0"])
+        tabA = point_table(W, points)
         tabB = pe_linear(dirs, W["Wt0d"], None)
         max_tiles = n * cap // T
         vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_grad)
@@ -306,44 +332,90 @@ class _DiffuseVis(torch.autograd.Function):
 
 class _SpecVis(torch.autograd.Function):
     """brdf_vis[n] = weighted mean of the visibility MLP over S per-point sample directions
-    (model/sg_render.py:242-301, single view)."""
+    (model/sg_render.py:242-301, single view).  inv = None: the batch holds the direct (rows [0, n)) and the indirect
+    (rows [n, 2n), class 0 = "inv") call of render_with_all_sg over the same n points -> out [2n]."""
 
     @staticmethod
     def forward(ctx, points, normals, dirs, w, S, inv, testing, weights, need_grad):
         W = weights.get()
         points, normals, dirs, w = map(f32, (points, normals, dirs, w))
         n = points.shape[0]
+        copies = 2 if inv is None else 1
+        nq = n * copies
         T = tile_rows()
-        rows = ((n * S + T - 1) // T) * T
+        rows = ((nq * S + T - 1) // T) * T
         dev = points
         rowA = _empty(rows, dtype=torch.int32, like=dev)
         rowB = _empty(rows, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
-        check(lib().robir_spec_rows(n, S, rows, T, ptr(normals), ptr(dirs), ptr(rowA), ptr(rowB), ptr(n_tiles),
-                                    ptr(Stats.pairs_tensor(dev)), stream()))
-        tabA = pe_linear(points, W["Wt0p"], W["b0"])
+        check(lib().robir_spec_rows(nq, S, rows, T, n if copies > 1 else 0, ptr(normals), ptr(dirs), ptr(rowA),
+                                    ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
+        tabA = point_table(W, points)
         tabB = pe_linear(dirs, W["Wt0d"], None)
         vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, rows // T, need_grad)
-        out = _empty(n, like=dev)
-        check(lib().robir_spec_reduce_fwd(n, S, int(inv), int(testing), ptr(rowB), ptr(vis), ptr(w), ptr(out),
-                                          stream()))
+        out = _empty(nq, like=dev)
+        for c in range(copies):
+            o = c * n * S
+            check(lib().robir_spec_reduce_fwd(n, S, int(inv) if inv is not None else c, int(testing),
+                                              c_ptr(rowB, o * 4), c_ptr(vis, o * 4), c_ptr(w, o * 4),
+                                              c_ptr(out, c * n * 4), stream()))
         if need_grad:
             ctx.save_for_backward(dirs, w, rowB, n_tiles, vis, mask, out)
-            ctx.meta = (n, S, int(inv), rows, weights, T, ENGINE["vis"])
+            ctx.meta = (n, S, inv, rows, weights, T, ENGINE["vis"])
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         dirs, w, rowB, n_tiles, vis, mask, out = ctx.saved_tensors
         n, S, inv, rows, weights, T, engine = ctx.meta
+        copies = 2 if inv is None else 1
         W = weights.get()
         g_out = f32(g_out)
         g_vis = _zeros(rows, like=vis)
-        g_w = _empty(n * S, like=vis)
-        check(lib().robir_spec_reduce_bwd(n, S, inv, ptr(rowB), ptr(vis), ptr(w), ptr(out), ptr(g_out), ptr(g_vis),
-                                          ptr(g_w), stream()))
+        g_w = _empty(n * copies * S, like=vis)
+        for c in range(copies):
+            o = c * n * S
+            check(lib().robir_spec_reduce_bwd(n, S, int(inv) if inv is not None else c, c_ptr(rowB, o * 4),
+                                              c_ptr(vis, o * 4), c_ptr(w, o * 4), c_ptr(out, c * n * 4),
+                                              c_ptr(g_out, c * n * 4), c_ptr(g_vis, o * 4), c_ptr(g_w, o * 4), stream()))
         g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, rows // T, vis, g_vis, mask, dirs, engine)
         return None, None, g_dirs, g_w, None, None, None, None, None
+
+
+class _SpecPrep(torch.autograd.Function):
+    """Sampling inputs shared by the direct and the indirect BRDF-lobe visibility call (csrc/vis.cu spec_prep_*):
+    (normal, view, roughness [n,1], valid) -> ref [2n,3], wl [2n,3], sharp [2n], sg_range [1].  Only the roughness is
+    differentiable (render_with_all_sg passes detached normals / view directions, sg_render.py:324-327)."""
+
+    @staticmethod
+    def forward(ctx, normal, view, rough, valid):
+        normal, view, r = f32(normal), f32(view), f32(rough).reshape(-1)
+        n = normal.shape[0]
+        ref, wl = _empty(2 * n, 3, like=normal), _empty(2 * n, 3, like=normal)
+        sharp, sg_range, wlam = _empty(2 * n, like=normal), _empty(1, like=normal), _empty(n, like=normal)
+        argmin = _empty(1, dtype=torch.int32, like=normal)
+        v8 = valid.to(torch.uint8).contiguous() if valid is not None else None
+        check(lib().robir_spec_prep_fwd(n, ptr(normal), ptr(view), ptr(r), ptr(v8), ptr(ref), ptr(wl), ptr(sharp),
+                                        ptr(sg_range), ptr(wlam), ptr(argmin), stream()))
+        ctx.save_for_backward(r, wlam, argmin)
+        ctx.rshape = tuple(rough.shape)
+        ctx.mark_non_differentiable(ref, wl)
+        return ref, wl, sharp, sg_range
+
+    @staticmethod
+    def backward(ctx, _g_ref, _g_wl, g_sharp, g_range):
+        r, wlam, argmin = ctx.saved_tensors
+        n = r.shape[0]
+        g_sharp = f32(g_sharp) if g_sharp is not None else _zeros(2 * n, like=r)
+        g_range = f32(g_range) if g_range is not None else _zeros(1, like=r)
+        g_rough = _empty(n, like=r)
+        check(lib().robir_spec_prep_bwd(n, ptr(r), ptr(wlam), ptr(argmin), ptr(g_sharp), ptr(g_range), ptr(g_rough),
+                                        stream()))
+        return None, None, g_rough.reshape(ctx.rshape), None
+
+
+def spec_prep(normal, view, rough, valid=None):
+    return _SpecPrep.apply(normal, view, rough, valid)
 
 
 def diffuse_vis(points, normals, dirs, w, M, S, weights, need_grad):
@@ -730,12 +802,16 @@ class _FusedMLP(torch.autograd.Function):
         check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
         grads = []
         if ctx.want_param_grad:
-            prev = x0
-            for l, d in enumerate(packed):
+            # dW_l = G_l^T A_{l-1} (plain library GEMMs) and db_l: independent per layer -> parallel branches
+            prevs = [x0] + list(saves)
+
+            def layer_grads(l):
+                d = packed[l]
                 G = Gs[l][:, :d["N"]]
-                grads.append(G.t() @ prev[:, :d["K"]])     # plain library GEMM: dW = G^T A
-                grads.append(G.sum(0))
-                prev = saves[l] if l < len(saves) else None
+                return G.t() @ prevs[l][:, :d["K"]], G.sum(0)
+            for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))]):
+                grads.append(gw)
+                grads.append(gb)
         gx = g_x[:, :packed[0]["K"]] if chain.in_mode == 0 else None
         g_extra = g_x[:, 63].reshape(ctx.extra_shape) if ctx.has_extra else None
         return (None, gx, g_extra, None, None, None, None, *grads)

@@ -62,6 +62,15 @@ def rand(shape, device):
     return _draw(torch.rand, shape, device)
 
 
+def rand_pairs(n, S, device):
+    """theta, phi for two consecutive get_specular_visibility calls, stacked: ([2n, S], [2n, S]).  Host / replay modes
+    draw theta_1, phi_1, theta_2, phi_2 in the reference's order; the device mode draws each stack at once."""
+    if _mode == "device" and _record is None:
+        return rand((2 * n, S), device), rand((2 * n, S), device)
+    u = [rand((n, S), device) for _ in range(4)]
+    return torch.cat([u[0], u[2]], 0), torch.cat([u[1], u[3]], 0)
+
+
 def randn(shape, device):
     return _draw(torch.randn, shape, device)
 

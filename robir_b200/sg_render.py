@@ -95,6 +95,13 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
                          "not on the accelerated path (CESR extras are a later row, SURVEY.md section 8f)")
     if lgtSGs.dim() != 2:
         raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
+    with ops.point_table_scope():
+        return _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
+                                   indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid)
+
+
+def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
+                        indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid):
     n = normal.shape[0]
     M = lgtSGs.shape[0]
     viewdirs = viewdirs.detach()
@@ -104,15 +111,25 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
     light_vis = get_diffuse_visibility(points, normal.detach(), VisModel, lobes, lambdas, nsamp=32,
                                        testing=testing).permute(1, 0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
-    wl, wlam = _spec_warp(normal, viewdirs, roughness)
-    bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing, inv=False,
-                                     valid=valid)
     bv_ind = None
     if indir_lgtSGs is not None:
         if indir_integral is None:
             raise RobirError("render_with_all_sg: indirect SGs need indir_integral (PBR-stage configuration)")
-        bv_ind = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
-                                         inv=True, valid=valid)
+        # both get_specular_visibility calls (inv = False / True) share their sampling inputs: one prep kernel, one
+        # launch chain over 2n "points" (rows [0, n) direct, [n, 2n) indirect)
+        S = 8
+        dev = points.device
+        ref, wl2, sharp, sg_range = ops.spec_prep(normal, viewdirs, roughness, valid)
+        u_theta, u_phi = rng.rand_pairs(n, S, dev)           # theta, phi (direct), theta, phi (indirect)
+        dirs, w = ops.sample_dirs(ref, wl2, sharp, sharp, sg_range, u_theta, u_phi, False)
+        need_grad = torch.is_grad_enabled() and not testing and (dirs.requires_grad or w.requires_grad)
+        bv = ops.spec_vis(points.detach(), normal.detach(), dirs.detach() if testing else dirs, w, S, None, testing,
+                          _weights_of(VisModel), need_grad)
+        bv_dir, bv_ind = bv[:n], bv[n:]
+    else:
+        wl, wlam = _spec_warp(normal, viewdirs, roughness)
+        bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
+                                         inv=False, valid=valid)
     outs = ops.sg_render(normal.detach(), viewdirs, roughness, diffuse_albedo, specular_reflectance.reshape(1), lgtSGs,
                          indir_lgtSGs, light_vis.contiguous(), bv_dir, bv_ind, indir_integral, lin_diff)
     sg_rgb, sg_spec, sg_diff, vis_shadow, ind_rgb, ind_spec, ind_diff = outs
