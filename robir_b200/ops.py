@@ -710,6 +710,7 @@ class MlpChain:
         return ch
 
     weightnorm = False
+    wgrad_streams = None      # side streams of this chain's weight-gradient GEMMs (created on first backward)
 
     def params(self):
         if self.weightnorm:
@@ -809,7 +810,9 @@ class _FusedMLP(torch.autograd.Function):
                 d = packed[l]
                 G = Gs[l][:, :d["N"]]
                 return G.t() @ prevs[l][:, :d["K"]], G.sum(0)
-            for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))]):
+            if chain.wgrad_streams is None:
+                chain.wgrad_streams = [torch.cuda.Stream() for _ in range(len(packed) - 1)]
+            for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))], chain.wgrad_streams):
                 grads.append(gw)
                 grads.append(gb)
         gx = g_x[:, :packed[0]["K"]] if chain.in_mode == 0 else None
@@ -844,18 +847,23 @@ def _tensors_in(obj):
 _fork_state = {"depth": 0, "next": 0}
 
 
-def fork_join(fns):
-    """Run the callables concurrently: fns[0] on the current stream, the others on pooled side streams that fork from
-    and join back into it.  Host-side call order (hence the order of random draws) stays sequential.  Calls nest: every
-    branch of one outermost call gets its own stream, so sibling sub-branches never queue behind each other."""
+def fork_join(fns, streams=None):
+    """Run the callables concurrently: fns[0] on the current stream, the others on side streams that fork from and join
+    back into it.  Host-side call order (hence the order of random draws) stays sequential.  Calls nest: every branch
+    of one outermost call gets its own pooled stream, so sibling sub-branches never queue behind each other.
+    streams: caller-owned side streams instead of the pool (autograd backward nodes, whose joins must not wait on
+    unrelated work queued on the forward's pool streams)."""
     main = torch.cuda.current_stream()
     st = _fork_state
     base = st["next"]
-    st["next"] = base + len(fns) - 1
+    if streams is None:
+        st["next"] = base + len(fns) - 1
+        while len(_side_streams) < st["next"]:
+            _side_streams.append(torch.cuda.Stream())
+        sides = _side_streams[base:base + len(fns) - 1]
+    else:
+        sides = list(streams)[:len(fns) - 1]
     st["depth"] += 1
-    while len(_side_streams) < st["next"]:
-        _side_streams.append(torch.cuda.Stream())
-    sides = _side_streams[base:base + len(fns) - 1]
     results = [None] * len(fns)
     try:
         fork = torch.cuda.Event()
