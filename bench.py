@@ -202,7 +202,7 @@ def main():
     model.generate()                                   # octree build: excluded from the metric
     loss_fn = InvLoss()
     params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters())
-    opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=True)   # training/train_pbr.py:104-105, hotdog.conf:25
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=bool(int(os.environ.get("ROBIR_FUSED_ADAM", "1"))))   # training/train_pbr.py:104-105, hotdog.conf:25
     reducer = rdist.GradAllReducer(params)
     pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
 
@@ -222,6 +222,7 @@ def main():
         loss.backward()
         reducer()
         opt.step()
+        ops.invalidate_packed_weights()     # fused Adam updates in place without bumping tensor versions
         return loss, out["network_object_mask"]
 
     graphed = None
@@ -299,6 +300,7 @@ def main():
         def train_step(uv, om, gt):   # noqa: F811
             loss = graphed._fwd_bwd()
             opt.step()
+            ops.invalidate_packed_weights()
             return loss, None
     ops.PROFILE = []
     ops.Stats.reset()

@@ -23,6 +23,9 @@ def __getattr__(name):
     if name == "install":
         from .integration import install
         return install
+    if name == "invalidate_packed_weights":
+        from .ops import invalidate_packed_weights
+        return invalidate_packed_weights
     if name in ("InvLoss", "pbr_step_loss"):
         from . import loss
         return getattr(loss, name)

@@ -4,7 +4,7 @@ collapse into one graph launch.  Needs ``model.static_shapes = True`` (no data-d
 device-side random numbers."""
 import torch
 
-from . import rng
+from . import ops, rng
 from .loss import pbr_step_loss
 
 
@@ -35,6 +35,7 @@ class GraphedPBRStep:
                 if split:
                     reducer()
                 self.opt.step()
+                ops.invalidate_packed_weights()   # optimizers with fused multi-tensor kernels do not bump versions
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
@@ -53,6 +54,7 @@ class GraphedPBRStep:
 
     def _fwd_bwd(self):
         m = self.model
+        ops.invalidate_packed_weights()      # the optimizer ran since the last forward: trained weights are re-packed once
         inp = {"uv": self.uv, "object_mask": self.om, "pose": self.pose, "intrinsics": self.K,
                "hdr_shift": m.gamma.hdr_shift.as_input().expand(self.n, 1)}
         out = m(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)

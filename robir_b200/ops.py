@@ -24,14 +24,38 @@ def _zeros(*shape, dtype=torch.float32, like=None):
 # ----------------------------------------------------------------------------------------------------------------------
 # weight packing (cached on parameter versions; weights that are being trained are re-packed when they change)
 # ----------------------------------------------------------------------------------------------------------------------
+_pack_epoch = [0]
+
+
+def invalidate_packed_weights():
+    """Call after an in-place parameter update that does not bump the tensors' version counters (e.g.
+    torch.optim.Adam(fused=True): its multi-tensor kernel leaves ``_version`` untouched), so that the packed copies of
+    trainable weights are rebuilt on the next use.  Optimizers that go through ordinary in-place ops (the reference's
+    torch.optim.Adam default) need nothing."""
+    _pack_epoch[0] += 1
+
+
 class _PackCache:
+    """Packed / transposed / tensor-core images of a set of parameters, keyed on their storage and version counters.
+    While a CUDA graph is being captured, parameters that are being trained are always re-packed: the replayed graph
+    must contain the packing kernels whatever the cache state was at capture time (the optimizer runs inside the same
+    graph)."""
+
     def __init__(self):
         self.key = None
         self.val = None
 
     def get(self, tensors, build):
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
-        if key != self.key:
+        # "being trained" = has received a gradient (an optimizer may have updated it in place since the last use)
+        trainable = any(t.requires_grad and t.grad is not None for t in tensors)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + \
+            ((_pack_epoch[0],) if trainable else ())
+        # Safety net for callers that capture a graph without ever announcing parameter updates: parameters that
+        # have received a gradient are re-packed on every use during capture.  GraphedPBRStep announces every step
+        # (invalidate_packed_weights at the top of the captured region), which makes the key change exactly once.
+        capturing = trainable and _pack_epoch[0] == 0 and tensors[0].is_cuda and \
+            torch.cuda.is_current_stream_capturing()
+        if key != self.key or capturing:
             self.val = build()
             self.key = key
         return self.val
@@ -778,6 +802,7 @@ class _FusedMLP(torch.autograd.Function):
         p.out, p.ldo = ptr(out), n_out
         check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
         ctx.chain, ctx.n, ctx.want_param_grad = chain, n, want_param_grad
+        ctx.packed = packed                 # the backward of this step uses the very same packed copies
         ctx.has_extra = extra is not None
         ctx.save_for_backward(x, extra, noise, x0, n_active, *saves)
         ctx.noise_scale, ctx.segments = noise_scale, segments
@@ -787,7 +812,7 @@ class _FusedMLP(torch.autograd.Function):
     def backward(ctx, g_out):
         chain, n = ctx.chain, ctx.n
         x, extra, noise, x0, n_active, *saves = ctx.saved_tensors
-        packed = chain.packed()
+        packed = ctx.packed
         g_out = f32(g_out)
         p = _mlp_params(chain, packed, n, x, extra, noise, ctx.noise_scale, n_active, ctx.segments)
         for l, sv in enumerate(saves):

@@ -67,6 +67,15 @@ class IDRNetwork(nn.Module):
             self.ray_tracer.bind(self.implicit_network)
             self.octree_ray_tracer.generate(sdf_fn, None, implicit_network=self.implicit_network)
 
+    def prepack(self):
+        """Touch the packed weight copies of every fused chain that already exists (they are created lazily by the
+        first forward); a no-op for copies that are up to date."""
+        for mod in self.modules():
+            for v in list(mod.__dict__.values()):
+                if isinstance(v, ops.MlpChain):
+                    v.packed()
+        return None
+
     def _trace(self, tracer, cam_loc, object_mask, ray_dirs):
         return tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc, object_mask=object_mask,
                       ray_directions=ray_dirs)
@@ -156,8 +165,11 @@ class IDRNetwork(nn.Module):
         object_mask = input["object_mask"].reshape(-1)
         ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
         batch_size, num_pixels, _ = ray_dirs.shape
-        with torch.no_grad():
-            _, mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+        def trace():
+            with torch.no_grad():
+                return self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+        # packed copies of the weights that are being trained are rebuilt while the tracer walks the octree
+        (_, mask, dists), _ = ops.fork_join([trace, self.prepack])
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
         ray_dirs = ray_dirs.reshape(-1, 3)
         total, dev = points.shape[0], points.device
