@@ -220,19 +220,28 @@ def sample_dirs(axis_f, axis_w, sharp, lam_w, sg_range, u_theta, u_phi, renorm):
 # fused visibility queries
 # ----------------------------------------------------------------------------------------------------------------------
 class Stats:
-    """Device-side counters of executed work (for the algorithmic-FLOP roofline)."""
-    n_pairs = None  # int64 device tensor, accumulated over calls
+    """Device-side counters of executed work (for the algorithmic-FLOP roofline): executed
+    visibility queries of the per-lobe diffuse list ([0]) and of the BRDF-lobe lists ([1]), accumulated over calls."""
+    n_pairs = None          # int64 device tensor [2]
 
     @classmethod
-    def pairs_tensor(cls, like):
+    def pairs_tensor(cls, like, kind=0):
         if cls.n_pairs is None or cls.n_pairs.device != like.device:
-            cls.n_pairs = torch.zeros(1, dtype=torch.int64, device=like.device)
-        return cls.n_pairs
+            cls.n_pairs = torch.zeros(2, dtype=torch.int64, device=like.device)
+        return cls.n_pairs[kind:kind + 1]
 
     @classmethod
     def reset(cls):
         if cls.n_pairs is not None:
             cls.n_pairs.zero_()
+
+    @classmethod
+    def total(cls):
+        return int(cls.n_pairs.sum().item()) if cls.n_pairs is not None else 0
+
+    @classmethod
+    def diffuse(cls):
+        return int(cls.n_pairs[0].item()) if cls.n_pairs is not None else 0
 
 
 class active_rows:
@@ -373,7 +382,7 @@ class _SpecVis(torch.autograd.Function):
         rowB = _empty(rows, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
         check(lib().robir_spec_rows(nq, S, rows, T, n if copies > 1 else 0, ptr(normals), ptr(dirs), ptr(rowA),
-                                    ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
+                                    ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev, 1)), stream()))
         tabA = point_table(W, points)
         tabB = pe_linear(dirs, W["Wt0d"], None)
         vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, rows // T, need_grad)
