@@ -234,6 +234,12 @@ typedef struct {
 int robir_pack_pad(const float* W, int N, int K, float* out /*[Np][Kp]*/, int Np, int Kp, void* stream);
 int robir_mlp_fwd(const robir_mlp_params* p, int sm_count, void* stream);
 int robir_mlp_bwd(const robir_mlp_params* p, int sm_count, void* stream);
+/* weight / bias gradient of one layer of the chain from its pre-activation gradient G (robir_mlp_bwd) and its input A
+ * (x0_save or the previous layer's save): dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums (db may be NULL).
+ * splits > 1 divides the rows over that many CTAs per 64 x 64 tile (deterministic in-kernel reduction of the partials) */
+int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K, const int* n_active, int seg,
+                    int splits, float* partial /*[splits * tiles * 4160]*/, int* tickets /*[tiles], zero-initialised once*/,
+                    float* dW, float* db, void* stream);
 
 /* ---- loss epilogue: model/loss.py:61-125 (InvLoss: masked L1/L2 on the ACES tone-mapped radiance,
  * latent-smooth L1, KL sparsity of the BRDF latent), model/color_correction.py:31-59 (hdr2ldr with the learnable

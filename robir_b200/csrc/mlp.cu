@@ -3,8 +3,8 @@
 // (model/implicit_differentiable_renderer.py:170-222) run as ONE launch per chain instead of ~40 library kernels:
 // input encoding (PE10 / PE10+hdr / IPE, optional additive noise in embedding space) -> up to 8 Linear(+ReLU|LeakyReLU)
 // layers on 16-row tiles held in shared memory (fp32 FFMA, column-per-lane mapping, cp.async weight ring).  The backward kernel runs the
-// input-gradient chain and emits the per-layer pre-activation gradients G_l; weight gradients are then plain GEMMs
-// G_l^T A_{l-1} (library calls on the host side).
+// input-gradient chain and emits the per-layer pre-activation gradients G_l; wgrad_kernel turns them into dW_l = G_l^T A_{l-1}
+// and db_l (split over the rows, deterministic in-kernel reduction).
 #include "mlp_engine.cuh"
 
 namespace robir {
@@ -329,6 +329,122 @@ __global__ void __launch_bounds__(256, 2) mlp_bwd_kernel(MlpParams p) {
   }
 }
 
+// Weight / bias gradient of one Linear layer from the pre-activation gradients G [n][ldg] and the layer input
+// A [n][lda]:  dW[i][j] = sum_r G[r][i] A[r][j],  db[i] = sum_r G[r][i]   (i < N, j < K), fp32, fixed summation order.
+// Rows are visited in chunks of 32; chunks that lie entirely in the inactive tail of a segment (n_active, see
+// MlpParams) are skipped.  One CTA per (64 x 64 tile of dW, row split z of S): chunk c belongs to split c % S; the next
+// chunk is prefetched into registers while the current one is multiplied.  With S > 1 every CTA writes its partial tile
+// to a workspace and the last one to arrive (ticket counter, reset for the next launch) adds the S partials in split
+// order -- a deterministic split-K without a second launch.
+constexpr int kWgRows = 32;
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ A,
+                                                    int lda, int n, int N, int K, const int* __restrict__ n_active,
+                                                    int seg, float* __restrict__ partial, int* __restrict__ tickets,
+                                                    float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ __align__(16) float Gs[kWgRows][64];
+  __shared__ __align__(16) float As[kWgRows][64];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64, z = blockIdx.z, S = gridDim.z;
+  const int sg = seg > 0 ? seg : (n > 0 ? n : 1);
+  const int n_act = n_active ? min(__ldg(n_active), sg) : sg;
+  const int nchunk = (n + kWgRows - 1) / kWgRows;
+  float acc[4][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  auto active = [&](int c) {
+    const int o = (c * kWgRows) % sg;
+    return !(o >= n_act && o + kWgRows <= sg);
+  };
+  auto next_chunk = [&](int c) {          // next active chunk of this split at or after c (c % S == z)
+    while (c < nchunk && !active(c)) c += S;
+    return c;
+  };
+  // each thread stages 8 G and 8 A values per chunk: rows lr, lr + 4, ...  (column = tid & 63)
+  const int lc = tid & 63, lr = tid >> 6;
+  float rg[8], ra[8];
+  auto fetch = [&](int c) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int row = c * kWgRows + lr + 4 * q;
+      rg[q] = (row < n && i0 + lc < N) ? __ldg(G + (size_t)row * ldg + i0 + lc) : 0.f;
+      ra[q] = (row < n && j0 + lc < K) ? __ldg(A + (size_t)row * lda + j0 + lc) : 0.f;
+    }
+  };
+  int c = next_chunk(z);
+  if (c < nchunk) fetch(c);
+  while (c < nchunk) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { Gs[lr + 4 * q][lc] = rg[q]; As[lr + 4 * q][lc] = ra[q]; }
+    __syncthreads();
+    c = next_chunk(c + S);
+    if (c < nchunk) fetch(c);              // in flight during the multiply below
+#pragma unroll 8
+    for (int r = 0; r < kWgRows; ++r) {
+      const float4 g = *reinterpret_cast<const float4*>(&Gs[r][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[r][tx * 4]);
+      const float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        bsum[x] += gv[x];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(gv[x], av[y], acc[x][y]);
+      }
+    }
+  }
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (S > 1) {
+    // partial layout: [z][tile][64 x 64 values | 64 bias sums]
+    float* mine = partial + ((size_t)z * gridDim.x * gridDim.y + tile) * (64 * 64 + 64);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+#pragma unroll
+      for (int y = 0; y < 4; ++y) mine[(ty * 4 + x) * 64 + tx * 4 + y] = acc[x][y];
+      if (tx == 0) mine[64 * 64 + ty * 4 + x] = bsum[x];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int t = atomicAdd(&tickets[tile], 1);
+      s_last = (t == S - 1);
+      if (s_last) tickets[tile] = 0;       // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      bsum[x] = 0.f;
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+    }
+    for (int s = 0; s < S; ++s) {
+      const float* src = partial + ((size_t)s * gridDim.x * gridDim.y + tile) * (64 * 64 + 64);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] += __ldcg(src + (ty * 4 + x) * 64 + tx * 4 + y);
+        if (tx == 0) bsum[x] += __ldcg(src + 64 * 64 + ty * 4 + x);
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + ty * 4 + x;
+    if (i >= N) continue;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int j = j0 + tx * 4 + y;
+      if (j < K) dW[(size_t)i * K + j] = acc[x][y];
+    }
+    if (db != nullptr && blockIdx.y == 0 && tx == 0) db[i] = bsum[x];
+  }
+}
+
 // W [N][K] -> Wb [Npad16][Kpad256] (zero padded row-major copy for the backward chain)
 __global__ void pack_pad_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out, int Np, int Kp) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,6 +506,22 @@ int robir_mlp_bwd(const MlpParams* p, int sm_count, void* stream) {
   for (int l = 0; l < p->n_layers - 1; ++l)
     RB_REQUIRE(p->L[l].save != nullptr, "mlp_bwd: hidden activations must have been saved by the forward");
   return mlp_launch<false>(p, sm_count, stream);
+}
+
+// dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums of G (db may be null); G / A row strides ldg / lda (floats).
+// splits > 1: rows are divided over that many CTAs per tile; workspace (caller-owned): partial
+// [splits * tiles * 4160] floats and tickets [tiles] int32 (zero before the first call; the kernel re-zeroes them),
+// tiles = ceil(N / 64) * ceil(K / 64).
+int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K, const int* n_active, int seg,
+                    int splits, float* partial, int* tickets, float* dW, float* db, void* stream) {
+  if (N == 0 || K == 0) return 0;
+  RB_REQUIRE(seg == 0 || seg % kWgRows == 0 || n_active == nullptr, "mlp_wgrad: segment length must be a multiple of 32");
+  RB_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || (partial != nullptr && tickets != nullptr)),
+             "mlp_wgrad: 1..64 splits, workspace required for splits > 1");
+  dim3 grid((N + 63) / 64, (K + 63) / 64, splits);
+  wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, A, lda, n, N, K, n_active, seg, partial, tickets, dW, db);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

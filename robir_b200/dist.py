@@ -34,7 +34,6 @@ class GradAllReducer:
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = None
 
     def __call__(self):
         if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -42,20 +41,15 @@ class GradAllReducer:
         ps = [p for p in self.params if p.grad is not None]
         if not ps:
             return
-        if self.flat is None or self.flat.device != ps[0].grad.device:
-            self.flat = torch.empty(self.numel, dtype=torch.float32, device=ps[0].grad.device)
-        off = 0
-        views = []
-        for p in ps:
-            v = self.flat[off:off + p.numel()]
-            v.copy_(p.grad.reshape(-1))
-            views.append((p, v))
-            off += p.numel()
-        buf = self.flat[:off]
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        buf.div_(dist.get_world_size())
-        for p, v in views:
-            p.grad.copy_(v.view_as(p.grad))
+        grads = [p.grad for p in ps]
+        flat = torch.cat([g.reshape(-1) for g in grads])              # one gather kernel
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+        views, off = [], 0
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(grads, views)                            # one scatter kernel
 
 
 def allreduce_min_scalar(t):

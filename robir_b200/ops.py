@@ -745,6 +745,13 @@ class MlpChain:
     weightnorm = False
     wgrad_streams = None      # side streams of this chain's weight-gradient GEMMs (created on first backward)
 
+    def wgrad_tickets(self, layer, tiles, like):
+        """Persistent zero-initialised ticket counters of robir_mlp_wgrad's in-kernel split reduction (it re-zeroes them)."""
+        t = self.__dict__.setdefault("_tickets", {})
+        if layer not in t or t[layer].numel() < tiles or t[layer].device != like.device:
+            t[layer] = torch.zeros(tiles, dtype=torch.int32, device=like.device)
+        return t[layer]
+
     def params(self):
         if self.weightnorm:
             return [t for l in self.linears for t in (l.weight_v, l.weight_g, l.bias)]
@@ -837,13 +844,20 @@ class _FusedMLP(torch.autograd.Function):
         check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
         grads = []
         if ctx.want_param_grad:
-            # dW_l = G_l^T A_{l-1} (plain library GEMMs) and db_l: independent per layer -> parallel branches
+            # dW_l = G_l^T A_{l-1} and db_l (csrc/mlp.cu wgrad_kernel): independent per layer -> parallel branches
             prevs = [x0] + list(saves)
 
             def layer_grads(l):
                 d = packed[l]
-                G = Gs[l][:, :d["N"]]
-                return G.t() @ prevs[l][:, :d["K"]], G.sum(0)
+                gw, gb = _empty(d["N"], d["K"], like=x), _empty(d["N"], like=x)
+                seg = n // ctx.segments
+                tiles = ((d["N"] + 63) // 64) * ((d["K"] + 63) // 64)
+                splits = max(1, min(32, 160 // tiles, (n + 63) // 64))      # ~one wave of CTAs per layer
+                part = _empty(splits * tiles * 4160, like=x) if splits > 1 else None
+                check(lib().robir_mlp_wgrad(ptr(Gs[l]), Gs[l].shape[1], ptr(prevs[l]), prevs[l].shape[1], n, d["N"],
+                                            d["K"], ptr(n_active) if seg % 32 == 0 else None, seg, splits, ptr(part),
+                                            ptr(chain.wgrad_tickets(l, tiles, x)), ptr(gw), ptr(gb), stream()))
+                return gw, gb
             if chain.wgrad_streams is None:
                 chain.wgrad_streams = [torch.cuda.Stream() for _ in range(len(packed) - 1)]
             for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))], chain.wgrad_streams):
