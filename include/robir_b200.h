@@ -241,6 +241,11 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
                     int splits, float* partial /*[splits * tiles * 4160]*/, int* tickets /*[tiles], zero-initialised once*/,
                     float* dW, float* db, void* stream);
 
+/* ---- a6: lobe decoding of IndirctIllumNetwork (implicit_differentiable_renderer.py:207-219): raw [total][6] ->
+ * [axis(theta = 2 pi sigmoid, phi = pi sigmoid), 30 sigmoid + 0.1, relu x3] [total][7], total = points x lobes --------- */
+int robir_decode_lobes_fwd(int total, const float* raw, float* sgs, void* stream);
+int robir_decode_lobes_bwd(int total, const float* raw, const float* g_sgs, float* g_raw, void* stream);
+
 /* ---- loss epilogue: model/loss.py:61-125 (InvLoss: masked L1/L2 on the ACES tone-mapped radiance,
  * latent-smooth L1, KL sparsity of the BRDF latent), model/color_correction.py:31-59 (hdr2ldr with the learnable
  * exposure shift), training/train_pbr.py:313-346 (white_loss; loss = rgb + kl + 0.1 smooth + white).  One launch

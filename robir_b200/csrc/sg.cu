@@ -223,6 +223,48 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// IndirctIllumNetwork lobe decoding (model/implicit_differentiable_renderer.py:207-219): per (point, lobe) the six raw
+// network outputs -> [unit axis (theta = 2 pi sigmoid, phi = pi sigmoid), lambda = 30 sigmoid + 0.1, mu = relu] (7 values).
+// One thread per (point, lobe); the backward recomputes the forward from the raw outputs.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void decode_lobes_fwd_kernel(int total, const float* __restrict__ raw, float* __restrict__ sgs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float* o = raw + (size_t)idx * 6;
+  const float theta = sigmoidf_(o[0]) * 6.283185307179586f, phi = sigmoidf_(o[1]) * 3.141592653589793f;
+  float st, ct, sp, cp;
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
+  float* d = sgs + (size_t)idx * 7;
+  d[0] = ct * sp; d[1] = st * sp; d[2] = cp;
+  d[3] = sigmoidf_(o[2]) * 30.f + 0.1f;
+  d[4] = fmaxf(o[3], 0.f); d[5] = fmaxf(o[4], 0.f); d[6] = fmaxf(o[5], 0.f);
+}
+
+__global__ void decode_lobes_bwd_kernel(int total, const float* __restrict__ raw, const float* __restrict__ g_sgs,
+                                        float* __restrict__ g_raw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float* o = raw + (size_t)idx * 6;
+  const float* g = g_sgs + (size_t)idx * 7;
+  const float a0 = sigmoidf_(o[0]), a1 = sigmoidf_(o[1]), s2 = sigmoidf_(o[2]);
+  float st, ct, sp, cp;
+  sincosf(a0 * 6.283185307179586f, &st, &ct);
+  sincosf(a1 * 3.141592653589793f, &sp, &cp);
+  const float g_theta = g[0] * (-st * sp) + g[1] * (ct * sp);
+  const float g_phi = g[0] * (ct * cp) + g[1] * (st * cp) - g[2] * sp;
+  float* d = g_raw + (size_t)idx * 6;
+  d[0] = g_theta * 6.283185307179586f * a0 * (1.f - a0);
+  d[1] = g_phi * 3.141592653589793f * a1 * (1.f - a1);
+  d[2] = g[3] * 30.f * s2 * (1.f - s2);
+  d[3] = o[3] > 0.f ? g[4] : 0.f;
+  d[4] = o[4] > 0.f ? g[5] : 0.f;
+  d[5] = o[5] > 0.f ? g[6] : 0.f;
+}
+
 }  // namespace robir
 
 using namespace robir;
@@ -241,6 +283,21 @@ int robir_sg_render_fwd(const SgParams* p, void* stream) {
 int robir_sg_render_bwd(const SgParams* p, void* stream) {
   if (p->n == 0) return 0;
   sg_render_bwd_kernel<<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// raw [n * lobes][6] -> sgs [n * lobes][7]  (and its backward); total = n * lobes
+int robir_decode_lobes_fwd(int total, const float* raw, float* sgs, void* stream) {
+  if (total == 0) return 0;
+  decode_lobes_fwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(total, raw, sgs);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int robir_decode_lobes_bwd(int total, const float* raw, const float* g_sgs, float* g_raw, void* stream) {
+  if (total == 0) return 0;
+  decode_lobes_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(total, raw, g_sgs, g_raw);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

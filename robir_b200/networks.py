@@ -333,7 +333,7 @@ class IndirctIllumNetwork(nn.Module):
                 lambda: self.integral_layer.forward_points(pts, "pe10_extra", extra=hdr_shift, train=train,
                                                            noisy_only=True)])
             out = out.reshape(pts.shape[0], self.num_lgt_sgs, 6)
-            return self._decode_lobes(out), torch.abs(env_r)
+            return ops.decode_lobes(out), torch.abs(env_r)
         x = torch.cat([positional_encoding(points, 10), hdr_shift], -1)
         out = self.lobe_layer(x).reshape(x.shape[0], self.num_lgt_sgs, 6)
         env_int = torch.abs(self.integral_layer(x)[1])

@@ -520,6 +520,31 @@ def sg_render(normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, b
                            ind_integral, lin_diff)
 
 
+class _DecodeLobes(torch.autograd.Function):
+    """IndirctIllumNetwork._decode_lobes (implicit_differentiable_renderer.py:207-219) in one launch each way."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        raw = f32(raw)
+        n, L = raw.shape[0], raw.shape[1]
+        sgs = _empty(n, L, 7, like=raw)
+        check(lib().robir_decode_lobes_fwd(n * L, ptr(raw), ptr(sgs), stream()))
+        ctx.save_for_backward(raw)
+        return sgs
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, = ctx.saved_tensors
+        g_raw = _empty(*raw.shape, like=raw)
+        check(lib().robir_decode_lobes_bwd(raw.shape[0] * raw.shape[1], ptr(raw), ptr(f32(g)), ptr(g_raw), stream()))
+        return g_raw
+
+
+def decode_lobes(raw):
+    """raw [n, lobes, 6] -> SGs [n, lobes, 7]"""
+    return _DecodeLobes.apply(raw)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # SDF network
 # ----------------------------------------------------------------------------------------------------------------------

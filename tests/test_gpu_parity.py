@@ -648,3 +648,97 @@ def test_idr_network_with_sphere_tracer(synth_sd16):
     assert sdf.abs().max() < 1e-3                       # hit points lie on the zero level set
     for k in ("sg_rgb", "indir_rgb", "normals"):
         assert torch.isfinite(out[k]).all() and (out[k][~m] == 1).all(), k
+
+
+def test_wgrad_kernel_shapes_and_active_rows():
+    """csrc/mlp.cu wgrad_kernel against torch matmul: ragged shapes, row splits, segments with an inactive tail."""
+    import ctypes
+    from robir_b200._lib import check, lib, ptr, stream
+    gen = torch.Generator().manual_seed(11)
+    for n, N, K, ldg, lda, seg, n_act, splits in [(77, 5, 63, 256, 64, 0, None, 1), (1024, 512, 512, 512, 512, 0, None, 2),
+                                                  (2048, 32, 512, 256, 512, 1024, 300, 16), (96, 144, 512, 256, 512, 0, 40, 4),
+                                                  (1, 3, 7, 8, 8, 0, None, 1)]:
+        G = torch.randn(n, ldg, generator=gen).cuda()
+        A = torch.randn(n, lda, generator=gen).cuda()
+        Gr, Ar = G.clone(), A.clone()
+        na = None
+        if n_act is not None:
+            sg = seg or n
+            rows = torch.arange(n) % sg
+            # rows outside the active head carry zero gradient in the product; whole inactive 32-row chunks are skipped
+            Gr[(rows >= n_act).cuda()] = 0
+            G = Gr.clone()
+            na = torch.tensor([n_act], dtype=torch.int32).cuda()
+        tiles = ((N + 63) // 64) * ((K + 63) // 64)
+        part = torch.empty(splits * tiles * 4160).cuda()
+        tick = torch.zeros(tiles, dtype=torch.int32).cuda()
+        dW, db = torch.empty(N, K).cuda(), torch.empty(N).cuda()
+        for _ in range(2):        # twice: the ticket counters must come back to zero
+            check(lib().robir_mlp_wgrad(ptr(G), ldg, ptr(A), lda, n, N, K, ptr(na), seg, splits,
+                                        ptr(part) if splits > 1 else None, ptr(tick), ptr(dW), ptr(db), stream()))
+        ref_w = (Gr[:, :N].double().t() @ Ar[:, :K].double()).float()
+        ref_b = Gr[:, :N].double().sum(0).float()
+        assert rel_err(dW, ref_w) < 1e-5 and rel_err(db, ref_b) < 1e-5, (n, N, K)
+        assert int(tick.abs().sum()) == 0
+
+
+def test_fused_loss_edge_sizes():
+    """csrc/loss.cu on batches that are not a multiple of the CTA width, a single ray, and no valid latent row."""
+    from robir_b200 import loss as L
+    gen = torch.Generator().manual_seed(2)
+    for N, n_lat, valid_rows in [(1, 1, 1), (1500, 1500, 700), (1024, 37, 37), (64, 64, 0)]:
+        t = lambda *s: torch.rand(*s, generator=gen).cuda().requires_grad_(True)
+        sg, ind, alb, albr, r, rr = t(N, 3), t(N, 3), t(N, 3), t(N, 3), t(N, 1), t(N, 1)
+        z = (torch.randn(n_lat, 32, generator=gen)).cuda().requires_grad_(True)
+        lgt = torch.randn(16, 7, generator=gen).cuda().requires_grad_(True)
+        a = torch.tensor(0.01).cuda().requires_grad_(True)
+        gt = torch.rand(1, N, 3, generator=gen).cuda()
+        mask = (torch.rand(N, generator=gen) > 0.3).cuda()
+        zv = (torch.arange(n_lat) < valid_rows).cuda()
+        loss, parts = L._FusedPBRLoss.apply(sg, ind, a, alb, albr, r, rr, z, lgt, gt, mask, zv, (1.0, 1.0, 0.1, False))
+        # torch restatement (model/loss.py:61-125, train_pbr.py:313-346)
+        shift = torch.clamp(torch.clamp(a * 10 + 0.5, 0, 1), 1e-4, 1)
+        x = sg + ind
+        ldr = x * (2.51 * x + 0.03) / (x * (2.43 * x + 0.59) + 0.14) / shift ** 0.2
+        rgb = ((ldr - gt.reshape(-1, 3)).abs() * mask[:, None]).sum() / N
+        smooth = (alb - albr).abs().mean() + (r[:, 0] - rr[:, 0]).abs().mean() * 0.2
+        rho_hat = (torch.sigmoid(z) * zv[:, None]).sum(0) / zv.sum().clamp(min=1)
+        kl = torch.mean(0.05 * torch.log(0.05 / (rho_hat + 1e-4)) + 0.95 * torch.log(0.95 / (1 - rho_hat + 1e-4)))
+        ref = rgb + kl + 0.1 * smooth + L.white_loss(lgt)
+        assert abs(loss.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (N, loss.item(), ref.item())
+        leaves = [sg, ind, a, alb, albr, r, rr, z, lgt]
+        for g1, g2 in zip(torch.autograd.grad(loss, leaves), torch.autograd.grad(ref, leaves)):
+            assert torch.isfinite(g1).all()
+            assert (g1 - g2).abs().max().item() <= 2e-4 * max(1e-7, g2.abs().max().item()), N
+
+
+def test_static_step_without_any_hit(synth_sd16):
+    """Fixed-capacity path with a camera that sees nothing: zero active rows everywhere, finite loss and gradients."""
+    import robir_b200
+    from robir_b200 import rng
+    from robir_b200.loss import InvLoss, pbr_step_loss
+    m = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=16)))
+    m.load_state_dict(synth_sd16, strict=True)
+    m.cuda().train()
+    m.generate()
+    m.static_shapes = True
+    fn = InvLoss()
+    fn.static_shapes = True
+    N = 128
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(1, n=N)).items()}
+    inp["pose"] = inp["pose"].clone()
+    inp["pose"][0, :3, 3] = torch.tensor([5.0, 5.0, 5.0]).cuda()        # looking along -z from far off axis: no hit
+    inp["hdr_shift"] = m.gamma.hdr_shift.as_input().expand(N, 1)
+    rng.set_mode("device")
+    try:
+        out = m(inp, trainstage="Material", train_spec=True)
+        assert int(out["network_object_mask"].sum()) == 0
+        for k in ("sg_rgb", "indir_rgb", "normals", "roughness"):
+            assert torch.all(out[k] == 1.0), k
+        loss, _ = pbr_step_loss(m, fn, out, {"rgb": torch.full((1, N, 3), 0.5).cuda()})
+        loss.backward()
+        assert torch.isfinite(loss)
+        for p in m.envmap_material_network.parameters():
+            assert p.grad is None or torch.isfinite(p.grad).all()
+    finally:
+        rng.set_mode("cpu")
