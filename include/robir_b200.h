@@ -241,6 +241,12 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
                     int splits, float* partial /*[splits * tiles * 4160]*/, int* tickets /*[tiles], zero-initialised once*/,
                     float* dW, float* db, void* stream);
 
+/* ---- a1: hit compaction of a fixed-capacity ray batch (device-side counterpart of the boolean indexing at
+ * implicit_differentiable_renderer.py:341-347): hits first (stable), misses after; pos / order int64 [N], n_act [1],
+ * valid [N] (slot < n_act), pts [N][3] = hit points in slot order (0 for misses), view [N][3] = -dirs in slot order */
+int robir_compact_hits(int N, const unsigned char* hit, const float* points, const float* dirs, long long* pos,
+                       long long* order, int* n_act, unsigned char* valid, float* pts, float* view, void* stream);
+
 /* ---- a6: lobe decoding of IndirctIllumNetwork (implicit_differentiable_renderer.py:207-219): raw [total][6] ->
  * [axis(theta = 2 pi sigmoid, phi = pi sigmoid), 30 sigmoid + 0.1, relu x3] [total][7], total = points x lobes --------- */
 int robir_decode_lobes_fwd(int total, const float* raw, float* sgs, void* stream);

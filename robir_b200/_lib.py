@@ -120,6 +120,7 @@ _SIGNATURES = {
     "robir_sphere_trace": [POINTER(SphereTraceParams), _I, _P],
     "robir_sphere_trace_launches": [_I],
     "robir_mlp_wgrad": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P],
+    "robir_compact_hits": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_decode_lobes_fwd": [_I, _P, _P, _P],
     "robir_decode_lobes_bwd": [_I, _P, _P, _P, _P],
     "robir_pbr_loss": [POINTER(LossParams), _P],

@@ -224,6 +224,83 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Hit compaction of the fixed-capacity batch (the device-side counterpart of the reference's boolean indexing,
+// implicit_differentiable_renderer.py:341-347): stable partition of the N rays into hits first, misses after.
+//   pos[i]   = slot of ray i,  order[slot] = ray,  n_act = number of hits,  valid[slot] = slot < n_act,
+//   pts[slot] = hit ? cam + dist * dir : 0,  view[slot] = -dir of that ray.
+// One CTA (N is a training batch: ~1e3 rays); block-wide exclusive scan in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) compact_hits_kernel(int N, const unsigned char* __restrict__ hit,
+                                                               const float* __restrict__ points,
+                                                               const float* __restrict__ dirs, long long* __restrict__ pos,
+                                                               long long* __restrict__ order, int* __restrict__ n_act,
+                                                               unsigned char* __restrict__ valid, float* __restrict__ pts,
+                                                               float* __restrict__ view) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  // pass 1: hit ranks (chunks of 1024 rays, running base)
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int i = c0 + tid;
+    const int h = (i < N && hit[i]) ? 1 : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int base = s_base;
+    const int rank = base + before + __popc(b & ((1u << lane) - 1u));
+    if (i < N && h) pos[i] = rank;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base = base + tot;
+    }
+    __syncthreads();
+  }
+  const int nh = s_base;
+  if (tid == 0) n_act[0] = nh;
+  // pass 2: misses go after the hits, in ray order: slot = nh + (i - hits before i)
+  for (int i = tid; i < N; i += 1024) valid[i] = i < nh ? 1 : 0;
+  __syncthreads();
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int i = c0 + tid;
+    const int m = (i < N && !hit[i]) ? 1 : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int base = s_base;
+    if (i < N && m) pos[i] = nh + base + before + __popc(b & ((1u << lane) - 1u));
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base = base + tot;
+    }
+    __syncthreads();
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int i = tid; i < N; i += 1024) {
+    const long long slot = pos[i];
+    order[slot] = i;
+    const bool h = hit[i] != 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      pts[3 * slot + c] = h ? points[3 * i + c] : 0.f;
+      view[3 * slot + c] = -dirs[3 * i + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // IndirctIllumNetwork lobe decoding (model/implicit_differentiable_renderer.py:207-219): per (point, lobe) the six raw
 // network outputs -> [unit axis (theta = 2 pi sigmoid, phi = pi sigmoid), lambda = 30 sigmoid + 0.1, mu = relu] (7 values).
 // One thread per (point, lobe); the backward recomputes the forward from the raw outputs.
@@ -298,6 +375,15 @@ int robir_decode_lobes_fwd(int total, const float* raw, float* sgs, void* stream
 int robir_decode_lobes_bwd(int total, const float* raw, const float* g_sgs, float* g_raw, void* stream) {
   if (total == 0) return 0;
   decode_lobes_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(total, raw, g_sgs, g_raw);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Stable hit-first partition of one ray batch (see compact_hits_kernel); pos / order are int64 [N].
+int robir_compact_hits(int N, const unsigned char* hit, const float* points, const float* dirs, long long* pos,
+                       long long* order, int* n_act, unsigned char* valid, float* pts, float* view, void* stream) {
+  if (N == 0) return 0;
+  compact_hits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(N, hit, points, dirs, pos, order, n_act, valid, pts, view);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -520,6 +520,23 @@ def sg_render(normal, view, rough, albedo, spec_refl, lgt, ind_lgt, light_vis, b
                            ind_integral, lin_diff)
 
 
+def compact_hits(hit, points, dirs):
+    """Stable hit-first partition of a ray batch on the device (no host sync): -> pos [N] int64 (slot of ray i),
+    order [N] int64 (ray in slot), n_act [1] int32, valid [N] bool (slot < n_act), pts [N,3] (hit points in slot order,
+    0 for the misses), view [N,3] (= -dirs in slot order).  No autograd (points / dirs come from the no-grad tracer)."""
+    hit8 = hit.to(torch.uint8).contiguous()
+    points, dirs = f32(points), f32(dirs)
+    N = hit8.shape[0]
+    pos = _empty(N, dtype=torch.int64, like=points)
+    order = _empty(N, dtype=torch.int64, like=points)
+    n_act = _empty(1, dtype=torch.int32, like=points)
+    valid = _empty(N, dtype=torch.uint8, like=points)
+    pts, view = _empty(N, 3, like=points), _empty(N, 3, like=points)
+    check(lib().robir_compact_hits(N, ptr(hit8), ptr(points), ptr(dirs), ptr(pos), ptr(order), ptr(n_act), ptr(valid),
+                                   ptr(pts), ptr(view), stream()))
+    return pos, order, n_act, valid.view(torch.bool), pts, view
+
+
 class _DecodeLobes(torch.autograd.Function):
     """IndirctIllumNetwork._decode_lobes (implicit_differentiable_renderer.py:207-219) in one launch each way."""
 

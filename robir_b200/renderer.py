@@ -176,15 +176,7 @@ class IDRNetwork(nn.Module):
         # hit rays are compacted to the front of the fixed-capacity batch (device-side permutation, no host sync); the
         # per-point networks then evaluate n_act rows instead of N (ops.active_rows), like the reference's boolean
         # indexing (implicit_differentiable_renderer.py:341-347) but capturable in a CUDA graph
-        hit = mask
-        n_act = hit.sum().to(torch.int32).reshape(1)
-        csum = torch.cumsum(hit, 0)
-        pos = torch.where(hit, csum - 1, n_act.to(torch.int64) + torch.arange(total, device=dev) - csum)
-        order = torch.empty_like(pos).scatter_(0, pos, torch.arange(total, device=dev))
-        valid = torch.arange(total, device=dev) < n_act
-        v1 = valid[:, None]
-        pts = torch.where(v1, points.index_select(0, order), torch.zeros_like(points))   # finite inputs for inactive rows
-        view = -ray_dirs.index_select(0, order)
+        pos, order, n_act, valid, pts, view = ops.compact_hits(mask, points, ray_dirs)   # inactive rows: finite inputs
         hdr = input['hdr_shift'].index_select(0, order)
         # the indirect-illumination net, the material net, the SDF normal and the reported sdf_output are independent
         # given the hit points: parallel branches (random draws keep the reference order: indirect, BRDF latent,
