@@ -247,6 +247,17 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
 int robir_compact_hits(int N, const unsigned char* hit, const float* points, const float* dirs, long long* pos,
                        long long* order, int* n_act, unsigned char* valid, float* pts, float* view, void* stream);
 
+/* ---- a7: SparseAE glue of the BRDF auto-encoder (model/sg_envmap_material.py:74-94, 214-232): the decoder's doubled
+ * latent batch [sigmoid(z); sigmoid(z) + 0.01 noise] and the output head (sigmoid + affine -> albedo / roughness /
+ * metallic and their random_xi twins), one launch each way.  Null upstream gradients count as zero. ---------------- */
+int robir_latent_pair_fwd(int n, const float* z /*[n][32]*/, const float* noise, float* out /*[2n][32]*/, void* stream);
+int robir_latent_pair_bwd(int n, const float* z, const float* g /*[2n][32]*/, float* g_z, void* stream);
+int robir_brdf_head_fwd(int n, const float* y2 /*[2n][5]*/, float* albedo, float* rough, float* metal, float* xi_albedo,
+                        float* xi_rough, float* xi_metal, void* stream);
+int robir_brdf_head_bwd(int n, const float* y2, const float* g_albedo, const float* g_rough, const float* g_metal,
+                        const float* g_xi_albedo, const float* g_xi_rough, const float* g_xi_metal, float* g_y2,
+                        void* stream);
+
 /* ---- a6: lobe decoding of IndirctIllumNetwork (implicit_differentiable_renderer.py:207-219): raw [total][6] ->
  * [axis(theta = 2 pi sigmoid, phi = pi sigmoid), 30 sigmoid + 0.1, relu x3] [total][7], total = points x lobes --------- */
 int robir_decode_lobes_fwd(int total, const float* raw, float* sgs, void* stream);

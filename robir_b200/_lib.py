@@ -121,6 +121,10 @@ _SIGNATURES = {
     "robir_sphere_trace_launches": [_I],
     "robir_mlp_wgrad": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P],
     "robir_compact_hits": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "robir_latent_pair_fwd": [_I, _P, _P, _P, _P],
+    "robir_latent_pair_bwd": [_I, _P, _P, _P, _P],
+    "robir_brdf_head_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "robir_brdf_head_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_decode_lobes_fwd": [_I, _P, _P, _P],
     "robir_decode_lobes_bwd": [_I, _P, _P, _P, _P],
     "robir_pbr_loss": [POINTER(LossParams), _P],

@@ -300,13 +300,75 @@ __global__ void __launch_bounds__(1024, 1) compact_hits_kernel(int N, const unsi
   }
 }
 
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// SparseAE glue of the BRDF auto-encoder (model/sg_envmap_material.py:74-94, 214-232), one launch each way:
+//  latent_pair: lc = sigmoid(z) (rows [0, n)), lc_r = lc + 0.01 noise (rows [n, 2n)) -- the decoder's doubled batch;
+//  brdf_head:   decoder outputs y (rows [0, n)) / y_r (rows [n, 2n)) [2n][5] -> albedo = sigmoid(y[:3]),
+//               roughness = 0.9 sigmoid(y3) + 0.09, metallic = 0.99 sigmoid(y4) + 0.01 and the random_xi twins
+//               (xi_metallic is the bare sigmoid, sg_envmap_material.py:231).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void latent_pair_fwd_kernel(int total, int n32, const float* __restrict__ z, const float* __restrict__ noise,
+                                       float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float s = sigmoidf_(z[i]);
+  out[i] = s;
+  out[n32 + i] = s + noise[i] * 0.01f;
+}
+__global__ void latent_pair_bwd_kernel(int total, int n32, const float* __restrict__ z, const float* __restrict__ g,
+                                       float* __restrict__ g_z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float s = sigmoidf_(z[i]);
+  g_z[i] = (g[i] + g[n32 + i]) * s * (1.f - s);
+}
+__global__ void brdf_head_fwd_kernel(int n, const float* __restrict__ y2, float* __restrict__ albedo,
+                                     float* __restrict__ rough, float* __restrict__ metal, float* __restrict__ xi_albedo,
+                                     float* __restrict__ xi_rough, float* __restrict__ xi_metal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* y = y2 + (size_t)i * 5;
+  const float* r = y2 + (size_t)(n + i) * 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    albedo[3 * i + c] = sigmoidf_(y[c]);
+    xi_albedo[3 * i + c] = sigmoidf_(r[c]);
+  }
+  rough[i] = sigmoidf_(y[3]) * 0.9f + 0.09f;
+  metal[i] = sigmoidf_(y[4]) * 0.99f + 0.01f;
+  xi_rough[i] = sigmoidf_(r[3]) * 0.9f + 0.09f;
+  xi_metal[i] = sigmoidf_(r[4]);
+}
+// any of the six upstream gradients may be null (treated as zero)
+__global__ void brdf_head_bwd_kernel(int n, const float* __restrict__ y2, const float* __restrict__ g_albedo,
+                                     const float* __restrict__ g_rough, const float* __restrict__ g_metal,
+                                     const float* __restrict__ g_xi_albedo, const float* __restrict__ g_xi_rough,
+                                     const float* __restrict__ g_xi_metal, float* __restrict__ g_y2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* y = y2 + (size_t)i * 5;
+  const float* r = y2 + (size_t)(n + i) * 5;
+  float* gy = g_y2 + (size_t)i * 5;
+  float* gr = g_y2 + (size_t)(n + i) * 5;
+  auto ds = [](float x) { const float s = sigmoidf_(x); return s * (1.f - s); };
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    gy[c] = g_albedo ? g_albedo[3 * i + c] * ds(y[c]) : 0.f;
+    gr[c] = g_xi_albedo ? g_xi_albedo[3 * i + c] * ds(r[c]) : 0.f;
+  }
+  gy[3] = g_rough ? g_rough[i] * 0.9f * ds(y[3]) : 0.f;
+  gy[4] = g_metal ? g_metal[i] * 0.99f * ds(y[4]) : 0.f;
+  gr[3] = g_xi_rough ? g_xi_rough[i] * 0.9f * ds(r[3]) : 0.f;
+  gr[4] = g_xi_metal ? g_xi_metal[i] * ds(r[4]) : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // IndirctIllumNetwork lobe decoding (model/implicit_differentiable_renderer.py:207-219): per (point, lobe) the six raw
 // network outputs -> [unit axis (theta = 2 pi sigmoid, phi = pi sigmoid), lambda = 30 sigmoid + 0.1, mu = relu] (7 values).
 // One thread per (point, lobe); the backward recomputes the forward from the raw outputs.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
 __global__ void decode_lobes_fwd_kernel(int total, const float* __restrict__ raw, float* __restrict__ sgs) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -384,6 +446,37 @@ int robir_compact_hits(int N, const unsigned char* hit, const float* points, con
                        long long* order, int* n_act, unsigned char* valid, float* pts, float* view, void* stream) {
   if (N == 0) return 0;
   compact_hits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(N, hit, points, dirs, pos, order, n_act, valid, pts, view);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// SparseAE glue of the BRDF auto-encoder (see latent_pair_* / brdf_head_* above).  z / noise [n][32]; out, g [2n][32].
+int robir_latent_pair_fwd(int n, const float* z, const float* noise, float* out, void* stream) {
+  if (n == 0) return 0;
+  latent_pair_fwd_kernel<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n * 32, n * 32, z, noise, out);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int robir_latent_pair_bwd(int n, const float* z, const float* g, float* g_z, void* stream) {
+  if (n == 0) return 0;
+  latent_pair_bwd_kernel<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n * 32, n * 32, z, g, g_z);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int robir_brdf_head_fwd(int n, const float* y2, float* albedo, float* rough, float* metal, float* xi_albedo,
+                        float* xi_rough, float* xi_metal, void* stream) {
+  if (n == 0) return 0;
+  brdf_head_fwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, y2, albedo, rough, metal, xi_albedo, xi_rough,
+                                                                          xi_metal);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int robir_brdf_head_bwd(int n, const float* y2, const float* g_albedo, const float* g_rough, const float* g_metal,
+                        const float* g_xi_albedo, const float* g_xi_rough, const float* g_xi_metal, float* g_y2,
+                        void* stream) {
+  if (n == 0) return 0;
+  brdf_head_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, y2, g_albedo, g_rough, g_metal, g_xi_albedo,
+                                                                          g_xi_rough, g_xi_metal, g_y2);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

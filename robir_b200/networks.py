@@ -240,6 +240,23 @@ class SparseAE(nn.Module):
             y_r = self.out_act(y_r)
         return y, y_r, z
 
+    def brdf_points(self, points, train=None):
+        """The BRDF auto-encoder of EnvmapMaterialNetwork on raw points (sg_envmap_material.py:214-232): encoder chain,
+        fused latent pair, decoder chain on the doubled batch, fused output head -> the six material tensors + z."""
+        train = self._wants_grad() if train is None else train
+        if not self.smooth_on_latent or self.latent_dim != 32 or self.var is not None or \
+                self.lc_act is not torch.sigmoid or self.out_act is not torch.sigmoid:
+            y, y_r, z = self.forward_points(points, "pe10", train=train)
+            return dict(z=z, sg_roughness=y[..., 3:4] * 0.9 + 0.09, sg_metallic=y[..., 4:5] * 0.99 + 0.01,
+                        sg_diffuse_albedo=y[..., :3], random_xi_roughness=y_r[..., 3:4] * 0.9 + 0.09,
+                        random_xi_diffuse_albedo=y_r[..., :3], random_xi_metallic=y_r[..., 4:5])
+        z = self.encode_points(points, "pe10", None, None, train)
+        lc2 = ops.latent_pair(z, rng.randn(z.shape, z.device))
+        y2 = ops.fused_mlp(self._chain("dec", "raw"), lc2, want_param_grad=train, segments=2)
+        alb, rough, metal, alb_r, rough_r, metal_r = ops.brdf_head(y2)
+        return dict(z=z, sg_roughness=rough, sg_metallic=metal, sg_diffuse_albedo=alb, random_xi_roughness=rough_r,
+                    random_xi_diffuse_albedo=alb_r, random_xi_metallic=metal_r)
+
     def forward(self, x):
         lc = self.lc_act(self.encode(x))
         y = self.brdf_decoder_layer(lc)
@@ -279,18 +296,20 @@ class EnvmapMaterialNetwork(nn.Module):
             if fused:
                 # the BRDF and the normal auto-encoders only share the input points: two parallel branches (host call
                 # order = random-draw order of the reference: BRDF latent noise, then normal input noise)
-                (brdf, brdf_r, z), (nm, nm_r, _) = ops.fork_join([
-                    lambda: self.spec_brdf_encoder_layer.forward_points(points.detach(), "pe10",
-                                                                        train=None if train_spec else False),
+                head, (nm, nm_r, _) = ops.fork_join([
+                    lambda: self.spec_brdf_encoder_layer.brdf_points(points.detach(), train=None if train_spec else False),
                     lambda: self.normal_decoder_layer.forward_points(points.detach(), "ipe10")])
-                self._last_spec_latent = z          # reused by the KL term of the loss (same points, same encoder)
+                self._last_spec_latent = head.pop("z")   # reused by the KL term of the loss (same points, same encoder)
+                if train_spec is False:
+                    head = {k: v.detach() for k, v in head.items()}
+                ret.update(head)
             else:
                 brdf, brdf_r = self.spec_brdf_encoder_layer(emb)
-            if train_spec is False:
-                brdf, brdf_r = brdf.detach(), brdf_r.detach()
-            ret.update(sg_roughness=brdf[..., 3:4] * 0.9 + 0.09, sg_metallic=brdf[..., 4:5] * 0.99 + 0.01,
-                       sg_diffuse_albedo=brdf[..., :3], random_xi_roughness=brdf_r[..., 3:4] * 0.9 + 0.09,
-                       random_xi_diffuse_albedo=brdf_r[..., :3], random_xi_metallic=brdf_r[..., 4:5])
+                if train_spec is False:
+                    brdf, brdf_r = brdf.detach(), brdf_r.detach()
+                ret.update(sg_roughness=brdf[..., 3:4] * 0.9 + 0.09, sg_metallic=brdf[..., 4:5] * 0.99 + 0.01,
+                           sg_diffuse_albedo=brdf[..., :3], random_xi_roughness=brdf_r[..., 3:4] * 0.9 + 0.09,
+                           random_xi_diffuse_albedo=brdf_r[..., :3], random_xi_metallic=brdf_r[..., 4:5])
         if fused:
             if nm is None:
                 nm, nm_r, _ = self.normal_decoder_layer.forward_points(points.detach(), "ipe10")

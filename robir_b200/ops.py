@@ -537,6 +537,56 @@ def compact_hits(hit, points, dirs):
     return pos, order, n_act, valid.view(torch.bool), pts, view
 
 
+class _LatentPair(torch.autograd.Function):
+    """[sigmoid(z); sigmoid(z) + 0.01 noise] -> [2n, 32]  (SparseAE.forward with smooth_on_latent, latent_dim 32)"""
+
+    @staticmethod
+    def forward(ctx, z, noise):
+        z, noise = f32(z), f32(noise)
+        n = z.shape[0]
+        out = _empty(2 * n, 32, like=z)
+        check(lib().robir_latent_pair_fwd(n, ptr(z), ptr(noise), ptr(out), stream()))
+        ctx.save_for_backward(z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, = ctx.saved_tensors
+        g_z = _empty(*z.shape, like=z)
+        check(lib().robir_latent_pair_bwd(z.shape[0], ptr(z), ptr(f32(g)), ptr(g_z), stream()))
+        return g_z, None
+
+
+class _BrdfHead(torch.autograd.Function):
+    """decoder outputs [2n, 5] -> albedo [n,3], roughness [n,1], metallic [n,1] and their random_xi twins"""
+
+    @staticmethod
+    def forward(ctx, y2):
+        y2 = f32(y2)
+        n = y2.shape[0] // 2
+        outs = [_empty(n, 3, like=y2), _empty(n, 1, like=y2), _empty(n, 1, like=y2),
+                _empty(n, 3, like=y2), _empty(n, 1, like=y2), _empty(n, 1, like=y2)]
+        check(lib().robir_brdf_head_fwd(n, ptr(y2), *[ptr(o) for o in outs], stream()))
+        ctx.save_for_backward(y2)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        y2, = ctx.saved_tensors
+        g_y2 = _empty(*y2.shape, like=y2)
+        check(lib().robir_brdf_head_bwd(y2.shape[0] // 2, ptr(y2), *[ptr(f32(g)) if g is not None else None for g in gs],
+                                        ptr(g_y2), stream()))
+        return g_y2
+
+
+def latent_pair(z, noise):
+    return _LatentPair.apply(z, noise)
+
+
+def brdf_head(y2):
+    return _BrdfHead.apply(y2)
+
+
 class _DecodeLobes(torch.autograd.Function):
     """IndirctIllumNetwork._decode_lobes (implicit_differentiable_renderer.py:207-219) in one launch each way."""
 
