@@ -234,6 +234,8 @@ typedef struct {
 int robir_pack_pad(const float* W, int N, int K, float* out /*[Np][Kp]*/, int Np, int Kp, void* stream);
 int robir_mlp_fwd(const robir_mlp_params* p, int sm_count, void* stream);
 int robir_mlp_bwd(const robir_mlp_params* p, int sm_count, void* stream);
+/* embedded input of a chain alone -> p->x0_save [n][in_pad] (front end of the tensor-core layer engine) */
+int robir_mlp_encode(const robir_mlp_params* p, int sm_count, void* stream);
 /* weight / bias gradient of one layer of the chain from its pre-activation gradient G (robir_mlp_bwd) and its input A
  * (x0_save or the previous layer's save): dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums (db may be NULL).
  * splits > 1 divides the rows over that many CTAs per 64 x 64 tile (deterministic in-kernel reduction of the partials) */
@@ -241,6 +243,30 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
                     int splits, float* partial /*[splits * tiles * 4160]*/, int* tickets /*[tiles], zero-initialised once*/,
                     float* dW, float* db, void* stream);
 
+/* ---- a6 / a7, tensor-core layer engine (tcgen05 + TMEM, bf16 hi/lo 3-term split = fp32 parity) for the 512-wide
+ * encoder / lobe networks: one launch per Linear layer over bf16 hi/lo images (K-major SWIZZLE_128B k-blocks of
+ * 128 rows x 64 k, 32 KB each: robir_tl_block_bytes()).  forward: Y = act(A W^T + b); backward: G_prev = (G W) act'(ref).
+ * The fp32 rows written by a layer are what robir_mlp_wgrad and the next backward layer consume. ---------------------- */
+typedef struct {
+  const void* a_img;        /* [ceil(n / 128)][nkb][32 KB] activation (or gradient) image */
+  const void* w_img;        /* [ceil(N / 128)][nkb][32 KB] weight image (robir_tl_pack_weight) */
+  const float* bias;        /* zero padded to a multiple of 128, or NULL */
+  int n, N, nkb, mode, act; /* mode 0 forward / 1 backward; act: this layer's (fwd) or the previous layer's (bwd) */
+  const float* ref;         /* backward: saved post-activation rows of the previous layer [n][ld_ref], or NULL */
+  int ld_ref;
+  float* out;               /* fp32 rows [n][ld_out], columns < N, or NULL */
+  int ld_out;
+  void* out_img;            /* image of the output = next layer's A, [ceil(n / 128)][nkb_out][32 KB], or NULL */
+  int nkb_out;
+  const int* n_active;      /* as robir_mlp_params */
+  int seg;
+} robir_tl_params;
+int robir_tl_block_bytes(void);
+int robir_tl_pack_weight(const float* W, int ldw, int N, int K, int transpose, int col_blocks, int nkb, void* img,
+                         void* stream);
+int robir_tl_pack_rows(const float* X, int ldx, int n, int K, const float* ref, int ld_ref, int act, int nkb, void* img,
+                       void* stream);
+int robir_tl_layer(const robir_tl_params* p, void* stream);
 /* ---- a1: hit compaction of a fixed-capacity ray batch (device-side counterpart of the boolean indexing at
  * implicit_differentiable_renderer.py:341-347): hits first (stable), misses after; pos / order int64 [N], n_act [1],
  * valid [N] (slot < n_act), pts [N][3] = hit points in slot order (0 for misses), view [N][3] = -dirs in slot order */

@@ -47,6 +47,12 @@ class SphereTraceParams(Structure):
                                 "flags", "samp_list", "sec_list", "sec_state", "min_list", "vals", "counters")]
 
 
+class TlParams(Structure):
+    _fields_ = [("a_img", c_void_p), ("w_img", c_void_p), ("bias", c_void_p), ("n", c_int), ("N", c_int), ("nkb", c_int),
+                ("mode", c_int), ("act", c_int), ("ref", c_void_p), ("ld_ref", c_int), ("out", c_void_p),
+                ("ld_out", c_int), ("out_img", c_void_p), ("nkb_out", c_int), ("n_active", c_void_p), ("seg", c_int)]
+
+
 class LossParams(Structure):
     _fields_ = [("N", c_int), ("n_lat", c_int), ("M", c_int), ("l2", c_int), ("sg_rgb", c_void_p),
                 ("indir_rgb", c_void_p), ("ld_sg", c_int), ("ld_ind", c_int), ("gt", c_void_p), ("mask", c_void_p),
@@ -127,6 +133,11 @@ _SIGNATURES = {
     "robir_brdf_head_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_decode_lobes_fwd": [_I, _P, _P, _P],
     "robir_decode_lobes_bwd": [_I, _P, _P, _P, _P],
+    "robir_tl_block_bytes": [],
+    "robir_tl_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "robir_tl_pack_rows": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P],
+    "robir_tl_layer": [POINTER(TlParams), _P],
+    "robir_mlp_encode": [POINTER(MlpParams), _I, _P],
     "robir_pbr_loss": [POINTER(LossParams), _P],
     "robir_device_info": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     "robir_abi_version": [],
@@ -136,7 +147,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ["robir_last_error"])
 
 # kernels launched per C call (for bench.py's gpu_launches claim); everything not listed launches exactly one
 _KERNELS_PER_CALL = {"robir_diffuse_rows": 3, "robir_sphere_trace": 7, "robir_sphere_trace_launches": 0, "robir_octree_counters_len": 0, "robir_device_info": 0,
-                     "robir_tc_image_bytes": 0,
+                     "robir_tc_image_bytes": 0, "robir_tl_block_bytes": 0,
                      "robir_abi_version": 0, "robir_last_error": 0}
 launch_count = 0
 

@@ -21,6 +21,7 @@ obj vis_tc.cu build/vis_tc.o "-Xptxas -v" &
 obj mlp.cu build/mlp.o "-Xptxas -v" &
 obj sphere_trace.cu build/sphere_trace.o "-Xptxas -v" &
 obj loss.cu build/loss.o "" &
+obj tc_mlp.cu build/tc_mlp.o "-Xptxas -v" &
 wait
-$NVCC $ARCH -shared -o ../librobir_b200.so build/capi.o build/vis.o build/sg.o build/sdf.o build/trace.o build/vis_tc.o build/mlp.o build/sphere_trace.o build/loss.o -lcudart_static -lpthread -ldl -lrt
+$NVCC $ARCH -shared -o ../librobir_b200.so build/capi.o build/vis.o build/sg.o build/sdf.o build/trace.o build/vis_tc.o build/mlp.o build/sphere_trace.o build/loss.o build/tc_mlp.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(cd .. && pwd)/librobir_b200.so"

@@ -445,6 +445,30 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ G,
   }
 }
 
+// Embedded network input alone (PE / IPE / raw + noise + extra column) -> x0_save [n][in_pad]; rows outside the active
+// head are written as zeros.  Front end of the tensor-core layer engine (tc_mlp.cu).
+__global__ void __launch_bounds__(256) mlp_encode_kernel(MlpParams p) {
+  constexpr int R = 8, RP = R + 4;
+  __shared__ float Xs[kMlpKMax / 4 * RP];        // in_pad <= 128 rows of the k-major tile
+  const int tid = threadIdx.x;
+  const MlpActive act = mlp_active(p);
+  const int ntile = (p.n + R - 1) / R;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int row0 = tile * R;
+    __syncthreads();
+    if (tid < R) {
+      MlpParams q = p;
+      q.x0_save = nullptr;
+      encode_row(Xs, RP, tid, q, row0 + tid, row0 + tid < p.n && mlp_row_active(row0 + tid, act));
+    }
+    __syncthreads();
+    for (int i = tid; i < R * p.in_pad; i += 256) {
+      const int r = i / p.in_pad, k = i % p.in_pad;
+      if (row0 + r < p.n) p.x0_save[(size_t)(row0 + r) * p.in_pad + k] = Xs[k * RP + r];
+    }
+  }
+}
+
 // W [N][K] -> Wb [Npad16][Kpad256] (zero padded row-major copy for the backward chain)
 __global__ void pack_pad_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out, int Np, int Kp) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,6 +544,17 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
              "mlp_wgrad: 1..64 splits, workspace required for splits > 1");
   dim3 grid((N + 63) / 64, (K + 63) / 64, splits);
   wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, A, lda, n, N, K, n_active, seg, partial, tickets, dW, db);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// x0_save [n][in_pad] = embedded input of the chain (only n, in_mode, in_dim, in_pad, x, extra, noise, noise_scale,
+// n_active, seg and x0_save of the parameter block are read)
+int robir_mlp_encode(const MlpParams* p, int sm_count, void* stream) {
+  if (p->n == 0) return 0;
+  RB_REQUIRE(p->x0_save != nullptr && p->in_pad <= kMlpKMax / 4 && p->in_dim <= p->in_pad, "mlp_encode: bad input block");
+  const int tiles = (p->n + 7) / 8;
+  mlp_encode_kernel<<<tiles < 4 * sm_count ? tiles : 4 * sm_count, 256, 0, (cudaStream_t)stream>>>(*p);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

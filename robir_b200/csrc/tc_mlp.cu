@@ -1,0 +1,308 @@
+// Tensor-core (tcgen05 / TMEM) layer engine for the 512-wide material / indirect-illumination networks (SURVEY.md rows
+// a6 / a7): one launch per Linear layer, one CTA per (128-row tile, 128-column block) of the output.
+//
+//   forward  : Y = act(A . W^T + b)                      A = previous layer's activations
+//   backward : G_prev = (G . W) * act'(saved A_prev)     (input-gradient chain; weight gradients: wgrad_kernel, mlp.cu)
+//
+// Both operands are bf16 hi/lo images in global memory (L2-resident), K-major SWIZZLE_128B tiles that are exactly the
+// shared-memory layout tcgen05.mma reads, so a pipeline stage is two 1-D bulk copies (UBLKCP): the A k-block of this
+// row tile (128 rows x 64 k: hi 16 KB | lo 16 KB) and the W k-block of this column block (same shape).  Every product
+// is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (fp32 parity, like vis_tc.cu).  The epilogue (one thread per
+// row) applies bias / activation (or the activation derivative), writes the fp32 rows that the backward and the weight
+// gradients need, and emits the hi/lo image of its 128 output columns = two k-blocks of the next layer's A operand.
+// Warp roles: warp 0 producer, warp 1 MMA issuer (elect.sync lane), warps 2-5 epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace robir {
+using namespace tc;
+
+constexpr int kTlStages = 3;
+constexpr int kTlStageBytes = 65536;     // A k-block (32 KB) + W k-block (32 KB)
+constexpr int kTlBlockBytes = 32768;     // one 128 x 64 hi|lo k-block
+constexpr int kTlThreads = 192;
+constexpr uint32_t kTlIdesc = idesc_bf16(128, 128);
+constexpr int kTlSmem = kTlStages * kTlStageBytes + 1024;
+
+struct TcLayerParams {
+  const uint8_t* a_img;      // [row_tiles][nkb][32 KB]
+  const uint8_t* w_img;      // [col_blocks][nkb][32 KB]
+  const float* bias;         // [>= 128 * col_blocks] (zero padded) or null
+  int n, N, nkb;             // rows, valid output columns, k-blocks of the contraction
+  int mode;                  // 0 forward, 1 backward
+  int act;                   // forward: activation of this layer; backward: activation whose derivative is applied
+  const float* ref;          // backward: saved post-activation values of the previous layer [n][ld_ref] (null: none)
+  int ld_ref;
+  float* out;                // fp32 rows [n][ld_out], columns < N written (null: skip)
+  int ld_out;
+  uint8_t* out_img;          // [row_tiles][nkb_out][32 KB] image of the output (null: skip)
+  int nkb_out;
+  const int* n_active;       // see MlpParams (mlp.cu)
+  int seg;
+};
+
+__device__ __forceinline__ float tl_act(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
+  return x;
+}
+__device__ __forceinline__ float tl_dact(float y, int act) {
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ACT_LEAKY02) return y > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// hi / lo words of 32 consecutive columns of row r -> image k-block(s); col0 % 32 == 0
+__device__ __forceinline__ void tl_store_image(uint8_t* img_tile, int nkb_out, int r, int col0, const float (&x)[32]) {
+  const int kb = col0 >> 6;
+  if (kb >= nkb_out) return;
+  uint8_t* blk = img_tile + (size_t)kb * kTlBlockBytes + r * 128;
+  const int c16_0 = (col0 & 63) >> 3;                 // first 16-byte chunk (8 bf16) of this 32-column group
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_pack(x[8 * j + 2 * e], x[8 * j + 2 * e + 1], hi[e], lo[e]);
+    const int off = ((c16_0 + j) ^ (r & 7)) << 4;
+    *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kTlStages], empty_bar[kTlStages], d_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, cb = blockIdx.y;        // row tile, 128-column block
+  const int row0 = tile * 128, col_base = cb * 128;
+
+  // ---- inactive row tile (hit rays are compacted to the front of every segment): zero outputs, no arithmetic
+  {
+    const int sg = p.seg > 0 ? p.seg : (p.n > 0 ? p.n : 1);
+    const int n_act = p.n_active ? min(__ldg(p.n_active), sg) : sg;
+    const int o = row0 % sg;
+    if (o >= n_act && o + 128 <= sg) {
+      if (p.out != nullptr)
+        for (int i = tid; i < 128 * 128; i += kTlThreads) {
+          const int r = row0 + (i >> 7), c = col_base + (i & 127);
+          if (r < p.n && c < p.N) p.out[(size_t)r * p.ld_out + c] = 0.f;
+        }
+      if (p.out_img != nullptr)
+        for (int kb = 2 * cb; kb < 2 * cb + 2 && kb < p.nkb_out; ++kb) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out_img + ((size_t)tile * p.nkb_out + kb) * kTlBlockBytes);
+          for (int i = tid; i < kTlBlockBytes / 16; i += kTlThreads) dst[i] = make_uint4(0, 0, 0, 0);
+        }
+      return;
+    }
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < kTlStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================================== producer =====================================
+    const uint8_t* a_src = p.a_img + (size_t)tile * p.nkb * kTlBlockBytes;
+    const uint8_t* w_src = p.w_img + (size_t)cb * p.nkb * kTlBlockBytes;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int st = kb % kTlStages;
+      mbar_wait(&empty_bar[st], ((kb / kTlStages) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full_bar[st], kTlStageBytes);
+        bulk_g2s(ring + (size_t)st * kTlStageBytes, a_src + (size_t)kb * kTlBlockBytes, kTlBlockBytes, &full_bar[st]);
+        bulk_g2s(ring + (size_t)st * kTlStageBytes + kTlBlockBytes, w_src + (size_t)kb * kTlBlockBytes, kTlBlockBytes,
+                 &full_bar[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int st = kb % kTlStages;
+      mbar_wait(&full_bar[st], (kb / kTlStages) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint8_t* sa = ring + (size_t)st * kTlStageBytes;
+        const uint8_t* sb = sa + kTlBlockBytes;
+        const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + 16384);
+        const uint64_t b_hi = smem_desc_sw128(sb), b_lo = smem_desc_sw128(sb + 16384);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (kb == 0 && q == 0) umma_ss<0>(tmem_base, a_hi + 2u * q, b_hi + 2u * q, kTlIdesc);
+          else umma_ss<1>(tmem_base, a_hi + 2u * q, b_hi + 2u * q, kTlIdesc);
+          umma_ss<1>(tmem_base, a_lo + 2u * q, b_hi + 2u * q, kTlIdesc);
+          umma_ss<1>(tmem_base, a_hi + 2u * q, b_lo + 2u * q, kTlIdesc);
+        }
+        umma_commit(&empty_bar[st]);
+        if (kb == p.nkb - 1) umma_commit(&d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;
+    const int r = q * 32 + lane, row = row0 + r;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* img_tile = p.out_img ? p.out_img + (size_t)tile * p.nkb_out * kTlBlockBytes : nullptr;
+    mbar_wait(&d_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = col_base + 32 * c;
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
+      float x[32];
+      if (p.mode == 0) {
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float b = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
+          x[i] = (col0 + i < p.N) ? tl_act(__uint_as_float(acc[i]) + b, p.act) : 0.f;
+        }
+      } else {
+        float d[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          d[i] = (p.ref != nullptr && row < p.n && col0 + i < p.N)
+                     ? tl_dact(__ldg(p.ref + (size_t)row * p.ld_ref + col0 + i), p.act) : 1.f;
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = (col0 + i < p.N && row < p.n) ? __uint_as_float(acc[i]) * d[i] : 0.f;
+      }
+      if (p.out != nullptr && row < p.n) {
+        float* dst = p.out + (size_t)row * p.ld_out + col0;
+        if (col0 + 32 <= p.N && (p.ld_out & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) dst[i] = x[i];
+        }
+      }
+      if (img_tile != nullptr) tl_store_image(img_tile, p.nkb_out, r, col0, x);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// images
+// ------------------------------------------------------------------------------------------------------------------
+// weights: B[nn][kk] = transpose ? W[kk][nn] : W[nn][kk] (W row-major, leading dimension ldw), nn < N, kk < K, zero
+// padded to [col_blocks * 128][nkb * 64]; layout [col_block][kb][hi 16 KB | lo 16 KB], SWIZZLE_128B rows of 64 k
+__global__ void tl_pack_weight_kernel(const float* __restrict__ W, int ldw, int N, int K, int transpose, int col_blocks,
+                                      int nkb, uint8_t* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)col_blocks * nkb * 128 * 8;
+  if (idx >= total) return;
+  const int chunk = idx & 7, r = (idx >> 3) & 127;
+  const int blk = (int)(idx >> 10), kb = blk % nkb, cbk = blk / nkb;
+  const int nn = cbk * 128 + r;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = kb * 64 + chunk * 8 + 2 * q + e;
+      float v = 0.f;
+      if (nn < N && kk < K) v = transpose ? W[(size_t)kk * ldw + nn] : W[(size_t)nn * ldw + kk];
+      x[e] = v;
+    }
+    split_pack(x[0], x[1], hi[q], lo[q]);
+  }
+  uint8_t* b = img + (size_t)blk * kTlBlockBytes;
+  const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(b + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(b + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// activations: fp32 rows X [n][ldx] (columns < K valid, optionally multiplied by act'(ref)) -> image
+// [row_tiles][nkb][hi | lo]; rows >= n and columns >= K are zero
+__global__ void tl_pack_rows_kernel(const float* __restrict__ X, int ldx, int n, int K, const float* __restrict__ ref,
+                                    int ld_ref, int act, int nkb, uint8_t* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int tiles = (n + 127) / 128;
+  const long long total = (long long)tiles * nkb * 128 * 8;
+  if (idx >= total) return;
+  const int chunk = idx & 7, r = (idx >> 3) & 127;
+  const int blk = (int)(idx >> 10), kb = blk % nkb, tile = blk / nkb;
+  const int row = tile * 128 + r;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = kb * 64 + chunk * 8 + 2 * q + e;
+      float v = 0.f;
+      if (row < n && kk < K) {
+        v = X[(size_t)row * ldx + kk];
+        if (ref != nullptr) v *= tl_dact(ref[(size_t)row * ld_ref + kk], act);
+      }
+      x[e] = v;
+    }
+    split_pack(x[0], x[1], hi[q], lo[q]);
+  }
+  uint8_t* b = img + (size_t)blk * kTlBlockBytes;
+  const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(b + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(b + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+}  // namespace robir
+
+using namespace robir;
+
+extern "C" {
+
+int robir_tl_block_bytes(void) { return kTlBlockBytes; }
+
+// W [N][K] (ldw) -> weight image [ceil(N'/128)][nkb][32 KB]; transpose = 1 packs W^T (N' = K rows, contraction over N)
+int robir_tl_pack_weight(const float* W, int ldw, int N, int K, int transpose, int col_blocks, int nkb, void* img,
+                         void* stream) {
+  RB_REQUIRE(col_blocks * 128 >= N && nkb * 64 >= K, "tl_pack_weight: image smaller than the matrix");
+  const long long total = (long long)col_blocks * nkb * 128 * 8;
+  tl_pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, ldw, N, K, transpose,
+                                                                                           col_blocks, nkb, (uint8_t*)img);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 rows -> activation image (optionally times act'(ref): the last layer's activation derivative of a backward chain)
+int robir_tl_pack_rows(const float* X, int ldx, int n, int K, const float* ref, int ld_ref, int act, int nkb, void* img,
+                       void* stream) {
+  if (n == 0) return 0;
+  RB_REQUIRE(nkb * 64 >= K, "tl_pack_rows: image smaller than the rows");
+  const long long total = (long long)((n + 127) / 128) * nkb * 128 * 8;
+  tl_pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n, K, ref, ld_ref, act, nkb,
+                                                                                        (uint8_t*)img);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int robir_tl_layer(const TcLayerParams* p, void* stream) {
+  if (p->n == 0) return 0;
+  RB_REQUIRE(p->nkb >= 1 && p->nkb <= 8 && p->N >= 1, "tl_layer: 1..8 k-blocks (K <= 512)");
+  RB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTlSmem));
+  dim3 grid((p->n + 127) / 128, (p->N + 127) / 128);
+  tc_layer_kernel<<<grid, kTlThreads, kTlSmem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -7,7 +7,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, SphereTraceParams, check, f32, lib, ptr,
+from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, SphereTraceParams, TlParams, check, f32, lib, ptr,
                    sm_count, stream)
 
 TINY = 1e-6
@@ -261,7 +261,9 @@ class active_rows:
         return False
 
 
-ENGINE = {"vis": "tc"}     # "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
+# vis: visibility MLP; mlp: the 512-wide encoder / lobe chains of the material and indirect-illumination networks.
+# "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
+ENGINE = {"vis": "tc", "mlp": "tc"}
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
 
 
@@ -837,6 +839,35 @@ class MlpChain:
     weightnorm = False
     wgrad_streams = None      # side streams of this chain's weight-gradient GEMMs (created on first backward)
 
+    def tc_ok(self, n):
+        """The tensor-core layer engine takes chains with a 512-wide hidden layer (the encoders and the lobe network);
+        the narrow decoders stay on the FFMA chain kernel."""
+        if ENGINE["mlp"] != "tc" or self.weightnorm or self.in_mode == 0 or n < 128:
+            return False
+        dims = [(l.weight.shape[0], l.weight.shape[1]) for l in self.linears]
+        return max(d[0] for d in dims) >= 256 and all(d[0] <= 512 and d[1] <= 512 for d in dims)
+
+    def packed_tc(self):
+        """Per layer: forward image of W and backward image of W^T (csrc/tc_mlp.cu), cached like packed()."""
+        if "_tc_cache" not in self.__dict__:
+            self.__dict__["_tc_cache"] = _PackCache()
+        blk = 32768
+
+        def build():
+            out = []
+            for lin in self.linears:
+                W = f32(lin.weight)
+                N, K = W.shape
+                cbn, nkbk = (N + 127) // 128, (K + 63) // 64          # forward: rows N, contraction K
+                cbk, nkbn = (K + 127) // 128, (N + 63) // 64          # backward: rows K, contraction N
+                fw = torch.empty(cbn * nkbk * blk, dtype=torch.uint8, device=W.device)
+                bw = torch.empty(cbk * nkbn * blk, dtype=torch.uint8, device=W.device)
+                check(lib().robir_tl_pack_weight(ptr(W), K, N, K, 0, cbn, nkbk, ptr(fw), stream()))
+                check(lib().robir_tl_pack_weight(ptr(W), K, K, N, 1, cbk, nkbn, ptr(bw), stream()))
+                out.append(dict(fw=fw, bw=bw, nkb_fw=nkbk, nkb_bw=nkbn))
+            return out
+        return self.__dict__["_tc_cache"].get(self.params(), build)
+
     def wgrad_tickets(self, layer, tiles, like):
         """Persistent zero-initialised ticket counters of robir_mlp_wgrad's in-kernel split reduction (it re-zeroes them)."""
         t = self.__dict__.setdefault("_tickets", {})
@@ -884,6 +915,65 @@ def _mlp_params(chain, packed, n, x, extra, noise, noise_scale, n_active=None, s
     return p
 
 
+def _tl_params(a_img, w_img, bias, n, N, nkb, mode, act, ref, out, out_img, nkb_out, n_active, seg):
+    q = TlParams()
+    q.a_img, q.w_img, q.bias, q.n, q.N, q.nkb, q.mode, q.act = ptr(a_img), ptr(w_img), ptr(bias), n, N, nkb, mode, act
+    q.ref, q.ld_ref = ptr(ref), (ref.shape[1] if ref is not None else 0)
+    q.out, q.ld_out = ptr(out), (out.shape[1] if out is not None else 0)
+    q.out_img, q.nkb_out, q.n_active, q.seg = ptr(out_img), nkb_out, ptr(n_active), seg
+    return q
+
+
+def _tl_image(tiles, nkb, like):
+    return torch.empty(tiles * nkb * 32768, dtype=torch.uint8, device=like.device)
+
+
+def _tl_forward(chain, packed, p, n, x0, saves, out, n_active, segments):
+    """Forward of a chain on the tensor-core layer engine (csrc/tc_mlp.cu): embedding -> image -> one launch per layer.
+    saves[l] (post-activation rows of the hidden layers) are written when the caller allocated them."""
+    tc = chain.packed_tc()
+    tiles, seg = (n + 127) // 128, n // segments
+    seg_ok = seg % 128 == 0
+    na = n_active if seg_ok else None
+    check(lib().robir_mlp_encode(ctypes.byref(p), sm_count(), stream()))
+    img = _tl_image(tiles, tc[0]["nkb_fw"], x0)
+    check(lib().robir_tl_pack_rows(ptr(x0), x0.shape[1], n, packed[0]["K"], None, 0, 0, tc[0]["nkb_fw"], ptr(img), stream()))
+    L = len(packed)
+    for l, d in enumerate(packed):
+        last = l == L - 1
+        dst = out if last else (saves[l] if saves else None)
+        nkb_out = tc[l + 1]["nkb_fw"] if not last else 0
+        nxt = _tl_image(tiles, nkb_out, x0) if not last else None
+        q = _tl_params(img, tc[l]["fw"], d["bias"], n, d["N"], tc[l]["nkb_fw"], 0, chain.acts[l], None, dst, nxt, nkb_out,
+                       na, seg)
+        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+        img = nxt
+
+
+def _tl_backward(chain, packed, n, g_out, saves, Gs, g_x, n_active, segments, want_param_grad):
+    """Input-gradient chain on the layer engine: G_{l-1} = (G_l W_l) act'(A_{l-1}); Gs[l] (fp32, for the weight
+    gradients) are filled when requested; g_x receives the gradient of the embedded input."""
+    tc = chain.packed_tc()
+    tiles, seg = (n + 127) // 128, n // segments
+    na = n_active if seg % 128 == 0 else None
+    L = len(packed)
+    n_out = packed[-1]["N"]
+    if want_param_grad:
+        Gs[L - 1][:, :n_out].copy_(g_out)
+    img = _tl_image(tiles, tc[L - 1]["nkb_bw"], g_out)
+    check(lib().robir_tl_pack_rows(ptr(g_out), g_out.shape[1], n, n_out, None, 0, 0, tc[L - 1]["nkb_bw"], ptr(img), stream()))
+    for l in range(L - 1, -1, -1):
+        d = packed[l]
+        first = l == 0
+        dst = g_x if first else (Gs[l - 1] if want_param_grad else None)
+        nkb_out = tc[l - 1]["nkb_bw"] if not first else 0
+        nxt = _tl_image(tiles, nkb_out, g_out) if not first else None
+        q = _tl_params(img, tc[l]["bw"], None, n, d["K"], tc[l]["nkb_bw"], 1, chain.acts[l - 1] if not first else 0,
+                       saves[l - 1] if not first else None, dst, nxt, nkb_out, na, seg)
+        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+        img = nxt
+
+
 class _FusedMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, chain, x, extra, noise, noise_scale, want_param_grad, segments, *params):
@@ -908,7 +998,14 @@ class _FusedMLP(torch.autograd.Function):
                 x0 = _empty(n, packed[0]["Kpad"], like=x)
                 p.x0_save = x0.data_ptr()
         p.out, p.ldo = ptr(out), n_out
-        check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
+        ctx.tc = chain.tc_ok(n)
+        if ctx.tc:
+            if x0 is None:
+                x0 = _empty(n, packed[0]["Kpad"], like=x)
+                p.x0_save = x0.data_ptr()
+            _tl_forward(chain, packed, p, n, x0, saves, out, n_active, segments)
+        else:
+            check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
         ctx.chain, ctx.n, ctx.want_param_grad = chain, n, want_param_grad
         ctx.packed = packed                 # the backward of this step uses the very same packed copies
         ctx.has_extra = extra is not None
@@ -933,7 +1030,10 @@ class _FusedMLP(torch.autograd.Function):
                 p.L[l].G = G.data_ptr()
         g_x = _empty(n, packed[0]["Kpad"], like=x)
         p.g_out, p.ldo, p.g_x = ptr(g_out), packed[-1]["N"], ptr(g_x)
-        check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
+        if ctx.tc:
+            _tl_backward(chain, packed, n, g_out, saves, Gs, g_x, n_active, ctx.segments, ctx.want_param_grad)
+        else:
+            check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
         grads = []
         if ctx.want_param_grad:
             # dW_l = G_l^T A_{l-1} and db_l (csrc/mlp.cu wgrad_kernel): independent per layer -> parallel branches
