@@ -161,19 +161,39 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
       uint32_t acc[32];
       tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
       float x[32];
+      const bool full = col0 + 32 <= p.N;               // whole chunk inside the valid columns (the common case)
       if (p.mode == 0) {
+        float b[32];
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);   // zero padded to 128
+            b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) b[i] = 0.f;
+        }
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float b = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
-          x[i] = (col0 + i < p.N) ? tl_act(__uint_as_float(acc[i]) + b, p.act) : 0.f;
-        }
+        for (int i = 0; i < 32; ++i)
+          x[i] = (full || col0 + i < p.N) ? tl_act(__uint_as_float(acc[i]) + b[i], p.act) : 0.f;
       } else {
         float d[32];
+        if (p.ref != nullptr && row < p.n && full && (p.ld_ref & 3) == 0) {
+          const float4* rp = reinterpret_cast<const float4*>(p.ref + (size_t)row * p.ld_ref + col0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          d[i] = (p.ref != nullptr && row < p.n && col0 + i < p.N)
-                     ? tl_dact(__ldg(p.ref + (size_t)row * p.ld_ref + col0 + i), p.act) : 1.f;
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(rp + i);
+            d[4 * i] = tl_dact(v.x, p.act); d[4 * i + 1] = tl_dact(v.y, p.act);
+            d[4 * i + 2] = tl_dact(v.z, p.act); d[4 * i + 3] = tl_dact(v.w, p.act);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            d[i] = (p.ref != nullptr && row < p.n && col0 + i < p.N)
+                       ? tl_dact(__ldg(p.ref + (size_t)row * p.ld_ref + col0 + i), p.act) : 1.f;
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = (col0 + i < p.N && row < p.n) ? __uint_as_float(acc[i]) * d[i] : 0.f;
