@@ -44,10 +44,13 @@ class _PackCache:
     def __init__(self):
         self.key = None
         self.val = None
+        self.trained = False
 
     def get(self, tensors, build):
-        # "being trained" = has received a gradient (an optimizer may have updated it in place since the last use)
-        trainable = any(t.requires_grad and t.grad is not None for t in tensors)
+        # "being trained" = has received a gradient at some point (an optimizer may have updated it in place since the
+        # last use); sticky, because zero_grad(set_to_none=True) clears the gradients between forward and backward
+        self.trained = self.trained or any(t.requires_grad and t.grad is not None for t in tensors)
+        trainable = self.trained
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + \
             ((_pack_epoch[0],) if trainable else ())
         # Safety net for callers that capture a graph without ever announcing parameter updates: parameters that
@@ -928,10 +931,9 @@ def _tl_image(tiles, nkb, like):
     return torch.empty(tiles * nkb * 32768, dtype=torch.uint8, device=like.device)
 
 
-def _tl_forward(chain, packed, p, n, x0, saves, out, n_active, segments):
+def _tl_forward(chain, packed, tc, p, n, x0, saves, out, n_active, segments):
     """Forward of a chain on the tensor-core layer engine (csrc/tc_mlp.cu): embedding -> image -> one launch per layer.
     saves[l] (post-activation rows of the hidden layers) are written when the caller allocated them."""
-    tc = chain.packed_tc()
     tiles, seg = (n + 127) // 128, n // segments
     seg_ok = seg % 128 == 0
     na = n_active if seg_ok else None
@@ -950,10 +952,9 @@ def _tl_forward(chain, packed, p, n, x0, saves, out, n_active, segments):
         img = nxt
 
 
-def _tl_backward(chain, packed, n, g_out, saves, Gs, g_x, n_active, segments, want_param_grad):
+def _tl_backward(chain, packed, tc, n, g_out, saves, Gs, g_x, n_active, segments, want_param_grad):
     """Input-gradient chain on the layer engine: G_{l-1} = (G_l W_l) act'(A_{l-1}); Gs[l] (fp32, for the weight
     gradients) are filled when requested; g_x receives the gradient of the embedded input."""
-    tc = chain.packed_tc()
     tiles, seg = (n + 127) // 128, n // segments
     na = n_active if seg % 128 == 0 else None
     L = len(packed)
@@ -1003,7 +1004,8 @@ class _FusedMLP(torch.autograd.Function):
             if x0 is None:
                 x0 = _empty(n, packed[0]["Kpad"], like=x)
                 p.x0_save = x0.data_ptr()
-            _tl_forward(chain, packed, p, n, x0, saves, out, n_active, segments)
+            ctx.tc_images = chain.packed_tc()      # shared with this step's backward, like ctx.packed
+            _tl_forward(chain, packed, ctx.tc_images, p, n, x0, saves, out, n_active, segments)
         else:
             check(lib().robir_mlp_fwd(ctypes.byref(p), sm_count(), stream()))
         ctx.chain, ctx.n, ctx.want_param_grad = chain, n, want_param_grad
@@ -1031,7 +1033,8 @@ class _FusedMLP(torch.autograd.Function):
         g_x = _empty(n, packed[0]["Kpad"], like=x)
         p.g_out, p.ldo, p.g_x = ptr(g_out), packed[-1]["N"], ptr(g_x)
         if ctx.tc:
-            _tl_backward(chain, packed, n, g_out, saves, Gs, g_x, n_active, ctx.segments, ctx.want_param_grad)
+            _tl_backward(chain, packed, ctx.tc_images, n, g_out, saves, Gs, g_x, n_active, ctx.segments,
+                         ctx.want_param_grad)
         else:
             check(lib().robir_mlp_bwd(ctypes.byref(p), sm_count(), stream()))
         grads = []

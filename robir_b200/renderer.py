@@ -201,7 +201,12 @@ class IDRNetwork(nn.Module):
         keys = ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb', 'indir_specular_rgb',
                 'normals', 'diffuse_albedo', 'normal_map', 'vis_shadow', 'random_xi_diffuse_albedo', 'metallic',
                 'random_xi_metallic', 'roughness', 'random_xi_roughness')
-        wide = torch.cat([r[k] for k in keys], 1)
+        # only what the PBR loss differentiates keeps its graph (the others would drag zero gradients through the
+        # normal auto-encoder's backward; the reference's gradient contract has them at zero)
+        with_grad = ('sg_rgb', 'indir_rgb', 'diffuse_albedo', 'roughness', 'random_xi_diffuse_albedo',
+                     'random_xi_roughness', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb',
+                     'indir_specular_rgb')
+        wide = torch.cat([r[k] if k in with_grad else r[k].detach() for k in keys], 1)
         wide = torch.where(mask[:, None], wide.index_select(0, pos), torch.ones((), device=dev))
         c = 0
         for k in keys:
