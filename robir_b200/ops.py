@@ -1102,7 +1102,7 @@ def fork_join(fns, streams=None):
     if streams is None:
         st["next"] = base + len(fns) - 1
         while len(_side_streams) < st["next"]:
-            _side_streams.append(torch.cuda.Stream())
+            _side_streams.append(torch.cuda.Stream(priority=-1))
         sides = _side_streams[base:base + len(fns) - 1]
     else:
         sides = list(streams)[:len(fns) - 1]

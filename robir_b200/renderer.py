@@ -186,11 +186,19 @@ class IDRNetwork(nn.Module):
                 with ops.active_rows(n_act):
                     return fn()
             return run
-        (sgs, integ), mat, nrm, sdf_output = ops.fork_join([
+        # sdf_output is only reported (no consumer inside the step): it runs on its own low-priority stream and joins
+        # at the end of the forward instead of holding up the visibility kernels
+        main = torch.cuda.current_stream()
+        if getattr(self, "_aux_stream", None) is None or self._aux_stream.device != main.device:
+            self._aux_stream = torch.cuda.Stream(priority=0)
+        aux = self._aux_stream
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            sdf_output = self.implicit_network.sdf(points)[:, None]
+        (sgs, integ), mat, nrm = ops.fork_join([
             act(lambda: self.indirect_illum_network(pts, hdr)),
             act(lambda: self.envmap_material_network(pts, train_spec=train_spec)),
-            act(lambda: self.get_idr_render(pts, None, normal_only=True)),
-            lambda: self.implicit_network.sdf(points)[:, None]])
+            act(lambda: self.get_idr_render(pts, None, normal_only=True))])
         self.envmap_material_network._last_latent_valid = valid
         ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
@@ -216,6 +224,9 @@ class IDRNetwork(nn.Module):
         ret['roughness'] = ret['roughness'].expand(-1, 3)
         ret['random_xi_roughness'] = ret['random_xi_roughness'].expand(-1, 3)
         total, dev = points.shape[0], points.device
+        main.wait_stream(aux)
+        if not torch.cuda.is_current_stream_capturing():
+            sdf_output.record_stream(main)
         ret.update({'final_t': torch.ones(total, 1, device=dev), 'gradient_error': torch.zeros((), device=dev),
                     'acc': torch.ones(total, 1, device=dev), 'bg_rgb': torch.ones(total, 3, device=dev),
                     'surface_mask': mask})
