@@ -298,7 +298,10 @@ typedef struct {
   const float* sg_rgb; const float* indir_rgb;   /* [N][3], row strides ld_sg / ld_ind (floats) */
   int ld_sg, ld_ind;
   const float* gt;                                /* [N][3] */
-  const unsigned char* mask;                      /* [N] network_object_mask & object_mask */
+  const unsigned char* mask;                      /* [N] network_object_mask & object_mask (ray order) */
+  const unsigned char* hit;                       /* optional [N] network_object_mask (ray order), used with order */
+  const long long* order;                         /* optional [N]: input row i belongs to ray order[i] (hit rays compacted
+                                                     to the front); gt / mask / hit stay in ray order */
   const float* adapt_illum;                       /* [1] */
   const float* albedo; const float* albedo_r;     /* [N][3], strides ld_alb / ld_albr */
   int ld_alb, ld_albr;

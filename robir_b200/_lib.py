@@ -56,7 +56,7 @@ class TlParams(Structure):
 class LossParams(Structure):
     _fields_ = [("N", c_int), ("n_lat", c_int), ("M", c_int), ("l2", c_int), ("sg_rgb", c_void_p),
                 ("indir_rgb", c_void_p), ("ld_sg", c_int), ("ld_ind", c_int), ("gt", c_void_p), ("mask", c_void_p),
-                ("adapt_illum", c_void_p), ("albedo", c_void_p), ("albedo_r", c_void_p), ("ld_alb", c_int),
+                ("hit", c_void_p), ("order", c_void_p), ("adapt_illum", c_void_p), ("albedo", c_void_p), ("albedo_r", c_void_p), ("ld_alb", c_int),
                 ("ld_albr", c_int), ("rough", c_void_p), ("rough_r", c_void_p), ("ld_r", c_int), ("ld_rr", c_int),
                 ("z", c_void_p), ("z_valid", c_void_p), ("lgt", c_void_p), ("w_rgb", c_float), ("w_kl", c_float),
                 ("w_smooth", c_float), ("rho", c_float)] + [

@@ -16,8 +16,11 @@ struct LossParams {
   int l2;                // 0: L1 (hotdog.conf loss_type), 1: L2
   const float* sg_rgb; const float* indir_rgb;            // [N][3], row strides ld_sg / ld_ind (floats)
   int ld_sg, ld_ind;
-  const float* gt;                                         // [N][3]
-  const unsigned char* mask;                               // [N] network_object_mask & object_mask
+  const float* gt;                                         // [N][3]   (ray order)
+  const unsigned char* mask;                               // [N] network_object_mask & object_mask (ray order)
+  const unsigned char* hit;                                // optional [N] network_object_mask (ray order), with order
+  const long long* order;                                  // optional [N]: row i of the inputs is ray order[i] (the
+                                                           // fixed-capacity path keeps hit rays compacted to the front)
   const float* adapt_illum;                                // [1] gamma.hdr_shift.adapt_illum
   const float* albedo; const float* albedo_r;              // [N][3], strides ld_alb / ld_albr
   int ld_alb, ld_albr;
@@ -60,25 +63,28 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
 
   // ---- pass 1 over rays: rgb term (value + gradient), smooth terms (value + gradient)
   for (int i = tid; i < p.N; i += kLossThreads) {
-    const float m = p.mask[i] ? 1.f : 0.f;
+    const long long ray = p.order ? p.order[i] : i;
+    const float m = p.mask[ray] ? 1.f : 0.f;
+    // compacted inputs: the twins of a ray that missed are both 1.0 in the reference's ray-order buffers
+    const float hitrow = (p.order && p.hit) ? (p.hit[ray] ? 1.f : 0.f) : 1.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = p.sg_rgb[(size_t)i * p.ld_sg + c] + p.indir_rgb[(size_t)i * p.ld_ind + c];
       const float num = x * (2.51f * x + 0.03f), den = x * (2.43f * x + 0.59f) + 0.14f;
       const float ac = num / den;
       const float dac = ((5.02f * x + 0.03f) * den - num * (4.86f * x + 0.59f)) / (den * den);
-      const float diff = ac * inv_s02 - p.gt[(size_t)i * 3 + c];
+      const float diff = ac * inv_s02 - p.gt[(size_t)ray * 3 + c];
       const float dper = (p.l2 ? 2.f * diff : sgnf(diff)) * m;            // d per / d ldr
       acc[0] += (p.l2 ? diff * diff : fabsf(diff)) * m;
       acc[1] += dper * ac;                                                // times d (s^-0.2) / d s below
       p.g_pred[(size_t)i * 3 + c] = p.w_rgb * inv_N * dper * dac * inv_s02;
-      const float da = p.albedo[(size_t)i * p.ld_alb + c] - p.albedo_r[(size_t)i * p.ld_albr + c];
+      const float da = hitrow * (p.albedo[(size_t)i * p.ld_alb + c] - p.albedo_r[(size_t)i * p.ld_albr + c]);
       acc[2] += fabsf(da);
       const float ga = p.w_smooth * sgnf(da) * inv_N * (1.f / 3.f);
       p.g_albedo[(size_t)i * 3 + c] = ga;
       p.g_albedo_r[(size_t)i * 3 + c] = -ga;
     }
-    const float dr = p.rough[(size_t)i * p.ld_r] - p.rough_r[(size_t)i * p.ld_rr];
+    const float dr = hitrow * (p.rough[(size_t)i * p.ld_r] - p.rough_r[(size_t)i * p.ld_rr]);
     acc[3] += fabsf(dr);
     const float gr = p.w_smooth * 0.2f * sgnf(dr) * inv_N;
     p.g_rough[i] = gr;

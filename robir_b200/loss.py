@@ -80,7 +80,8 @@ class _FusedPBRLoss(torch.autograd.Function):
     the kernel also writes every input gradient, so backward is a scaling by the upstream gradient."""
 
     @staticmethod
-    def forward(ctx, sg_rgb, indir_rgb, adapt_illum, albedo, albedo_r, rough, rough_r, z, lgt, gt, mask, z_valid, cfg):
+    def forward(ctx, sg_rgb, indir_rgb, adapt_illum, albedo, albedo_r, rough, rough_r, z, lgt, gt, mask, z_valid, cfg,
+                hit=None, order=None):
         from . import _lib
         from ._lib import LossParams, check, lib, ptr, stream
         w_rgb, w_kl, w_smooth, l2 = cfg
@@ -109,32 +110,48 @@ class _FusedPBRLoss(torch.autograd.Function):
         lgt_c = lgt.detach().float().contiguous()
         a_c = adapt_illum.detach().float().reshape(1).contiguous()
         p.gt, p.mask, p.adapt_illum, p.z, p.z_valid, p.lgt = ptr(gt_c), ptr(mask_c), ptr(a_c), ptr(z_c), ptr(zv), ptr(lgt_c)
+        if order is not None:
+            hit_c = hit.detach().to(torch.uint8).contiguous()
+            order_c = order.detach().to(torch.int64).contiguous()
+            p.hit, p.order = ptr(hit_c), ptr(order_c)
         p.w_rgb, p.w_kl, p.w_smooth, p.rho = float(w_rgb), float(w_kl), float(w_smooth), 0.05
         losses = torch.empty(5, device=dev)
-        g = dict(g_pred=torch.empty(N, 3, device=dev), g_adapt=torch.empty(1, device=dev),
-                 g_albedo=torch.empty(N, 3, device=dev), g_albedo_r=torch.empty(N, 3, device=dev),
-                 g_rough=torch.empty(N, device=dev), g_rough_r=torch.empty(N, device=dev),
-                 g_z=torch.empty(n_lat, 32, device=dev), g_lgt=torch.empty(M, 7, device=dev))
+        # every gradient lives in one flat buffer: the backward scales it with a single launch
+        sizes = dict(g_pred=N * 3, g_adapt=1, g_albedo=N * 3, g_albedo_r=N * 3, g_rough=N, g_rough_r=N, g_z=n_lat * 32,
+                     g_lgt=M * 7)
+        flat = torch.empty(sum(-(-v // 4) * 4 for v in sizes.values()), device=dev)
+        g, off = {}, 0
+        for k, v in sizes.items():
+            g[k] = (off, v)
+            off += -(-v // 4) * 4
         p.losses = ptr(losses)
-        for k, t in g.items():
-            setattr(p, k, ptr(t))
+        for k, (o, v) in g.items():
+            setattr(p, k, ctypes.c_void_p(flat.data_ptr() + 4 * o))
         check(lib().robir_pbr_loss(ctypes.byref(p), stream()))
-        ctx.save_for_backward(*g.values())
+        ctx.save_for_backward(flat)
+        ctx.layout = (g, N, n_lat, M)
         ctx.shapes = (tuple(adapt_illum.shape), tuple(rough.shape), tuple(rough_r.shape))
         ctx.mark_non_differentiable(losses)
         return losses[0], losses
 
     @staticmethod
     def backward(ctx, g_loss, _g_all):
-        g_pred, g_adapt, g_alb, g_albr, g_r, g_rr, g_z, g_lgt = ctx.saved_tensors
+        flat, = ctx.saved_tensors
+        g, N, n_lat, M = ctx.layout
         sa, sr, srr = ctx.shapes
+        scaled = flat * g_loss
+        view = lambda k, *shape: scaled[g[k][0]:g[k][0] + g[k][1]].view(*shape)
+        g_pred = view("g_pred", N, 3)
 
-        def col0(g, shape):         # roughness arrives as [N, 1] or [N, 3] (expanded): the loss reads column 0 only
-            out = torch.zeros(shape, device=g.device)
-            out[:, 0] = g * g_loss
+        def col0(k, shape):         # roughness arrives as [N, 1] or [N, 3] (expanded): the loss reads column 0 only
+            if shape[1] == 1:
+                return view(k, N, 1)
+            out = torch.zeros(shape, device=flat.device)
+            out[:, 0] = view(k, N)
             return out
-        return (g_pred * g_loss, g_pred * g_loss, (g_adapt * g_loss).reshape(sa), g_alb * g_loss, g_albr * g_loss,
-                col0(g_r, sr), col0(g_rr, srr), g_z * g_loss, g_lgt * g_loss, None, None, None, None)
+        return (g_pred, g_pred, view("g_adapt", 1).reshape(sa), view("g_albedo", N, 3), view("g_albedo_r", N, 3),
+                col0("g_rough", sr), col0("g_rough_r", srr), view("g_z", n_lat, 32), view("g_lgt", M, 7),
+                None, None, None, None, None, None)
 
 
 def fused_pbr_loss(model, loss_fn, model_outputs, ground_truth):
@@ -154,9 +171,18 @@ def fused_pbr_loss(model, loss_fn, model_outputs, ground_truth):
             return None
     nm = o['network_object_mask'] & o['object_mask']
     cfg = (loss_fn.sg_rgb_weight, loss_fn.kl_weight * 1.0, loss_fn.latent_smooth_weight * 0.1, loss_fn.l2)
-    loss, parts = _FusedPBRLoss.apply(o['sg_rgb'], o['indir_rgb'], model.gamma.hdr_shift.adapt_illum,
-                                      o['diffuse_albedo'], o['random_xi_diffuse_albedo'], o['roughness'],
-                                      o['random_xi_roughness'], z, mat.lgtSGs, ground_truth['rgb'], nm, z_valid, cfg)
+    c = getattr(model, "_static_compact", None) if loss_fn.static_shapes else None
+    if c is not None and c["ret_sg_rgb"] is o['sg_rgb']:
+        # fixed-capacity forward: feed the kernel the compacted tensors (row i = ray order[i]); same value, and the
+        # backward goes straight into the render / material graph without the un-permute
+        loss, parts = _FusedPBRLoss.apply(c['sg_rgb'], c['indir_rgb'], model.gamma.hdr_shift.adapt_illum,
+                                          c['diffuse_albedo'], c['random_xi_diffuse_albedo'], c['roughness'],
+                                          c['random_xi_roughness'], z, mat.lgtSGs, ground_truth['rgb'], nm, z_valid, cfg,
+                                          o['network_object_mask'], c['order'])
+    else:
+        loss, parts = _FusedPBRLoss.apply(o['sg_rgb'], o['indir_rgb'], model.gamma.hdr_shift.adapt_illum,
+                                          o['diffuse_albedo'], o['random_xi_diffuse_albedo'], o['roughness'],
+                                          o['random_xi_roughness'], z, mat.lgtSGs, ground_truth['rgb'], nm, z_valid, cfg)
     if loss_fn.static_shapes:
         normal_loss = torch.zeros((), device=loss.device)
     else:

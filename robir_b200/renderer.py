@@ -224,6 +224,12 @@ class IDRNetwork(nn.Module):
         ret['roughness'] = ret['roughness'].expand(-1, 3)
         ret['random_xi_roughness'] = ret['random_xi_roughness'].expand(-1, 3)
         total, dev = points.shape[0], points.device
+        # the same quantities in compacted row order, for robir_b200.loss.pbr_step_loss: its fused kernel reads them
+        # directly (gathering gt / masks through `order`), so the backward never walks the un-permute above
+        self._static_compact = dict(order=order, ret_sg_rgb=ret['sg_rgb'], sg_rgb=r['sg_rgb'], indir_rgb=r['indir_rgb'],
+                                    diffuse_albedo=r['diffuse_albedo'], roughness=r['roughness'],
+                                    random_xi_diffuse_albedo=r['random_xi_diffuse_albedo'],
+                                    random_xi_roughness=r['random_xi_roughness'])
         main.wait_stream(aux)
         if not torch.cuda.is_current_stream_capturing():
             sdf_output.record_stream(main)

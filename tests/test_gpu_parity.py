@@ -794,3 +794,39 @@ def test_tc_layer_engine_matches_ffma_chain(model16):
     finally:
         ops.ENGINE["mlp"] = "tc"
         ind.train_weights = False
+
+
+def test_static_compact_loss_matches_ray_order_loss(model16):
+    """Fixed-capacity forward: the fused loss on the compacted tensors (rows gathered through `order`) against the torch
+    restatement on the ray-order outputs of the same forward -- value and gradients."""
+    from robir_b200 import loss as L, rng
+    model16.generate()
+    N = 512
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(12, n=N, crop=460)).items()}
+    inp["hdr_shift"] = model16.gamma.hdr_shift.as_input().expand(N, 1)
+    gen = torch.Generator().manual_seed(9)
+    gt = {"rgb": torch.rand(1, N, 3, generator=gen).cuda()}
+    fn = L.InvLoss()
+    fn.static_shapes = True
+    model16.static_shapes = True
+    rng.set_mode("device")
+    try:
+        out = model16(inp, trainstage="Material", train_spec=True)
+        assert 0 < int(out["network_object_mask"].sum()) < N
+        got, parts = L.pbr_step_loss(model16, fn, out, gt)
+        L.FUSED_LOSS = False
+        try:
+            ref, ref_parts = L.pbr_step_loss(model16, fn, out, gt)
+        finally:
+            L.FUSED_LOSS = True
+        assert abs(got.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+        mat = model16.envmap_material_network
+        enc = mat.spec_brdf_encoder_layer.brdf_encoder_layer
+        leaves = [mat.lgtSGs, mat.specular_reflectance, model16.gamma.hdr_shift.adapt_illum, enc[0].bias, enc[8].weight]
+        g_ref = torch.autograd.grad(ref, leaves, retain_graph=True)
+        g_got = torch.autograd.grad(got, leaves, retain_graph=True)
+        for a, b in zip(g_got, g_ref):
+            assert (a - b).abs().max().item() <= 5e-4 * max(1e-7, b.abs().max().item())
+    finally:
+        rng.set_mode("cpu")
+        model16.static_shapes = False
