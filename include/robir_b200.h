@@ -132,8 +132,9 @@ int robir_sample_dirs_bwd(int K, int S, const float* axis_f, const float* axis_w
 int robir_pe_linear(const float* x, int n, const float* Wt, const float* bias, float* tab, void* stream);
 
 /* ---- a10: (point, direction) pair lists.  live(i,j) = n_i . dir_j > 1e-6 (model/sg_render.py:155, :246) ----------- */
-/* tile_rows = 64 (FFMA engine) or 128 (tensor-core engine): every point's rows are padded to that multiple. */
-int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals, const float* dirs,
+/* tile_rows = 64 (FFMA engine) or 128 (tensor-core engine).  pad_points != 0: every point's rows are padded to a tile
+ * multiple (one point per tile); 0: points are packed back to back, only the last tile is padded (rowB = -1). */
+int robir_diffuse_rows(int n, int M, int S, int tile_rows, int pad_points, const float* normals, const float* dirs,
                        uint32_t* bits /*[n][M]*/, int* lobe_off /*[n][M+1]*/, int* start /*[n]*/, int* rowA,
                        int* rowB /*[n*roundup(M*S,tile_rows)]*/, int* n_tiles /*[1]*/,
                        long long* n_pairs /*[1], accumulated*/, void* stream);

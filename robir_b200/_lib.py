@@ -99,7 +99,7 @@ _SIGNATURES = {
     "robir_pe_linear": [_P, _I, _P, _P, _P, _P],
     "robir_sample_dirs_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "robir_sample_dirs_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
-    "robir_diffuse_rows": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "robir_diffuse_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_spec_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "robir_spec_prep_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_spec_prep_bwd": [_I, _P, _P, _P, _P, _P, _P, _P],

@@ -193,8 +193,12 @@ __global__ void diffuse_count_kernel(int n, int M, int S, const float* __restric
 }
 
 // exclusive scan of 64-padded per-point counts; writes start[i] (row offset) and counters: n_tiles, n_pairs
-__global__ void diffuse_scan_kernel(int n, int M, int pad, const int* __restrict__ lobe_off, int* __restrict__ start,
-                                    int* __restrict__ n_tiles, long long* __restrict__ n_pairs) {
+// pad = tile: every point is padded to a tile multiple; pad = 1: points are packed back to back and only the last
+// tile is padded (rowB = -1 on its tail), which saves ~half a tile of dead rows per point
+__global__ void diffuse_scan_kernel(int n, int M, int pad, int tile, const int* __restrict__ lobe_off,
+                                    int* __restrict__ start, int* __restrict__ n_tiles, long long* __restrict__ n_pairs,
+                                    int* __restrict__ rowA, int* __restrict__ rowB) {
+  __shared__ int s_total;
   __shared__ int s_part[1024];
   __shared__ long long s_pairs[1024];
   const int t = threadIdx.x, T = blockDim.x;
@@ -221,10 +225,15 @@ __global__ void diffuse_scan_kernel(int n, int M, int pad, const int* __restrict
       run += v;
       p += s_pairs[q];
     }
-    *n_tiles = run / pad;
+    *n_tiles = (run + tile - 1) / tile;
     *n_pairs += p;
+    s_total = run;
   }
   __syncthreads();
+  for (int q = s_total + t; q < ((s_total + tile - 1) / tile) * tile; q += T) {   // tail of the last tile
+    rowA[q] = 0;
+    rowB[q] = -1;
+  }
   int run = s_part[t];
   for (int q = 0; q < per; ++q) {
     const int i = t * per + q;
@@ -684,11 +693,11 @@ int robir_sample_dirs_bwd(int K, int S, const float* axis_f, const float* axis_w
   return 0;
 }
 
-// Builds the diffuse row list, every point padded to a multiple of tile_rows (64: FFMA engine, 128: tensor-core
-// engine).  Workspace (caller-owned, int32 unless noted): bits [n*M] (u32), lobe_off [n*(M+1)], start [n],
+// Builds the diffuse row list for tiles of tile_rows rows (64: FFMA engine, 128: tensor-core engine); pad_points != 0
+// pads every point to a tile multiple (one point per tile), 0 packs the points back to back (tensor-core engine).  Workspace (caller-owned, int32 unless noted): bits [n*M] (u32), lobe_off [n*(M+1)], start [n],
 // rowA/rowB [n * roundup(M*S, tile_rows)], counters: n_tiles [1] (int), n_pairs [1] (int64, accumulated).
-int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals, const float* dirs, uint32_t* bits,
-                       int* lobe_off, int* start, int* rowA, int* rowB, int* n_tiles, long long* n_pairs,
+int robir_diffuse_rows(int n, int M, int S, int tile_rows, int pad_points, const float* normals, const float* dirs,
+                       uint32_t* bits, int* lobe_off, int* start, int* rowA, int* rowB, int* n_tiles, long long* n_pairs,
                        void* stream) {
   RB_REQUIRE(S >= 1 && S <= 32, "diffuse_rows: S must be in [1,32]");
   RB_REQUIRE(tile_rows == 64 || tile_rows == 128, "diffuse_rows: tile_rows must be 64 or 128");
@@ -698,8 +707,9 @@ int robir_diffuse_rows(int n, int M, int S, int tile_rows, const float* normals,
     return 0;
   }
   diffuse_count_kernel<<<n, 256, M * sizeof(int), st>>>(n, M, S, normals, dirs, bits, lobe_off);
-  diffuse_scan_kernel<<<1, 1024, 0, st>>>(n, M, tile_rows, lobe_off, start, n_tiles, n_pairs);
-  diffuse_fill_kernel<<<n, 256, 0, st>>>(n, M, S, tile_rows, bits, lobe_off, start, rowA, rowB);
+  const int pad = pad_points ? tile_rows : 1;
+  diffuse_scan_kernel<<<1, 1024, 0, st>>>(n, M, pad, tile_rows, lobe_off, start, n_tiles, n_pairs, rowA, rowB);
+  diffuse_fill_kernel<<<n, 256, 0, st>>>(n, M, S, pad, bits, lobe_off, start, rowA, rowB);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -340,7 +340,9 @@ class _DiffuseVis(torch.autograd.Function):
         rowA = _empty(n * cap, dtype=torch.int32, like=dev)
         rowB = _empty(n * cap, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
-        check(lib().robir_diffuse_rows(n, M, S, T, ptr(normals), ptr(dirs), ptr(bits), ptr(lobe_off), ptr(start),
+        # tensor-core engine: points packed back to back (rows of one tile may belong to two points)
+        check(lib().robir_diffuse_rows(n, M, S, T, 0 if ENGINE["vis"] == "tc" else 1, ptr(normals), ptr(dirs), ptr(bits),
+                                       ptr(lobe_off), ptr(start),
                                        ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
         tabA = point_table(W, points)
         tabB = pe_linear(dirs, W["Wt0d"], None)
