@@ -468,30 +468,55 @@ __global__ void diffuse_reduce_fwd_kernel(int n, int M, int S, const uint32_t* _
   light_vis[idx] = num / (den + kTiny);
 }
 
-// diffuse backward: g_vis[q] and g_w[m,s] from g_LV[i][m]
-__global__ void diffuse_reduce_bwd_kernel(int n, int M, int S, const uint32_t* __restrict__ bits,
-                                          const int* __restrict__ lobe_off, const int* __restrict__ start,
-                                          const float* __restrict__ vis, const float* __restrict__ w,
-                                          const float* __restrict__ light_vis, const float* __restrict__ g_lv,
-                                          float* __restrict__ g_vis, float* __restrict__ g_w) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * M) return;
-  const int i = idx / M, m = idx % M;
-  const float g = g_lv[idx];
-  const unsigned b = bits[idx];
-  int q = start[i] + lobe_off[(size_t)i * (M + 1) + m];
+// diffuse backward: g_vis[q] and g_w[m,s] from g_LV[i][m].  One CTA per lobe m, threads over the points: the S
+// per-sample sums over the points are reduced inside the CTA and written once (no atomics, fixed summation order).
+__global__ void __launch_bounds__(256) diffuse_reduce_bwd_kernel(int n, int M, int S, const uint32_t* __restrict__ bits,
+                                                                 const int* __restrict__ lobe_off,
+                                                                 const int* __restrict__ start,
+                                                                 const float* __restrict__ vis, const float* __restrict__ w,
+                                                                 const float* __restrict__ light_vis,
+                                                                 const float* __restrict__ g_lv, float* __restrict__ g_vis,
+                                                                 float* __restrict__ g_w) {
+  __shared__ float s_w[32];
+  __shared__ float s_red[8][32];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 32) s_w[tid] = tid < S ? w[m * S + tid] : 0.f;
+  __syncthreads();
   float den = 0.f;
-  for (int s = 0; s < S; ++s) den += w[m * S + s];
+  for (int s = 0; s < S; ++s) den += s_w[s];
   const float inv = 1.f / (den + kTiny);
-  const float lv = light_vis[idx];
-  for (int s = 0; s < S; ++s) {
-    float v = 0.f;
-    if ((b >> s) & 1u) {
-      v = vis[q];
-      g_vis[q] = g * w[m * S + s] * inv;
-      ++q;
+  float acc[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) acc[s] = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const size_t idx = (size_t)i * M + m;
+    const float g = g_lv[idx];
+    const unsigned b = bits[idx];
+    if (g == 0.f && b == 0u) continue;
+    int q = start[i] + lobe_off[(size_t)i * (M + 1) + m];
+    const float lv = light_vis[idx];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      if (s >= S) break;
+      float v = 0.f;
+      if ((b >> s) & 1u) {
+        v = vis[q];
+        g_vis[q] = g * s_w[s] * inv;
+        ++q;
+      }
+      acc[s] += g * (v - lv) * inv;
     }
-    if (g != 0.f) atomicAdd(g_w + m * S + s, g * (v - lv) * inv);
+  }
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const float v = warp_sum(acc[s]);
+    if (lane == 0) s_red[warp][s] = v;
+  }
+  __syncthreads();
+  if (tid < S) {
+    float t = 0.f;
+    for (int wp = 0; wp < 8; ++wp) t += s_red[wp][tid];
+    g_w[m * S + tid] = t;
   }
 }
 
@@ -772,13 +797,13 @@ int robir_diffuse_reduce_fwd(int n, int M, int S, const uint32_t* bits, const in
   return 0;
 }
 
-// g_w must be zero-initialised by the caller.
+// g_w [M*S] is written (not accumulated); g_vis rows of dead samples are not touched (zero-initialise).
 int robir_diffuse_reduce_bwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,
                              const float* vis, const float* w, const float* light_vis, const float* g_lv, float* g_vis,
                              float* g_w, void* stream) {
   if (n * M == 0) return 0;
-  diffuse_reduce_bwd_kernel<<<cdiv((long long)n * M, 128), 128, 0, (cudaStream_t)stream>>>(
-      n, M, S, bits, lobe_off, start, vis, w, light_vis, g_lv, g_vis, g_w);
+  diffuse_reduce_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(n, M, S, bits, lobe_off, start, vis, w, light_vis, g_lv,
+                                                                 g_vis, g_w);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
