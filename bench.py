@@ -321,7 +321,7 @@ def main():
     achieved = FLOP_PER_QUERY * pairs_prof / max(t_fwd, 1e-9) / 1e12
     traffic = None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_v8_ncu_vis_tc.json")))["fwd_diffuse"]["dram_bytes"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_v12_ncu_vis_tc.json")))["fwd_diffuse"]["dram_bytes"]
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "vis_tc_kernel<0> (visibility MLP forward, diffuse pair list)",
