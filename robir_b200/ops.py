@@ -327,7 +327,7 @@ class _DiffuseVis(torch.autograd.Function):
     (model/sg_render.py:148-195).  Differentiable w.r.t. dirs and w only."""
 
     @staticmethod
-    def forward(ctx, points, normals, dirs, w, M, S, weights, need_grad):
+    def forward(ctx, points, normals, dirs, w, M, S, weights, need_grad, tabB=None):
         W = weights.get()
         points, normals, dirs, w = map(f32, (points, normals, dirs, w))
         n = points.shape[0]
@@ -345,7 +345,8 @@ class _DiffuseVis(torch.autograd.Function):
                                        ptr(lobe_off), ptr(start),
                                        ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
         tabA = point_table(W, points)
-        tabB = pe_linear(dirs, W["Wt0d"], None)
+        if tabB is None:
+            tabB = pe_linear(dirs, W["Wt0d"], None)
         max_tiles = n * cap // T
         vis, mask = _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_grad)
         lv = _empty(n, M, like=dev)
@@ -367,7 +368,7 @@ class _DiffuseVis(torch.autograd.Function):
         check(lib().robir_diffuse_reduce_bwd(n, M, S, ptr(bits), ptr(lobe_off), ptr(start), ptr(vis), ptr(w), ptr(lv),
                                              ptr(g_lv), ptr(g_vis), ptr(g_w), stream()))
         g_dirs = _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs, engine)
-        return None, None, g_dirs, g_w, None, None, None, None
+        return None, None, g_dirs, g_w, None, None, None, None, None
 
 
 class _SpecVis(torch.autograd.Function):
@@ -458,8 +459,9 @@ def spec_prep(normal, view, rough, valid=None):
     return _SpecPrep.apply(normal, view, rough, valid)
 
 
-def diffuse_vis(points, normals, dirs, w, M, S, weights, need_grad):
-    return _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad)
+def diffuse_vis(points, normals, dirs, w, M, S, weights, need_grad, tabB=None):
+    """tabB: optional pre-computed direction table pe_linear(dirs, Wt0d) of the same weights."""
+    return _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad, tabB)
 
 
 def spec_vis(points, normals, dirs, w, S, inv, testing, weights, need_grad):

@@ -195,15 +195,29 @@ class IDRNetwork(nn.Module):
         aux.wait_stream(main)
         with torch.cuda.stream(aux):
             sdf_output = self.implicit_network.sdf(points)[:, None]
-        (sgs, integ), mat, nrm = ops.fork_join([
+        def diffuse_samples():
+            # light-lobe sample directions and their layer-0 table only need the light SGs and the random draws: made
+            # while the networks run (last in the list: its draws follow the networks' draws, as in the reference)
+            mnet = self.envmap_material_network
+            lgt = mnet.lgtSGs
+            if mnet.upper_hemi:
+                lgt = torch.cat((lgt[..., :1], torch.abs(lgt[..., 1:2]), lgt[..., 2:]), dim=-1)
+            lobes, lambdas = sg_render.light_lobes(lgt)
+            dirs, w = sg_render.sample_diffuse_dirs(lobes, lambdas, 32, dev)
+            if ops.ENGINE["vis"] != "tc":
+                return dirs, w
+            W = sg_render._weights_of(self.visibility_network).get()
+            return dirs, w, ops.pe_linear(dirs.detach(), W["Wt0d"], None)
+        (sgs, integ), mat, nrm, presampled = ops.fork_join([
             act(lambda: self.indirect_illum_network(pts, hdr)),
             act(lambda: self.envmap_material_network(pts, train_spec=train_spec)),
-            act(lambda: self.get_idr_render(pts, None, normal_only=True))])
+            act(lambda: self.get_idr_render(pts, None, normal_only=True)),
+            diffuse_samples])
         self.envmap_material_network._last_latent_valid = valid
         ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
         r = pbr_get_sg_render(self, pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
-                              valid=valid, precomputed=(nrm, mat))
+                              valid=valid, precomputed=(nrm, mat), diffuse_presampled=presampled)
         # back to ray order, 1.0 for the rays that missed (implicit_differentiable_renderer.py:365-385): one gather over
         # the column-concatenated outputs instead of one per tensor
         keys = ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb', 'indir_specular_rgb',
@@ -257,7 +271,8 @@ class IDRNetwork(nn.Module):
 
 
 def pbr_get_sg_render(model, points, view_dirs, indir_lgtSGs, albedo_ratio=None, fun_spec=False, lin_diff=False,
-                      train_spec=False, indir_integral=None, valid=None, precomputed=None, **kwargs):
+                      train_spec=False, indir_integral=None, valid=None, precomputed=None, diffuse_presampled=None,
+                      **kwargs):
     """training/train_pbr.py:348-396 (model.no_normal / model.is_training play the runner's attributes).
     valid: optional [n] bool mask of the static-shape mode (rows that are not surface hits are carried along with a
     zero normal, which culls all of their visibility queries)."""
@@ -278,7 +293,8 @@ def pbr_get_sg_render(model, points, view_dirs, indir_lgtSGs, albedo_ratio=None,
                                       specular_reflectance=mat['sg_specular_reflectance'].abs(),
                                       roughness=mat['sg_roughness'], diffuse_albedo=mat['sg_diffuse_albedo'],
                                       indir_lgtSGs=indir_lgtSGs, VisModel=model.visibility_network, fun_spec=False,
-                                      lin_diff=False, testing=not model.is_training, metallic=None, valid=valid)
+                                      lin_diff=False, testing=not model.is_training, metallic=None, valid=valid,
+                                      diffuse_presampled=diffuse_presampled)
     ret.update(sg)
     ret.update({'diffuse_albedo': mat['sg_diffuse_albedo'], 'roughness': mat['sg_roughness'],
                 'metallic': mat['sg_metallic'], 'normal_map': normal_map,

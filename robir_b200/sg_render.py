@@ -29,25 +29,42 @@ def _norm_axis(x):
     return x / (torch.norm(x, dim=-1, keepdim=True) + TINY_NUMBER)
 
 
-def get_diffuse_visibility(points, normals, VisModel, lgtSGLobes, lgtSGLambdas, nsamp=8, testing=False, thr=1.0,
-                           bounding=False, argmax_vis=False):
-    """[n,3], [n,3], VisModel, lobes [M,3], lambdas [M,1] -> vis [M, n]."""
-    if bounding or argmax_vis:
-        raise RobirError("bounding / argmax_vis variants are not on the accelerated path")
+def sample_diffuse_dirs(lgtSGLobes, lgtSGLambdas, nsamp, dev, thr=1.0):
+    """Sample directions / weights of get_diffuse_visibility (model/sg_render.py:122-147): they depend on the light SGs
+    and the random draws only, so the fixed-capacity forward draws them while the per-point networks run."""
     M = lgtSGLobes.shape[0]
-    n = points.shape[0]
-    dev = points.device
     sharp = torch.clamp(lgtSGLambdas[:, 0], min=1e-4)
     sg_range = torch.clamp(sharp.min(), max=thr).reshape(1)
     u_theta = rng.rand((M, nsamp), dev)
     u_phi = rng.rand((M, nsamp), dev)
-    dirs, w = ops.sample_dirs(lgtSGLobes, lgtSGLobes, sharp, lgtSGLambdas[:, 0], sg_range, u_theta, u_phi, True)
+    return ops.sample_dirs(lgtSGLobes, lgtSGLobes, sharp, lgtSGLambdas[:, 0], sg_range, u_theta, u_phi, True)
+
+
+def light_lobes(lgtSGs):
+    """(lobes [M,3], lambdas [M,1]) of the shared light SGs as render_with_sg normalises them (sg_render.py:364-366)."""
+    return lgtSGs[:, :3] / (torch.norm(lgtSGs[:, :3], dim=-1, keepdim=True) + TINY_NUMBER), torch.abs(lgtSGs[:, 3:4])
+
+
+def get_diffuse_visibility(points, normals, VisModel, lgtSGLobes, lgtSGLambdas, nsamp=8, testing=False, thr=1.0,
+                           bounding=False, argmax_vis=False, presampled=None):
+    """[n,3], [n,3], VisModel, lobes [M,3], lambdas [M,1] -> vis [M, n].  presampled: (dirs, w[, tabB]) drawn earlier
+    with sample_diffuse_dirs on the same lobes."""
+    if bounding or argmax_vis:
+        raise RobirError("bounding / argmax_vis variants are not on the accelerated path")
+    M = lgtSGLobes.shape[0]
+    tabB = None
+    if presampled is None:
+        dirs, w = sample_diffuse_dirs(lgtSGLobes, lgtSGLambdas, nsamp, points.device, thr)
+    else:
+        dirs, w = presampled[0], presampled[1]
+        tabB = presampled[2] if len(presampled) > 2 else None
     need_grad = torch.is_grad_enabled() and not testing and (dirs.requires_grad or w.requires_grad)
     if testing:
         dirs_q, w_q = dirs.detach(), w   # the reference runs VisModel under no_grad but keeps the weights' graph
     else:
         dirs_q, w_q = dirs, w
-    lv = ops.diffuse_vis(points.detach(), normals.detach(), dirs_q, w_q, M, nsamp, _weights_of(VisModel), need_grad)
+    lv = ops.diffuse_vis(points.detach(), normals.detach(), dirs_q, w_q, M, nsamp, _weights_of(VisModel), need_grad,
+                         tabB)
     return lv.permute(1, 0)
 
 
@@ -88,7 +105,8 @@ def _spec_warp(normal, viewdirs, roughness):
 
 def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
                        indir_integral=None, indir_lgtSGs=None, VisModel=None, fun_spec=False, lin_diff=False,
-                       testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False, valid=None):
+                       testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False, valid=None,
+                       diffuse_presampled=None):
     """model/sg_render.py:304-337 for the PBR-stage configuration (fun_spec=False, metallic=None, diffuse_vis=None)."""
     if fun_spec or metallic is not None or diffuse_vis is not None or argmax_vis or viewdirs.dim() != 2:
         raise RobirError("render_with_all_sg: fun_spec / metallic / diffuse_vis / argmax_vis / multi-view variants are "
@@ -97,19 +115,18 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
         raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
     with ops.point_table_scope():
         return _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
-                                   indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid)
+                                   indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled)
 
 
 def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
-                        indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid):
+                        indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled=None):
     n = normal.shape[0]
     M = lgtSGs.shape[0]
     viewdirs = viewdirs.detach()
     # ---- direct light visibility per lobe (sg_render.py:364-366, 388-391)
-    lobes = lgtSGs[:, :3] / (torch.norm(lgtSGs[:, :3], dim=-1, keepdim=True) + TINY_NUMBER)
-    lambdas = torch.abs(lgtSGs[:, 3:4])
+    lobes, lambdas = light_lobes(lgtSGs)
     light_vis = get_diffuse_visibility(points, normal.detach(), VisModel, lobes, lambdas, nsamp=32,
-                                       testing=testing).permute(1, 0)
+                                       testing=testing, presampled=diffuse_presampled).permute(1, 0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
     bv_ind = None
     if indir_lgtSGs is not None:
