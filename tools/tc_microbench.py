@@ -1,5 +1,5 @@
-"""Diagnostic: times robir_vis_tc_fwd / bwd alone on a synthetic pair list, with the ROBIR_TC_DEBUG knock-outs
-(csrc/vis_tc.cu) to see which of {tensor pipe, epilogue, gathers, mask stores} bounds the kernel.  Not a bench."""
+"""Diagnostic: times robir_vis_tc_fwd / bwd alone on a synthetic pair list (148 x 40 tiles by default) and prints the
+time per tile round and the algorithmic TFLOP/s.  Not a bench (no clocks record, no L2 flush)."""
 import os
 import sys
 import torch
@@ -42,21 +42,18 @@ def main():
 
     flop = 458752.0 * rows
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
-        for flags in (0,):
-            os.environ["ROBIR_TC_DEBUG"] = str(flags)
-            for _ in range(2):
-                fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 5
-            print("%s flags=%2d  %.3f ms  %.2f us/tile-round  %.1f TFLOP/s(alg)" % (
-                name, flags, ms, 1e3 * ms / (tiles / 148.0), flop / ms / 1e9), flush=True)
-    os.environ["ROBIR_TC_DEBUG"] = "0"
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("%s  %.3f ms  %.2f us/tile-round  %.1f TFLOP/s(alg)" % (
+            name, ms, 1e3 * ms / (tiles / 148.0), flop / ms / 1e9), flush=True)
 
 
 if __name__ == "__main__":
