@@ -6,6 +6,7 @@
 //   training/train_pbr.py:313-346 (white_loss, loss = rgb + kl + 0.1 smooth + white).
 // One CTA of 1024 threads strides over the rays; sums are reduced in a fixed order (deterministic).
 #include "common.cuh"
+#include "loss_math.h"
 
 namespace robir {
 
@@ -42,8 +43,6 @@ struct LossParams {
 constexpr int kLossThreads = 1024;
 constexpr int kLossSums = 40;   // 0 rgb, 1 d rgb / d shift, 2 albedo L1, 3 rough L1, 4 n_valid, 5 white, 8..39 sigmoid(z) columns
 
-__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
-
 __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p) {
   __shared__ float s_part[32][kLossSums];
   __shared__ float s_tot[kLossSums];
@@ -54,10 +53,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
   for (int i = 0; i < kLossSums; ++i) acc[i] = 0.f;
 
   // exposure shift: clamp(clamp(10 a + 0.5, 0, 1), 1e-4, 1) ** 0.2   (color_correction.py:37-45)
-  const float a = __ldg(p.adapt_illum);
-  const float raw = 10.f * a + 0.5f;
-  const float shift = fminf(fmaxf(fminf(fmaxf(raw, 0.f), 1.f), 1e-4f), 1.f);
-  const bool shift_live = raw >= 1e-4f && raw <= 1.f;      // torch.clamp passes the gradient on [min, max] inclusive
+  bool shift_live;
+  const float shift = loss_shift(__ldg(p.adapt_illum), &shift_live);
   const float inv_s02 = powf(shift, -0.2f);
   const float inv_N = 1.f / (float)p.N;
 
@@ -70,23 +67,20 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = p.sg_rgb[(size_t)i * p.ld_sg + c] + p.indir_rgb[(size_t)i * p.ld_ind + c];
-      const float num = x * (2.51f * x + 0.03f), den = x * (2.43f * x + 0.59f) + 0.14f;
-      const float ac = num / den;
-      const float dac = ((5.02f * x + 0.03f) * den - num * (4.86f * x + 0.59f)) / (den * den);
-      const float diff = ac * inv_s02 - p.gt[(size_t)ray * 3 + c];
-      const float dper = (p.l2 ? 2.f * diff : sgnf(diff)) * m;            // d per / d ldr
-      acc[0] += (p.l2 ? diff * diff : fabsf(diff)) * m;
-      acc[1] += dper * ac;                                                // times d (s^-0.2) / d s below
-      p.g_pred[(size_t)i * 3 + c] = p.w_rgb * inv_N * dper * dac * inv_s02;
+      float per, d_pred, d_shift;
+      loss_rgb_channel(x, p.gt[(size_t)ray * 3 + c], inv_s02, p.l2, m, &per, &d_pred, &d_shift);
+      acc[0] += per;
+      acc[1] += d_shift;                                                  // times d (s^-0.2) / d a below
+      p.g_pred[(size_t)i * 3 + c] = p.w_rgb * inv_N * d_pred;
       const float da = hitrow * (p.albedo[(size_t)i * p.ld_alb + c] - p.albedo_r[(size_t)i * p.ld_albr + c]);
       acc[2] += fabsf(da);
-      const float ga = p.w_smooth * sgnf(da) * inv_N * (1.f / 3.f);
+      const float ga = p.w_smooth * loss_sgn(da) * inv_N * (1.f / 3.f);
       p.g_albedo[(size_t)i * 3 + c] = ga;
       p.g_albedo_r[(size_t)i * 3 + c] = -ga;
     }
     const float dr = hitrow * (p.rough[(size_t)i * p.ld_r] - p.rough_r[(size_t)i * p.ld_rr]);
     acc[3] += fabsf(dr);
-    const float gr = p.w_smooth * 0.2f * sgnf(dr) * inv_N;
+    const float gr = p.w_smooth * 0.2f * loss_sgn(dr) * inv_N;
     p.g_rough[i] = gr;
     p.g_rough_r[i] = -gr;
   }
@@ -98,33 +92,23 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 v = __ldg(zr + q);
-      acc[8 + 4 * q] += 1.f / (1.f + expf(-v.x));
-      acc[9 + 4 * q] += 1.f / (1.f + expf(-v.y));
-      acc[10 + 4 * q] += 1.f / (1.f + expf(-v.z));
-      acc[11 + 4 * q] += 1.f / (1.f + expf(-v.w));
+      acc[8 + 4 * q] += loss_sigmoid(v.x);
+      acc[9 + 4 * q] += loss_sigmoid(v.y);
+      acc[10 + 4 * q] += loss_sigmoid(v.z);
+      acc[11 + 4 * q] += loss_sigmoid(v.w);
     }
   }
   // ---- white-light regulariser: var_c(|mu| / (||mu|| + 1e-4)) averaged over the lobes, * 0.01  (train_pbr.py:313-317)
   for (int i = tid; i < p.M; i += kLossThreads) {
     const float* r = p.lgt + (size_t)i * 7;
     const float x[3] = {r[4], r[5], r[6]};
-    const float c[3] = {fabsf(x[0]), fabsf(x[1]), fabsf(x[2])};
-    const float nrm = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-    const float mu = nrm + 1e-4f;
-    const float u[3] = {c[0] / mu, c[1] / mu, c[2] / mu};
-    const float ub = (u[0] + u[1] + u[2]) * (1.f / 3.f);
-    const float d[3] = {u[0] - ub, u[1] - ub, u[2] - ub};
-    acc[5] += 0.5f * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);          // unbiased variance over 3 channels
-    // d var / d u_k = d_k;  d u_k / d c_j = delta_kj / mu - c_k c_j / (mu^2 nrm)
-    const float dc = d[0] * c[0] + d[1] * c[1] + d[2] * c[2];
+    float gx[3];
+    acc[5] += loss_white_lobe(x, gx);
     const float scale = 0.01f / (float)p.M;
     float* g = p.g_lgt + (size_t)i * 7;
     g[0] = g[1] = g[2] = g[3] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float gcj = d[j] / mu - (nrm > 0.f ? dc * c[j] / (mu * mu * nrm) : 0.f);
-      g[4 + j] = scale * gcj * sgnf(x[j]);
-    }
+    for (int j = 0; j < 3; ++j) g[4 + j] = scale * gx[j];
   }
   // ---- block reduction (fixed order)
 #pragma unroll
@@ -142,9 +126,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
   const float n_valid = fmaxf(s_tot[4], 1.f);
   if (tid < 32) {
     const float rh = s_tot[8 + tid] / n_valid;
-    const float term = p.rho * logf(p.rho / (rh + 1e-4f)) + (1.f - p.rho) * logf((1.f - p.rho) / (1.f - rh + 1e-4f));
-    s_part[0][tid] = term;                                                // reuse as scratch (all reads are done)
-    s_dkl[tid] = (-p.rho / (rh + 1e-4f) + (1.f - p.rho) / (1.f - rh + 1e-4f)) * (1.f / 32.f);
+    float d_rh;
+    s_part[0][tid] = loss_kl_column(p.rho, rh, &d_rh);                    // reuse as scratch (all reads are done)
+    s_dkl[tid] = d_rh * (1.f / 32.f);
   }
   __syncthreads();
   if (tid == 0) {
@@ -173,8 +157,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) pbr_loss_kernel(LossParams p)
       if (ok) {
         const float4 v = __ldg(zr + q);
         const float k = p.w_kl / n_valid;
-        const float s0 = 1.f / (1.f + expf(-v.x)), s1 = 1.f / (1.f + expf(-v.y));
-        const float s2 = 1.f / (1.f + expf(-v.z)), s3 = 1.f / (1.f + expf(-v.w));
+        const float s0 = loss_sigmoid(v.x), s1 = loss_sigmoid(v.y);
+        const float s2 = loss_sigmoid(v.z), s3 = loss_sigmoid(v.w);
         o.x = k * s_dkl[4 * q] * s0 * (1.f - s0);
         o.y = k * s_dkl[4 * q + 1] * s1 * (1.f - s1);
         o.z = k * s_dkl[4 * q + 2] * s2 * (1.f - s2);

@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE: host build (g++) of the host+device math headers used by the CUDA kernels
-// (robir_b200/csrc/sg_math.h, octree_walk.h) so their logic can be checked against the oracle on machines without a
+// (robir_b200/csrc/sg_math.h, octree_walk.h, loss_math.h) so their logic can be checked against the oracle on machines without a
 // GPU.  Never linked into or reachable from the product library.
 #include <cstring>
 #include <vector>
 
+#include "loss_math.h"
 #include "octree_walk.h"
 #include "sg_math.h"
 
@@ -196,6 +197,72 @@ void hc_sample_dirs(int K, int S, const float* axis_f, const float* axis_w, cons
     for (int i = 0; i < 3; ++i) { g_axis_f[3 * k + i] = g[i]; g_axis_w[3 * k + i] = g[3 + i]; }
     g_sharp[k] = g[6]; g_lam_w[k] = g[7]; *g_sg_range += g[8];
   }
+}
+
+
+// fused PBR loss, mirroring pbr_loss_kernel (loss.cu) sequentially with the helpers of loss_math.h.
+// losses [5] = total, rgb, kl, smooth, white; gradients as in robir_loss_params (contiguous inputs, no compaction).
+void hc_pbr_loss(int N, int n_lat, int M, int l2, const float* sg_rgb, const float* indir_rgb, const float* gt,
+                 const unsigned char* mask, float adapt, const float* albedo, const float* albedo_r, const float* rough,
+                 const float* rough_r, const float* z, const unsigned char* z_valid, const float* lgt, float w_rgb,
+                 float w_kl, float w_smooth, float rho, float* losses, float* g_pred, float* g_adapt, float* g_albedo,
+                 float* g_albedo_r, float* g_rough, float* g_rough_r, float* g_z, float* g_lgt) {
+  bool live;
+  const float shift = loss_shift(adapt, &live);
+  const float inv_s02 = powf(shift, -0.2f), inv_N = 1.f / (float)N;
+  double rgb = 0, dshift = 0, sa = 0, sr = 0, white = 0;
+  for (int i = 0; i < N; ++i) {
+    const float m = mask[i] ? 1.f : 0.f;
+    for (int c = 0; c < 3; ++c) {
+      float per, d_pred, d_shift;
+      loss_rgb_channel(sg_rgb[3 * i + c] + indir_rgb[3 * i + c], gt[3 * i + c], inv_s02, l2, m, &per, &d_pred, &d_shift);
+      rgb += per;
+      dshift += d_shift;
+      g_pred[3 * i + c] = w_rgb * inv_N * d_pred;
+      const float da = albedo[3 * i + c] - albedo_r[3 * i + c];
+      sa += fabsf(da);
+      g_albedo[3 * i + c] = w_smooth * loss_sgn(da) * inv_N * (1.f / 3.f);
+      g_albedo_r[3 * i + c] = -g_albedo[3 * i + c];
+    }
+    const float dr = rough[i] - rough_r[i];
+    sr += fabsf(dr);
+    g_rough[i] = w_smooth * 0.2f * loss_sgn(dr) * inv_N;
+    g_rough_r[i] = -g_rough[i];
+  }
+  double col[32] = {0};
+  double nv = 0;
+  for (int i = 0; i < n_lat; ++i) {
+    if (z_valid && !z_valid[i]) continue;
+    nv += 1;
+    for (int j = 0; j < 32; ++j) col[j] += loss_sigmoid(z[32 * i + j]);
+  }
+  const float n_valid = nv > 1 ? (float)nv : 1.f;
+  float dkl[32];
+  double kl = 0;
+  for (int j = 0; j < 32; ++j) {
+    float d;
+    kl += loss_kl_column(rho, (float)(col[j] / n_valid), &d);
+    dkl[j] = d * (1.f / 32.f);
+  }
+  kl /= 32.0;
+  for (int i = 0; i < n_lat; ++i)
+    for (int j = 0; j < 32; ++j) {
+      const float s = loss_sigmoid(z[32 * i + j]);
+      g_z[32 * i + j] = (z_valid && !z_valid[i]) ? 0.f : w_kl / n_valid * dkl[j] * s * (1.f - s);
+    }
+  for (int i = 0; i < M; ++i) {
+    const float x[3] = {lgt[7 * i + 4], lgt[7 * i + 5], lgt[7 * i + 6]};
+    float gx[3];
+    white += loss_white_lobe(x, gx);
+    for (int k = 0; k < 4; ++k) g_lgt[7 * i + k] = 0.f;
+    for (int j = 0; j < 3; ++j) g_lgt[7 * i + 4 + j] = 0.01f / (float)M * gx[j];
+  }
+  const float rgb_l = (float)rgb * inv_N;
+  const float smooth = (float)sa * inv_N * (1.f / 3.f) + 0.2f * (float)sr * inv_N;
+  const float white_l = 0.01f * (float)white / (float)M;
+  losses[0] = w_rgb * rgb_l + w_kl * (float)kl + w_smooth * smooth + white_l;
+  losses[1] = rgb_l; losses[2] = (float)kl; losses[3] = smooth; losses[4] = white_l;
+  g_adapt[0] = live ? w_rgb * inv_N * (float)dshift * (-0.2f) * powf(shift, -1.2f) * 10.f : 0.f;
 }
 
 }  // extern "C"

@@ -20,7 +20,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "robir_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def hc():
-    deps = [SRC, os.path.join(CSRC, "sg_math.h"), os.path.join(CSRC, "octree_walk.h")]
+    deps = [SRC, os.path.join(CSRC, "sg_math.h"), os.path.join(CSRC, "octree_walk.h"), os.path.join(CSRC, "loss_math.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I" + CSRC, SRC,
                                "-o", SO])
@@ -176,3 +176,46 @@ def test_sample_dirs_forward_backward_vs_oracle(hc):
     g_lam[int(torch.argmin(sharp))] += g_r.value if sharp.min() < 1.0 else 0.0
     ref = lam.grad[:, 0]
     assert (g_lam - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+def test_fused_loss_math_matches_torch(hc):
+    """loss_math.h (the per-element math of csrc/loss.cu) against torch autograd of the restated PBR loss
+    (model/loss.py:61-125, color_correction.py:31-59, train_pbr.py:313-346): value and every gradient, L1 and L2."""
+    from robir_b200.loss import white_loss
+    gen = torch.Generator().manual_seed(4)
+    for N, n_lat, valid_rows, l2, a0 in [(257, 257, 200, 0, 0.01), (64, 40, 40, 1, -0.03), (5, 5, 0, 0, 0.2)]:
+        t = lambda *s: torch.rand(*s, generator=gen).requires_grad_(True)
+        sg, ind, alb, albr, r, rr = t(N, 3), t(N, 3), t(N, 3), t(N, 3), t(N), t(N)
+        z = torch.randn(n_lat, 32, generator=gen).requires_grad_(True)
+        lgt = torch.randn(16, 7, generator=gen).requires_grad_(True)
+        a = torch.tensor(a0).requires_grad_(True)
+        gt = torch.rand(N, 3, generator=gen)
+        mask = torch.rand(N, generator=gen) > 0.3
+        zv = torch.arange(n_lat) < valid_rows
+        shift = torch.clamp(torch.clamp(a * 10 + 0.5, 0, 1), 1e-4, 1)
+        x = sg + ind
+        ldr = x * (2.51 * x + 0.03) / (x * (2.43 * x + 0.59) + 0.14) / shift ** 0.2
+        diff = ldr - gt
+        rgb = ((diff * diff if l2 else diff.abs()) * mask[:, None]).sum() / N
+        smooth = (alb - albr).abs().mean() + (r - rr).abs().mean() * 0.2
+        rho_hat = (torch.sigmoid(z) * zv[:, None]).sum(0) / zv.sum().clamp(min=1)
+        kl = torch.mean(0.05 * torch.log(0.05 / (rho_hat + 1e-4)) + 0.95 * torch.log(0.95 / (1 - rho_hat + 1e-4)))
+        ref = rgb + kl + 0.1 * smooth + white_loss(lgt)
+        leaves = [sg, a, alb, albr, r, rr, z, lgt]
+        g_ref = torch.autograd.grad(ref, leaves)
+        outs = dict(losses=np.empty(5, np.float32), g_pred=np.empty((N, 3), np.float32), g_adapt=np.empty(1, np.float32),
+                    g_albedo=np.empty((N, 3), np.float32), g_albedo_r=np.empty((N, 3), np.float32),
+                    g_rough=np.empty(N, np.float32), g_rough_r=np.empty(N, np.float32),
+                    g_z=np.empty((n_lat, 32), np.float32), g_lgt=np.empty((16, 7), np.float32))
+        ins = [arr(v) for v in (sg, ind, gt)] + [arr(mask, np.uint8)]
+        ins2 = [arr(v) for v in (alb, albr, r, rr, z)] + [arr(zv, np.uint8), arr(lgt)]
+        hc.hc_pbr_loss(N, n_lat, 16, l2, *[fp(v) for v in ins], ctypes.c_float(a0), *[fp(v) for v in ins2],
+                       ctypes.c_float(1.0), ctypes.c_float(1.0), ctypes.c_float(0.1), ctypes.c_float(0.05),
+                       *[fp(v) for v in outs.values()])
+        assert abs(outs["losses"][0] - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (N, outs["losses"], ref.item())
+        got = [outs["g_pred"], outs["g_adapt"], outs["g_albedo"], outs["g_albedo_r"], outs["g_rough"], outs["g_rough_r"],
+               outs["g_z"], outs["g_lgt"]]
+        for g1, g2 in zip(got, g_ref):
+            g2 = g2.detach().numpy().reshape(g1.shape)
+            assert np.isfinite(g1).all()
+            assert np.abs(g1 - g2).max() <= 2e-4 * max(1e-7, np.abs(g2).max()), N
