@@ -54,10 +54,69 @@ def pbr_get_sg_render(sd, points, view_dirs, indir_lgtSGs, indir_integral, rnd, 
     return ret
 
 
-def idr_forward(sd, inp, tracer, rnd, trainstage="Material", no_normal=True, is_training=True, stats=None):
+def white_loss(lgtSGs):
+    """training/train_pbr.py:313-317 == training/train_cesr.py:460-463."""
+    lgt = torch.abs(lgtSGs[..., -3:])
+    mu = lgt.norm(dim=-1, keepdim=True) + 1e-4
+    return (lgt / mu).var(-1).mean() * 0.01
+
+
+def cesr_prefit_option(cur_iter, explore_iter, proj_iter):
+    """training/train_cesr.py:546-559 (is_explore_step / prefit_option)."""
+    explore = cur_iter > 500 and cur_iter % (explore_iter + proj_iter) >= proj_iter
+    if not explore:
+        return "warmup" if cur_iter <= 500 else "project"
+    return "explore"
+
+
+def cesr_get_sg_render(sd, sd_shadow, sd_normal, points, view_dirs, indir_lgtSGs, indir_integral, rnd, cur_iter=600,
+                       prefit="explore", white_light=True, is_training=True, stats=None):
+    """ClusteredAlbedoTrainRunner.get_sg_render (training/train_cesr.py:465-544).  sd_shadow / sd_normal are the state
+    dicts of shadow_net = SDFNetwork(63+128, 2, 512, 8, [4], 0) and normal_net = SDFNetwork(63, 3, 512, 8, [4], 0)
+    (:106-110), keys ``lin{l}.weight_g|weight_v|bias``.  rnd as for the PBR hook but diff_theta / diff_phi are [M,8]."""
+    view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
+    normals = O.implicit_gradient(sd, points)[:, 0, :]
+    normals = normals / torch.clamp(torch.norm(normals, dim=-1, keepdim=True), 1e-4)
+    mat = O.envmap_material(sd, points, rnd["brdf_noise"], rnd["normal_noise"])
+    lgtSGs = mat["sg_lgtSGs"]
+    M = lgtSGs.shape[0]
+    assert M == 128, "the CESR hook hard-codes 128 light lobes (train_cesr.py:492-493)"
+    indir_integral = indir_integral * 2 * np.pi
+    normal_map = mat["sg_normal_map"].detach()
+    emb = O.pe(points.detach(), 10)                                                    # get_embedder(10), :106
+    shadow_in = torch.cat([emb[:, None, :].expand(-1, 128, -1), torch.eye(128)[None].expand(emb.shape[0], -1, -1)], -1)
+    with torch.set_grad_enabled(is_training and torch.is_grad_enabled()):
+        diffuse_vis = O.wn_mlp(sd_shadow, "", shadow_in.reshape(-1, shadow_in.shape[-1]), prefix_dot=False)
+        normal_new = O.wn_mlp(sd_normal, "", emb, prefix_dot=False)
+    normal_new = normal_new / torch.clamp(normal_new.norm(dim=-1, keepdim=True), 1e-4)
+    diffuse_vis = torch.softmax(diffuse_vis, -1)[..., 1]
+    vis_fn = lambda p, d: O.vis_network(sd, p, d)
+    sg = O.render_with_all_sg(points.detach(), normal_new if cur_iter > 1000 else normal_map, view_dirs, lgtSGs,
+                              mat["sg_specular_reflectance"].abs(), mat["sg_roughness"], mat["sg_diffuse_albedo"],
+                              vis_fn, rnd, indir_integral=indir_integral, indir_lgtSGs=indir_lgtSGs, lin_diff=True,
+                              testing=not is_training, stats=stats, diffuse_vis=diffuse_vis, prefit=prefit)
+    albedo = mat["sg_diffuse_albedo"]
+    sg["sg_rgb"] = sg["sg_diffuse_rgb"] * albedo / np.pi + sg["sg_specular_rgb"]
+    sg["indir_rgb"] = sg["indir_diffuse_rgb"] * albedo / np.pi + sg["indir_specular_rgb"]
+    supervise = sg["supervise"]
+    if white_light and prefit != "warmup":
+        supervise = supervise + white_loss(lgtSGs)
+    supervise = supervise + ((normal_map - normal_new) ** 2).mean()
+    ret = {"normals": normals}
+    ret.update(sg)
+    ret.update(diffuse_albedo=albedo, roughness=mat["sg_roughness"], metallic=mat["sg_metallic"],
+               normal_map=normal_new, gradient_error=supervise, random_xi_roughness=mat["random_xi_roughness"],
+               random_xi_metallic=mat["random_xi_metallic"],
+               random_xi_diffuse_albedo=mat["random_xi_diffuse_albedo"])
+    return ret
+
+
+def idr_forward(sd, inp, tracer, rnd, trainstage="Material", no_normal=True, is_training=True, stats=None, hook=None):
     """IDRNetwork.forward (implicit_differentiable_renderer.py:290-479), camera-input branch, hdr_shift present.
     tracer(cam_loc[B,3], object_mask[B*N], ray_dirs[B,N,3]) -> points, mask, dists   (no_grad).
-    rnd may be a dict or a callable n_hit -> dict (the shapes depend on the hit count)."""
+    rnd may be a dict or a callable n_hit -> dict (the shapes depend on the hit count).
+    hook(points, view_dirs, indir_lgtSGs, indir_integral, rnd) replaces the PBR-stage get_sg_render (:400-409), e.g.
+    a closure over cesr_get_sg_render."""
     uv, pose, K = inp["uv"], inp["pose"], inp["intrinsics"]
     object_mask = inp["object_mask"].reshape(-1)
     ray_dirs, cam_loc = O.camera_rays(uv, pose, K)
@@ -98,9 +157,15 @@ def idr_forward(sd, inp, tracer, rnd, trainstage="Material", no_normal=True, is_
                indir_diffuse_rgb=ones3(), indir_specular_rgb=ones3(), normals=ones3(), diffuse_albedo=ones3(),
                roughness=ones3(), metallic=ones1(), normal_map=ones3(), vis_shadow=ones3(),
                random_xi_diffuse_albedo=ones3(), random_xi_roughness=ones3(), random_xi_metallic=ones1())
+    gradient_error = torch.tensor(0.0)
     if n_hit > 0:
-        ret = pbr_get_sg_render(sd, points[sm], -ray_dirs[sm], indirect_sgs[sm], indirect_integral[sm], rnd,
-                                no_normal=no_normal, is_training=is_training, stats=stats)
+        if hook is not None:
+            ret = hook(points[sm], -ray_dirs[sm], indirect_sgs[sm], indirect_integral[sm], rnd)
+        else:
+            ret = pbr_get_sg_render(sd, points[sm], -ray_dirs[sm], indirect_sgs[sm], indirect_integral[sm], rnd,
+                                    no_normal=no_normal, is_training=is_training, stats=stats)
+        if "gradient_error" in ret:
+            gradient_error = gradient_error + ret["gradient_error"]                    # :446-447
         for k in buf:
             v = ret[k]
             if k in ("roughness", "random_xi_roughness"):
@@ -108,7 +173,7 @@ def idr_forward(sd, inp, tracer, rnd, trainstage="Material", no_normal=True, is_
             b = buf[k].clone()
             b[sm] = v
             buf[k] = b
-    out.update(final_t=ones1(), gradient_error=torch.tensor(0.0), acc=ones1(), bg_rgb=ones3(), surface_mask=sm)
+    out.update(final_t=ones1(), gradient_error=gradient_error, acc=ones1(), bg_rgb=ones3(), surface_mask=sm)
     out.update(buf)
     return out
 

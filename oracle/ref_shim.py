@@ -177,6 +177,31 @@ def bind_pbr_runner(model, no_normal=True, is_training=True):
     return runner
 
 
+def bind_cesr_runner(model, cur_iter=600, white_light=False, explore_iter=1000, proj_iter=0, explore_smooth=0.1,
+                     explore_kl=1.0, proj_smooth=0.01, proj_kl=0.01, is_training=True, seed=0):
+    """A bare ClusteredAlbedoTrainRunner carrying what get_sg_render / pbr_step (training/train_cesr.py:387-430,465-559)
+    read; shadow_net / normal_net are built exactly as at :102-110 (their own default initialisation, torch seed)."""
+    install()
+    from training.train_cesr import ClusteredAlbedoTrainRunner
+    from model.neus_model import SDFNetwork
+    from model.embedder import get_embedder
+    runner = ClusteredAlbedoTrainRunner.__new__(ClusteredAlbedoTrainRunner)
+    runner.model = model
+    runner.train_spec = True
+    runner.is_training = is_training
+    runner.cur_iter = cur_iter
+    runner.white_light = white_light
+    runner.conf = DictConf(train=dict(argmax_vis=False, explore_iter=explore_iter, proj_iter=proj_iter,
+                                      explore_smooth=explore_smooth, explore_kl=explore_kl, proj_smooth=proj_smooth,
+                                      proj_kl=proj_kl))
+    torch.manual_seed(seed)
+    runner.shadow_embed, in_dim = get_embedder(10)
+    runner.shadow_net = SDFNetwork(in_dim + 128, 2, 512, 8, [4], 0)
+    runner.normal_net = SDFNetwork(in_dim, 3, 512, 8, [4], 0)
+    model.get_sg_render = runner.get_sg_render
+    return runner
+
+
 class ReplayRandom:
     """Context manager: record (mode='record') or replay (mode='replay') torch.rand / torch.randn /
     Tensor.uniform_ draws, in call order, so reference and oracle/product see identical randoms."""

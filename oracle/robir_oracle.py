@@ -89,6 +89,29 @@ def sdf_network(sd, pts, chunk=1024):
     return torch.cat(res, 0)
 
 
+def wn_mlp(sd, prefix, x, n_lin=9, skip_in=(4,), chunk=1024, prefix_dot=True):
+    """SDFNetwork.forward with multires=0 (neus_model.py:385-417), the form of the CESR stage's shadow_net / normal_net
+    (training/train_cesr.py:106-110): ``n_lin`` weight-normed linears under ``prefix.lin{l}``, the layer input is
+    cat([x, inputs]) / sqrt(2) at the skip layers, softplus(100) between layers, evaluated in 1024-row chunks."""
+    if x.numel() == 0:
+        return torch.ones_like(x)
+    shape = list(x.shape[:-1]) + [-1]
+    inputs = x.reshape(-1, x.shape[-1])
+    res = []
+    for c in range(inputs.shape[0] // chunk + 1):
+        e = inputs[chunk * c: chunk * (c + 1)]
+        h = e
+        for l in range(n_lin):
+            if l in skip_in:
+                h = torch.cat([h, e], 1) / np.sqrt(2)
+            key = ("%s.lin%d" if prefix_dot else "%slin%d") % (prefix, l)
+            h = F.linear(h, wn_weight(sd, key), sd[key + ".bias"])
+            if l < n_lin - 1:
+                h = softplus100(h)
+        res.append(h)
+    return torch.cat(res, 0).reshape(shape)
+
+
 def implicit_forward(sd, pts):
     """ImplicitNetworkMy.forward (neus_model.py:785-792): net(2 p) / 2 on all 257 channels."""
     return sdf_network(sd, pts * 2.0) / 2.0
@@ -373,14 +396,27 @@ def get_specular_visibility(points, normals, viewdirs, vis_fn, lobes, lambdas, u
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# SG renderer (model/sg_render.py:304-565), single-view, metallic=None, fun_spec=False, diffuse_vis=None
+# SG renderer (model/sg_render.py:304-565), single-view, metallic=None, fun_spec=False, argmax_vis=False
 # ----------------------------------------------------------------------------------------------------------------------
+def kl_divergence(x, mu=0.05):
+    """utils/utils.py:14-17: KL(mu || mean_0(x)) averaged over the columns (the CESR supervise term)."""
+    rho_hat = torch.mean(x, 0)
+    rho = torch.full_like(rho_hat, mu)
+    return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4)) + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
+
+
+PREFIT_WEIGHT = {"warmup": 0.1, "project": 0.2}   # sg_render.py:397-403; anything else ("explore", False): 1.0
+
+
 MU_COS, LAMBDA_COS, ALPHA_COS = 32.7080, 0.0315, 31.7003
 
 
 def render_with_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo, vis_fn, rnd,
-                   comp_vis=True, lin_diff=False, testing=False, indir_integral=None, stats=None):
-    """rnd: dict with 'diff_theta','diff_phi' [M,32] (only comp_vis) and 'spec_theta','spec_phi' [n,8]."""
+                   comp_vis=True, lin_diff=False, testing=False, indir_integral=None, stats=None, diffuse_vis=None,
+                   prefit=False):
+    """rnd: dict with 'diff_theta','diff_phi' [M,S] (only comp_vis; S = 32, or 8 when diffuse_vis is given,
+    sg_render.py:389) and 'spec_theta','spec_phi' [n,8].  diffuse_vis [n*M] / prefit: the CESR branch
+    (sg_render.py:393-407)."""
     M = lgtSGs.shape[1]
     n = normal.shape[0]
     lobes = lgtSGs[..., :3] / (torch.norm(lgtSGs[..., :3], dim=-1, keepdim=True) + TINY)
@@ -391,14 +427,24 @@ def render_with_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, rough
     spec_refl = specular_reflectance.unsqueeze(1).expand(n, M, 3)
 
     vis_shadow = torch.zeros(n, 3)
+    supervise = torch.tensor(0.0)
     if comp_vis:
         lv, aux = get_diffuse_visibility(points, nrm[:, 0, :].detach(), vis_fn, lobes[0], lambdas[0],
                                          rnd["diff_theta"], rnd["diff_phi"], testing=testing, return_aux=True)
         if stats is not None:
             stats["n_query"] = stats.get("n_query", 0) + aux["n_query"]
-        light_vis = lv.permute(1, 0).unsqueeze(-1).expand(n, M, 3)
+        light_vis_gt = lv.permute(1, 0).unsqueeze(-1).expand(n, M, 3)
+        if diffuse_vis is not None:
+            assert rnd["diff_theta"].shape[1] == 8
+            light_vis = diffuse_vis.reshape(-1, M, 1).expand(n, M, 3)
+            if prefit == "warmup":
+                supervise = kl_divergence((light_vis_gt.detach() - light_vis).abs()[..., 0], 0.01) * 0.1
+                light_vis = light_vis_gt
+            else:
+                supervise = kl_divergence((light_vis_gt - light_vis).abs()[..., 0], 0.01) * PREFIT_WEIGHT.get(prefit, 1.0)
+        else:
+            light_vis = light_vis_gt
         vis_shadow = ((light_vis * mus0).sum(1) / torch.clamp(mus0.sum(1), 1e-4)).detach()
-    supervise = torch.tensor(0.0)
 
     # ---- specular (sg_render.py:414-500)
     inv_r4 = 2.0 / (roughness * roughness * roughness * roughness)
@@ -448,7 +494,8 @@ def render_with_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, rough
 
 
 def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo, vis_fn,
-                       rnd, indir_integral=None, indir_lgtSGs=None, lin_diff=False, testing=False, stats=None):
+                       rnd, indir_integral=None, indir_lgtSGs=None, lin_diff=False, testing=False, stats=None,
+                       diffuse_vis=None, prefit=False):
     """sg_render.py:304-337.  rnd keys: diff_theta, diff_phi [M,32]; spec_theta, spec_phi [n,8] (direct pass);
     ind_theta, ind_phi [n,8] (indirect pass) -- the draw order of SURVEY.md A.4."""
     n = normal.shape[0]
@@ -456,7 +503,8 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
     if lgtSGs.dim() == 2:
         lgtSGs = lgtSGs.unsqueeze(0).expand(n, M, 7)
     ret = render_with_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo, vis_fn,
-                         rnd, comp_vis=True, lin_diff=lin_diff, testing=testing, stats=stats)
+                         rnd, comp_vis=True, lin_diff=lin_diff, testing=testing, stats=stats, diffuse_vis=diffuse_vis,
+                         prefit=prefit)
     ind = dict(indir_rgb=torch.zeros_like(points), indir_diffuse_rgb=torch.zeros_like(points),
                indir_specular_rgb=torch.zeros_like(points))
     if indir_lgtSGs is not None:
@@ -550,6 +598,18 @@ def pbr_loss(sd, out, rgb_gt, sg_rgb_weight=1.0, kl_weight=1.0, latent_smooth_we
     white = (lgt / (lgt.norm(dim=-1, keepdim=True) + 1e-4)).var(-1).mean() * 0.01
     loss = sg_rgb_weight * rgb_loss + kl_weight * kl * 1.0 + latent_smooth_weight * smooth * 0.1 + white
     return loss, dict(rgb_loss=rgb_loss, kl=kl, smooth=smooth, white=white)
+
+
+def cesr_loss(sd, out, rgb_gt, cur_iter, smooth_w, kl_w, sg_rgb_weight=1.0, kl_weight=1.0, latent_smooth_weight=1.0):
+    """ClusteredAlbedoTrainRunner.pbr_step (training/train_cesr.py:387-430): InvLoss terms only after iteration 500,
+    weighted by the explore / project (smooth_w, kl_w) of the conf, plus the hook's supervise term (gradient_error)."""
+    loss = torch.tensor(0.0)
+    parts = {}
+    if cur_iter > 500:
+        _, parts = pbr_loss(sd, out, rgb_gt, sg_rgb_weight, kl_weight, latent_smooth_weight)
+        loss = sg_rgb_weight * parts["rgb_loss"] + kl_weight * parts["kl"] * kl_w \
+            + latent_smooth_weight * parts["smooth"] * smooth_w
+    return loss + out["gradient_error"], parts
 
 
 def illum_loss(out, tr, anneal_t=0.0):

@@ -139,3 +139,82 @@ def test_vis_stage_losses_match_reference(ref_model):
             assert (gref[k] - sd[k].grad).abs().max().item() < 1e-5 * max(1.0, gref[k].abs().max().item()), k
             checked += 1
     assert checked >= 20
+
+
+@pytest.fixture(scope="module")
+def ref_model_128():
+    sdn = ref_shim.reference_neus_state_dict(0)
+    model = ref_shim.build_reference_model(sdn, num_lgt_sgs=128)
+    lgt = torch.from_numpy(np.load(ref_shim.REF_ROOT + "/envmaps/envmap6/sg_128.npy")).float()
+    model.envmap_material_network.lgtSGs.data = lgt.clone()
+    model.train()
+    model.ray_tracer.generate(lambda x: model.implicit_network(x)[:, 0], None)
+    from model.loss import InvLoss
+    return model, InvLoss(1.0, 0.1, 100.0, 50.0, 1.0, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("cur_iter,sched,white", [(300, (1000, 0), True), (600, (1000, 0), True),
+                                                   (1200, (0, 1000), False)])
+def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
+    """CESR hook (training/train_cesr.py:465-544: shadow_net / normal_net, diffuse_vis / prefit branches of
+    render_with_sg, supervise KL) + its step loss (:387-430) vs the oracle, in the warm-up, explore and project
+    phases (the last one renders with normal_net's normals, :508)."""
+    model, inv_loss = ref_model_128
+    smooth = dict(explore_smooth=0.1, explore_kl=1.0, proj_smooth=0.01, proj_kl=0.01)
+    runner = ref_shim.bind_cesr_runner(model, cur_iter=cur_iter, white_light=white, explore_iter=sched[0],
+                                       proj_iter=sched[1], seed=3, **smooth)
+    runner.loss = inv_loss
+    prefit = runner.prefit_option()
+    assert prefit == P.cesr_prefit_option(cur_iter, *sched) == {300: "warmup", 600: "explore", 1200: "project"}[cur_iter]
+    N = 40
+    inp = synthetic.camera_inputs(synthetic.training_pixels(9, n=N, crop=300))
+    gt = {"rgb": torch.full((1, N, 3), 0.4)}
+    torch.manual_seed(4321)
+    with ref_shim.ReplayRandom() as rec:
+        i2 = dict(inp)
+        i2["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+        out_ref = model(i2, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss_ref, _ = runner.pbr_step(out_ref, gt)
+    nets = {"model": model, "shadow": runner.shadow_net, "normal": runner.normal_net}
+    for m in nets.values():
+        m.zero_grad()
+    loss_ref.backward()
+    gref = {n: {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None} for n, m in nets.items()}
+
+    sds = {n: {k: v.detach().clone() for k, v in m.state_dict().items()} for n, m in nets.items()}
+    sd = sds["model"]
+    train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    for n in ("shadow", "normal"):
+        for v in sds[n].values():
+            v.requires_grad_(True)
+    octree = T.OctreeOracle(lambda x: O.implicit_forward(sd, x)[:, 0], lambda x: O.implicit_gradient(sd, x)[:, 0, :])
+    i3 = dict(inp)
+    i3["hdr_shift"] = O.hdr_shift_as_input(sd).expand(N, 1)
+    hook = lambda p, v, sg, integ, rnd: P.cesr_get_sg_render(sd, sds["shadow"], sds["normal"], p, v, sg, integ, rnd,
+                                                             cur_iter=cur_iter, prefit=prefit, white_light=white)
+    out = P.idr_forward(sd, i3, lambda c, m, d: octree.trace(c, d), P.tape_to_rnd(rec.tape), hook=hook)
+    assert set(out.keys()) == set(out_ref.keys())
+    for k, a in out_ref.items():
+        if a.dtype == torch.bool:
+            assert torch.equal(a, out[k]), k
+        else:
+            assert a.shape == out[k].shape, k
+            assert (a - out[k]).abs().max().item() < 2e-5, k
+    w = ("proj_smooth", "proj_kl") if prefit == "project" else ("explore_smooth", "explore_kl")
+    loss, _ = O.cesr_loss(sd, out, gt["rgb"], cur_iter, smooth[w[0]], smooth[w[1]])
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    loss.backward()
+    checked = {}
+    for n in nets:
+        for k, g in gref[n].items():
+            if n == "model" and k not in train:
+                continue
+            mine = sds[n][k].grad
+            assert mine is not None, (n, k)
+            assert (g - mine).abs().max().item() < 2e-5 * max(1.0, g.abs().max().item()), (n, k)
+            checked[n] = checked.get(n, 0) + 1
+    assert checked["shadow"] == 27 and checked["normal"] == 27       # 9 x (weight_g, weight_v, bias)
+    if cur_iter > 500:
+        assert checked["model"] >= 19
