@@ -123,6 +123,27 @@ def synthetic_state_dict(seed=0, num_lgt_sgs=128, sdf_radius=0.5, perturb=0.0, v
     return sd
 
 
+def cesr_state_dicts(seed=0, gain=2.0):
+    """Seeded weights of the CESR stage's two extra weight-normed MLPs (training/train_cesr.py:106-110; state-dict keys
+    of the reference SDFNetwork: ``lin{l}.weight_g | weight_v | bias``): shadow_net 191 -> 512 x8 -> 2 and normal_net
+    63 -> 512 x8 -> 3, skip concat at layer 4.  He-style hidden layers; the output layer is scaled by ``gain`` so the
+    shadow classifier is not stuck at 0.5 (the reference's geometric init makes both logits equal)."""
+    gen = torch.Generator().manual_seed(seed + 7919)
+    out = []
+    for d_in, d_out in ((191, 2), (63, 3)):
+        dims = [d_in] + [512] * 8 + [d_out]
+        sd = {}
+        for l in range(9):
+            o = dims[l + 1] - dims[0] if l + 1 == 4 else dims[l + 1]
+            std = math.sqrt(2) / math.sqrt(o) if l < 8 else gain / math.sqrt(dims[l])
+            w = torch.randn(o, dims[l], generator=gen) * std
+            b = (torch.rand(o, generator=gen) * 2 - 1) * 0.05
+            _put_wn(sd, "lin%d" % l, w, b)
+            sd["lin%d.weight_g" % l] = sd["lin%d.weight_g" % l] * (0.9 + 0.2 * torch.rand(o, 1, generator=gen))
+        out.append(sd)
+    return out[0], out[1]
+
+
 def neus_checkpoint_from(sd):
     """The stage-1 ``model`` dict (NeuSModel.state_dict() keys) contained in a stage-2 state dict."""
     pre = "implicit_network.neus_model."

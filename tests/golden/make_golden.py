@@ -39,6 +39,50 @@ def build(use_octree=True, n_steps=100, perturb=0.0):
     return sd, model
 
 
+def cesr_golden(g):
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=128)
+    model = ref_shim.build_reference_model(synthetic.neus_checkpoint_from(sd), num_lgt_sgs=128)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    model.ray_tracer.generate(lambda x: model.implicit_network(x)[:, 0], None)
+    from model.loss import InvLoss
+    runner = ref_shim.bind_cesr_runner(model, cur_iter=600, white_light=True, explore_iter=1000, proj_iter=0,
+                                       explore_smooth=0.1, explore_kl=1.0)
+    runner.loss = InvLoss(1.0, 0.1, 100.0, 50.0, 1.0, 1.0, 1.0)
+    sh, nr = synthetic.cesr_state_dicts(SEED)
+    runner.shadow_net.load_state_dict(sh, strict=True)
+    runner.normal_net.load_state_dict(nr, strict=True)
+    N = 48
+    pix = synthetic.training_pixels(3, n=N, crop=400)
+    inp = synthetic.camera_inputs(pix)
+    gt = torch.rand(1, N, 3, generator=g)
+    torch.manual_seed(1234)
+    with ref_shim.ReplayRandom() as rec:
+        i2 = dict(inp)
+        i2["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+        out = model(i2, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = runner.pbr_step(out, {"rgb": gt})
+    for m in (model, runner.shadow_net, runner.normal_net):
+        m.zero_grad()
+    loss.backward()
+    keep = ["points", "network_object_mask", "sg_rgb", "indir_rgb", "sg_diffuse_rgb", "sg_specular_rgb",
+            "indir_diffuse_rgb", "indir_specular_rgb", "normals", "diffuse_albedo", "roughness", "normal_map",
+            "vis_shadow", "gradient_error"]
+    d = {"out_" + k: out[k] for k in keep}
+    d.update({"rnd_%d" % i: t for i, (_, t) in enumerate(rec.tape)})
+    mat = model.envmap_material_network
+    d.update(pix=pix, gt=gt, loss=loss, g_lgtSGs=mat.lgtSGs.grad, g_spec=mat.specular_reflectance.grad,
+             g_adapt=model.gamma.hdr_shift.adapt_illum.grad,
+             g_shadow_lin8_v=runner.shadow_net.lin8.weight_v.grad, g_shadow_lin8_bias=runner.shadow_net.lin8.bias.grad,
+             g_shadow_lin4_g=runner.shadow_net.lin4.weight_g.grad, g_shadow_lin0_bias=runner.shadow_net.lin0.bias.grad,
+             g_shadow_lin0_v_colsum=runner.shadow_net.lin0.weight_v.grad.sum(0),
+             g_normal_lin8_v=runner.normal_net.lin8.weight_v.grad, g_normal_lin0_bias=runner.normal_net.lin0.bias.grad,
+             g_normal_lin3_g=runner.normal_net.lin3.weight_g.grad)
+    np.savez_compressed(os.path.join(HERE, "cesr_step.npz"), **npy(d))
+    print("cesr: hits", int(out["network_object_mask"].sum()), "loss", float(loss), "supervise",
+          float(out["gradient_error"]))
+
+
 def main():
     torch.set_num_threads(8)
     sd, model = build()
@@ -126,6 +170,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pbr_step.npz"), **npy(d))
     print("pbr: hits", int(out["network_object_mask"].sum()), "loss", float(loss))
 
+    # ---------------- 3b. CESR step (M = 128 lobes, N = 48 rays, explore phase, iteration 600): the hook of
+    # training/train_cesr.py:465-544 with seeded shadow_net / normal_net weights, loss of :387-430, backward
+    cesr_golden(torch.Generator().manual_seed(11))
+
     # ---------------- 4. Illum forward + trace_radiance (N=48, nsamp=16)
     model.zero_grad()
     pix = synthetic.training_pixels(2, n=48, crop=360)
@@ -165,4 +213,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["cesr"]:
+        torch.set_num_threads(8)
+        cesr_golden(torch.Generator().manual_seed(11))
+    else:
+        main()

@@ -85,6 +85,45 @@ def test_pbr_step_forward_backward(golden, synth_sd16, oracle_octrees):
     assert close(sd[enc + "8.weight"].grad.sum(0), g["g_enc8_weight_sum"], 1e-4)
 
 
+def test_cesr_step_forward_backward(golden, oracle_octrees):
+    """CESR hook + step loss of the oracle vs. the reference's golden outputs, explore
+    phase at iteration 600, 128 lobes.  The SDF weights (hence the octree) do not depend on the lobe count."""
+    g = golden("cesr_step")
+    sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=128)
+    train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    sh, nr = synthetic.cesr_state_dicts(0)
+    for v in list(sh.values()) + list(nr.values()):
+        v.requires_grad_(True)
+    inp, rnd = _pbr_inputs(g, sd)
+    assert rnd["diff_theta"].shape == (128, 8)
+    prim, _ = oracle_octrees
+    hook = lambda p, v, sgs, integ, r: P.cesr_get_sg_render(sd, sh, nr, p, v, sgs, integ, r, cur_iter=600,
+                                                            prefit=P.cesr_prefit_option(600, 1000, 0), white_light=True)
+    out = P.idr_forward(sd, inp, lambda c, m, d: prim.trace(c, d), rnd, hook=hook)
+    assert torch.equal(out["network_object_mask"], g["out_network_object_mask"])
+    for k in [k[4:] for k in g if k.startswith("out_") and k != "out_network_object_mask"]:
+        # normal_net sees PE(10) of the traced points through He-initialised 512-wide layers: one ulp of the hit
+        # point (1.2e-7) moves its output by ~3e-5
+        assert close(out[k], g["out_" + k], 1e-4 if k == "normal_map" else TOL), k
+    loss, _ = O.cesr_loss(sd, out, g["gt"], 600, 0.1, 1.0)
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    loss.backward()
+    pre = "envmap_material_network."
+    assert close(sd[pre + "lgtSGs"].grad, g["g_lgtSGs"], 1e-4)
+    assert close(sd[pre + "specular_reflectance"].grad, g["g_spec"], 1e-4)
+    assert close(sd["gamma.hdr_shift.adapt_illum"].grad, g["g_adapt"], 1e-4)
+    assert close(sh["lin8.weight_v"].grad, g["g_shadow_lin8_v"], 1e-4)
+    assert close(sh["lin8.bias"].grad, g["g_shadow_lin8_bias"], 1e-4)
+    assert close(sh["lin4.weight_g"].grad, g["g_shadow_lin4_g"], 1e-4)
+    assert close(sh["lin0.bias"].grad, g["g_shadow_lin0_bias"], 1e-4)
+    assert close(sh["lin0.weight_v"].grad.sum(0), g["g_shadow_lin0_v_colsum"], 1e-4)
+    assert close(nr["lin8.weight_v"].grad, g["g_normal_lin8_v"], 1e-4)
+    assert close(nr["lin0.bias"].grad, g["g_normal_lin0_bias"], 1e-4)
+    assert close(nr["lin3.weight_g"].grad, g["g_normal_lin3_g"], 1e-4)
+
+
 def test_vis_stage(golden, synth_sd16, oracle_octrees):
     g, sd = golden("vis_stage"), synth_sd16
     prim, sec = oracle_octrees
