@@ -44,11 +44,14 @@ struct TcLayerParams {
 __device__ __forceinline__ float tl_act(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
+  if (act == ACT_SOFTPLUS100) return softplus100(x);
   return x;
 }
 __device__ __forceinline__ float tl_dact(float y, int act) {
   if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == ACT_LEAKY02) return y > 0.f ? 1.f : 0.2f;
+  // softplus(beta = 100): y = log(1 + e^(100 x)) / 100  =>  sigmoid(100 x) = 1 - e^(-100 y)
+  if (act == ACT_SOFTPLUS100) return -expm1f(-100.f * y);
   return 1.f;
 }
 

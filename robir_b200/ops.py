@@ -266,7 +266,8 @@ class active_rows:
 
 # vis: visibility MLP; mlp: the 512-wide encoder / lobe chains of the material and indirect-illumination networks.
 # "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
-ENGINE = {"vis": "tc", "mlp": "tc"}
+# wn: the CESR stage's weight-normed 512-wide chains (shadow_net / normal_net): "tc" | "torch" (cuBLAS cross-check)
+ENGINE = {"vis": "tc", "mlp": "tc", "wn": "tc"}
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
 
 
@@ -977,6 +978,119 @@ def _tl_backward(chain, packed, tc, n, g_out, saves, Gs, g_x, n_active, segments
                        saves[l - 1] if not first else None, dst, nxt, nkb_out, na, seg)
         check(lib().robir_tl_layer(ctypes.byref(q), stream()))
         img = nxt
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# weight-normed softplus chains with a skip concat (CESR shadow_net / normal_net) on the tensor-core layer engine
+# ----------------------------------------------------------------------------------------------------------------------
+def _tl_weight_images(W, rows_bw):
+    """Forward image of W [N,K] and backward image of W^T restricted to its first rows_bw rows (the columns of W that
+    lead back to the previous layer; the rest belongs to the skip input, which needs no gradient)."""
+    N, K = W.shape
+    cbn, nkbk = (N + 127) // 128, (K + 63) // 64
+    fw = torch.empty(cbn * nkbk * 32768, dtype=torch.uint8, device=W.device)
+    check(lib().robir_tl_pack_weight(ptr(W), K, N, K, 0, cbn, nkbk, ptr(fw), stream()))
+    bw = None
+    if rows_bw > 0:
+        cbk, nkbn = (rows_bw + 127) // 128, (N + 63) // 64
+        bw = torch.empty(cbk * nkbn * 32768, dtype=torch.uint8, device=W.device)
+        check(lib().robir_tl_pack_weight(ptr(W), K, rows_bw, N, 1, cbk, nkbn, ptr(bw), stream()))
+    return fw, bw
+
+
+def _tl_rows_image(X, K):
+    n = X.shape[0]
+    nkb = (K + 63) // 64
+    img = _tl_image((n + 127) // 128, nkb, X)
+    check(lib().robir_tl_pack_rows(ptr(X), X.shape[1], n, K, None, 0, 0, nkb, ptr(img), stream()))
+    return img
+
+
+class _WnChain(torch.autograd.Function):
+    """y = lin_{L-1}( ... softplus100(lin_l(a_l)) ... ), a_l = cat([h_{l-1}, x]) / sqrt(2) at the skip layers
+    (SDFNetwork.forward with multires = 0, model/neus_model.py:397-415), one csrc/tc_mlp.cu launch per layer.
+    The 1/sqrt(2) is folded into the skip layer's weight; the concat is a 512-column buffer that the previous layer
+    writes its columns into.  backward: input-gradient chain on the same engine, dW / db by robir_mlp_wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, skip, L, *wb):
+        Ws, bs = wb[:L], wb[L:]
+        if x.requires_grad:
+            raise _lib.RobirError("wn_chain: gradients with respect to the input rows are not produced")
+        x = f32(x)
+        R, d_in = x.shape
+        tiles = (R + 127) // 128
+        SOFTPLUS = 3
+        We, imgs, a_rows = [], [], []
+        a, img = x, _tl_rows_image(x, d_in)
+        out = None
+        for l in range(L):
+            W = f32(Ws[l]) * (1.0 / math.sqrt(2.0)) if l in skip else f32(Ws[l])
+            N, K = W.shape
+            if K > 512 or N > 512 or a.shape[1] != K:
+                raise _lib.RobirError("wn_chain: layer %d is %dx%d on %d input columns (engine limit 512)" % (l, N, K, a.shape[1]))
+            fw, bw = _tl_weight_images(W, 0 if l == 0 else (K - d_in if l in skip else K))
+            We.append(W)
+            imgs.append((fw, bw))
+            a_rows.append(a)
+            bias = _zeros(((N + 127) // 128) * 128, like=x)
+            bias[:N] = f32(bs[l])
+            last, next_skip = l == L - 1, (l + 1) in skip
+            if next_skip:
+                out = _empty(R, N + d_in, like=x)                   # [h_l | x]: the next layer's input rows
+                out[:, N:] = x
+            else:
+                out = _empty(R, N, like=x)
+            nkb_out = 0 if (last or next_skip) else (N + 63) // 64
+            nxt = _tl_image(tiles, nkb_out, x) if nkb_out else None
+            q = _tl_params(img, fw, bias, R, N, (K + 63) // 64, 0, 0 if last else SOFTPLUS, None, out, nxt, nkb_out,
+                           None, 0)
+            check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+            a = out
+            img = _tl_rows_image(out, N + d_in) if next_skip else nxt
+        ctx.meta = (R, d_in, L, tuple(skip))
+        ctx.imgs = imgs
+        ctx.save_for_backward(*a_rows, *We)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        R, d_in, L, skip = ctx.meta
+        a_rows, We = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
+        tiles = (R + 127) // 128
+        SOFTPLUS = 3
+        G = f32(g_out)
+        img = _tl_rows_image(G, G.shape[1])
+        gW, gb = [None] * L, [None] * L
+        for l in range(L - 1, -1, -1):
+            N, K = We[l].shape
+            A = a_rows[l]
+            # ---- dW_l = G_l^T A_l, db_l = column sums of G_l
+            dW, db = _empty(N, K, like=G), _empty(N, like=G)
+            wt = ((N + 63) // 64) * ((K + 63) // 64)
+            splits = max(1, min(64, (4 * sm_count()) // wt, (R + 63) // 64))
+            part = _empty(splits * wt * 4160, like=G) if splits > 1 else None
+            tickets = _zeros(wt, dtype=torch.int32, like=G)
+            check(lib().robir_mlp_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, None, 0, splits, ptr(part),
+                                        ptr(tickets), ptr(dW), ptr(db), stream()))
+            gW[l] = dW * (1.0 / math.sqrt(2.0)) if l in skip else dW
+            gb[l] = db
+            if l == 0:
+                break
+            # ---- G_{l-1} = (G_l W_l)[:, :N_{l-1}] * softplus'(h_{l-1}); h_{l-1} = the first N_{l-1} columns of A_l
+            Np = K - d_in if l in skip else K
+            Gp = _empty(R, Np, like=G)
+            nkb_out = (Np + 63) // 64
+            nxt = _tl_image(tiles, nkb_out, G)
+            q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, None, 0)
+            check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+            G, img = Gp, nxt
+        return (None, None, None, *gW, *gb)
+
+
+def wn_chain(x, Ws, bs, skip=(4,)):
+    """x [R, d_in] (no gradient), Ws[l] [N_l, K_l] the folded weight-norm weights, bs[l] [N_l] -> [R, N_last]."""
+    return _WnChain.apply(x, tuple(skip), len(Ws), *Ws, *bs)
 
 
 class _FusedMLP(torch.autograd.Function):

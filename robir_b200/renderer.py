@@ -142,6 +142,7 @@ class IDRNetwork(nn.Module):
                                     'vis_shadow', 'random_xi_diffuse_albedo', 'random_xi_roughness')}
         buf['metallic'] = ones1()
         buf['random_xi_metallic'] = ones1()
+        gradient_error = torch.tensor(0.0, device=dev)
         if n_hit > 0:
             if hit_sgs is None:
                 hit_sgs, hit_int = indirect_sgs[hit_idx], indirect_integral[hit_idx]
@@ -156,7 +157,9 @@ class IDRNetwork(nn.Module):
                 if k in ('roughness', 'random_xi_roughness'):
                     v = v.expand(-1, 3)
                 buf[k] = buf[k].index_copy(0, hit_idx, v)
-        ret.update({'final_t': ones1(), 'gradient_error': torch.tensor(0.0, device=dev), 'acc': ones1(),
+            if 'gradient_error' in r:                   # the CESR hook's supervise term (:446-447)
+                gradient_error = gradient_error + r['gradient_error']
+        ret.update({'final_t': ones1(), 'gradient_error': gradient_error, 'acc': ones1(),
                     'bg_rgb': ones3(), 'surface_mask': surface_mask})
         ret.update(buf)
         return ret

@@ -107,26 +107,51 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
                        indir_integral=None, indir_lgtSGs=None, VisModel=None, fun_spec=False, lin_diff=False,
                        testing=False, metallic=None, diffuse_vis=None, prefit=False, argmax_vis=False, valid=None,
                        diffuse_presampled=None):
-    """model/sg_render.py:304-337 for the PBR-stage configuration (fun_spec=False, metallic=None, diffuse_vis=None)."""
-    if fun_spec or metallic is not None or diffuse_vis is not None or argmax_vis or viewdirs.dim() != 2:
-        raise RobirError("render_with_all_sg: fun_spec / metallic / diffuse_vis / argmax_vis / multi-view variants are "
-                         "not on the accelerated path (CESR extras are a later row, SURVEY.md section 8f)")
+    """model/sg_render.py:304-337 for the PBR-stage configuration (fun_spec=False, metallic=None) and, with
+    diffuse_vis [n*M] / prefit, the CESR-stage one (sg_render.py:389-407)."""
+    if fun_spec or metallic is not None or argmax_vis or viewdirs.dim() != 2:
+        raise RobirError("render_with_all_sg: fun_spec / metallic / argmax_vis / multi-view variants are not on the "
+                         "accelerated path")
     if lgtSGs.dim() != 2:
         raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
+    if normal.requires_grad:
+        raise RobirError("render_with_all_sg: a normal that carries a gradient (CESR after iteration 1000, "
+                         "train_cesr.py:508) is not on the accelerated path; pass normal.detach()")
     with ops.point_table_scope():
         return _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
-                                   indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled)
+                                   indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled,
+                                   diffuse_vis, prefit)
+
+
+def kl_divergence(x, mu=0.05):
+    """utils/utils.py:14-17."""
+    rho_hat = torch.mean(x, 0)
+    rho = torch.full_like(rho_hat, mu)
+    return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4)) + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
 
 
 def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
-                        indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled=None):
+                        indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled=None,
+                        diffuse_vis=None, prefit=False):
     n = normal.shape[0]
     M = lgtSGs.shape[0]
     viewdirs = viewdirs.detach()
-    # ---- direct light visibility per lobe (sg_render.py:364-366, 388-391)
+    # ---- direct light visibility per lobe (sg_render.py:364-366, 388-391): 32 samples per lobe, 8 when a learned
+    # per-lobe visibility (the CESR shadow_net) stands in for it and the MLP average only supervises it
     lobes, lambdas = light_lobes(lgtSGs)
-    light_vis = get_diffuse_visibility(points, normal.detach(), VisModel, lobes, lambdas, nsamp=32,
+    light_vis = get_diffuse_visibility(points, normal.detach(), VisModel, lobes, lambdas,
+                                       nsamp=32 if diffuse_vis is None else 8,
                                        testing=testing, presampled=diffuse_presampled).permute(1, 0)
+    supervise = torch.zeros((), device=points.device)
+    if diffuse_vis is not None:
+        if valid is not None:
+            raise RobirError("render_with_all_sg: diffuse_vis is not supported in the fixed-capacity mode")
+        light_vis_gt, light_vis = light_vis, diffuse_vis.reshape(-1, M)
+        if prefit == "warmup":                                                          # sg_render.py:397-399
+            supervise = kl_divergence((light_vis_gt.detach() - light_vis).abs(), 0.01) * 0.1
+            light_vis = light_vis_gt
+        else:                                                                           # :400-403
+            supervise = kl_divergence((light_vis_gt - light_vis).abs(), 0.01) * (0.2 if prefit == "project" else 1.0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
     bv_ind = None
     if indir_lgtSGs is not None:
@@ -151,5 +176,5 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
                          indir_lgtSGs, light_vis.contiguous(), bv_dir, bv_ind, indir_integral, lin_diff)
     sg_rgb, sg_spec, sg_diff, vis_shadow, ind_rgb, ind_spec, ind_diff = outs
     return {'sg_rgb': sg_rgb, 'sg_specular_rgb': sg_spec, 'sg_diffuse_rgb': sg_diff, 'vis_shadow': vis_shadow,
-            'supervise': torch.zeros((), device=points.device), 'indir_rgb': ind_rgb,
+            'supervise': supervise, 'indir_rgb': ind_rgb,
             'indir_diffuse_rgb': ind_diff, 'indir_specular_rgb': ind_spec}

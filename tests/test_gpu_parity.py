@@ -830,3 +830,132 @@ def test_static_compact_loss_matches_ray_order_loss(model16):
     finally:
         rng.set_mode("cpu")
         model16.static_shapes = False
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CESR extras
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(params=["torch", "tc"])
+def wn_engine(request):
+    """Engines of the CESR stage's weight-normed 512-wide chains: cuBLAS cross-check and the tcgen05 layer engine."""
+    from robir_b200 import ops
+    old = ops.ENGINE["wn"]
+    ops.ENGINE["wn"] = request.param
+    yield request.param
+    ops.ENGINE["wn"] = old
+
+
+def _cesr_nets():
+    from robir_b200 import cesr
+    sh, nr = synthetic.cesr_state_dicts(0)
+    shadow, normal = cesr.WnMLP(191, 2), cesr.WnMLP(63, 3)
+    shadow.load_state_dict(sh, strict=True)
+    normal.load_state_dict(nr, strict=True)
+    return shadow.cuda(), normal.cuda(), sh, nr
+
+
+@pytest.mark.parametrize("which,rows", [("shadow", 1024), ("shadow", 1000), ("normal", 333)])
+def test_wn_chain_vs_oracle(which, rows, wn_engine):
+    """shadow_net / normal_net (weight-normed, softplus(100), skip concat at layer 4) forward + every parameter
+    gradient against the oracle's wn_mlp (neus_model.py:385-417) on CPU, ragged row counts included."""
+    from robir_b200 import cesr
+    shadow, normal, sh, nr = _cesr_nets()
+    net, sd = (shadow, sh) if which == "shadow" else (normal, nr)
+    gen = torch.Generator().manual_seed(23)
+    pts = torch.nn.functional.normalize(torch.randn(rows, 3, generator=gen), dim=-1) * 0.33
+    emb = O.pe(pts, 10)
+    if which == "shadow":
+        lab = torch.eye(128)[torch.randint(0, 128, (rows,), generator=gen)]
+        emb = torch.cat([emb, lab], -1)
+    gup = torch.randn(rows, 2 if which == "shadow" else 3, generator=gen)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.wn_mlp(sdr, "", emb, prefix_dot=False)
+    (ref * gup).sum().backward()
+    net.zero_grad()
+    out = cesr.wn_mlp(net, emb.cuda())
+    (out * gup.cuda()).sum().backward()
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < REL, rel_err(out, ref)
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        grad_close(p.grad, sdr[k].grad, 1e-3, 1e-2, engine="tc" if wn_engine == "tc" else "ffma")
+
+
+@pytest.fixture(scope="module")
+def model128():
+    import robir_b200
+    m = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=128)))
+    m.load_state_dict(synthetic.synthetic_state_dict(0, num_lgt_sgs=128), strict=True)
+    m.cuda().train()
+    m.generate()
+    return m
+
+
+def test_cesr_step_vs_golden(golden, model128, wn_engine):
+    """IDRNetwork.forward('Material') with the CESR hook bound (train_cesr.py:465-544,588) + the stage's step loss
+    (:387-430) + backward against the reference's golden outputs and gradients: explore phase, iteration 600."""
+    from robir_b200 import cesr, rng
+    from robir_b200.loss import InvLoss
+    g = golden("cesr_step")
+    shadow, normal, _, _ = _cesr_nets()
+    hook = cesr.ClusteredAlbedoHook(model128, shadow, normal, white_light=True, explore_iter=1000, proj_iter=0,
+                                    explore_smooth=0.1, explore_kl=1.0, cur_iter=600)
+    assert hook.prefit_option() == "explore"
+    old_hook, old_static = model128.get_sg_render, model128.static_shapes
+    model128.get_sg_render, model128.static_shapes = hook.get_sg_render, False
+    try:
+        model128.zero_grad()
+        N = g["pix"].shape[0]
+        inp = {k: v.cuda() for k, v in synthetic.camera_inputs(g["pix"]).items()}
+        inp["hdr_shift"] = model128.gamma.hdr_shift.as_input().expand(N, 1)
+        with rng.replay([g["rnd_%d" % i] for i in range(9)]):
+            out = model128(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = hook.pbr_step(InvLoss(), out, {"rgb": g["gt"]})
+    finally:
+        model128.get_sg_render, model128.static_shapes = old_hook, old_static
+    mask = out["network_object_mask"].cpu()
+    assert (mask != g["out_network_object_mask"]).sum() == 0, "tracer mask differs from the reference"
+    for k in [k[4:] for k in g if k.startswith("out_") and k != "out_network_object_mask"]:
+        assert out[k].shape == g["out_" + k].shape, k
+        assert rel_err(out[k], g["out_" + k]) < REL, (k, rel_err(out[k], g["out_" + k]))
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * max(1.0, abs(g["loss"].item()))
+    loss.backward()
+    mat = model128.envmap_material_network
+    eng = "tc" if wn_engine == "tc" else "ffma"
+    checks = [(mat.lgtSGs.grad, g["g_lgtSGs"]), (mat.specular_reflectance.grad, g["g_spec"]),
+              (model128.gamma.hdr_shift.adapt_illum.grad, g["g_adapt"]),
+              (shadow.lin8.weight_v.grad, g["g_shadow_lin8_v"]), (shadow.lin8.bias.grad, g["g_shadow_lin8_bias"]),
+              (shadow.lin4.weight_g.grad, g["g_shadow_lin4_g"]), (shadow.lin0.bias.grad, g["g_shadow_lin0_bias"]),
+              (shadow.lin0.weight_v.grad.sum(0), g["g_shadow_lin0_v_colsum"]),
+              (normal.lin8.weight_v.grad, g["g_normal_lin8_v"]), (normal.lin0.bias.grad, g["g_normal_lin0_bias"]),
+              (normal.lin3.weight_g.grad, g["g_normal_lin3_g"])]
+    for a, b in checks:
+        grad_close(a, b, 5e-3, 3e-2, eng)
+
+
+def test_cesr_schedule_and_refusals(model128):
+    """Warm-up phase (iteration <= 500: the MLP visibility renders, shadow_net is only supervised, the step loss is the
+    supervise term alone) runs; the project phase after iteration 1000 needs d render / d normal and must refuse."""
+    from robir_b200 import RobirError, cesr
+    from robir_b200.loss import InvLoss
+    shadow, normal, _, _ = _cesr_nets()
+    hook = cesr.ClusteredAlbedoHook(model128, shadow, normal, cur_iter=300)
+    assert hook.prefit_option() == "warmup"
+    N = 256
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(4, n=N, crop=400)).items()}
+    inp["hdr_shift"] = model128.gamma.hdr_shift.as_input().expand(N, 1)
+    old_hook, old_static = model128.get_sg_render, model128.static_shapes
+    model128.get_sg_render, model128.static_shapes = hook.get_sg_render, False
+    try:
+        out = model128(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        assert int(out["network_object_mask"].sum()) > 0
+        loss, _ = hook.pbr_step(InvLoss(), out, {"rgb": torch.full((1, N, 3), 0.4)})
+        assert loss is out["gradient_error"] or torch.equal(loss, out["gradient_error"])
+        shadow.zero_grad()
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in shadow.parameters())
+        hook.cur_iter = 1200
+        with pytest.raises(RobirError):
+            model128(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+    finally:
+        model128.get_sg_render, model128.static_shapes = old_hook, old_static
