@@ -127,8 +127,13 @@ def cesr_state_dicts(seed=0, gain=2.0):
     """Seeded weights of the CESR stage's two extra weight-normed MLPs (training/train_cesr.py:106-110; state-dict keys
     of the reference SDFNetwork: ``lin{l}.weight_g | weight_v | bias``): shadow_net 191 -> 512 x8 -> 2 and normal_net
     63 -> 512 x8 -> 3, skip concat at layer 4.  He-style hidden layers; the output layer is scaled by ``gain`` so the
-    shadow classifier is not stuck at 0.5 (the reference's geometric init makes both logits equal)."""
+    shadow classifier is not stuck at 0.5 (the reference's geometric init makes both logits equal).  The columns that
+    multiply PE band k are attenuated by 2^-k (the spectral decay of a trained network): without it one ulp of a traced
+    hit point moves the outputs by 3e-5 and the parity tests would measure the tracer, not these networks."""
     gen = torch.Generator().manual_seed(seed + 7919)
+    band = torch.ones(63)
+    for k in range(10):
+        band[3 + 6 * k: 9 + 6 * k] = 2.0 ** -k
     out = []
     for d_in, d_out in ((191, 2), (63, 3)):
         dims = [d_in] + [512] * 8 + [d_out]
@@ -137,6 +142,10 @@ def cesr_state_dicts(seed=0, gain=2.0):
             o = dims[l + 1] - dims[0] if l + 1 == 4 else dims[l + 1]
             std = math.sqrt(2) / math.sqrt(o) if l < 8 else gain / math.sqrt(dims[l])
             w = torch.randn(o, dims[l], generator=gen) * std
+            if l == 0:
+                w[:, :63] *= band
+            elif l == 4:
+                w[:, dims[l] - d_in: dims[l] - d_in + 63] *= band
             b = (torch.rand(o, generator=gen) * 2 - 1) * 0.05
             _put_wn(sd, "lin%d" % l, w, b)
             sd["lin%d.weight_g" % l] = sd["lin%d.weight_g" % l] * (0.9 + 0.2 * torch.rand(o, 1, generator=gen))

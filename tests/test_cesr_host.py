@@ -55,3 +55,99 @@ def test_schedule_matches_reference_restatement(explore_iter, proj_iter):
     for it in (0, 1, 499, 500, 501, 600, 999, 1000, 1001, 1200, 1499, 1500, 2750):
         hook.cur_iter = it
         assert hook.prefit_option() == P.cesr_prefit_option(it, explore_iter, proj_iter), it
+
+
+class _EmulatedEngine:
+    """Stand-in for the four C-ABI entry points that ops._WnChain drives, with the documented semantics of
+    csrc/tc_mlp.cu / csrc/mlp.cu restated in torch on CPU tensors (images are tracked as logical matrices).  It checks
+    the HOST logic of the chain -- buffer plumbing, skip concat, gradient chain, scaling -- not the kernels."""
+
+    def __init__(self):
+        self.mats = {}
+
+    @staticmethod
+    def _act(x, act):
+        return torch.nn.functional.softplus(x, beta=100) if act == 3 else x
+
+    @staticmethod
+    def _dact(y, act):
+        return -torch.expm1(-100.0 * y) if act == 3 else torch.ones_like(y)
+
+    def robir_tl_pack_weight(self, W, ldw, N, K, transpose, col_blocks, nkb, img, stream):
+        assert W.shape[1] == ldw and col_blocks * 128 >= N and nkb * 64 >= K
+        B = W.t()[:N, :K] if transpose else W[:N, :K]
+        assert B.shape == (N, K)
+        assert img.numel() == col_blocks * nkb * 32768
+        self.mats[id(img)] = (B.clone(), nkb)
+        return 0
+
+    def robir_tl_pack_rows(self, X, ldx, n, K, ref, ld_ref, act, nkb, img, stream):
+        assert X.shape[1] == ldx and nkb * 64 >= K and ref is None
+        assert img.numel() == ((n + 127) // 128) * nkb * 32768
+        self.mats[id(img)] = (X[:n, :K].clone(), nkb)
+        return 0
+
+    def robir_tl_layer(self, q, stream):
+        (A, nkb_a), (B, nkb_b) = self.mats[id(q.a_img)], self.mats[id(q.w_img)]
+        assert nkb_a == nkb_b == q.nkb <= 8 and A.shape[0] == q.n
+        assert B.shape[0] == q.N, "weight image rows must equal the valid output columns"
+        K = min(A.shape[1], B.shape[1])
+        assert not A[:, K:].any() and not B[:, K:].any()        # anything beyond the shorter operand must be padding
+        acc = A[:, :K] @ B[:, :K].t()
+        if q.mode == 0:
+            assert q.bias.numel() >= ((q.N + 127) // 128) * 128
+            x = self._act(acc + q.bias[:q.N], q.act)
+        else:
+            x = acc * (self._dact(q.ref[:, :q.N], q.act) if q.ref is not None else 1.0)
+        if q.out is not None:
+            assert q.ld_out == q.out.shape[1]
+            q.out[:, :q.N] = x
+        if q.out_img is not None:
+            assert q.nkb_out == (q.N + 63) // 64
+            self.mats[id(q.out_img)] = (x.clone(), q.nkb_out)
+        return 0
+
+    def robir_mlp_wgrad(self, G, ldg, A, lda, n, N, K, n_active, seg, splits, partial, tickets, dW, db, stream):
+        assert G.shape[1] == ldg and A.shape[1] == lda and 1 <= splits <= 64
+        assert splits == 1 or partial.numel() >= splits * ((N + 63) // 64) * ((K + 63) // 64) * 4160
+        dW.copy_(G[:n, :N].t() @ A[:n, :K])
+        db.copy_(G[:n, :N].sum(0))
+        return 0
+
+
+@pytest.mark.parametrize("d_in,d_out,rows", [(191, 2, 256), (191, 2, 200), (63, 3, 130)])
+def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows):
+    import types
+    from robir_b200 import ops
+    eng = _EmulatedEngine()
+
+    def params(a_img, w_img, bias, n, N, nkb, mode, act, ref, out, out_img, nkb_out, n_active, seg):
+        return types.SimpleNamespace(a_img=a_img, w_img=w_img, bias=bias, n=n, N=N, nkb=nkb, mode=mode, act=act, ref=ref,
+                                     out=out, ld_out=out.shape[1] if out is not None else 0, out_img=out_img,
+                                     nkb_out=nkb_out)
+    monkeypatch.setattr(ops, "lib", lambda: eng)
+    monkeypatch.setattr(ops, "ptr", lambda t: t)
+    monkeypatch.setattr(ops, "stream", lambda: None)
+    monkeypatch.setattr(ops, "check", lambda status: None)
+    monkeypatch.setattr(ops, "sm_count", lambda: 148)
+    monkeypatch.setattr(ops, "_tl_params", params)
+    monkeypatch.setattr(ops, "ctypes", types.SimpleNamespace(byref=lambda q: q))
+
+    sh, nr = synthetic.cesr_state_dicts(0)
+    net = cesr.WnMLP(d_in, d_out)
+    net.load_state_dict(sh if d_in == 191 else nr)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(rows, d_in, generator=gen) * 0.5
+    gup = torch.randn(rows, d_out, generator=gen)
+    lins, skip = cesr._layers(net)
+    res = []
+    for fn in (lambda Ws, bs: ops.wn_chain(x, Ws, bs, skip), lambda Ws, bs: cesr._wn_rows_torch(Ws, bs, skip, x)):
+        net.zero_grad()
+        out = fn([l.folded() for l in lins], [l.bias for l in lins])
+        (out * gup).sum().backward()
+        res.append((out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    (o1, g1), (o2, g2) = res
+    assert (o1 - o2).abs().max().item() < 1e-5 * max(1.0, o2.abs().max().item())
+    assert set(g1) == set(g2) and len(g1) == 27
+    for k in g2:
+        assert (g1[k] - g2[k]).abs().max().item() < 2e-4 * max(1e-6, g2[k].abs().max().item()), k
