@@ -247,12 +247,17 @@ int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int
 /* ---- a6 / a7, tensor-core layer engine (tcgen05 + TMEM, bf16 hi/lo 3-term split = fp32 parity) for the 512-wide
  * encoder / lobe networks: one launch per Linear layer over bf16 hi/lo images (K-major SWIZZLE_128B k-blocks of
  * 128 rows x 64 k, 32 KB each: robir_tl_block_bytes()).  forward: Y = act(A W^T + b); backward: G_prev = (G W) act'(ref).
- * The fp32 rows written by a layer are what robir_mlp_wgrad and the next backward layer consume. ---------------------- */
+ * The fp32 rows written by a layer are what robir_mlp_wgrad and the next backward layer consume.
+ * Also the engine of the CESR stage's weight-normed chains (section 8f row 1: shadow_net / normal_net,
+ * training/train_cesr.py:106-110 = SDFNetwork.forward with multires 0, model/neus_model.py:397-415): act 3 =
+ * Softplus(beta = 100), whose derivative is recovered from the saved output (1 - exp(-100 y)); the skip concat is a
+ * 512-column row buffer (ld_out > N) that the previous layer fills and robir_tl_pack_rows turns into the next image. */
 typedef struct {
   const void* a_img;        /* [ceil(n / 128)][nkb][32 KB] activation (or gradient) image */
   const void* w_img;        /* [ceil(N / 128)][nkb][32 KB] weight image (robir_tl_pack_weight) */
   const float* bias;        /* zero padded to a multiple of 128, or NULL */
-  int n, N, nkb, mode, act; /* mode 0 forward / 1 backward; act: this layer's (fwd) or the previous layer's (bwd) */
+  int n, N, nkb, mode, act; /* mode 0 forward / 1 backward; act: this layer's (fwd) or the previous layer's (bwd):
+                               0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 Softplus(beta = 100) */
   const float* ref;         /* backward: saved post-activation rows of the previous layer [n][ld_ref], or NULL */
   int ld_ref;
   float* out;               /* fp32 rows [n][ld_out], columns < N, or NULL */
