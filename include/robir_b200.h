@@ -196,6 +196,8 @@ typedef struct {
   const float *g_sg_rgb, *g_sg_spec, *g_sg_diff, *g_ind_rgb, *g_ind_spec, *g_ind_diff;   /* NULL = zero */
   float *g_lgt /*[M][7] zero-init*/, *g_ind_lgt, *g_light_vis, *g_bv_dir, *g_bv_ind, *g_rough, *g_albedo,
       *g_spec_refl /*[1] zero-init*/, *g_ind_integral;
+  float* g_normal;   /* [n][3] or NULL: gradient of the shading normal (CESR renders with normal_net's normals after
+                        iteration 1000, training/train_cesr.py:508; the PBR stage passes a detached normal) */
 } robir_sg_params;
 int robir_sg_render_fwd(const robir_sg_params* p, void* stream);
 int robir_sg_render_bwd(const robir_sg_params* p, void* stream);

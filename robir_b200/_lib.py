@@ -24,7 +24,7 @@ class SgParams(Structure):
             "normal", "view", "rough", "albedo", "spec_refl", "lgt", "ind_lgt", "light_vis", "bv_dir", "bv_ind",
             "ind_integral", "sg_rgb", "sg_spec", "sg_diff", "vis_shadow", "ind_rgb", "ind_spec", "ind_diff", "pre",
             "g_sg_rgb", "g_sg_spec", "g_sg_diff", "g_ind_rgb", "g_ind_spec", "g_ind_diff", "g_lgt", "g_ind_lgt",
-            "g_light_vis", "g_bv_dir", "g_bv_ind", "g_rough", "g_albedo", "g_spec_refl", "g_ind_integral")]
+            "g_light_vis", "g_bv_dir", "g_bv_ind", "g_rough", "g_albedo", "g_spec_refl", "g_ind_integral", "g_normal")]
 
 
 class SdfParams(Structure):

@@ -37,6 +37,8 @@ struct SgParams {
   float* g_albedo;            // [n][3]
   float* g_spec_refl;         // [1] atomically accumulated
   float* g_ind_integral;      // [n][3]
+  float* g_normal;            // [n][3] or null: gradient of the shading normal (CESR after iteration 1000 renders with
+                              // normal_net's normals, training/train_cesr.py:508; the PBR stage passes a detached normal)
 };
 
 template <int NV>
@@ -109,8 +111,41 @@ __global__ void __launch_bounds__(128) sg_render_fwd_kernel(SgParams p) {
 }
 
 // dual layout, specular: 0-6 raw SG, 7 rough, 8 spec_refl, 9 brdf_vis;  diffuse: 0-6 raw SG, 7 light_vis
+// one specular lobe of the backward: tangents of sum_c g[c] * mu_c * bv * F * Ks with respect to the raw SG (-> g_raw) and
+// to the per-point inputs (-> acc: 0 rough, 1 spec_refl, bv_slot brdf_vis, 7-9 normal)
+template <bool NG, typename DS>
+__device__ __forceinline__ void spec_lobe_bwd(const V3<DS>& nS, const SpecPoint<DS>& sp, const DS& F, const float* raw,
+                                              float bv, const float (&g)[3], float* g_raw, int bv_slot, float* acc) {
+  DS r[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) r[k] = DS::seed(raw[k], k);
+  const LightSG<DS> l = decode_light<DS>(r);
+  const DS Ks = spec_lobe_kernel<DS>(nS, sp, l.lobe, l.lam);
+  const DS common = DS::seed(bv, 9) * F * Ks;
+  DS tot(0.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tot = tot + (l.mu[c] * common) * g[c];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) g_raw[k] = tot.d[k];
+  acc[0] += tot.d[7];
+  acc[1] += tot.d[8];
+  acc[bv_slot] += tot.d[9];
+  if constexpr (NG) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[7 + k] += tot.d[10 + k];
+  }
+}
+
+template <typename T, bool NG, int BASE>
+__device__ __forceinline__ V3<T> seed_normal(const V3<float>& n) {
+  if constexpr (NG) return {T::seed(n.x, BASE), T::seed(n.y, BASE + 1), T::seed(n.z, BASE + 2)};
+  else return lift3<T>(n);
+}
+
+// NG: also differentiate with respect to the shading normal (three more dual components per lobe evaluation)
+template <bool NG>
 __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
-  __shared__ float sh[8 * 4];
+  __shared__ float sh[10 * 4];
   const int i = blockIdx.x, tid = threadIdx.x;
   const V3<float> nrm = {p.normal[3 * i], p.normal[3 * i + 1], p.normal[3 * i + 2]};
   const V3<float> view = {p.view[3 * i], p.view[3 * i + 1], p.view[3 * i + 2]};
@@ -133,42 +168,35 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
     bool any = false;
 #pragma unroll
     for (int c = 0; c < 3; ++c) any |= (gs[c] != 0.f) | (gd[c] != 0.f) | (gis[c] != 0.f) | (gid[c] != 0.f);
-    if (!any) return;
+    if (!any) {
+      if constexpr (NG) {
+        if (tid < 3) p.g_normal[3 * i + tid] = 0.f;
+      }
+      return;
+    }
   }
-  typedef Dual<10> DS;
-  typedef Dual<8> DD;
-  const V3<DS> nS = lift3<DS>(nrm), vS = lift3<DS>(view);
+  // dual slots, specular: 0-6 raw SG, 7 rough, 8 spec_refl, 9 brdf_vis, (10-12 normal);  diffuse: 0-6 raw SG,
+  // 7 light_vis, (8-10 normal)
+  constexpr int NA = NG ? 10 : 7;
+  typedef Dual<NG ? 13 : 10> DS;
+  typedef Dual<NG ? 11 : 8> DD;
+  const V3<DS> nS = seed_normal<DS, NG, 10>(nrm);
+  const V3<DD> nD = seed_normal<DD, NG, 8>(nrm);
+  const V3<DS> vS = lift3<DS>(view);
   const SpecPoint<DS> sp = spec_point<DS>(nS, vS, DS::seed(rough, 7));
   const DS F = fresnel<DS>(DS::seed(sr, 8), sp.v_dot_h);
-  const V3<DD> nD = lift3<DD>(nrm);
-  // per-point accumulators: 0 rough, 1 spec_refl, 2 bv_dir, 3 bv_ind, 4-6 albedo
-  float acc[7];
+  // per-point accumulators: 0 rough, 1 spec_refl, 2 bv_dir, 3 bv_ind, 4-6 albedo, (7-9 normal)
+  float acc[NA];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NA; ++k) acc[k] = 0.f;
 
-  auto spec_lobe = [&](const float* raw, float bv, const float (&g)[3], float* g_raw, int bv_slot) {
-    DS r[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) r[k] = DS::seed(raw[k], k);
-    const LightSG<DS> l = decode_light<DS>(r);
-    const DS Ks = spec_lobe_kernel<DS>(nS, sp, l.lobe, l.lam);
-    const DS common = DS::seed(bv, 9) * F * Ks;
-    DS tot(0.f);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tot = tot + (l.mu[c] * common) * g[c];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) g_raw[k] = tot.d[k];
-    acc[0] += tot.d[7];
-    acc[1] += tot.d[8];
-    acc[bv_slot] += tot.d[9];
-  };
 
   const bool any_dir = (gs[0] != 0.f) | (gs[1] != 0.f) | (gs[2] != 0.f) | (gd[0] != 0.f) | (gd[1] != 0.f) | (gd[2] != 0.f);
   for (int m = tid; m < p.M; m += blockDim.x) {
     float g_raw[7] = {0, 0, 0, 0, 0, 0, 0};
     float g_lv = 0.f;
     if (any_dir) {
-      spec_lobe(p.lgt + 7 * m, p.bv_dir[i], gs, g_raw, 2);
+      spec_lobe_bwd<NG, DS>(nS, sp, F, p.lgt + 7 * m, p.bv_dir[i], gs, g_raw, 2, acc);
       // diffuse
       DD r[7];
 #pragma unroll
@@ -187,6 +215,10 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
 #pragma unroll
       for (int k = 0; k < 7; ++k) g_raw[k] += tot.d[k];
       g_lv = tot.d[7];
+      if constexpr (NG) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[7 + k] += tot.d[8 + k];
+      }
 #pragma unroll
       for (int k = 0; k < 7; ++k)
         if (g_raw[k] != 0.f) atomicAdd(p.g_lgt + 7 * m + k, g_raw[k]);
@@ -195,12 +227,16 @@ __global__ void __launch_bounds__(128) sg_render_bwd_kernel(SgParams p) {
   }
   for (int m = tid; m < p.Mi; m += blockDim.x) {
     float g_raw[7] = {0, 0, 0, 0, 0, 0, 0};
-    spec_lobe(p.ind_lgt + ((size_t)i * p.Mi + m) * 7, p.bv_ind[i], gis, g_raw, 3);
+    spec_lobe_bwd<NG, DS>(nS, sp, F, p.ind_lgt + ((size_t)i * p.Mi + m) * 7, p.bv_ind[i], gis, g_raw, 3, acc);
 #pragma unroll
     for (int k = 0; k < 7; ++k) p.g_ind_lgt[((size_t)i * p.Mi + m) * 7 + k] = g_raw[k];
   }
-  block_sum<7>(acc, sh);
+  block_sum<NA>(acc, sh);
   if (tid == 0) {
+    if constexpr (NG) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p.g_normal[3 * i + k] = acc[7 + k];
+    }
     p.g_rough[i] = acc[0];
     if (acc[1] != 0.f) atomicAdd(p.g_spec_refl, acc[1]);
     p.g_bv_dir[i] = acc[2];
@@ -421,7 +457,8 @@ int robir_sg_render_fwd(const SgParams* p, void* stream) {
 
 int robir_sg_render_bwd(const SgParams* p, void* stream) {
   if (p->n == 0) return 0;
-  sg_render_bwd_kernel<<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
+  if (p->g_normal != nullptr) sg_render_bwd_kernel<true><<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
+  else sg_render_bwd_kernel<false><<<p->n, 128, 0, (cudaStream_t)stream>>>(*p);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

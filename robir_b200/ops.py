@@ -509,6 +509,7 @@ class _SgRender(torch.autograd.Function):
         z = lambda *s: _zeros(*s, like=normal)
         g_lgt, g_ind_lgt, g_lv = z(M, 7), (z(n, Mi, 7) if has_ind else None), z(n, M)
         g_bvd, g_bvi, g_rough, g_alb, g_sr, g_int = z(n), z(n), z(n), z(n, 3), z(1), z(n, 3)
+        g_nrm = z(n, 3) if ctx.needs_input_grad[0] else None      # shading normal: only the CESR stage asks for it
         p = SgParams()
         p.n, p.M, p.Mi, p.lin_diff = n, M, Mi, lin_diff
         fz = lambda g: f32(g) if g is not None else None
@@ -517,10 +518,11 @@ class _SgRender(torch.autograd.Function):
                          ind_integral=ind_integral, pre=pre, g_sg_rgb=fz(g_rgb), g_sg_spec=fz(g_spec),
                          g_sg_diff=fz(g_diff), g_ind_rgb=fz(g_irgb), g_ind_spec=fz(g_ispec), g_ind_diff=fz(g_idiff),
                          g_lgt=g_lgt, g_ind_lgt=g_ind_lgt, g_light_vis=g_lv, g_bv_dir=g_bvd, g_bv_ind=g_bvi,
-                         g_rough=g_rough, g_albedo=g_alb, g_spec_refl=g_sr, g_ind_integral=g_int).items():
+                         g_rough=g_rough, g_albedo=g_alb, g_spec_refl=g_sr, g_ind_integral=g_int,
+                         g_normal=g_nrm).items():
             setattr(p, k, ptr(t))
         check(lib().robir_sg_render_bwd(ctypes.byref(p), stream()))
-        return (None, None, g_rough.reshape(rough_shape), g_alb, g_sr.reshape(spec_refl.shape), g_lgt, g_ind_lgt, g_lv,
+        return (g_nrm, None, g_rough.reshape(rough_shape), g_alb, g_sr.reshape(spec_refl.shape), g_lgt, g_ind_lgt, g_lv,
                 g_bvd, g_bvi if has_ind else None, g_int if has_ind else None, None)
 
 

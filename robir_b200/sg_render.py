@@ -114,9 +114,9 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
                          "accelerated path")
     if lgtSGs.dim() != 2:
         raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
-    if normal.requires_grad:
+    if normal.requires_grad and valid is not None:
         raise RobirError("render_with_all_sg: a normal that carries a gradient (CESR after iteration 1000, "
-                         "train_cesr.py:508) is not on the accelerated path; pass normal.detach()")
+                         "train_cesr.py:508) is not supported in the fixed-capacity mode")
     with ops.point_table_scope():
         return _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
                                    indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled,
@@ -154,9 +154,21 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
             supervise = kl_divergence((light_vis_gt - light_vis).abs(), 0.01) * (0.2 if prefit == "project" else 1.0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
     bv_ind = None
-    if indir_lgtSGs is not None:
-        if indir_integral is None:
-            raise RobirError("render_with_all_sg: indirect SGs need indir_integral (PBR-stage configuration)")
+    normal_grad = normal.requires_grad and torch.is_grad_enabled() and not testing
+    if indir_lgtSGs is not None and indir_integral is None:
+        raise RobirError("render_with_all_sg: indirect SGs need indir_integral (PBR-stage configuration)")
+    if normal_grad:
+        # the shading normal is being trained (CESR after iteration 1000 renders with normal_net's output,
+        # train_cesr.py:508; render_with_sg never detaches it, sg_render.py:369-371): the reflection frame and the
+        # warped lobe stay in torch so that autograd carries d/d normal, the sample directions / weights and the SG
+        # render differentiate on the device (robir_sample_dirs_bwd, robir_sg_render_bwd with g_normal)
+        wl, wlam = _spec_warp(normal, viewdirs, roughness)
+        bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
+                                         inv=False)
+        if indir_lgtSGs is not None:
+            bv_ind = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
+                                             inv=True)
+    elif indir_lgtSGs is not None:
         # both get_specular_visibility calls (inv = False / True) share their sampling inputs: one prep kernel, one
         # launch chain over 2n "points" (rows [0, n) direct, [n, 2n) indirect)
         S = 8
@@ -172,7 +184,8 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
         wl, wlam = _spec_warp(normal, viewdirs, roughness)
         bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
                                          inv=False, valid=valid)
-    outs = ops.sg_render(normal.detach(), viewdirs, roughness, diffuse_albedo, specular_reflectance.reshape(1), lgtSGs,
+    outs = ops.sg_render(normal if normal_grad else normal.detach(), viewdirs, roughness, diffuse_albedo,
+                         specular_reflectance.reshape(1), lgtSGs,
                          indir_lgtSGs, light_vis.contiguous(), bv_dir, bv_ind, indir_integral, lin_diff)
     sg_rgb, sg_spec, sg_diff, vis_shadow, ind_rgb, ind_spec, ind_diff = outs
     return {'sg_rgb': sg_rgb, 'sg_specular_rgb': sg_spec, 'sg_diffuse_rgb': sg_diff, 'vis_shadow': vis_shadow,

@@ -147,6 +147,9 @@ def cesr_state_dicts(seed=0, gain=2.0):
             elif l == 4:
                 w[:, dims[l] - d_in: dims[l] - d_in + 63] *= band
             b = (torch.rand(o, generator=gen) * 2 - 1) * 0.05
+            if l == 8 and d_out == 3:
+                b = b + torch.tensor([0.2, -0.3, 2.0])   # normals that mostly face the +z camera of camera_pose(), so that
+                #                                          the specular lobe (and its normal gradient) is exercised
             _put_wn(sd, "lin%d" % l, w, b)
             sd["lin%d.weight_g" % l] = sd["lin%d.weight_g" % l] * (0.9 + 0.2 * torch.rand(o, 1, generator=gen))
         out.append(sd)

@@ -39,15 +39,21 @@ def build(use_octree=True, n_steps=100, perturb=0.0):
     return sd, model
 
 
-def cesr_golden(g):
+CESR_CASES = {   # file -> runner settings (confs_sg/hotdog.conf:34-43 explore schedule; confs_sg/truck.conf project schedule)
+    "cesr_step": dict(cur_iter=600, white_light=True, explore_iter=1000, proj_iter=0, explore_smooth=0.1, explore_kl=1.0),
+    "cesr_step_1200": dict(cur_iter=1200, white_light=False, explore_iter=0, proj_iter=1000, proj_smooth=0.001,
+                           proj_kl=0.01),
+}
+
+
+def cesr_golden(g, name="cesr_step"):
     sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=128)
     model = ref_shim.build_reference_model(synthetic.neus_checkpoint_from(sd), num_lgt_sgs=128)
     model.load_state_dict(sd, strict=True)
     model.train()
     model.ray_tracer.generate(lambda x: model.implicit_network(x)[:, 0], None)
     from model.loss import InvLoss
-    runner = ref_shim.bind_cesr_runner(model, cur_iter=600, white_light=True, explore_iter=1000, proj_iter=0,
-                                       explore_smooth=0.1, explore_kl=1.0)
+    runner = ref_shim.bind_cesr_runner(model, **CESR_CASES[name])
     runner.loss = InvLoss(1.0, 0.1, 100.0, 50.0, 1.0, 1.0, 1.0)
     sh, nr = synthetic.cesr_state_dicts(SEED)
     runner.shadow_net.load_state_dict(sh, strict=True)
@@ -78,8 +84,8 @@ def cesr_golden(g):
              g_shadow_lin0_v_colsum=runner.shadow_net.lin0.weight_v.grad.sum(0),
              g_normal_lin8_v=runner.normal_net.lin8.weight_v.grad, g_normal_lin0_bias=runner.normal_net.lin0.bias.grad,
              g_normal_lin3_g=runner.normal_net.lin3.weight_g.grad)
-    np.savez_compressed(os.path.join(HERE, "cesr_step.npz"), **npy(d))
-    print("cesr: hits", int(out["network_object_mask"].sum()), "loss", float(loss), "supervise",
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **npy(d))
+    print(name, runner.prefit_option(), ": hits", int(out["network_object_mask"].sum()), "loss", float(loss), "supervise",
           float(out["gradient_error"]))
 
 
@@ -172,7 +178,8 @@ def main():
 
     # ---------------- 3b. CESR step (M = 128 lobes, N = 48 rays, explore phase, iteration 600): the hook of
     # training/train_cesr.py:465-544 with seeded shadow_net / normal_net weights, loss of :387-430, backward
-    cesr_golden(torch.Generator().manual_seed(11))
+    for name in CESR_CASES:
+        cesr_golden(torch.Generator().manual_seed(11), name)
 
     # ---------------- 4. Illum forward + trace_radiance (N=48, nsamp=16)
     model.zero_grad()
@@ -215,6 +222,7 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["cesr"]:
         torch.set_num_threads(8)
-        cesr_golden(torch.Generator().manual_seed(11))
+        for name in CESR_CASES:
+            cesr_golden(torch.Generator().manual_seed(11), name)
     else:
         main()

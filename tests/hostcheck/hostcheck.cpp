@@ -78,9 +78,11 @@ void hc_sg_render(int n, int M, int Mi, const float* normal, const float* view, 
                   float* out /*[n][7][3]: rgb spec diff shadow irgb ispec idiff*/,
                   const float* g_out /*[n][7][3] upstream*/, float* g_lgt /*[M][7]*/, float* g_ind_lgt,
                   float* g_light_vis, float* g_bv_dir, float* g_bv_ind, float* g_rough, float* g_albedo,
-                  float* g_spec_refl, float* g_ind_integral) {
-  typedef Dual<10> DS;
-  typedef Dual<8> DD;
+                  float* g_spec_refl, float* g_ind_integral, float* g_normal /*[n][3] or null*/) {
+  // the widest instantiation of sg_render_bwd_kernel (NG = true): specular duals carry the normal in slots 10-12,
+  // diffuse duals in slots 8-10
+  typedef Dual<13> DS;
+  typedef Dual<11> DD;
   memset(g_lgt, 0, sizeof(float) * M * 7);
   *g_spec_refl = 0.f;
   for (int i = 0; i < n; ++i) {
@@ -121,10 +123,11 @@ void hc_sg_render(int n, int M, int Mi, const float* normal, const float* view, 
       gid[c] = g[12 + c] + g[18 + c];
     }
     // backward
-    V3<DS> nS = lift3<DS>(nrm), vS = lift3<DS>(vw);
+    V3<DS> nS = {DS::seed(nrm.x, 10), DS::seed(nrm.y, 11), DS::seed(nrm.z, 12)}, vS = lift3<DS>(vw);
+    float gn[3] = {0.f, 0.f, 0.f};
     SpecPoint<DS> spd = spec_point<DS>(nS, vS, DS::seed(rough[i], 7));
     DS Fd = fresnel<DS>(DS::seed(spec_refl, 8), spd.v_dot_h);
-    V3<DD> nD = lift3<DD>(nrm);
+    V3<DD> nD = {DD::seed(nrm.x, 8), DD::seed(nrm.y, 9), DD::seed(nrm.z, 10)};
     float acc[7] = {0};
     auto spec_lobe = [&](const float* raw, float bv, const float* g, float* g_raw, int slot) {
       DS r[7];
@@ -136,6 +139,7 @@ void hc_sg_render(int n, int M, int Mi, const float* normal, const float* view, 
       for (int c = 0; c < 3; ++c) tot = tot + (l.mu[c] * common) * g[c];
       for (int k = 0; k < 7; ++k) g_raw[k] = tot.d[k];
       acc[0] += tot.d[7]; acc[1] += tot.d[8]; acc[slot] += tot.d[9];
+      for (int k = 0; k < 3; ++k) gn[k] += tot.d[10 + k];
     };
     for (int m = 0; m < M; ++m) {
       float g_raw[7];
@@ -153,8 +157,10 @@ void hc_sg_render(int n, int M, int Mi, const float* normal, const float* view, 
       }
       for (int k = 0; k < 7; ++k) g_lgt[7 * m + k] += g_raw[k] + tot.d[k];
       g_light_vis[i * M + m] = tot.d[7];
+      for (int k = 0; k < 3; ++k) gn[k] += tot.d[8 + k];
     }
     for (int m = 0; m < Mi; ++m) spec_lobe(ind_lgt + (i * Mi + m) * 7, bv_ind[i], gis, g_ind_lgt + (i * Mi + m) * 7, 3);
+    if (g_normal) for (int k = 0; k < 3; ++k) g_normal[3 * i + k] = gn[k];
     g_rough[i] = acc[0];
     *g_spec_refl += acc[1];
     g_bv_dir[i] = acc[2];

@@ -30,7 +30,7 @@ def test_header_symbols_exported(built):
 
 def test_struct_layouts_match_header(built):
     # ctypes mirrors of the POD argument blocks: sizes as the C compiler lays them out (LP64)
-    assert ctypes.sizeof(built.SgParams) == 4 * 4 + 34 * 8
+    assert ctypes.sizeof(built.SgParams) == 4 * 4 + 35 * 8
     assert ctypes.sizeof(built.SdfParams) == 8 + 4 + 3 * 4 + 8 * 8 * 2 + 7 * 8
     assert ctypes.sizeof(built.OctreeView) == 2 * 8 + 4 * 4 + 6 * 4
     assert ctypes.sizeof(built.OctCastParams) == ctypes.sizeof(built.OctreeView) + 3 * 8 + 3 * 4 + 3 * 4 + 6 * 8

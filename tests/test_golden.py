@@ -1,5 +1,6 @@
 """Oracle (CPU restatement) vs. the golden vectors generated from the unmodified reference
 (tests/golden/make_golden.py).  Runs anywhere; no GPU, no /root/reference."""
+import pytest
 import torch
 
 import pipeline as P
@@ -85,10 +86,18 @@ def test_pbr_step_forward_backward(golden, synth_sd16, oracle_octrees):
     assert close(sd[enc + "8.weight"].grad.sum(0), g["g_enc8_weight_sum"], 1e-4)
 
 
-def test_cesr_step_forward_backward(golden, oracle_octrees):
-    """CESR hook + step loss of the oracle vs. the reference's golden outputs, explore
-    phase at iteration 600, 128 lobes.  The SDF weights (hence the octree) do not depend on the lobe count."""
-    g = golden("cesr_step")
+CESR_CASES = {   # tests/golden/make_golden.py CESR_CASES: (cur_iter, white_light, explore_iter, proj_iter, smooth_w, kl_w)
+    "cesr_step": (600, True, 1000, 0, 0.1, 1.0),            # explore phase, renders with the material net's normal map
+    "cesr_step_1200": (1200, False, 0, 1000, 0.001, 0.01),  # project phase, renders with normal_net's normals (:508)
+}
+
+
+@pytest.mark.parametrize("case", sorted(CESR_CASES))
+def test_cesr_step_forward_backward(golden, oracle_octrees, case):
+    """CESR hook + step loss of the oracle vs. the reference's golden outputs, 128 lobes.
+    The SDF weights (hence the octree) do not depend on the lobe count."""
+    g = golden(case)
+    cur_iter, white, explore_iter, proj_iter, smooth_w, kl_w = CESR_CASES[case]
     sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=128)
     train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
     for k in train:
@@ -99,13 +108,14 @@ def test_cesr_step_forward_backward(golden, oracle_octrees):
     inp, rnd = _pbr_inputs(g, sd)
     assert rnd["diff_theta"].shape == (128, 8)
     prim, _ = oracle_octrees
-    hook = lambda p, v, sgs, integ, r: P.cesr_get_sg_render(sd, sh, nr, p, v, sgs, integ, r, cur_iter=600,
-                                                            prefit=P.cesr_prefit_option(600, 1000, 0), white_light=True)
+    prefit = P.cesr_prefit_option(cur_iter, explore_iter, proj_iter)
+    hook = lambda p, v, sgs, integ, r: P.cesr_get_sg_render(sd, sh, nr, p, v, sgs, integ, r, cur_iter=cur_iter,
+                                                            prefit=prefit, white_light=white)
     out = P.idr_forward(sd, inp, lambda c, m, d: prim.trace(c, d), rnd, hook=hook)
     assert torch.equal(out["network_object_mask"], g["out_network_object_mask"])
     for k in [k[4:] for k in g if k.startswith("out_") and k != "out_network_object_mask"]:
         assert close(out[k], g["out_" + k]), k
-    loss, _ = O.cesr_loss(sd, out, g["gt"], 600, 0.1, 1.0)
+    loss, _ = O.cesr_loss(sd, out, g["gt"], cur_iter, smooth_w, kl_w)
     assert abs(loss.item() - g["loss"].item()) < 1e-5
     loss.backward()
     pre = "envmap_material_network."
@@ -117,9 +127,16 @@ def test_cesr_step_forward_backward(golden, oracle_octrees):
     assert close(sh["lin4.weight_g"].grad, g["g_shadow_lin4_g"], 1e-4)
     assert close(sh["lin0.bias"].grad, g["g_shadow_lin0_bias"], 1e-4)
     assert close(sh["lin0.weight_v"].grad.sum(0), g["g_shadow_lin0_v_colsum"], 1e-4)
-    assert close(nr["lin8.weight_v"].grad, g["g_normal_lin8_v"], 1e-4)
-    assert close(nr["lin0.bias"].grad, g["g_normal_lin0_bias"], 1e-4)
-    assert close(nr["lin3.weight_g"].grad, g["g_normal_lin3_g"], 1e-4)
+    # after iteration 1000 the render loss reaches normal_net through the sample directions of the ReLU visibility MLP:
+    # piecewise-continuous, a borderline unit that flips between two fp32 evaluation orders moves a few entries by
+    # O(1e-3) (the same effect as in tests/test_gpu_parity.py:grad_close) -> relative L2 bound there
+    for key, gk in (("lin8.weight_v", "g_normal_lin8_v"), ("lin0.bias", "g_normal_lin0_bias"),
+                    ("lin3.weight_g", "g_normal_lin3_g")):
+        a, b = nr[key].grad, g[gk]
+        if cur_iter > 1000:
+            assert ((a - b).norm() / b.norm()).item() < 3e-3, (key, ((a - b).norm() / b.norm()).item())
+        else:
+            assert close(a, b, 1e-4), key
 
 
 def test_vis_stage(golden, synth_sd16, oracle_octrees):

@@ -120,7 +120,7 @@ def _oracle_sg(s, leaf_names):
 def test_sg_render_forward_backward_vs_oracle(hc):
     n, M, Mi = 24, 16, 5
     s = _rand_scene(n, M, Mi)
-    names = ["rough", "albedo", "spec", "lgt", "ind", "lv", "bvd", "bvi", "integ"]
+    names = ["rough", "albedo", "spec", "lgt", "ind", "lv", "bvd", "bvi", "integ", "normal"]
     out, leaves = _oracle_sg(s, names)
     keys = ["sg_rgb", "sg_specular_rgb", "sg_diffuse_rgb", "vis_shadow", "indir_rgb", "indir_specular_rgb",
             "indir_diffuse_rgb"]
@@ -137,7 +137,7 @@ def test_sg_render_forward_backward_vs_oracle(hc):
                     ctypes.c_float(float(s["spec"].abs())), fp(arr(s["lgt"])), fp(arr(s["ind"])), fp(arr(s["lv"])),
                     fp(arr(s["bvd"])), fp(arr(s["bvi"])), fp(arr(s["integ"])), fp(o), fp(g_out), fp(res["lgt"]),
                     fp(res["ind"]), fp(res["lv"]), fp(res["bvd"]), fp(res["bvi"]), fp(res["rough"]),
-                    fp(res["albedo"]), fp(res["spec"]), fp(res["integ"]))
+                    fp(res["albedo"]), fp(res["spec"]), fp(res["integ"]), fp(res["normal"]))
     for j, k in enumerate(keys):
         ref = out[k].detach()
         err = (torch.from_numpy(o[:, j]) - ref).abs().max().item()

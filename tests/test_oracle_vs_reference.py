@@ -164,6 +164,12 @@ def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
     runner = ref_shim.bind_cesr_runner(model, cur_iter=cur_iter, white_light=white, explore_iter=sched[0],
                                        proj_iter=sched[1], seed=3, **smooth)
     runner.loss = inv_loss
+    if cur_iter > 1000:
+        # seeded weights whose normals face the camera, so that the specular lobe and the gradient of the render loss
+        # with respect to the shading normal (train_cesr.py:508) are exercised -- the default init looks away
+        sh, nr = synthetic.cesr_state_dicts(0)
+        runner.shadow_net.load_state_dict(sh)
+        runner.normal_net.load_state_dict(nr)
     prefit = runner.prefit_option()
     assert prefit == P.cesr_prefit_option(cur_iter, *sched) == {300: "warmup", 600: "explore", 1200: "project"}[cur_iter]
     N = 40
@@ -206,6 +212,8 @@ def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
     loss, _ = O.cesr_loss(sd, out, gt["rgb"], cur_iter, smooth[w[0]], smooth[w[1]])
     assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
     loss.backward()
+    if cur_iter > 1000:
+        assert out_ref["sg_specular_rgb"][out_ref["network_object_mask"]].max().item() > 1e-3
     checked = {}
     for n in nets:
         for k, g in gref[n].items():
@@ -213,6 +221,12 @@ def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
                 continue
             mine = sds[n][k].grad
             assert mine is not None, (n, k)
+            if n == "normal" and cur_iter > 1000:
+                # the render loss reaches normal_net through the sample directions of the ReLU visibility MLP and the
+                # 2 / r^4 specular lobe: fp32 evaluation-order noise of ~1e-4 relative (uniform over the layers)
+                assert ((g - mine).norm() / g.norm()).item() < 1e-3, (n, k)
+                checked[n] = checked.get(n, 0) + 1
+                continue
             assert (g - mine).abs().max().item() < 2e-5 * max(1.0, g.abs().max().item()), (n, k)
             checked[n] = checked.get(n, 0) + 1
     assert checked["shadow"] == 27 and checked["normal"] == 27       # 9 x (weight_g, weight_v, bias)
