@@ -153,8 +153,7 @@ class ClusteredAlbedoHook:
         diffuse_vis = torch.softmax(diffuse_vis, -1)[..., 1]
         prefit = self.prefit_option()
         # after iteration 1000 the reference renders with normal_net's normals and lets the render loss train them
-        # (:508); that gradient path (d render / d normal) is not on the accelerated path yet -- render_with_all_sg
-        # refuses a normal that requires grad rather than silently dropping the gradient
+        # (:508): render_with_all_sg differentiates with respect to a normal that requires grad
         sg = sg_render.render_with_all_sg(points=points.detach(),
                                           normal=normal_new if self.cur_iter > 1000 else normal_map,
                                           viewdirs=view_dirs, lgtSGs=lgtSGs, indir_integral=indir_integral,
