@@ -99,17 +99,42 @@ class ClusteredAlbedoHook:
     ``robir_b200.IDRNetwork`` (dynamic-shape forward) or a reference ``IDRNetwork`` after ``robir_b200.install``."""
 
     def __init__(self, model, shadow_net=None, normal_net=None, white_light=False, explore_iter=1000, proj_iter=0,
-                 explore_smooth=0.1, explore_kl=1.0, proj_smooth=0.01, proj_kl=0.01, cur_iter=0):
+                 explore_smooth=0.1, explore_kl=1.0, proj_smooth=0.01, proj_kl=0.01, cur_iter=0, runner=None):
+        """runner: optional live ``ClusteredAlbedoTrainRunner``; ``cur_iter`` / ``is_training`` / ``train_spec`` are then
+        read from it at every call (the reference's loop advances ``self.cur_iter`` on the runner, train_cesr.py:636)."""
         self.model = model
+        self.runner = runner
         self.shadow_embed, in_dim = (lambda x: positional_encoding(x, 10)), 63           # get_embedder(10), :106
         self.shadow_net = shadow_net if shadow_net is not None else WnMLP(in_dim + 128, 2)
         self.normal_net = normal_net if normal_net is not None else WnMLP(in_dim, 3)
         self.white_light = white_light
         self.explore_iter, self.proj_iter = explore_iter, proj_iter
         self.weights = dict(explore=(explore_smooth, explore_kl), project=(proj_smooth, proj_kl))
-        self.cur_iter = cur_iter
-        self.train_spec = True
-        self.is_training = True
+        self._state = dict(cur_iter=cur_iter, train_spec=True, is_training=True)
+
+    def _get(self, key):
+        if self.runner is not None and hasattr(self.runner, key):
+            return getattr(self.runner, key)
+        return self._state[key]
+
+    cur_iter = property(lambda self: self._get("cur_iter"), lambda self, v: self._state.__setitem__("cur_iter", v))
+    train_spec = property(lambda self: self._get("train_spec"), lambda self, v: self._state.__setitem__("train_spec", v))
+    is_training = property(lambda self: self._get("is_training"),
+                           lambda self, v: self._state.__setitem__("is_training", v))
+
+    @classmethod
+    def bind(cls, runner):
+        """Re-bind the seam of a live reference runner (what train_cesr.py:588 does with its own method): the hook
+        reads the runner's networks, conf and counters; nothing of the runner is modified except
+        ``runner.model.get_sg_render``.  Returns the hook."""
+        conf = runner.conf
+        hook = cls(runner.model, runner.shadow_net, runner.normal_net, white_light=runner.white_light,
+                   explore_iter=conf.get_int('train.explore_iter'), proj_iter=conf.get_int('train.proj_iter'),
+                   explore_smooth=conf.get_float('train.explore_smooth'), explore_kl=conf.get_float('train.explore_kl'),
+                   proj_smooth=conf.get_float('train.proj_smooth'), proj_kl=conf.get_float('train.proj_kl'),
+                   runner=runner)
+        runner.model.get_sg_render = hook.get_sg_render
+        return hook
 
     # ---- schedule (train_cesr.py:546-559)
     def is_explore_step(self):

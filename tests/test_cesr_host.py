@@ -151,3 +151,30 @@ def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows
     assert set(g1) == set(g2) and len(g1) == 27
     for k in g2:
         assert (g1[k] - g2[k]).abs().max().item() < 2e-4 * max(1e-6, g2[k].abs().max().item()), k
+
+
+def test_hook_binds_to_a_live_runner_and_follows_its_counters():
+    """ClusteredAlbedoHook.bind: conf keys of confs_sg/*.conf train{}, live cur_iter / is_training of the runner."""
+    import types
+
+    class Conf(dict):
+        get_int = lambda self, k: int(self[k])
+        get_float = lambda self, k: float(self[k])
+
+    model = types.SimpleNamespace(get_sg_render=None)
+    runner = types.SimpleNamespace(
+        model=model, shadow_net=object(), normal_net=object(), white_light=True, cur_iter=0, is_training=True,
+        train_spec=True, conf=Conf({'train.explore_iter': 0, 'train.proj_iter': 1000, 'train.explore_smooth': 0.001,
+                                    'train.explore_kl': 0.01, 'train.proj_smooth': 0.002, 'train.proj_kl': 0.03}))
+    hook = cesr.ClusteredAlbedoHook.bind(runner)
+    assert model.get_sg_render == hook.get_sg_render and hook.white_light
+    for it in (10, 700, 1500):
+        runner.cur_iter = it
+        assert hook.cur_iter == it and hook.prefit_option() == P.cesr_prefit_option(it, 0, 1000)
+    runner.is_training = False
+    assert hook.is_training is False
+    assert hook.weights == dict(explore=(0.001, 0.01), project=(0.002, 0.03))
+    # stand-alone use keeps its own counters
+    own = cesr.ClusteredAlbedoHook(None, object(), object(), cur_iter=5)
+    own.cur_iter = 900
+    assert own.cur_iter == 900 and own.prefit_option() == "explore"

@@ -232,3 +232,26 @@ def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
     assert checked["shadow"] == 27 and checked["normal"] == 27       # 9 x (weight_g, weight_v, bias)
     if cur_iter > 500:
         assert checked["model"] >= 19
+
+
+def test_cesr_hook_reads_the_reference_modules():
+    """The product hook accepts the reference's own SDFNetwork objects (legacy weight_norm: lin{l}.weight_g / weight_v /
+    bias) and its state dicts load into robir_b200.cesr.WnMLP unchanged; the library form of the chain on those tensors
+    equals the reference module's forward (1024-row chunk loop, neus_model.py:397-415)."""
+    from robir_b200 import cesr
+    ref_shim.install()
+    from model.neus_model import SDFNetwork
+    torch.manual_seed(5)
+    gen = torch.Generator().manual_seed(6)
+    for d_in, d_out in ((191, 2), (63, 3)):
+        ref = SDFNetwork(d_in, d_out, 512, 8, [4], 0)
+        x = torch.randn(1500, d_in, generator=gen) * 0.5            # spans two of the reference's chunks
+        lins, skip = cesr._layers(ref)
+        assert len(lins) == 9 and skip == (4,)
+        Ws = [l.weight_g * l.weight_v / l.weight_v.norm(dim=1, keepdim=True) for l in lins]
+        out = cesr._wn_rows_torch(Ws, [l.bias for l in lins], skip, x)
+        want = ref(x)
+        assert (out - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item())
+        mine = cesr.WnMLP(d_in, d_out)
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        assert set(mine.state_dict()) == set(ref.state_dict())
