@@ -40,6 +40,7 @@ def build(use_octree=True, n_steps=100, perturb=0.0):
 
 
 CESR_CASES = {   # file -> runner settings (confs_sg/hotdog.conf:34-43 explore schedule; confs_sg/truck.conf project schedule)
+    "cesr_step_300": dict(cur_iter=300, white_light=True, explore_iter=1000, proj_iter=0),      # warm-up phase
     "cesr_step": dict(cur_iter=600, white_light=True, explore_iter=1000, proj_iter=0, explore_smooth=0.1, explore_kl=1.0),
     "cesr_step_1200": dict(cur_iter=1200, white_light=False, explore_iter=0, proj_iter=1000, proj_smooth=0.001,
                            proj_kl=0.01),
@@ -84,6 +85,7 @@ def cesr_golden(g, name="cesr_step"):
              g_shadow_lin0_v_colsum=runner.shadow_net.lin0.weight_v.grad.sum(0),
              g_normal_lin8_v=runner.normal_net.lin8.weight_v.grad, g_normal_lin0_bias=runner.normal_net.lin0.bias.grad,
              g_normal_lin3_g=runner.normal_net.lin3.weight_g.grad)
+    d = {k: v for k, v in d.items() if v is not None}     # warm-up: the loss is the supervise term, no material gradients
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **npy(d))
     print(name, runner.prefit_option(), ": hits", int(out["network_object_mask"].sum()), "loss", float(loss), "supervise",
           float(out["gradient_error"]))

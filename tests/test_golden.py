@@ -87,6 +87,7 @@ def test_pbr_step_forward_backward(golden, synth_sd16, oracle_octrees):
 
 
 CESR_CASES = {   # tests/golden/make_golden.py CESR_CASES: (cur_iter, white_light, explore_iter, proj_iter, smooth_w, kl_w)
+    "cesr_step_300": (300, True, 1000, 0, 0.1, 1.0),        # warm-up phase: the loss is the supervise term alone
     "cesr_step": (600, True, 1000, 0, 0.1, 1.0),            # explore phase, renders with the material net's normal map
     "cesr_step_1200": (1200, False, 0, 1000, 0.001, 0.01),  # project phase, renders with normal_net's normals (:508)
 }
@@ -119,9 +120,12 @@ def test_cesr_step_forward_backward(golden, oracle_octrees, case):
     assert abs(loss.item() - g["loss"].item()) < 1e-5
     loss.backward()
     pre = "envmap_material_network."
-    assert close(sd[pre + "lgtSGs"].grad, g["g_lgtSGs"], 1e-4)
-    assert close(sd[pre + "specular_reflectance"].grad, g["g_spec"], 1e-4)
-    assert close(sd["gamma.hdr_shift.adapt_illum"].grad, g["g_adapt"], 1e-4)
+    if cur_iter > 500:
+        assert close(sd[pre + "lgtSGs"].grad, g["g_lgtSGs"], 1e-4)
+        assert close(sd[pre + "specular_reflectance"].grad, g["g_spec"], 1e-4)
+        assert close(sd["gamma.hdr_shift.adapt_illum"].grad, g["g_adapt"], 1e-4)
+    else:
+        assert "g_lgtSGs" not in g and sd[pre + "lgtSGs"].grad is None
     assert close(sh["lin8.weight_v"].grad, g["g_shadow_lin8_v"], 1e-4)
     assert close(sh["lin8.bias"].grad, g["g_shadow_lin8_bias"], 1e-4)
     assert close(sh["lin4.weight_g"].grad, g["g_shadow_lin4_g"], 1e-4)

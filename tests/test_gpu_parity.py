@@ -893,10 +893,11 @@ def model128():
     return m
 
 
-@pytest.mark.parametrize("case", ["cesr_step", "cesr_step_1200"])
+@pytest.mark.parametrize("case", ["cesr_step_300", "cesr_step", "cesr_step_1200"])
 def test_cesr_step_vs_golden(golden, model128, wn_engine, case):
     """IDRNetwork.forward('Material') with the CESR hook bound (train_cesr.py:465-544,588) + the stage's step loss
-    (:387-430) + backward against the reference's golden outputs and gradients: explore phase at iteration 600 (renders
+    (:387-430) + backward against the reference's golden outputs and gradients: warm-up phase at iteration 300 (the MLP
+    visibility renders, shadow_net is only supervised, the loss is the supervise term), explore phase at 600 (renders
     with the material network's normal map) and project phase at iteration 1200 (renders with normal_net's normals, so
     the render loss reaches normal_net through d render / d normal: 5-18 % of its gradient in this fixture)."""
     from robir_b200 import cesr, rng
@@ -908,7 +909,7 @@ def test_cesr_step_vs_golden(golden, model128, wn_engine, case):
     hook = cesr.ClusteredAlbedoHook(model128, shadow, normal, white_light=white, explore_iter=explore_iter,
                                     proj_iter=proj_iter, explore_smooth=smooth_w, explore_kl=kl_w, proj_smooth=smooth_w,
                                     proj_kl=kl_w, cur_iter=cur_iter)
-    assert hook.prefit_option() == {"cesr_step": "explore", "cesr_step_1200": "project"}[case]
+    assert hook.prefit_option() == {"cesr_step_300": "warmup", "cesr_step": "explore", "cesr_step_1200": "project"}[case]
     old_hook, old_static = model128.get_sg_render, model128.static_shapes
     model128.get_sg_render, model128.static_shapes = hook.get_sg_render, False
     try:
@@ -930,9 +931,13 @@ def test_cesr_step_vs_golden(golden, model128, wn_engine, case):
     loss.backward()
     mat = model128.envmap_material_network
     eng = "tc" if wn_engine == "tc" else "ffma"
-    checks = [(mat.lgtSGs.grad, g["g_lgtSGs"]), (mat.specular_reflectance.grad, g["g_spec"]),
-              (model128.gamma.hdr_shift.adapt_illum.grad, g["g_adapt"]),
-              (shadow.lin8.weight_v.grad, g["g_shadow_lin8_v"]), (shadow.lin8.bias.grad, g["g_shadow_lin8_bias"]),
+    checks = []
+    if cur_iter > 500:
+        checks = [(mat.lgtSGs.grad, g["g_lgtSGs"]), (mat.specular_reflectance.grad, g["g_spec"]),
+                  (model128.gamma.hdr_shift.adapt_illum.grad, g["g_adapt"])]
+    else:
+        assert mat.lgtSGs.grad is None or float(mat.lgtSGs.grad.abs().max()) == 0.0
+    checks += [(shadow.lin8.weight_v.grad, g["g_shadow_lin8_v"]), (shadow.lin8.bias.grad, g["g_shadow_lin8_bias"]),
               (shadow.lin4.weight_g.grad, g["g_shadow_lin4_g"]), (shadow.lin0.bias.grad, g["g_shadow_lin0_bias"]),
               (shadow.lin0.weight_v.grad.sum(0), g["g_shadow_lin0_v_colsum"]),
               (normal.lin8.weight_v.grad, g["g_normal_lin8_v"]), (normal.lin0.bias.grad, g["g_normal_lin0_bias"]),

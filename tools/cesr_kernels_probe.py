@@ -1,0 +1,78 @@
+"""One forward layer of the CESR shadow_net chain on the tensor-core layer engine (512x512, Softplus(100), rows = 542 hit
+points x 128 lobes as in tools/cesr_bench.py) and the weight-gradient launch of the same layer, inside a
+cudaProfilerStart/Stop range so that `ncu --profile-from-start off` captures exactly these two kernels:
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/cesr_kernels \\
+        python tools/cesr_kernels_probe.py
+
+Also prints their plain CUDA-event timings (outside the profiler range; never quote a number taken under ncu).
+"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from robir_b200 import ops  # noqa: E402
+from robir_b200._lib import check, lib, ptr, stream  # noqa: E402
+
+R, N, K = 542 * 128, 512, 512
+
+
+def main():
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(R, K, device=dev, generator=gen) * 0.05
+    W = torch.randn(N, K, device=dev, generator=gen) * (2.0 / N) ** 0.5
+    G = torch.randn(R, N, device=dev, generator=gen)
+    bias = torch.zeros(N, device=dev)
+    fw, _ = ops._tl_weight_images(W, 0)
+    img = ops._tl_rows_image(x, K)
+    tiles = (R + 127) // 128
+    out = torch.empty(R, N, device=dev)
+    nxt = ops._tl_image(tiles, N // 64, x)
+    q = ops._tl_params(img, fw, bias, R, N, K // 64, 0, 3, None, out, nxt, N // 64, None, 0)
+    wt = (N // 64) * (K // 64)
+    splits = max(1, min(64, (4 * ops.sm_count()) // wt, (R + 63) // 64))
+    part = torch.empty(splits * wt * 4160, device=dev)
+    tickets = torch.zeros(wt, dtype=torch.int32, device=dev)
+    dW, db = torch.empty(N, K, device=dev), torch.empty(N, device=dev)
+
+    def layer():
+        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+
+    def wgrad():
+        check(lib().robir_mlp_wgrad(ptr(G), N, ptr(x), K, R, N, K, None, 0, splits, ptr(part), ptr(tickets), ptr(dW),
+                                    ptr(db), stream()))
+
+    def timed(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    t_layer, t_wgrad = timed(layer), timed(wgrad)
+    flop = 2.0 * R * N * K
+    print("tc_layer fwd 512x512 on %d rows: %.3f ms = %.1f TFLOP/s algorithmic (x3 executed); wgrad: %.3f ms = %.1f TFLOP/s"
+          % (R, t_layer, flop / t_layer / 1e9, t_wgrad, flop / t_wgrad / 1e9))
+    ref = torch.nn.functional.softplus(x @ W.t(), beta=100)
+    print("max |layer - torch| = %.3e, max |dW - torch| rel = %.3e"
+          % ((out - ref).abs().max().item(), ((dW - G.t() @ x).abs().max() / (G.t() @ x).abs().max()).item()))
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    layer()
+    wgrad()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()
