@@ -1023,6 +1023,7 @@ class _WnChain(torch.autograd.Function):
         R, d_in = x.shape
         tiles = (R + 127) // 128
         SOFTPLUS = 3
+        need_bwd = any(ctx.needs_input_grad)      # evaluation (plots, testing=True): keep nothing, free layer by layer
         We, imgs, a_rows = [], [], []
         a, img = x, _tl_rows_image(x, d_in)
         out = None
@@ -1031,10 +1032,11 @@ class _WnChain(torch.autograd.Function):
             N, K = W.shape
             if K > 512 or N > 512 or a.shape[1] != K:
                 raise _lib.RobirError("wn_chain: layer %d is %dx%d on %d input columns (engine limit 512)" % (l, N, K, a.shape[1]))
-            fw, bw = _tl_weight_images(W, 0 if l == 0 else (K - d_in if l in skip else K))
-            We.append(W)
-            imgs.append((fw, bw))
-            a_rows.append(a)
+            fw, bw = _tl_weight_images(W, 0 if (l == 0 or not need_bwd) else (K - d_in if l in skip else K))
+            if need_bwd:
+                We.append(W)
+                imgs.append((fw, bw))
+                a_rows.append(a)
             bias = _zeros(((N + 127) // 128) * 128, like=x)
             bias[:N] = f32(bs[l])
             last, next_skip = l == L - 1, (l + 1) in skip

@@ -147,6 +147,9 @@ def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows
         (out * gup).sum().backward()
         res.append((out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
     (o1, g1), (o2, g2) = res
+    with torch.no_grad():                 # evaluation mode: same values, nothing kept for a backward
+        o3 = ops.wn_chain(x, [l.folded() for l in lins], [l.bias for l in lins], skip)
+    assert torch.equal(o3, o1) and not o3.requires_grad
     assert (o1 - o2).abs().max().item() < 1e-5 * max(1.0, o2.abs().max().item())
     assert set(g1) == set(g2) and len(g1) == 27
     for k in g2:
