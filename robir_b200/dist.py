@@ -29,11 +29,15 @@ def shard_rays(n_rays, rank, world):
 
 
 class GradAllReducer:
-    """Flat-bucket all-reduce(SUM)/world of the gradients of ``params`` (one NCCL call on the current stream)."""
+    """Flat-bucket all-reduce of the gradients of ``params`` (one NCCL call on the current stream).  average=True
+    (weak scaling: every rank steps on its own batch, the reference's DataParallel-free equivalent is the mean of the
+    per-batch gradients) divides by the world size; average=False is the plain sum that strong sharding of ONE batch
+    needs (every rank's loss terms are already normalised by the global ray count, model/loss.py:41)."""
 
-    def __init__(self, params):
+    def __init__(self, params, average=True):
         self.params = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
+        self.average = average
 
     def __call__(self):
         if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -44,12 +48,46 @@ class GradAllReducer:
         grads = [p.grad for p in ps]
         flat = torch.cat([g.reshape(-1) for g in grads])              # one gather kernel
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(dist.get_world_size())
+        if self.average:
+            flat.div_(dist.get_world_size())
         views, off = [], 0
         for g in grads:
             views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
         torch._foreach_copy_(grads, views)                            # one scatter kernel
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# batch statistics for bit-faithful STRONG sharding of one batch: besides the sampler's minimum
+# (allreduce_min_scalar) the losses contain two means over the batch axis -- the KL sparsity term of the spec-BRDF latent
+# (model/loss.py:75-79) and the CESR supervise term (utils/utils.py:14-17 through sg_render.py:397-403).
+# ----------------------------------------------------------------------------------------------------------------------
+STRONG_SHARDING = False     # set True when the ranks render slices of the SAME batch (bench.py is weak scaling: False)
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """S = sum over ranks of t.  Every rank evaluates the same loss L(S), so dL/dt_local = L'(S) = the incoming
+    gradient; the parameter gradients of the ranks then add up to the full-batch gradient (GradAllReducer(average=False))."""
+
+    @staticmethod
+    def forward(ctx, t):
+        out = t.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def batch_mean_rows(x):
+    """torch.mean(x, 0) over the rows of the whole batch: local mean unless STRONG_SHARDING is on and a process group with
+    more than one rank exists, in which case row sums and row counts are all-reduced (differentiable)."""
+    if not (STRONG_SHARDING and dist.is_initialized() and dist.get_world_size() > 1):
+        return torch.mean(x, 0)
+    n = torch.tensor([float(x.shape[0])], dtype=x.dtype, device=x.device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return _AllReduceSum.apply(x.sum(0)) / n
 
 
 def allreduce_min_scalar(t):

@@ -5,6 +5,7 @@ import ctypes
 import torch
 import torch.nn as nn
 
+from . import dist as rdist
 from .networks import positional_encoding
 
 
@@ -18,7 +19,7 @@ class InvLoss(nn.Module):
 
     @staticmethod
     def kl_divergence(rho, latent):
-        rho_hat = torch.mean(torch.sigmoid(latent), 0)
+        rho_hat = rdist.batch_mean_rows(torch.sigmoid(latent))
         rho = torch.full_like(rho_hat, rho)
         return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4))
                           + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
@@ -47,6 +48,9 @@ class InvLoss(nn.Module):
             return enc.encode(positional_encoding(pts, 10))
 
         if self.static_shapes:
+            if rdist.STRONG_SHARDING:
+                raise RuntimeError("InvLoss: the fixed-capacity mode reduces over the local batch only; strong sharding "
+                                   "of one batch (dist.STRONG_SHARDING) needs the dynamic-shape mode")
             # same statistics without data-dependent shapes (CUDA-graph capturable): masked batch mean of the latent
             hit = model_outputs['network_object_mask']
             pts = torch.where(hit[:, None], model_outputs['points'], torch.zeros_like(model_outputs['points']))
@@ -198,7 +202,7 @@ FUSED_LOSS = True
 
 
 def pbr_step_loss(model, loss_fn, model_outputs, ground_truth, train_spec=True):
-    if FUSED_LOSS and train_spec:
+    if FUSED_LOSS and train_spec and not rdist.STRONG_SHARDING:      # the fused kernel reduces over the local batch only
         fused = fused_pbr_loss(model, loss_fn, model_outputs, ground_truth)
         if fused is not None:
             return fused

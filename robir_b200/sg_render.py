@@ -6,6 +6,7 @@ five Linear layers, 126->256x4->2); an arbitrary callable (e.g. the reference's 
 import numpy as np
 import torch
 
+from . import dist as rdist
 from . import ops, rng
 from ._lib import RobirError
 
@@ -124,8 +125,8 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
 
 
 def kl_divergence(x, mu=0.05):
-    """utils/utils.py:14-17."""
-    rho_hat = torch.mean(x, 0)
+    """utils/utils.py:14-17 (the batch mean spans all ranks under dist.STRONG_SHARDING)."""
+    rho_hat = rdist.batch_mean_rows(x)
     rho = torch.full_like(rho_hat, mu)
     return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4)) + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
 
