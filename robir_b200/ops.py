@@ -817,7 +817,7 @@ def c_ptr(t, byte_offset):
 # ----------------------------------------------------------------------------------------------------------------------
 # fused small MLP chains (material / indirect networks)
 # ----------------------------------------------------------------------------------------------------------------------
-ACT = {"none": 0, "relu": 1, "leaky": 2}
+ACT = {"none": 0, "relu": 1, "leaky": 2, "softplus100": 3}     # enum Act of csrc/common.cuh
 IN_MODE = {"raw": 0, "pe10": 1, "pe10_extra": 2, "ipe10": 3, "pe10x2": 4}
 
 
@@ -1022,7 +1022,7 @@ class _WnChain(torch.autograd.Function):
         x = f32(x)
         R, d_in = x.shape
         tiles = (R + 127) // 128
-        SOFTPLUS = 3
+        SOFTPLUS = ACT["softplus100"]
         need_bwd = any(ctx.needs_input_grad)      # evaluation (plots, testing=True): keep nothing, free layer by layer
         We, imgs, a_rows = [], [], []
         a, img = x, _tl_rows_image(x, d_in)
@@ -1062,7 +1062,7 @@ class _WnChain(torch.autograd.Function):
         R, d_in, L, skip = ctx.meta
         a_rows, We = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
         tiles = (R + 127) // 128
-        SOFTPLUS = 3
+        SOFTPLUS = ACT["softplus100"]
         G = f32(g_out)
         img = _tl_rows_image(G, G.shape[1])
         gW, gb = [None] * L, [None] * L
