@@ -202,6 +202,40 @@ def bind_cesr_runner(model, cur_iter=600, white_light=False, explore_iter=1000, 
     return runner
 
 
+def load_stage1_renderer():
+    """The UNMODIFIED neus/volume_render/sdf_render.py as a module.  Its two star imports (``misc.utils`` / ``misc.defs``,
+    which drag in absl, PIL and the stage-1 package layout) are satisfied by stub modules that export exactly the names
+    the file uses: torch, F, np, gin (the pass-through stub of install()) and the Rays / IComp / ISDF definitions of
+    neus/misc/defs.py:8-37 (a namedtuple and two interface classes, restated)."""
+    install()
+    import collections
+    import importlib.util
+    import numpy as np
+    import torch.nn.functional as F
+    Rays = collections.namedtuple('Rays', ('origins', 'directions', 'viewdirs', 'radii', 'lossmult', 'near', 'far'))
+    IComp = type("IComp", (), {})
+    ISDF = type("ISDF", (IComp,), {})
+    saved = {k: sys.modules.get(k) for k in ("misc", "misc.utils", "misc.defs")}
+    pkg = _mod("misc")
+    pkg.__path__ = []
+    names = dict(torch=torch, F=F, np=np, gin=sys.modules["gin"])
+    _mod("misc.utils", __all__=list(names), **names)
+    defs = dict(Rays=Rays, IComp=IComp, ISDF=ISDF)
+    _mod("misc.defs", __all__=list(defs), **defs)
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "robir_ref_stage1_sdf_render", os.path.join(REF_ROOT, "neus", "volume_render", "sdf_render.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
 class ReplayRandom:
     """Context manager: record (mode='record') or replay (mode='replay') torch.rand / torch.randn /
     Tensor.uniform_ draws, in call order, so reference and oracle/product see identical randoms."""

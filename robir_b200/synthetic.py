@@ -22,6 +22,22 @@ SDF = "implicit_network.neus_model.sdf_network"
 COL = "implicit_network.neus_model.color_network"
 
 
+def _float32_default(fn):
+    """The weights are defined by the float32 random stream: a caller that switched torch's default dtype (the float64
+    oracle pins) must still get the same tensors."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float32)
+        try:
+            return fn(*a, **k)
+        finally:
+            torch.set_default_dtype(old)
+    return wrapped
+
+
 def _uniform_linear(gen, out_f, in_f):
     bound = 1.0 / math.sqrt(in_f)
     w = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
@@ -70,6 +86,7 @@ def synthetic_light_sgs(gen, M):
     return sg
 
 
+@_float32_default
 def synthetic_state_dict(seed=0, num_lgt_sgs=128, sdf_radius=0.5, perturb=0.0, vis_gain=2.0):
     """sdf_radius is the geometric-init bias; because softplus(0) != 0 the zero level set sits at a stage-2 radius of
     about 0.33 for 0.5 (small octree, used by tests/goldens) and about 0.60 for 0.87 (bench workload)."""
@@ -123,6 +140,7 @@ def synthetic_state_dict(seed=0, num_lgt_sgs=128, sdf_radius=0.5, perturb=0.0, v
     return sd
 
 
+@_float32_default
 def cesr_state_dicts(seed=0, gain=2.0):
     """Seeded weights of the CESR stage's two extra weight-normed MLPs (training/train_cesr.py:106-110; state-dict keys
     of the reference SDFNetwork: ``lin{l}.weight_g | weight_v | bias``): shadow_net 191 -> 512 x8 -> 2 and normal_net

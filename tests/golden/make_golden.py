@@ -91,6 +91,48 @@ def cesr_golden(g, name="cesr_step"):
           float(out["gradient_error"]))
 
 
+def stage1_golden():
+    """neus/volume_render/sdf_render.py render_neus (unmodified file, loaded by
+    ref_shim.load_stage1_renderer) on the synthetic stage-1 weights, in float64 so that the fixture pins the algorithm
+    rather than float32 evaluation order (the inverse-CDF sampler amplifies rounding noise by up to 1e5)."""
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M)     # the standard (float32-drawn) weights, widened below
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        R = ref_shim.load_stage1_renderer()
+        from model.neus_model import NeuSModel
+        model = NeuSModel(mode="idr", hashing=False, embed="PE")
+        model.load_state_dict(synthetic.neus_checkpoint_from(sd), strict=True)
+        model.double()
+        gen = torch.Generator().manual_seed(21)
+        B = 32
+        rays_o = torch.tensor([[0.026, 0.042, 4.0]]).expand(B, 3) + 0.02 * torch.randn(B, 3, generator=gen)
+        target = torch.nn.functional.normalize(torch.randn(B, 3, generator=gen), dim=-1) * 0.7
+        rays_d = torch.nn.functional.normalize(target - rays_o, dim=-1)
+        near, far = torch.full((B, 1), 2.5), torch.full((B, 1), 5.5)
+        rays = R.Rays(rays_o, rays_d, rays_d, None, torch.ones(B, 1), near, far)
+        gt = torch.rand(B, 3, generator=gen)
+        t_rand = torch.rand(B, 1, generator=gen)
+        with ref_shim.ReplayRandom(tape=[("rand", t_rand)]):
+            ret = R.render_neus(rays, model, 0.3, n_outside=0, white_bkgd=True, is_eval=False)
+        loss = ((ret["rgb"] - gt) ** 2).mean() + 0.1 * ret["sim_or_grad"]
+        model.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            ev = R.render_neus(rays, model, 0.3, n_outside=0, white_bkgd=True, is_eval=True)
+        d = {"out_" + k: v for k, v in ret.items()}
+        d.update({"eval_" + k: ev[k] for k in ("rgb", "dist", "acc")})
+        d.update(rays_o=rays_o, rays_d=rays_d, near=near, far=far, gt=gt, t_rand=t_rand, loss=loss,
+                 g_sdf_lin8_v_row0=model.sdf_network.lin8.weight_v.grad[0],
+                 g_sdf_lin8_v_rowsum=model.sdf_network.lin8.weight_v.grad.sum(1), g_sdf_lin0_bias=model.sdf_network.lin0.bias.grad,
+                 g_sdf_lin4_g=model.sdf_network.lin4.weight_g.grad, g_col_lin4_v=model.color_network.lin4.weight_v.grad,
+                 g_variance=model.deviation_network.variance.grad)
+        np.savez_compressed(os.path.join(HERE, "neus_stage1.npz"), **npy(d))
+        print("stage1: acc max", float(ret["acc"].max()), "loss", float(loss))
+    finally:
+        torch.set_default_dtype(old)
+
+
 def main():
     torch.set_num_threads(8)
     sd, model = build()
@@ -182,6 +224,7 @@ def main():
     # training/train_cesr.py:465-544 with seeded shadow_net / normal_net weights, loss of :387-430, backward
     for name in CESR_CASES:
         cesr_golden(torch.Generator().manual_seed(11), name)
+    stage1_golden()
 
     # ---------------- 4. Illum forward + trace_radiance (N=48, nsamp=16)
     model.zero_grad()
@@ -222,7 +265,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] == ["cesr"]:
+    if sys.argv[1:] == ["stage1"]:
+        stage1_golden()
+    elif sys.argv[1:] == ["cesr"]:
         torch.set_num_threads(8)
         for name in CESR_CASES:
             cesr_golden(torch.Generator().manual_seed(11), name)

@@ -143,6 +143,42 @@ def test_cesr_step_forward_backward(golden, oracle_octrees, case):
             assert close(a, b, 1e-4), key
 
 
+def test_neus_stage1_render(synth_sd16):
+    """SURVEY.md section 8f rank 4 (oracle only so far): stage-1 NeuS render_neus of the oracle vs. the reference's golden
+    outputs and gradients, float64 (tests/golden/make_golden.py stage1_golden explains why)."""
+    import os
+
+    import numpy as np
+
+    import neus_stage1 as N1
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "neus_stage1.npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        sd = {k: v.double().requires_grad_(True) for k, v in synth_sd16.items() if k.startswith("implicit_network.")}
+        ret = N1.render_neus(sd, g["rays_o"], g["rays_d"], g["near"], g["far"], g["t_rand"], 0.3, training=True)
+        for k in ("rgb", "dist", "acc", "sim_or_grad", "weights", "means"):
+            assert (ret[k] - g["out_" + k]).abs().max().item() < 1e-9, k
+        loss = ((ret["rgb"] - g["gt"]) ** 2).mean() + 0.1 * ret["sim_or_grad"]
+        assert abs(loss.item() - g["loss"].item()) < 1e-10
+        loss.backward()
+        pre = "implicit_network.neus_model."
+        for key, a in (("g_sdf_lin8_v_row0", sd[pre + "sdf_network.lin8.weight_v"].grad[0]),
+                       ("g_sdf_lin8_v_rowsum", sd[pre + "sdf_network.lin8.weight_v"].grad.sum(1)),
+                       ("g_sdf_lin0_bias", sd[pre + "sdf_network.lin0.bias"].grad),
+                       ("g_sdf_lin4_g", sd[pre + "sdf_network.lin4.weight_g"].grad),
+                       ("g_col_lin4_v", sd[pre + "color_network.lin4.weight_v"].grad),
+                       ("g_variance", sd[pre + "deviation_network.variance"].grad)):
+            assert (a - g[key]).abs().max().item() < 1e-8 * max(1.0, g[key].abs().max().item()), key
+        with torch.no_grad():
+            ev = N1.render_neus(sd, g["rays_o"], g["rays_d"], g["near"], g["far"], None, 0.3, training=False)
+        for k in ("rgb", "dist", "acc"):
+            assert (ev[k] - g["eval_" + k]).abs().max().item() < 1e-9, k
+    finally:
+        torch.set_default_dtype(old)
+
+
 def test_vis_stage(golden, synth_sd16, oracle_octrees):
     g, sd = golden("vis_stage"), synth_sd16
     prim, sec = oracle_octrees
