@@ -84,6 +84,10 @@ class IDRNetwork(nn.Module):
         if fun_spec:
             raise RobirError("fun_spec=True is not on the accelerated path")
         if self.static_shapes and trainstage != 'Illum' and "intrinsics" in input and 'hdr_shift' in input:
+            if getattr(self.get_sg_render, "__func__", None) is not IDRNetwork.get_sg_render:
+                raise RobirError("the fixed-capacity forward (static_shapes = True) implements the PBR runner's hook only; "
+                                 "a re-bound get_sg_render (e.g. robir_b200.cesr.ClusteredAlbedoHook) needs "
+                                 "static_shapes = False")
             return self._forward_static(input, lin_diff=lin_diff, train_spec=train_spec)
         if "intrinsics" in input:
             object_mask = input["object_mask"].reshape(-1)

@@ -181,3 +181,21 @@ def test_hook_binds_to_a_live_runner_and_follows_its_counters():
     own = cesr.ClusteredAlbedoHook(None, object(), object(), cur_iter=5)
     own.cur_iter = 900
     assert own.cur_iter == 900 and own.prefit_option() == "explore"
+
+
+def test_fixed_capacity_forward_refuses_a_rebound_hook():
+    """The fixed-capacity (CUDA-graph) forward inlines the PBR hook; with the CESR hook bound it must refuse instead of
+    silently rendering the PBR stage."""
+    import robir_b200
+    model = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=128)))
+    hook = cesr.ClusteredAlbedoHook(model, object(), object(), cur_iter=600)
+    inp = {"intrinsics": None, "hdr_shift": None, "uv": None, "pose": None, "object_mask": None}
+    model.static_shapes = True
+    default = model.get_sg_render
+    model.get_sg_render = hook.get_sg_render
+    with pytest.raises(RobirError, match="static_shapes"):
+        model(inp, trainstage="Material", train_spec=True)
+    model.get_sg_render = default                       # restoring the default bound method is not a re-binding
+    with pytest.raises(Exception) as e:
+        model(inp, trainstage="Material", train_spec=True)
+    assert "static_shapes = False" not in str(e.value)
