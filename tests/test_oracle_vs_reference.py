@@ -337,3 +337,13 @@ def _stage1_case(N1, dtype):
                     assert ((mine - p.grad).norm() / p.grad.norm().clamp(min=1e-12)).item() < 0.1, k
                 n += 1
             assert n >= 27 + 15 + 1       # sdf (9 x 3), colour (5 x 3), deviation
+    if exact:
+        # other sampling configurations of render_neus (:236-246): one coarse-to-fine round, no importance samples, black
+        # background
+        for kw in (dict(up_sample_steps=1), dict(n_importance=0), dict(white_bkgd=False, n_samples=32, n_importance=32)):
+            with torch.no_grad():
+                a = R.render_neus(rays, model, 1.0, n_outside=0, is_eval=True, **{"white_bkgd": True, **kw})
+                sd = {pre + k: v.detach().clone() for k, v in model.state_dict().items()}
+                b = N1.render_neus(sd, rays_o, rays_d, near, far, None, 1.0, training=False, **kw)
+            for k in a:
+                assert (a[k] - b[k]).abs().max().item() < 1e-9, (kw, k)
