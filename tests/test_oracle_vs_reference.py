@@ -232,6 +232,23 @@ def test_cesr_step_matches_reference(ref_model_128, cur_iter, sched, white):
     assert checked["shadow"] == 27 and checked["normal"] == 27       # 9 x (weight_g, weight_v, bias)
     if cur_iter > 500:
         assert checked["model"] >= 19
+    # evaluation mode (plots: is_training = False -> testing = True, the extra networks under no_grad, :496-499)
+    runner.is_training = False
+    try:
+        torch.manual_seed(4321)
+        with ref_shim.ReplayRandom() as rec, torch.no_grad():
+            ev_ref = model(i2, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        hook_ev = lambda p, v, sg, integ, rnd: P.cesr_get_sg_render(sd, sds["shadow"], sds["normal"], p, v, sg, integ, rnd,
+                                                                    cur_iter=cur_iter, prefit=prefit, white_light=white,
+                                                                    is_training=False)
+        with torch.no_grad():
+            ev = P.idr_forward(sd, i3, lambda c, m, d: octree.trace(c, d), P.tape_to_rnd(rec.tape), hook=hook_ev,
+                               is_training=False)
+        for k, a in ev_ref.items():
+            if a.dtype != torch.bool:
+                assert (a - ev[k]).abs().max().item() < 2e-5, ("eval", k)
+    finally:
+        runner.is_training = True
 
 
 def test_cesr_hook_reads_the_reference_modules():
