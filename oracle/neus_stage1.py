@@ -152,3 +152,11 @@ def render_neus(sd, rays_o, rays_d, near, far, t_rand, cos_anneal_ratio, n_sampl
     distance = torch.clip(torch.nan_to_num(distance, torch.inf), near.squeeze(), far.squeeze())
     return dict(rgb=fine["color"], dist=distance, acc=acc, sim_or_grad=fine["gradient_error"], weights=weights,
                 means=fine["mid_z_vals"])
+
+
+def stage1_loss(ret, mask, pixels, eikonal_weight=0.1):
+    """neus/optimization/trainer.py:136-175 with the shipped regulariser set (neus/config/blender.gin: eikonal only):
+    masked MSE of the composited colour + eikonal_weight * the relaxed Eikonal term that render_core already reduced
+    (regular.py:41-43 just scales it).  mask = rays.lossmult [B,1]."""
+    mse = (mask * (ret["rgb"] - pixels[..., :3]) ** 2).sum() / (mask.sum() + 1e-5)
+    return mse + eikonal_weight * ret["sim_or_grad"].sum(), dict(mse=mse)

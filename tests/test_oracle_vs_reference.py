@@ -335,11 +335,13 @@ def _stage1_case(N1, dtype):
                 assert (ret[k] - ret_ref[k]).abs().max().item() < tol * max(1.0, ret_ref[k].abs().max().item()), k
         assert float(ret["acc"].max()) > 0.5          # the rays do hit the initial sphere
         if training:
-            def loss_of(r):
-                return ((r["rgb"] - gt) ** 2).mean() + 0.1 * r["sim_or_grad"]
+            def loss_of(r):      # the trainer's loss restated inline for the reference side (trainer.py:136-175)
+                return ((r["rgb"] - gt) ** 2).sum() / (B + 1e-5) + 0.1 * r["sim_or_grad"].sum()
             model.zero_grad()
             loss_of(ret_ref).backward()
-            loss_of(ret).backward()
+            mine_loss, _ = N1.stage1_loss(ret, torch.ones(B, 1), gt, eikonal_weight=0.1)
+            assert abs(mine_loss.item() - loss_of(ret_ref).item()) < tol
+            mine_loss.backward()
             n = 0
             for k, p in model.named_parameters():
                 if p.grad is None:
