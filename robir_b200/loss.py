@@ -1,5 +1,6 @@
 """PBR-stage loss, the consumer of the hot path's outputs (model/loss.py:7-125 InvLoss, training/train_pbr.py:313-346
-pbr_step / white_loss).  Elementwise torch glue; fusing it into the render epilogue is a 'next' row."""
+pbr_step / white_loss): ``InvLoss`` is the reference-shaped torch form; ``fused_pbr_loss`` / ``pbr_step_loss`` run the
+same terms (value + every input gradient) on one kernel (csrc/loss.cu)."""
 import ctypes
 
 import torch
