@@ -199,3 +199,29 @@ def test_fixed_capacity_forward_refuses_a_rebound_hook():
     with pytest.raises(Exception) as e:
         model(inp, trainstage="Material", train_spec=True)
     assert "static_shapes = False" not in str(e.value)
+
+
+def test_shadow_net_rank_structure_of_the_one_hot_input():
+    """Design check for DESIGN.md section 6 item 2d: shadow_net's input rows are [PE(x_i) | onehot(m)], so layer 0 and the
+    skip columns of layer 4 are sums of a per-point table and a per-lobe table -- no 191-wide GEMM over n*128 rows."""
+    sh, _ = synthetic.cesr_state_dicts(0)
+    net = cesr.WnMLP(191, 2)
+    net.load_state_dict(sh)
+    gen = torch.Generator().manual_seed(8)
+    n, M = 5, 128
+    emb = O.pe(torch.randn(n, 3, generator=gen) * 0.3, 10)
+    x = torch.cat([emb[:, None, :].expand(-1, M, -1), torch.eye(M)[None].expand(n, -1, -1)], -1).reshape(n * M, -1)
+    lins, skip = cesr._layers(net)
+    Ws, bs = [l.folded().detach() for l in lins], [l.bias.detach() for l in lins]
+    full = cesr._wn_rows_torch(Ws, bs, skip, x)
+    sp = lambda t: torch.nn.functional.softplus(t, beta=100)
+    h = sp((emb @ Ws[0][:, :63].t() + bs[0])[:, None, :] + Ws[0][:, 63:].t()[None, :, :]).reshape(n * M, -1)
+    for l in (1, 2, 3):
+        h = sp(h @ Ws[l].t() + bs[l])
+    k = Ws[4].shape[1] - 191
+    tab = ((emb @ Ws[4][:, k:k + 63].t())[:, None, :] + Ws[4][:, k + 63:].t()[None, :, :]).reshape(n * M, -1)
+    h = sp((h @ Ws[4][:, :k].t() + tab) / 2 ** 0.5 + bs[4])
+    for l in (5, 6, 7):
+        h = sp(h @ Ws[l].t() + bs[l])
+    out = h @ Ws[8].t() + bs[8]
+    assert (out - full).abs().max().item() < 1e-5 * max(1.0, full.abs().max().item())
