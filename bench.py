@@ -1,20 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- rays/s (fwd+bwd) of the PBR-stage hot path on the synthetic hotdog-800x800 workload (BASELINE.json
-configs[1]): each step = one training iteration of the reference (1024 random pixels of one 800x800 view, M=128 light
-SGs, S=32 samples/lobe): camera rays -> octree trace -> SDF normals -> material/indirect nets -> fused visibility MLP
--> SG render -> loss -> backward -> Adam step.
+"""bench.py -- rays/s of RobIR's per-ray rendering hot path on synthetic inputs of BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5] [--impl reference|reference-cuda]
 
-One process per GPU (torchrun for N>1), weak scaling: every rank renders its own 1024-ray batch and the gradient of the
-trained parameters is all-reduced over NCCL each step.  Rank 0 prints ONE JSON line.  ``--impl reference`` times the
-CPU oracle port of the reference's path (the reference itself is Python and cannot travel to the GPU box) on the host
-cores, on a bounded ray sample of the same workload.
+Default = BASELINE config 2 (the configuration the metric is quoted on): each step = one training iteration of the
+reference's PBR stage (training/train_pbr.py:431-460): 1024 random pixels of one 800x800 view, M=128 light SGs, S=32
+samples/lobe: camera rays -> octree trace -> SDF normals -> material / indirect nets -> fused visibility MLP -> SG
+render -> loss -> backward -> Adam step.  The other configurations (parity-test cases in the contract, measured here
+for the record under profiles/):
+
+    c1  64x64 crop (4096 rays, one call), M=16, forward only; both tracers (octree = shipped default, sphere tracer with
+        ray_tracer.n_steps = 32 = the path the "march steps" knob controls)
+    c3  Vis stage step (training/train_visibility.py:286-324): forward('Illum') + trace_radiance(nsamp=512) on 256 primary
+        rays + IllumLoss + both backwards + both Adam steps; primary and secondary rays/s
+    c4  PBR + CESR step (training/train_cesr.py:465-559, explore phase, S=8, lin_diff) -- ray-sharded over the ranks
+    c5  the PBR step on a DTU-sized view (1600x1200, f=2892), ray-sharded over the ranks + gradient all-reduce
+
+One process per GPU (torchrun for N>1), weak scaling: every rank renders its own batch and the gradient of the trained
+parameters is all-reduced over NCCL each step.  Rank 0 prints ONE JSON line.
+
+``--impl reference`` times the reference's OWN implementation of the path on the host cores: the unmodified RobIR code
+staged under oracle/_ref (oracle/stage_ref.py; kind "reference"), or -- when no staged copy exists -- the oracle port
+(kind "port"), on a pinned ray sample of the same workload.  ``--impl reference-cuda`` runs the same unmodified code
+eagerly on the B200 (what RobIR's users run today); the default arm also reports it as ``cuda_baseline``.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,12 +41,19 @@ from robir_b200 import synthetic  # noqa: E402
 METRIC = "rays/sec (fwd+bwd) PBR stage, hotdog 800x800"
 N_RAYS, M_LOBES, SDF_RADIUS, SEED = 1024, 128, 0.87, 0
 FLOP_PER_QUERY = 458752.0  # 2 * (126*256 + 3*256^2 + 256*2)
+REF_SAMPLE_RAYS = 256      # --impl reference: rays per step of the CPU arm (pinned: comparable across runs and N)
+
+CAMERAS = {"hotdog": dict(H=800, W=800, focal=1111.1), "dtu": dict(H=1200, W=1600, focal=2892.0)}
 
 
-def workload_config(extra=None):
-    cfg = {"workload": "hotdog-synthetic 800x800 PBR stage: 1024 random pixels/step, M=128 light SGs, S=32, 24 indirect "
-                       "SGs, octree tracer, geometric-init NeuS SDF (stage-2 radius ~0.6), fwd+loss+bwd+Adam",
-           "rays_per_step_per_gpu": N_RAYS, "num_lgt_sgs": M_LOBES, "image": "800x800", "tracer": "octree",
+def workload_config(config="c2", extra=None):
+    cam = CAMERAS["dtu" if config == "c5" else "hotdog"]
+    names = {"c2": "hotdog-synthetic 800x800 PBR stage: 1024 random pixels/step, M=128 light SGs, S=32, 24 indirect SGs, "
+                   "octree tracer, geometric-init NeuS SDF (stage-2 radius ~0.6), fwd+loss+bwd+Adam",
+             "c5": "dtu-synthetic 1600x1200 (f=2892) PBR stage: 1024 random pixels/step/GPU, M=128 light SGs, S=32, 24 "
+                   "indirect SGs, octree tracer, geometric-init NeuS SDF (stage-2 radius ~0.6), fwd+loss+bwd+Adam"}
+    cfg = {"workload": names.get(config, config), "config": config, "rays_per_step_per_gpu": N_RAYS,
+           "num_lgt_sgs": M_LOBES, "image": "%dx%d" % (cam["W"], cam["H"]), "tracer": "octree",
            "l2": "per-step working set (ReLU masks + pair lists ~0.6 GB) exceeds the 126 MB L2; no explicit flush"}
     if extra:
         cfg.update(extra)
@@ -45,7 +64,7 @@ def workload_config(extra=None):
 class ClockSampler:
     """SM clock / throttle reasons sampled with NVML from a background thread during the timed region."""
 
-    def __init__(self, index, period=0.2):
+    def __init__(self, index, period=0.02):
         self.index, self.period, self.rows, self.stop_flag, self.thread = index, period, [], False, None
 
     def start(self):
@@ -69,6 +88,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.thread = None
+        return self
 
     def stop(self):
         self.stop_flag = True
@@ -82,8 +102,8 @@ class ClockSampler:
                  "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
         sm = sorted(r[0] for r in self.rows)
         reasons = [n for n, bit in names.items() if any(r[1] & bit for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm)}
 
 
 def measured_peaks():
@@ -93,11 +113,44 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def latest_ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (a profiler number can only come from a profiler run; the file is named in
+    the record)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_vis_tc.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+            if key in d and "dram_bytes" in d[key]:
+                return d[key]["dram_bytes"], os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
+def host_batch(step, cam, n=N_RAYS):
+    pix = synthetic.training_pixels(step, n=n, H=cam["H"], W=cam["W"])
+    uv = torch.stack([(pix % cam["W"]).float(), (pix // cam["W"]).float()], -1)[None]
+    return uv, torch.ones(1, n, dtype=torch.bool), torch.full((1, n, 3), 0.5)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU oracle leg (cpu_baseline and --impl reference)
+# reference arms (CPU: --impl reference; eager CUDA: --impl reference-cuda / cuda_baseline)
 # ----------------------------------------------------------------------------------------------------------------------
+def _oracle_paths():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def reference_available():
+    _oracle_paths()
+    import ref_shim
+    return ref_shim.available()
+
+
 def oracle_setup(sd, tree_arrays=None):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    _oracle_paths()
     import pipeline as P
     import robir_oracle as O
     import tracers as T
@@ -120,11 +173,10 @@ def oracle_setup(sd, tree_arrays=None):
     return O, P, tree
 
 
-def oracle_step(O, P, tree, sd, step, n_rays, gen):
-    """One reference-equivalent training iteration on the CPU: forward + loss + backward (+ SGD-free: the optimizer
-    step is excluded on both arms' CPU leg; it is < 0.1 % of the CPU time)."""
-    pix = synthetic.training_pixels(step, n=N_RAYS)[:n_rays]
-    inp = synthetic.camera_inputs(pix)
+def oracle_step(O, P, tree, sd, step, n_rays, gen, cam):
+    """One reference-equivalent training iteration of the oracle PORT on the CPU: forward + loss + backward."""
+    pix = synthetic.training_pixels(step, n=N_RAYS, H=cam["H"], W=cam["W"])[:n_rays]
+    inp = synthetic.camera_inputs(pix, **cam)
     train = [k for k in sd if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
     for k in train:
         sd[k].requires_grad_(True)
@@ -137,57 +189,122 @@ def oracle_step(O, P, tree, sd, step, n_rays, gen):
     return int(out["network_object_mask"].sum())
 
 
+def reference_pbr(device, sd):
+    """The unmodified reference's PBR runner objects (oracle/ref_runner.py), octree built by the reference."""
+    _oracle_paths()
+    import ref_runner
+    R = ref_runner.ReferencePBR(sd, M_LOBES, device=device)
+    R.generate()
+    return R
+
+
 def run_reference(args):
-    """--impl reference: rank 0 only, host cores only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: rank 0 only, host cores only (all of them)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.config not in ("c2", "c5"):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the PBR step "
+                                                              "(configs c2, c5); see --impl reference-cuda"}))
+        return
+    cam = CAMERAS["dtu" if args.config == "c5" else "hotdog"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M_LOBES, sdf_radius=SDF_RADIUS)
-    O, P, tree = oracle_setup(sd)
-    gen = torch.Generator().manual_seed(1234)
-    # size the per-step ray sample so that (warmup + steps) fits in ~150 s
-    t0 = time.time()
-    oracle_step(O, P, tree, sd, 0, 32, gen)
-    probe = (time.time() - t0) / 32
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_rays = int(max(16, min(N_RAYS, budget / max(probe, 1e-6))))
+    n_rays = REF_SAMPLE_RAYS
+    if reference_available():
+        kind = "reference"
+        R = reference_pbr("cpu", sd)
+        torch.manual_seed(1234)
+
+        def step(s):
+            pix = synthetic.training_pixels(s, n=N_RAYS, H=cam["H"], W=cam["W"])[:n_rays]
+            inp = synthetic.camera_inputs(pix, **cam)
+            inp.pop("hdr_shift")
+            R.step(inp, {"rgb": torch.full((1, n_rays, 3), 0.5)})
+    else:
+        kind = "port"
+        O, P, tree = oracle_setup(sd)
+        gen = torch.Generator().manual_seed(1234)
+
+        def step(s):
+            oracle_step(O, P, tree, sd, s, n_rays, gen, cam)
     for s in range(args.warmup):
-        oracle_step(O, P, tree, sd, s, n_rays, gen)
+        step(s)
     t0 = time.time()
     for s in range(args.steps):
-        oracle_step(O, P, tree, sd, 100 + s, n_rays, gen)
+        step(100 + s)
     dt = time.time() - t0
     value = n_rays * args.steps / dt
-    sample = "%d of the %d rays of each step (random pixels of the 800x800 view), %d steps" % (n_rays, N_RAYS, args.steps)
+    sample = ("%d of the %d rays of each step (the first %d of the step's random pixels of the %dx%d view), %d steps; %s"
+              % (n_rays, N_RAYS, n_rays, cam["W"], cam["H"], args.steps,
+                 "unmodified reference (oracle/_ref) incl. its Adam step" if kind == "reference"
+                 else "oracle port, no optimizer step"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config({"rays_per_step_sample": n_rays}),
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.config, {"rays_per_step_sample": n_rays}),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="robir_b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--engine", default=None, help="visibility-MLP engine: tc (default) | ffma")
-    ap.add_argument("--mode", default="graph", help="graph: whole step as one CUDA graph (default) | eager")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    args.warmup = max(args.warmup, 3)
+def reference_cuda_measure(sd, cam, steps, warmup):
+    """The unmodified reference eagerly on cuda:0: full 1024-ray training iterations incl. H2D of the batch (its loop
+    copies the inputs every iteration, train_pbr.py:438-439) and its own .item() syncs.  Returns a record."""
+    R = reference_pbr("cuda", sd)
+    torch.manual_seed(1234)
+    batches = [host_batch(s, cam) for s in range(steps + warmup)]
 
+    def step(s):
+        uv, om, gt = batches[s]
+        inp = {"uv": uv, "object_mask": om, "pose": synthetic.camera_pose(),
+               "intrinsics": synthetic.camera_intrinsics(**cam)}
+        return R.step(inp, {"rgb": gt})
+    for s in range(warmup):
+        step(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    hits = 0
+    for s in range(warmup, warmup + steps):
+        out, _ = step(s)
+        hits += int(out["network_object_mask"].sum())
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    return {"value": N_RAYS * steps / dt, "unit": "rays/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "kind": "reference-eager-cuda", "wall_ms_per_step": 1e3 * (time.time() - t0) / steps,
+            "hit_fraction": hits / float(N_RAYS * steps),
+            "what": "unmodified reference (oracle/_ref: IDRNetwork.forward + PBRTrainRunner.get_sg_render/pbr_step + "
+                    "InvLoss + torch Adam), eager PyTorch on this GPU, its own octree, host batches, 1024 rays/step"}
+
+
+def run_reference_cuda(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not reference_available() or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "needs the staged reference (oracle/_ref) and a GPU"}))
+        return
+    cam = CAMERAS["dtu" if args.config == "c5" else "hotdog"]
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M_LOBES, sdf_radius=SDF_RADIUS)
+    rec = reference_cuda_measure(sd, cam, args.steps, max(args.warmup, 2))
+    print(json.dumps({
+        "impl": "reference-cuda", "metric": METRIC, "value": rec["value"], "unit": "rays/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.config), "cuda_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": "rays/s", "h2d_bytes_per_step": 21504, "d2h_bytes_per_step": 4}}))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# configs c2 / c5: the PBR training step
+# ----------------------------------------------------------------------------------------------------------------------
+def run_pbr(args):
     import robir_b200
     from robir_b200 import _lib, dist as rdist, ops, rng
     from robir_b200.loss import InvLoss, pbr_step_loss
+    cam = CAMERAS["dtu" if args.config == "c5" else "hotdog"]
     rank, world, local = rdist.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -202,16 +319,13 @@ def main():
     model.generate()                                   # octree build: excluded from the metric
     loss_fn = InvLoss()
     params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters())
-    opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=bool(int(os.environ.get("ROBIR_FUSED_ADAM", "1"))))   # training/train_pbr.py:104-105, hotdog.conf:25
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=True,
+                           fused=bool(int(os.environ.get("ROBIR_FUSED_ADAM", "1"))))   # train_pbr.py:104-105
     reducer = rdist.GradAllReducer(params)
-    pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
+    pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics(**cam).to(dev)
 
-    def host_batch(step):
-        pix = synthetic.training_pixels(step * world + rank, n=N_RAYS)
-        uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None].pin_memory()
-        gt = torch.full((1, N_RAYS, 3), 0.5).pin_memory()
-        om = torch.ones(1, N_RAYS, dtype=torch.bool).pin_memory()
-        return uv, om, gt
+    def pinned_batch(step):
+        return tuple(t.pin_memory() for t in host_batch(step * world + rank, cam))
 
     def train_step(uv, om, gt):
         inp = {"uv": uv, "object_mask": om, "pose": pose, "intrinsics": K,
@@ -237,7 +351,7 @@ def main():
             return graphed(uv, om, gt), None
 
     total = args.warmup + args.steps
-    batches = [host_batch(s) for s in range(total)]
+    batches = [pinned_batch(s) for s in range(total)]
     dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
 
     def barrier():
@@ -245,13 +359,11 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
-        for s in range(args.warmup):
-            fn(s)
+    def timed(fn, first, last):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for s in range(args.warmup, total):
+        for s in range(first, last):
             fn(s)
         e1.record()
         barrier()
@@ -259,28 +371,27 @@ def main():
 
     # ---- (1) device-resident inputs: the headline `value`
     hits = []
-    clocks = ClockSampler(local)
     ops.Stats.reset()
     _lib.launch_count = 0
-    launches_before = None
 
     def step_resident(s):
-        nonlocal launches_before
-        if s == args.warmup:
-            launches_before = _lib.launch_count
-            ops.Stats.reset()
-        loss, m = train_step(*dev_batches[s])
-        if s >= args.warmup:
-            hits.append(graphed.hits.clone() if graphed is not None else m.sum())
+        loss, m = train_step(*dev_batches[s % total])
+        hits.append(graphed.hits.clone() if graphed is not None else m.sum())
 
-    clocks.start()
-    t_res = timed(step_resident)
+    for s in range(args.warmup):
+        step_resident(s)
+    hits.clear()
+    ops.Stats.reset()
+    launches_before = _lib.launch_count
+    clocks = ClockSampler(local).start()
+    t_res = timed(step_resident, args.warmup, total)
     clk = clocks.stop()
     launches = _lib.launch_count - launches_before
     if graphed is not None:
         launches = graphed.launches_per_step * args.steps
     pairs_total = ops.Stats.total()
     n_hits = int(torch.stack(hits).sum().item())
+    n_hits_all = rdist.sum_over_ranks(n_hits, dev)
     value = rdist.sum_over_ranks(N_RAYS * args.steps, dev) / t_res
 
     # ---- (2) end to end through the public API with host buffers: H2D of the batch + D2H of the loss inside the region
@@ -292,8 +403,22 @@ def main():
         loss, _ = train_step(uv, om, gt)
         losses.append(float(loss.item()))          # device -> host read of the step's result
 
-    t_e2e = timed(step_e2e)
+    for s in range(min(args.warmup, 3)):
+        step_e2e(s)
+    losses.clear()
+    t_e2e = timed(step_e2e, args.warmup, total)
     e2e = rdist.sum_over_ranks(N_RAYS * args.steps, dev) / t_e2e
+
+    # ---- (2b) sustained: >= 5 s of back-to-back replays (thousands of steps), clocks sampled -- the timed region above
+    # is ~70 ms at boost clocks; this is what a real training run sees under the power cap
+    sustained = None
+    if args.sustain > 0:
+        n_sus = int(max(50, args.sustain / max(t_res / args.steps, 1e-4)))
+        clocks = ClockSampler(local, period=0.05).start()
+        t_sus = timed(step_resident, 0, n_sus)
+        clk_sus = clocks.stop()
+        sustained = {"value": rdist.sum_over_ranks(N_RAYS * n_sus, dev) / t_sus, "unit": "rays/s", "steps": n_sus,
+                     "seconds": t_sus, "ms_per_step": 1e3 * t_sus / n_sus, "clocks": clk_sus}
 
     # ---- (3) dominant kernel, timed live with CUDA events on the launching stream (eager replays of the same step)
     if graphed is not None:
@@ -317,58 +442,94 @@ def main():
     t_bwd = sum(a.elapsed_time(b) for n, a, b, _ in big if n == "vis_mlp_bwd") * 1e-3
     n_fwd = sum(1 for n, *_ in big if n == "vis_mlp_fwd")
     peaks, peak_kind = measured_peaks()
-    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    # the kernel is timed alone by CUDA events inside a ~20 ms eager region at boost clocks: the BURST figure is the
+    # denominator (the sustained one is quoted beside it)
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
     achieved = FLOP_PER_QUERY * pairs_prof / max(t_fwd, 1e-9) / 1e12
-    traffic = None
-    try:      # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_v12_ncu_vis_tc.json")))["fwd_diffuse"]["dram_bytes"]
-    except Exception:
-        pass
+    terms = ops.vis_engine_terms() if hasattr(ops, "vis_engine_terms") else 3
+    traffic, traffic_src = latest_ncu_traffic("fwd_diffuse")
     roofline = {"bound": "tensor", "kernel": "vis_tc_kernel<0> (visibility MLP forward, diffuse pair list)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peak_kind,
+                "traffic_source": traffic_src,
+                "peak_source": "%s bf16 burst (MEASURED_PEAKS.json: bf16_tflops); sustained %.1f" %
+                               (peak_kind, peaks.get("bf16_tflops_sustained", 0.0)),
+                "frac_of_sustained": achieved / peaks.get("bf16_tflops_sustained", peak_tf),
                 "algorithmic_flop_per_launch": FLOP_PER_QUERY * pairs_prof / max(n_fwd, 1),
                 "avg_launch_ms": 1e3 * t_fwd / max(n_fwd, 1), "launches_timed": n_fwd,
-                "note": "fp32 parity costs 3 bf16 MMAs per logical one: executed tensor FLOP/s = 2.57 x achieved; the "
-                        "algorithmic fraction is capped at 0.389",
+                "executed_tflops": achieved * (terms * 3 * 65536 + 512) / (126 * 256 + 3 * 65536 + 512.0),
+                "note": "engine '%s': %d MMA term(s) per logical product (3 = fp32-parity split, 1 = single-pass fast "
+                        "mode); executed tensor FLOP/s = executed_tflops" % (ops.ENGINE["vis"], terms),
                 "bwd_kernel": {"achieved": FLOP_PER_QUERY * pairs_prof / max(t_bwd, 1e-9) / 1e12,
+                               "frac": FLOP_PER_QUERY * pairs_prof / max(t_bwd, 1e-9) / 1e12 / peak_tf,
                                "share_of_step": t_bwd / prof_steps / (t_res / args.steps)},
                 "share_of_step": t_fwd / prof_steps / (t_res / args.steps)}
 
-    # ---- (4) CPU baseline: the oracle port on the host cores, rank 0, bounded sample of the same workload
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        tree = model.ray_tracer.sdf_octree
-        O, P, otree = oracle_setup(sd, tree.host_arrays())
-        gen = torch.Generator().manual_seed(1234)
-        n_s = 128
-        oracle_step(O, P, otree, {k: v.clone() for k, v in sd.items()}, 0, 16, gen)   # warm-up
-        sd_cpu = {k: v.clone() for k, v in sd.items()}
-        t0 = time.time()
-        oracle_step(O, P, otree, sd_cpu, args.warmup, n_s, gen)
-        dt = time.time() - t0
-        cpu = {"value": n_s / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": "first %d of the %d rays of one step, fwd+loss+bwd, octree arrays copied from the GPU build"
-                         % (n_s, N_RAYS)}
+    # ---- (4) baselines on rank 0 at N=1: the reference's CPU path on a bounded sample, and the reference eagerly on
+    # this GPU (what RobIR's users run today)
+    cpu = cuda_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # a separate process: the reference needs its import shim in CPU mode (every .cuda() rewritten), which cannot
+        # coexist with the CUDA-mode shim of the cuda_baseline below nor with this process's thread settings
+        import subprocess
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=900,
+                               env=dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1"))
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            cpu = json.loads(line)["cpu_baseline"]
+        except Exception as exc:                                             # noqa: BLE001
+            cpu = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    if rank == 0 and world == 1 and not args.no_cuda_baseline and reference_available():
+        try:
+            # free our graph's memory pool first? not needed: 180 GB; the reference keeps ~10 GB of activations
+            cuda_ref = reference_cuda_measure(sd, cam, steps=5, warmup=2)
+        except Exception as exc:                                             # noqa: BLE001
+            cuda_ref = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     if world > 1:
         torch.distributed.barrier()
     if rank == 0:
+        hit_frac = n_hits_all / float(N_RAYS * args.steps * world)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config({"parallelism": "rays x%d (+ NCCL grad all-reduce)" % world,
-                                       "hit_fraction": n_hits / float(N_RAYS * args.steps),
-                                       "vis_queries_per_step": pairs_total / float(args.steps),
-                                       "vis_engine": ops.ENGINE["vis"], "rng": "device", "mode": args.mode}),
+            "config": workload_config(args.config, {
+                "parallelism": "rays x%d (+ NCCL grad all-reduce)" % world, "hit_fraction": hit_frac,
+                "vis_queries_per_step": pairs_total / float(args.steps), "vis_engine": ops.ENGINE["vis"],
+                "rng": "device", "mode": args.mode}),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
+            "hit_rays_per_s": value * hit_frac, "sustained": sustained,
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "final_loss": losses[-1] if losses else None}))
+            "cuda_baseline": cuda_ref, "final_loss": losses[-1] if losses else None}))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="robir_b200")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-baseline", action="store_true")
+    ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back replays for the sustained record")
+    ap.add_argument("--engine", default=None, help="visibility-MLP engine: tc (default, fp32 parity) | tc1 (single-pass "
+                                                   "fast mode) | ffma")
+    ap.add_argument("--mode", default="graph", help="graph: whole step as one CUDA graph (default) | eager | eager-static")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda(args)
+    args.warmup = max(args.warmup, 3)
+    if args.config in ("c2", "c5"):
+        return run_pbr(args)
+    import bench_configs
+    return getattr(bench_configs, "run_" + args.config)(args)
 
 
 if __name__ == "__main__":

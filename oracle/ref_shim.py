@@ -4,14 +4,17 @@ Makes the *unmodified* reference tree (/root/reference, read-only) importable an
 build container so that (a) the oracle restatement in ``oracle/robir_oracle.py`` can be validated against
 the real thing and (b) golden vectors under ``tests/golden/`` can be generated (``tests/golden/make_golden.py``).
 
-/root/reference does not exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` may import this module.  Recipe: SURVEY.md Appendix B.
+/root/reference does not exist on the GPU box; there the byte-for-byte staged copy ``oracle/_ref/`` (made by
+``oracle/stage_ref.py`` from ``__graft_entry__.build()``, git-ignored, shipped by gpurun) is used instead, by
+``bench.py --impl reference[-cuda]`` and by the ``-m gpu`` drop-in test of ``robir_b200.install()``.
+Recipe: SURVEY.md Appendix B.
 
-What it does (nothing under /root/reference is edited):
+What it does (nothing under the reference tree is edited):
   * stub modules for the reference's missing third-party imports (gin, imageio, torch_scatter, pyhocon, ...);
     ``torch_scatter.scatter_min`` (utils/octree.py:591) is restated as a segment-amin;
-  * ``.cuda()`` becomes a no-op and ``device='cuda'`` kwargs are rewritten to CPU;
-  * registers /root/reference/datasets under the name ``datasets`` (HF ``datasets`` shadows it).
+  * device="cpu" (default): ``.cuda()`` becomes a no-op and ``device='cuda'`` kwargs are rewritten to CPU;
+    device="cuda": nothing is rewritten -- the reference runs eagerly on the GPU exactly as its users run it;
+  * registers <reference>/datasets under the name ``datasets`` (HF ``datasets`` shadows it).
 """
 import os
 import sys
@@ -20,8 +23,18 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("ROBIR_REFERENCE", "/root/reference")
+def _find_root():
+    cands = [os.environ.get("ROBIR_REFERENCE"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "model")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 _installed = False
+DEVICE = "cpu"
 
 
 def available() -> bool:
@@ -45,15 +58,19 @@ def _scatter_min(src, index):
     # torch_scatter.scatter_min semantic used at utils/octree.py:591: per-segment minimum of src.
     if index.numel() == 0:
         return src.new_zeros((0,)), None
-    out = torch.full((int(index.max()) + 1,), torch.iinfo(src.dtype).max, dtype=src.dtype)
+    out = torch.full((int(index.max()) + 1,), torch.iinfo(src.dtype).max, dtype=src.dtype, device=src.device)
     return out.scatter_reduce(0, index, src, "amin", include_self=True), None
 
 
-def install():
-    """Idempotently install the shim and put the reference on sys.path."""
-    global _installed
+def install(device="cpu"):
+    """Idempotently install the shim and put the reference on sys.path.  device: "cpu" (rewrite every CUDA placement
+    to the host) or "cuda" (leave the reference's own .cuda() calls alone); fixed by the first call in a process."""
+    global _installed, DEVICE
     if _installed:
+        if device != DEVICE and device == "cuda":
+            raise RuntimeError("ref_shim was already installed in CPU mode in this process")
         return
+    DEVICE = device
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     gin = _mod("gin", configurable=_passthrough_decorator, register=_passthrough_decorator,
@@ -78,32 +95,34 @@ def install():
     ds.__path__ = [os.path.join(REF_ROOT, "datasets")]
     sys.modules["datasets"] = ds
 
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    from torch import storage as _storage
-    _storage._StorageBase.cuda = lambda self, *a, **k: self
-    torch.UntypedStorage.cuda = lambda self, *a, **k: self
+    if device == "cpu":
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        from torch import storage as _storage
+        _storage._StorageBase.cuda = lambda self, *a, **k: self
+        torch.UntypedStorage.cuda = lambda self, *a, **k: self
 
-    from torch.overrides import TorchFunctionMode
+        from torch.overrides import TorchFunctionMode
 
-    class _CpuDevice(TorchFunctionMode):
-        def __torch_function__(self, func, types_, args=(), kwargs=None):
-            kwargs = kwargs or {}
-            dev = kwargs.get("device")
-            if dev is not None and "cuda" in str(dev):
-                kwargs["device"] = "cpu"
-            return func(*args, **kwargs)
+        class _CpuDevice(TorchFunctionMode):
+            def __torch_function__(self, func, types_, args=(), kwargs=None):
+                kwargs = kwargs or {}
+                dev = kwargs.get("device")
+                if dev is not None and "cuda" in str(dev):
+                    kwargs["device"] = "cpu"
+                return func(*args, **kwargs)
 
-    _CpuDevice().__enter__()
+        _CpuDevice().__enter__()
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import utils.octree as uo
 
-    def _octree_cuda(self):
-        self.device = "cpu"
-        return self
+    if device == "cpu":
+        def _octree_cuda(self):
+            self.device = "cpu"
+            return self
 
-    uo.Octree.cuda = _octree_cuda
+        uo.Octree.cuda = _octree_cuda
     _installed = True
 
 
@@ -145,9 +164,10 @@ def hotdog_model_conf(num_lgt_sgs=128, use_octree=True, n_steps=100):
     )
 
 
-def build_reference_model(neus_state_dict, num_lgt_sgs=128, use_octree=True, n_steps=100, seed=0):
-    """Construct the reference IDRNetwork on CPU from a stage-1 NeuS state dict (our synthetic checkpoint)."""
-    install()
+def build_reference_model(neus_state_dict, num_lgt_sgs=128, use_octree=True, n_steps=100, seed=0, device="cpu"):
+    """Construct the reference IDRNetwork from a stage-1 NeuS state dict (our synthetic checkpoint); on the host
+    (device="cpu") or -- the caller then does ``model.cuda()`` like the runners, train_pbr.py:92-93 -- for the GPU."""
+    install(device)
     import confs_sg.env_path as env_path
     tmp = tempfile.mkdtemp(prefix="robir_neus_")
     torch.save({"global_step": 0, "model": neus_state_dict}, os.path.join(tmp, "000000.tar"))

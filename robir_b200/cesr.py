@@ -22,6 +22,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import dist as rdist
 from . import ops, sg_render
 from ._lib import RobirError
 from .loss import white_loss
@@ -128,6 +129,13 @@ class ClusteredAlbedoHook:
         reads the runner's networks, conf and counters; nothing of the runner is modified except
         ``runner.model.get_sg_render``.  Returns the hook."""
         conf = runner.conf
+        try:
+            argmax_vis = conf.get_bool('train.argmax_vis')          # train_cesr.py:522
+        except Exception:
+            argmax_vis = False
+        if argmax_vis:
+            raise RobirError("ClusteredAlbedoHook: train.argmax_vis = True is not on the accelerated path "
+                             "(sg_render.py:170,270 hard visibility); the shipped configs leave it off")
         hook = cls(runner.model, runner.shadow_net, runner.normal_net, white_light=runner.white_light,
                    explore_iter=conf.get_int('train.explore_iter'), proj_iter=conf.get_int('train.proj_iter'),
                    explore_smooth=conf.get_float('train.explore_smooth'), explore_kl=conf.get_float('train.explore_kl'),
@@ -191,8 +199,8 @@ class ClusteredAlbedoHook:
         sg["indir_rgb"] = sg["indir_diffuse_rgb"] * diffuse_albedo / np.pi + sg["indir_specular_rgb"]
         supervise = sg['supervise']
         if self.white_light and prefit != "warmup":
-            supervise = supervise + white_loss(lgtSGs)
-        supervise = supervise + ((normal_map - normal_new) ** 2).mean()
+            supervise = supervise + rdist.param_only(white_loss(lgtSGs))
+        supervise = supervise + rdist.global_mean((normal_map - normal_new) ** 2)
         ret.update(sg)
         ret.update({'diffuse_albedo': diffuse_albedo, 'roughness': roughness, 'metallic': mat['sg_metallic'],
                     'normal_map': normal_new, 'gradient_error': supervise,

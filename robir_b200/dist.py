@@ -32,7 +32,10 @@ class GradAllReducer:
     """Flat-bucket all-reduce of the gradients of ``params`` (one NCCL call on the current stream).  average=True
     (weak scaling: every rank steps on its own batch, the reference's DataParallel-free equivalent is the mean of the
     per-batch gradients) divides by the world size; average=False is the plain sum that strong sharding of ONE batch
-    needs (every rank's loss terms are already normalised by the global ray count, model/loss.py:41)."""
+    needs: under ``STRONG_SHARDING`` the loss code normalises every per-ray term by the GLOBAL ray / hit counts
+    (``global_count`` / ``global_mean``), shares the parameter-only terms out over the ranks (``param_only``) and takes
+    the batch means of both KL terms over all ranks (``batch_mean_rows``), so the summed per-rank gradients equal the
+    full-batch gradient (2-rank test: tests/test_dist_cpu.py)."""
 
     def __init__(self, params, average=True):
         self.params = [p for p in params if p.requires_grad]
@@ -88,6 +91,35 @@ def batch_mean_rows(x):
     n = torch.tensor([float(x.shape[0])], dtype=x.dtype, device=x.device)
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
     return _AllReduceSum.apply(x.sum(0)) / n
+
+
+def _strong():
+    return STRONG_SHARDING and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def global_count(n, like):
+    """Number of rows of the whole batch given the local count ``n`` (python number): model/loss.py:41 divides the
+    image loss by ``object_mask.shape[0]`` of the full batch."""
+    if not _strong():
+        return float(n)
+    t = torch.tensor([float(n)], dtype=torch.float64, device=like.device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def global_mean(x):
+    """x.mean() over the elements of the whole batch (all ranks hold slices with the same trailing shape)."""
+    if not _strong():
+        return x.mean()
+    n = torch.tensor([float(x.numel())], dtype=x.dtype, device=x.device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return _AllReduceSum.apply(x.sum().reshape(1))[0] / n[0]
+
+
+def param_only(term):
+    """A loss term that depends on parameters only (white-light regulariser, ...): every rank evaluates it, the summed
+    gradient must count it once."""
+    return term / dist.get_world_size() if _strong() else term
 
 
 def allreduce_min_scalar(t):

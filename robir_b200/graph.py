@@ -14,7 +14,10 @@ class GraphedPBRStep:
     With ``reducer`` (multi-GPU gradient all-reduce) the step is split into two graphs -- forward+backward and the
     optimizer update -- with the NCCL collective issued eagerly in between."""
 
-    def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3):
+    def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3,
+                 record_randoms=False):
+        """record_randoms: keep references to the random tensors drawn inside the captured step (``self.random_tape``, in
+        draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes)."""
         if rng._mode != "device":
             raise RuntimeError("GraphedPBRStep needs robir_b200.rng.set_mode('device')")
         model.static_shapes = True
@@ -42,10 +45,13 @@ class GraphedPBRStep:
         self.g1 = torch.cuda.CUDAGraph()
         self.g2 = None
         before = _lib.launch_count
-        with torch.cuda.graph(self.g1):
-            self.loss = self._fwd_bwd()
-            if not split:
-                self.opt.step()
+        import contextlib
+        with (rng.record(on_device=True) if record_randoms else contextlib.nullcontext()) as tape:
+            with torch.cuda.graph(self.g1):
+                self.loss = self._fwd_bwd()
+                if not split:
+                    self.opt.step()
+        self.random_tape = list(tape) if record_randoms else None
         self.launches_per_step = _lib.launch_count - before    # kernels of the C-ABI library inside one replay
         if split:
             self.g2 = torch.cuda.CUDAGraph()
@@ -72,4 +78,7 @@ class GraphedPBRStep:
         if self.g2 is not None:
             self.reducer()
             self.g2.replay()
+        # the replay's optimizer update changed the trained weights without touching tensor versions or the host-side
+        # epoch: an eager forward after training (plots, evaluation) must not hit the packed copies of the step before
+        ops.invalidate_packed_weights()
         return self.loss

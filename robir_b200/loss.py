@@ -14,6 +14,9 @@ class InvLoss(nn.Module):
     def __init__(self, idr_rgb_weight=1.0, eikonal_weight=0.1, mask_weight=100.0, alpha=50.0, sg_rgb_weight=1.0,
                  kl_weight=1.0, latent_smooth_weight=1.0, brdf_multires=10, loss_type='L1'):
         super().__init__()
+        if brdf_multires != 10:
+            raise ValueError("InvLoss: the hit points are re-encoded with 10 frequencies (shipped configs, "
+                             "model/loss.py:20,86); brdf_multires = %r is not supported" % (brdf_multires,))
         self.sg_rgb_weight, self.kl_weight, self.latent_smooth_weight = sg_rgb_weight, kl_weight, latent_smooth_weight
         self.l2 = loss_type == 'L2'
         self.static_shapes = False
@@ -32,9 +35,11 @@ class InvLoss(nn.Module):
         pred = hdr_fn(pred) if hdr_fn is not None else pred / (pred + 1)
         diff = pred - rgb_gt.reshape(-1, 3)
         per = (diff * diff if self.l2 else diff.abs()) * nm[:, None]
-        sg_rgb_loss = per.sum() / float(model_outputs['object_mask'].shape[0])
-        smooth = (model_outputs['diffuse_albedo'] - model_outputs['random_xi_diffuse_albedo']).abs().mean() + \
-            (model_outputs['roughness'][..., 0] - model_outputs['random_xi_roughness'][..., 0]).abs().mean() * 0.2
+        # per-ray terms are normalised by the counts of the WHOLE batch (all ranks under dist.STRONG_SHARDING)
+        sg_rgb_loss = per.sum() / rdist.global_count(model_outputs['object_mask'].shape[0], per)
+        smooth = rdist.global_mean((model_outputs['diffuse_albedo'] - model_outputs['random_xi_diffuse_albedo']).abs()) + \
+            rdist.global_mean((model_outputs['roughness'][..., 0] - model_outputs['random_xi_roughness'][..., 0]).abs()) \
+            * 0.2
         enc = mat_model.spec_brdf_encoder_layer if train_spec else mat_model.brdf_encoder_layer
         sm = model_outputs['surface_mask']
 
@@ -210,7 +215,7 @@ def pbr_step_loss(model, loss_fn, model_outputs, ground_truth, train_spec=True):
     out = loss_fn(model_outputs, ground_truth, mat_model=model.envmap_material_network, train_idr=False,
                   train_spec=train_spec, hdr_fn=model.gamma.hdr_shift.hdr2ldr)
     loss = out['loss'] + out['kl_loss'] * 1.0 + out['latent_smooth_loss'] * 0.1
-    return loss + white_loss(model.envmap_material_network.lgtSGs), out
+    return loss + rdist.param_only(white_loss(model.envmap_material_network.lgtSGs)), out
 
 
 def query_indir_illum(lgtSGs, sample_dirs):

@@ -244,8 +244,8 @@ class SparseAE(nn.Module):
         """The BRDF auto-encoder of EnvmapMaterialNetwork on raw points (sg_envmap_material.py:214-232): encoder chain,
         fused latent pair, decoder chain on the doubled batch, fused output head -> the six material tensors + z."""
         train = self._wants_grad() if train is None else train
-        if not self.smooth_on_latent or self.latent_dim != 32 or self.var is not None or \
-                self.lc_act is not torch.sigmoid or self.out_act is not torch.sigmoid:
+        sig = (torch.sigmoid, F.sigmoid)
+        if not self.smooth_on_latent or self.latent_dim != 32 or self.lc_act not in sig or self.out_act not in sig:
             y, y_r, z = self.forward_points(points, "pe10", train=train)
             return dict(z=z, sg_roughness=y[..., 3:4] * 0.9 + 0.09, sg_metallic=y[..., 4:5] * 0.99 + 0.01,
                         sg_diffuse_albedo=y[..., :3], random_xi_roughness=y_r[..., 3:4] * 0.9 + 0.09,

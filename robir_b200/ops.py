@@ -749,6 +749,8 @@ def octree_cast(tree, rays_o, rays_d, max_iter=-1, o_div=1, return_stats=False):
     out_t, out_x = _empty(K, like=dev), _empty(K, 3, like=dev)
     out_hit = _empty(K, dtype=torch.uint8, like=dev)
     if K == 0:
+        if return_stats:
+            return out_x, out_hit.bool(), out_t, _zeros(lib().robir_octree_counters_len(), dtype=torch.int32, like=dev)
         return out_x, out_hit.bool(), out_t
     st_t, st_p = _empty(K, like=dev), _empty(K, dtype=torch.int32, like=dev)
     counters = _zeros(lib().robir_octree_counters_len(), dtype=torch.int32, like=dev)

@@ -13,6 +13,7 @@ import torch
 _mode = "cpu"
 _tape = None
 _record = None
+_record_on_device = False
 
 
 def set_mode(mode):
@@ -34,13 +35,17 @@ def replay(tensors):
 
 
 @contextlib.contextmanager
-def record():
-    global _record
-    _record = []
+def record(on_device=False):
+    """Collect every drawn tensor, in call order.  on_device=False: host copies (one D2H per draw; not capturable).
+    on_device=True: the drawn device tensors themselves, nothing else changes -- usable around a CUDA-graph capture:
+    the tensors then belong to the graph and hold, after each replay, the numbers that replay used (the parity tests
+    read the randoms of the benchmarked graph step this way)."""
+    global _record, _record_on_device
+    _record, _record_on_device = [], on_device
     try:
         yield _record
     finally:
-        _record = None
+        _record, _record_on_device = None, False
 
 
 def _draw(fn, shape, device):
@@ -54,7 +59,7 @@ def _draw(fn, shape, device):
     else:
         out = fn(shape).to(device, non_blocking=True)
     if _record is not None:
-        _record.append(out.detach().cpu().clone())
+        _record.append(out if _record_on_device else out.detach().cpu().clone())
     return out
 
 
@@ -65,7 +70,7 @@ def rand(shape, device):
 def rand_pairs(n, S, device):
     """theta, phi for two consecutive get_specular_visibility calls, stacked: ([2n, S], [2n, S]).  Host / replay modes
     draw theta_1, phi_1, theta_2, phi_2 in the reference's order; the device mode draws each stack at once."""
-    if _mode == "device" and _record is None:
+    if _mode == "device" and (_record is None or _record_on_device):
         return rand((2 * n, S), device), rand((2 * n, S), device)
     u = [rand((n, S), device) for _ in range(4)]
     return torch.cat([u[0], u[2]], 0), torch.cat([u[1], u[3]], 0)

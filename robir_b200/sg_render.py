@@ -26,6 +26,16 @@ def _weights_of(VisModel):
     return w
 
 
+def _batch_min(sg_range):
+    """The specular sampler's cone scale is a minimum over the WHOLE batch (model/sg_render.py:220-222): under
+    dist.STRONG_SHARDING the ranks hold slices of one batch, so the minimum is all-reduced; its gradient stays with the
+    rank that owns the minimum."""
+    if not rdist._strong():
+        return sg_range
+    g = rdist.allreduce_min_scalar(sg_range.detach().clone())
+    return torch.where(sg_range <= g, sg_range, g)
+
+
 def _norm_axis(x):
     return x / (torch.norm(x, dim=-1, keepdim=True) + TINY_NUMBER)
 
@@ -85,7 +95,7 @@ def get_specular_visibility(points, normals, viewdirs, VisModel, lgtSGLobes, lgt
     ref_dir = _spec_frame(normals, viewdirs)
     sharp = torch.clip(lgtSGLambdas[:, 0], min=0.1, max=50)
     sharp_for_min = sharp if valid is None else torch.where(valid, sharp, torch.full_like(sharp, float("inf")))
-    sg_range = torch.clamp(sharp_for_min.min(), max=1).reshape(1)
+    sg_range = _batch_min(torch.clamp(sharp_for_min.min(), max=1).reshape(1))
     u_theta = rng.rand((n, nsamp), dev)
     u_phi = rng.rand((n, nsamp), dev)
     dirs, w = ops.sample_dirs(ref_dir, lgtSGLobes, sharp, sharp, sg_range, u_theta, u_phi, False)
@@ -175,6 +185,7 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
         S = 8
         dev = points.device
         ref, wl2, sharp, sg_range = ops.spec_prep(normal, viewdirs, roughness, valid)
+        sg_range = _batch_min(sg_range)
         u_theta, u_phi = rng.rand_pairs(n, S, dev)           # theta, phi (direct), theta, phi (indirect)
         dirs, w = ops.sample_dirs(ref, wl2, sharp, sharp, sg_range, u_theta, u_phi, False)
         need_grad = torch.is_grad_enabled() and not testing and (dirs.requires_grad or w.requires_grad)
