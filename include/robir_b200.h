@@ -162,20 +162,23 @@ int robir_vis_mlp_bwd(const int* rowB, const int* n_tiles, int max_tiles, const 
                       const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
                       int sm_count, void* stream);
 
-/* ---- a10-a12, tensor-core engine (tcgen05 + TMEM, bf16 hi/lo 3-term split = fp32 parity): same contract as
- * robir_vis_mlp_fwd/bwd over 128-row tiles.  Weight images are built once per weight version with
- * robir_tc_pack_layer: forward = W1, W2, W3 (transpose=0); backward = W3^T, W2^T, W1^T (transpose=1) followed by the
- * 64-row image of W0[:, 63:126]^T.  mask words: [rows][4][8], word w bit i = sign of hidden unit 32 w + i. */
-int robir_tc_pack_layer(const float* W, int ldw, int N, int K, int transpose, int n_halves, void* img, void* stream);
-int robir_tc_image_bytes(int n_layers256, int n_layers64);
+/* ---- a10-a12, tensor-core engine (tcgen05 + TMEM): same contract as robir_vis_mlp_fwd/bwd over 128-row tiles.
+ * terms = 3: fp32-parity mode -- every product is hi*hi + lo*hi + hi*lo on power-of-two-scaled fp16 operands (22
+ * mantissa bits per operand, fp32 accumulation); terms = 1: single-pass fp16 fast mode (~1e-4, not the parity mode).
+ * Weight images are built once per weight version with robir_tc_pack_layer (same terms): forward = W1, W2, W3
+ * (transpose=0); backward = W3^T, W2^T, W1^T (transpose=1) followed by the 64-row image of W0[:, 63:126]^T
+ * (n_halves=1).  mask words: [tiles][4][8][128 rows], word w bit (31 - i) = sign of hidden unit 32 w + i. */
+int robir_tc_pack_layer(const float* W, int ldw, int N, int K, int transpose, int n_halves, int terms, void* img,
+                        void* stream);
+int robir_tc_image_bytes(int n_layers256, int n_layers64, int terms);
 int robir_vis_tc_fwd(const float* tabA, const float* tabB, const int* rowA, const int* rowB, const int* n_tiles,
                      int max_tiles, const void* img, const float* bias3x256, const float* wd, const float* bd,
-                     float* vis, uint32_t* mask, int sm_count, void* stream);
+                     float* vis, uint32_t* mask, int terms, int sm_count, void* stream);
 int robir_vis_tc_bwd(const int* rowB, const int* n_tiles, int max_tiles, const void* img, const float* wd,
                      const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
-                     int sm_count, void* stream);
+                     int terms, int sm_count, void* stream);
 /* unit-test hook: D[128][256] = A[128][256] . W[256][256]^T through the same pipeline (one layer image) */
-int robir_tc_selftest(const float* A, const void* img, float* D, void* stream);
+int robir_tc_selftest(const float* A, const void* img, float* D, int terms, void* stream);
 
 /* ---- a10/a11: weighted per-lobe / per-point means (model/sg_render.py:180-183, :283-294) -------------------------- */
 int robir_diffuse_reduce_fwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,

@@ -103,11 +103,11 @@ _SIGNATURES = {
     "robir_spec_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "robir_spec_prep_fwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_spec_prep_bwd": [_I, _P, _P, _P, _P, _P, _P, _P],
-    "robir_tc_pack_layer": [_P, _I, _I, _I, _I, _I, _P, _P],
-    "robir_tc_image_bytes": [_I, _I],
-    "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P],
-    "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
-    "robir_tc_selftest": [_P, _P, _P, _P],
+    "robir_tc_pack_layer": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "robir_tc_image_bytes": [_I, _I, _I],
+    "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "robir_tc_selftest": [_P, _P, _P, _I, _P],
     "robir_pack_pad": [_P, _I, _I, _P, _I, _I, _P],
     "robir_mlp_fwd": [POINTER(MlpParams), _I, _P],
     "robir_mlp_bwd": [POINTER(MlpParams), _I, _P],

@@ -4,6 +4,7 @@
 // copy_sm100.hpp, tmem_allocator_sm100.hpp, cutlass/arch/barrier.h).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace robir {
@@ -91,6 +92,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16, A = B = fp16 (K-major), D = f32, M x N
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // one lane of a converged warp (cute::elect_one_sync)
 __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
@@ -139,6 +145,31 @@ __device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uin
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
+// ---- fp16 hi/lo split (operands are pre-scaled into fp16's normal range by the caller) --------------------------------
+// hi = f16_rn(x), lo = f16_rn(x - hi); both packed two per register (low 16 bits = x0).
+__device__ __forceinline__ uint32_t pack_f16(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+__device__ __forceinline__ void split_pack_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(x0, x1);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(x0 - h.x, x1 - h.y);
+}
+
+// packed fp32 pair FMA (FFMA2 on sm_100)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 
 }  // namespace tc

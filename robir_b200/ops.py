@@ -116,33 +116,42 @@ class VisWeights:
             W4, b4 = f32(L[4].weight), f32(L[4].bias)
             d["wd"] = (W4[1] - W4[0]).contiguous()
             d["bd"] = (b4[1] - b4[0]).reshape(1).contiguous()
-            # tensor-core engine: pre-swizzled bf16 hi/lo weight images (csrc/vis_tc.cu)
-            stage = 32768
-            fwd = torch.empty(3 * 8 * stage, dtype=torch.uint8, device=W0.device)
-            bwd = torch.zeros(4 * 8 * stage, dtype=torch.uint8, device=W0.device)
-            for j, i in enumerate((1, 2, 3)):
-                tc_pack_layer(d["W%d" % i], 256, 256, 256, False, 2, fwd[j * 8 * stage:])
-            for j, i in enumerate((3, 2, 1)):
-                tc_pack_layer(d["W%d" % i], 256, 256, 256, True, 2, bwd[j * 8 * stage:])
+            # tensor-core engines: pre-swizzled, power-of-two-scaled fp16 weight images in streaming order
+            # (csrc/vis_tc.cu); terms = 3 -> hi/lo (fp32 parity, engine "tc"), terms = 1 -> hi only (engine "tc1")
             W0c = f32(W0)
-            tc_pack_layer(W0c.reshape(-1)[63:], 126, 63, 256, True, 1, bwd[3 * 8 * stage:])
-            d["tc_fwd"], d["tc_bwd"] = fwd, bwd
+            for terms in (3, 1):
+                sb = lib().robir_tc_image_bytes(1, 0, terms)
+                fwd = torch.empty(lib().robir_tc_image_bytes(3, 0, terms), dtype=torch.uint8, device=W0.device)
+                bwd = torch.zeros(lib().robir_tc_image_bytes(3, 1, terms), dtype=torch.uint8, device=W0.device)
+                for j, i in enumerate((1, 2, 3)):
+                    tc_pack_layer(d["W%d" % i], 256, 256, 256, False, 2, fwd[j * sb:], terms)
+                for j, i in enumerate((3, 2, 1)):
+                    tc_pack_layer(d["W%d" % i], 256, 256, 256, True, 2, bwd[j * sb:], terms)
+                tc_pack_layer(W0c.reshape(-1)[63:], 126, 63, 256, True, 1, bwd[3 * sb:], terms)
+                d["tc_fwd%d" % terms], d["tc_bwd%d" % terms] = fwd, bwd
             d["bias3"] = torch.stack([d["b1"], d["b2"], d["b3"]]).contiguous()
             return d
         return self.cache.get(tensors, build)
 
 
-def tc_pack_layer(W, ldw, N, K, transpose, n_halves, out):
-    check(lib().robir_tc_pack_layer(ptr(W), ldw, N, K, int(transpose), n_halves, ptr(out), stream()))
+def vis_engine_terms(engine=None):
+    """MMA terms per logical product of the visibility engine: 3 = fp32-parity split ("tc"), 1 = fast mode ("tc1")."""
+    engine = ENGINE["vis"] if engine is None else engine
+    return {"tc": 3, "tc1": 1}.get(engine, 0)
 
 
-def tc_selftest(A, W):
-    """D[128,256] = A[128,256] @ W[256,256]^T through the tcgen05 machinery (bf16x3 split) -- unit test hook."""
+def tc_pack_layer(W, ldw, N, K, transpose, n_halves, out, terms=3):
+    check(lib().robir_tc_pack_layer(ptr(W), ldw, N, K, int(transpose), n_halves, terms, ptr(out), stream()))
+
+
+def tc_selftest(A, W, terms=3):
+    """D[128,256] = A[128,256] @ W[256,256]^T through the tcgen05 machinery (terms = 3: scaled fp16 hi/lo split, fp32
+    parity; terms = 1: single-pass fp16) -- unit test hook."""
     A, W = f32(A), f32(W)
-    img = torch.empty(8 * 32768, dtype=torch.uint8, device=A.device)
-    tc_pack_layer(W, 256, 256, 256, False, 2, img)
+    img = torch.empty(lib().robir_tc_image_bytes(1, 0, terms), dtype=torch.uint8, device=A.device)
+    tc_pack_layer(W, 256, 256, 256, False, 2, img, terms)
     D = torch.zeros(128, 256, device=A.device)
-    check(lib().robir_tc_selftest(ptr(A), ptr(img), ptr(D), stream()))
+    check(lib().robir_tc_selftest(ptr(A), ptr(img), ptr(D), terms, stream()))
     return D
 
 
@@ -265,7 +274,8 @@ class active_rows:
 
 
 # vis: visibility MLP; mlp: the 512-wide encoder / lobe chains of the material and indirect-illumination networks.
-# "tc": tcgen05 bf16 hi/lo 3-term split (fp32 parity, default) | "ffma": exact-fp32 CUDA cores
+# vis: "tc": tcgen05, scaled fp16 hi/lo 3-term split (fp32 parity, default) | "tc1": tcgen05 single-pass fp16 (fast mode,
+# ~1e-4: NOT the parity mode) | "ffma": exact-fp32 CUDA cores.  mlp: "tc" (bf16 hi/lo layer engine) | "ffma"
 # wn: the CESR stage's weight-normed 512-wide chains (shadow_net / normal_net): "tc" | "torch" (cuBLAS cross-check)
 ENGINE = {"vis": "tc", "mlp": "tc", "wn": "tc"}
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
@@ -288,18 +298,19 @@ class _Timed:
 
 
 def tile_rows():
-    return 128 if ENGINE["vis"] == "tc" else 64
+    return 128 if ENGINE["vis"] in ("tc", "tc1") else 64
 
 
 def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
     rows = max_tiles * tile_rows()
     vis = _empty(rows, like=tabA)
     mask = _empty(rows, 4, 8, dtype=torch.int32, like=tabA) if need_mask else None
-    if ENGINE["vis"] == "tc":
+    terms = vis_engine_terms()
+    if terms:
         with _Timed("vis_mlp_fwd", max_tiles):
             check(lib().robir_vis_tc_fwd(ptr(tabA), ptr(tabB), ptr(rowA), ptr(rowB), ptr(n_tiles), max_tiles,
-                                         ptr(W["tc_fwd"]), ptr(W["bias3"]), ptr(W["wd"]), ptr(W["bd"]), ptr(vis),
-                                         ptr(mask), sm_count(), stream()))
+                                         ptr(W["tc_fwd%d" % terms]), ptr(W["bias3"]), ptr(W["wd"]), ptr(W["bd"]),
+                                         ptr(vis), ptr(mask), terms, sm_count(), stream()))
         return vis, mask
     with _Timed("vis_mlp_fwd", max_tiles):
         check(lib().robir_vis_mlp_fwd(ptr(tabA), ptr(tabB), ptr(rowA), ptr(rowB), ptr(n_tiles), max_tiles,
@@ -311,10 +322,12 @@ def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
 
 def _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs, engine):
     g_dirs = _zeros(dirs.shape[0], 3, like=dirs)
-    if engine == "tc":
+    terms = vis_engine_terms(engine)
+    if terms:
         with _Timed("vis_mlp_bwd", max_tiles):
-            check(lib().robir_vis_tc_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["tc_bwd"]), ptr(W["wd"]), ptr(vis),
-                                         ptr(g_vis), ptr(mask), ptr(dirs), ptr(g_dirs), sm_count(), stream()))
+            check(lib().robir_vis_tc_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["tc_bwd%d" % terms]), ptr(W["wd"]),
+                                         ptr(vis), ptr(g_vis), ptr(mask), ptr(dirs), ptr(g_dirs), terms, sm_count(),
+                                         stream()))
         return g_dirs
     with _Timed("vis_mlp_bwd", max_tiles):
         check(lib().robir_vis_mlp_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["W1"]), ptr(W["W2"]), ptr(W["W3"]),
@@ -342,7 +355,7 @@ class _DiffuseVis(torch.autograd.Function):
         rowB = _empty(n * cap, dtype=torch.int32, like=dev)
         n_tiles = _zeros(1, dtype=torch.int32, like=dev)
         # tensor-core engine: points packed back to back (rows of one tile may belong to two points)
-        check(lib().robir_diffuse_rows(n, M, S, T, 0 if ENGINE["vis"] == "tc" else 1, ptr(normals), ptr(dirs), ptr(bits),
+        check(lib().robir_diffuse_rows(n, M, S, T, 0 if vis_engine_terms() else 1, ptr(normals), ptr(dirs), ptr(bits),
                                        ptr(lobe_off), ptr(start),
                                        ptr(rowA), ptr(rowB), ptr(n_tiles), ptr(Stats.pairs_tensor(dev)), stream()))
         tabA = point_table(W, points)

@@ -211,7 +211,7 @@ class IDRNetwork(nn.Module):
                 lgt = torch.cat((lgt[..., :1], torch.abs(lgt[..., 1:2]), lgt[..., 2:]), dim=-1)
             lobes, lambdas = sg_render.light_lobes(lgt)
             dirs, w = sg_render.sample_diffuse_dirs(lobes, lambdas, 32, dev)
-            if ops.ENGINE["vis"] != "tc":
+            if not ops.vis_engine_terms():
                 return dirs, w
             W = sg_render._weights_of(self.visibility_network).get()
             return dirs, w, ops.pe_linear(dirs.detach(), W["Wt0d"], None)

@@ -1,6 +1,8 @@
 """-m gpu parity tests: the CUDA product (through the C ABI) against the CPU oracle on identical seeded inputs, and
 against the golden vectors generated from the unmodified reference.  Tolerances follow BASELINE.json north_star:
 <= 1e-4 relative for fp32 outputs (rel = |a-b| / max(|b|_max, 1)); tracer masks must agree exactly on the same tree."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -20,26 +22,35 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
 
 
+_ERR_LOG = os.environ.get("ROBIR_ERR_LOG")
+
+
 def grad_close(a, b, l2=3e-3, linf=3e-2, engine="ffma"):
     """Gradients that pass through the ReLU visibility MLP are only piecewise continuous: a hidden unit whose
-    pre-activation is ~0 can take a different sign on the GPU than in the CPU oracle (fp32 rounding), which changes a
-    few entries by O(weight x upstream) while everything else agrees to ~1e-6 (the fp32-vs-fp64 oracle shows the same
-    effect).  Hence: tight relative L2, looser relative max.  The tensor-core engine represents every operand with 16
-    mantissa bits (bf16 hi+lo), so its pre-activations differ from fp32 by ~1e-5 relative instead of ~1e-7 and
-    proportionally more borderline units flip: its gradient bounds are 4x wider (forward outputs stay < 1e-4)."""
-    if engine == "tc":
+    pre-activation is ~0 can take a different sign on the GPU than in the CPU oracle, which changes a few entries by
+    O(weight x upstream) while everything else agrees to ~1e-6.  How often that happens is set by the relative error of
+    the pre-activations: ~1e-7 for fp32 and for the tensor-core engine's scaled fp16 hi/lo split (22 mantissa bits per
+    operand; no flip in 2e7 units in tools/vis_numerics_study.py), ~1e-5 for the bf16 hi/lo split of round 1 (26 flips,
+    gradient rel L2 2e-3; with the oracle's masks forced the same backward agrees to 7e-6 -- test_numerics_study.py).
+    Both engines are therefore held to the same bounds now."""
+    if engine == "tc_bf16":      # the per-layer engine of the 512-wide chains still splits into bf16 hi/lo (16 bits)
         l2, linf = 4 * l2, 4 * linf
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     scale = max(b.abs().max().item(), 1e-12)
     e2 = (a - b).norm().item() / max(b.norm().item(), 1e-12)
     ei = (a - b).abs().max().item() / scale
+    if _ERR_LOG:
+        import inspect
+        with open(_ERR_LOG, "a") as f:
+            f.write("%-50s %-5s relL2 %.3e relmax %.3e (bounds %.1e %.1e)\n" %
+                    (inspect.stack()[1].function, engine, e2, ei, l2, linf))
     assert torch.isfinite(a).all(), "non-finite gradient"
     assert e2 < l2 and ei < linf, "gradient mismatch: rel L2 %.3e (< %.1e), rel max %.3e (< %.1e)" % (e2, l2, ei, linf)
 
 
 def ops_engine_mlp():
     from robir_b200 import ops
-    return ops.ENGINE["mlp"]
+    return "tc_bf16" if ops.ENGINE["mlp"] == "tc" else ops.ENGINE["mlp"]
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +70,7 @@ def test_extension_is_loaded():
 
 @pytest.fixture(params=["ffma", "tc"])
 def engine(request):
-    """Both visibility-MLP engines: exact-fp32 FFMA and tcgen05 bf16x3 (the fp32-parity tensor-core mode)."""
+    """Both fp32-parity visibility-MLP engines: exact-fp32 FFMA and tcgen05 scaled-fp16 hi/lo x3."""
     from robir_b200 import ops
     old = ops.ENGINE["vis"]
     ops.ENGINE["vis"] = request.param
@@ -67,16 +78,19 @@ def engine(request):
     ops.ENGINE["vis"] = old
 
 
-def test_tc_gemm_selftest():
-    """tcgen05 machinery in isolation: TMEM-resident A (bf16 hi/lo), swizzled weight ring, 3-term split."""
+@pytest.mark.parametrize("terms,tol", [(3, 2e-6), (1, 2e-3)])
+def test_tc_gemm_selftest(terms, tol):
+    """tcgen05 machinery in isolation: TMEM-resident A, swizzled weight ring in streaming order, scaled fp16 operands.
+    terms = 3: hi/lo 3-term split -- fp32-class accuracy (the bf16 split of round 1 sat at 3e-5 here);
+    terms = 1: single-pass fp16 fast mode."""
     from robir_b200 import ops
     gen = torch.Generator().manual_seed(21)
     A = torch.randn(128, 256, generator=gen)
     W = torch.randn(256, 256, generator=gen) / 16
-    D = ops.tc_selftest(A.cuda(), W.cuda()).cpu()
+    D = ops.tc_selftest(A.cuda(), W.cuda(), terms).cpu()
     ref = (A.double() @ W.double().t()).float()
     err = (D - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 3e-5, "tcgen05 GEMM self-test: max rel err %.3e" % err
+    assert err < tol, "tcgen05 GEMM self-test (terms=%d): max rel err %.3e" % (terms, err)
 
 
 def test_sdf_network(golden, synth_sd16, model16):
@@ -792,7 +806,7 @@ def test_tc_layer_engine_matches_ffma_chain(model16):
             for a, b in zip(res["tc"][0], res["ffma"][0]):
                 assert rel_err(a, b) < REL, (n, n_act, rel_err(a, b))
             for a, b in zip(res["tc"][1], res["ffma"][1]):
-                grad_close(a, b, 2e-3, 2e-2, engine="tc")
+                grad_close(a, b, 2e-3, 2e-2, engine="tc_bf16")
     finally:
         ops.ENGINE["mlp"] = "tc"
         ind.train_weights = False
@@ -880,7 +894,7 @@ def test_wn_chain_vs_oracle(which, rows, wn_engine):
     assert rel_err(out, ref) < REL, rel_err(out, ref)
     for k, p in net.named_parameters():
         assert p.grad is not None, k
-        grad_close(p.grad, sdr[k].grad, 1e-3, 1e-2, engine="tc" if wn_engine == "tc" else "ffma")
+        grad_close(p.grad, sdr[k].grad, 1e-3, 1e-2, engine="tc_bf16" if wn_engine == "tc" else "ffma")
 
 
 @pytest.fixture(scope="module")
@@ -930,7 +944,7 @@ def test_cesr_step_vs_golden(golden, model128, wn_engine, case):
     assert abs(loss.item() - g["loss"].item()) < 1e-4 * max(1.0, abs(g["loss"].item()))
     loss.backward()
     mat = model128.envmap_material_network
-    eng = "tc" if wn_engine == "tc" else "ffma"
+    eng = "tc_bf16" if wn_engine == "tc" else "ffma"
     checks = []
     if cur_iter > 500:
         checks = [(mat.lgtSGs.grad, g["g_lgtSGs"]), (mat.specular_reflectance.grad, g["g_spec"]),
