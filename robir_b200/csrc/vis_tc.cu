@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   constexpr int kXLayer = 2;                            // the layer during which X's K-half 0 dies (fwd: last, bwd: L2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[NST], empty_bar[NST], a_ready[2], d_full[2], d_free[2], x_free;
+  __shared__ uint64_t full_bar[NST], empty_bar[NST], s_ready[2], a_ready[2], d_full[2], d_free[2], x_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[3 * 256];
   __shared__ __align__(16) float s_wd[256];
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&a_ready[0], 256); mbar_init(&a_ready[1], 256);
+    mbar_init(&s_ready[0], 256); mbar_init(&s_ready[1], 256);
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
     mbar_init(&d_free[0], 256); mbar_init(&d_free[1], 256);
     mbar_init(&x_free, 1);
@@ -164,17 +165,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     // The whole warp runs the loop converged and one elected lane issues (elect.sync): tcgen05.mma / commit are
     // warp-uniform instructions, and inside a divergent `if (lane == 0)` ptxas wraps every one of them in an
     // ELECT / BRA.U.ANY retry loop (~75 issue cycles per MMA).
+    // A-operand hand-offs: s_ready[kh] = K-half kh of a tile's FIRST operand (written one tile ahead, possibly before the
+    // previous tile's last epilogues), a_ready[kh] = K-half kh produced by a layer epilogue of the current tile.  They are
+    // separate barriers because in the backward the next tile's first operand is ready before this tile's last hand-off.
     uint32_t it = 0, a_phase = 0, tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
-      for (int layer = 0; layer < kLayers; ++layer, ++a_phase) {
+      for (int layer = 0; layer < kLayers; ++layer) {
+        uint64_t* ready = layer == 0 ? s_ready : a_ready;
+        const uint32_t ready_par = (layer == 0 ? tile_it : a_phase) & 1;
+        if (layer > 0) ++a_phase;
         const uint32_t a_half = tmem_base + ((layer & 1) ? 256u : 0u);
         const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
         const bool last64 = (MODE == 1 && layer == 3);
         const int nst = last64 ? 4 : 8;
         for (int j = 0; j < nst; ++j, ++it) {
           const int nh = last64 ? 0 : tc_stage_nh(j), kb = last64 ? j : tc_stage_kb(j);
-          if (j == 0) mbar_wait(&a_ready[0], a_phase & 1);                       // K-half 0 of A is in TMEM
-          if (j == (last64 ? 2 : 4)) mbar_wait(&a_ready[1], a_phase & 1);        // K-half 1
+          if (j == 0) mbar_wait(&ready[0], ready_par);                           // K-half 0 of A is in TMEM
+          if (j == (last64 ? 2 : 4)) mbar_wait(&ready[1], ready_par);            // K-half 1
           if (MODE == 0 && layer == 0 && kb == 0) mbar_wait(&d_free[nh], (tile_it & 1) ^ 1);  // D half drained
           const int st = it % NST;
           mbar_wait(&full_bar[st], (it / NST) & 1);
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&a_ready[kh]);
+      mbar_arrive(&s_ready[kh]);
     };
 
     if (blockIdx.x < ntiles) {

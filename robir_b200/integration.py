@@ -65,7 +65,7 @@ def install(model, patch_modules=True, stage="PBR"):
         if old is None:
             continue
         if hasattr(old, "max_iter"):
-            new = tracing.OctreeTracing(max_iter=old.max_iter)
+            new = tracing.OctreeTracing(max_iter=old.max_iter).bind(net)
         else:                             # use_octree=False: the IDR sphere tracer (model/ray_tracing.py, row a3)
             from .sphere_tracing import RayTracing
             new = RayTracing(object_bounding_sphere=old.object_bounding_sphere, sdf_threshold=old.sdf_threshold,

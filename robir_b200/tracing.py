@@ -83,6 +83,13 @@ class OctreeTracing(nn.Module):
         self.max_iter = max_iter
         self.sdf_octree = None
         self.last_counters = None
+        self._net = None
+
+    def bind(self, implicit_network):
+        """Remember the network whose fused value + normal kernel builds the tree when ``generate`` is called the
+        reference's way, with a bare ``lambda x: model.implicit_network(x)[:, 0]`` (train_pbr.py:403-407)."""
+        self.__dict__["_net"] = implicit_network        # not a sub-module: state_dict keys stay the reference's
+        return self
 
     def generate(self, sdf_fn, tex_sampler=None, implicit_network=None):
         """Build the octree.  ``implicit_network`` (ours) gives value+normal in one fused kernel; with a bare sdf_fn the
@@ -93,7 +100,8 @@ class OctreeTracing(nn.Module):
             m = tex_sampler.tex_sampler.mask.view(-1) > 0.9
             box_max = [c.item() + 1e-3 for c in v[m].max(0)[0]]
             box_min = [c.item() - 1e-3 for c in v[m].min(0)[0]]
-        net = implicit_network if implicit_network is not None else getattr(sdf_fn, "__self__", None)
+        net = implicit_network if implicit_network is not None else (
+            self._net if self._net is not None else getattr(sdf_fn, "__self__", None))
         if net is not None and hasattr(net, "sdf_and_normal"):
             device = next(net.parameters()).device
 

@@ -116,12 +116,14 @@ def _vis_fn(sd):
     return lambda p, d: O.vis_network(sd, p, d)
 
 
-def test_vis_mlp_backward_stagewise(synth_sd16, model16, engine):
-    """Hot-kernel backward in isolation: d out / d sample_dir and d out / d weight against the oracle's autograd."""
+@pytest.mark.parametrize("n", [37, 700])
+def test_vis_mlp_backward_stagewise(synth_sd16, model16, engine, n):
+    """Hot-kernel backward in isolation: d out / d sample_dir and d out / d weight against the oracle's autograd.
+    n = 700 gives ~1400 tiles: every persistent CTA of the tensor-core engine walks ~10 tiles (cross-tile hand-offs)."""
     from robir_b200 import ops, sg_render
     sd = synth_sd16
     gen = torch.Generator().manual_seed(13)
-    n, M, S = 37, 16, 32
+    M, S = 16, 32
     pts = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1) * 0.33
     nrm = torch.nn.functional.normalize(pts + 0.1 * torch.randn(n, 3, generator=gen), dim=-1)
     dirs = torch.nn.functional.normalize(torch.randn(M * S, 3, generator=gen), dim=-1)
