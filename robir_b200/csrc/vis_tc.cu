@@ -354,10 +354,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         }
         if (last64) {
           // ---- backward tail (epilogue group 0 only): dPE[0..63] in X[128, 192) -> d dir via the PE jacobian
+          // (every epilogue thread observes the phase: a waiter may never fall two phases behind an mbarrier, or the
+          // parity test of its next wait aliases)
+          mbar_wait(&d_full[0], d_phase[0] & 1);
           ++d_phase[0];
+          tc_fence_after();
           if (ch == 0) {
-            mbar_wait(&d_full[0], (d_phase[0] - 1) & 1);
-            tc_fence_after();
             uint32_t r0[32], r1[32];
             tmem_ld32(tmem_base + 128u + lane_addr, r0);
             tmem_ld32(tmem_base + 160u + lane_addr, r1);

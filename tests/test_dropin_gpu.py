@@ -20,41 +20,27 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
 
 
-def _iteration(R, inp, gt, seed):
-    torch.manual_seed(seed)                      # the reference draws every random tensor on the CPU generator
+def _iteration(R, inp, gt, seed=None, tape=None):
     for p in R.model.parameters():
         p.grad = None
-    out, loss = R.forward_loss(inp, gt)
+    if tape is not None:                         # the reference's own recorded draws (golden fixture), in call order
+        with ref_shim.ReplayRandom(tape):
+            out, loss = R.forward_loss(inp, gt)
+    else:
+        torch.manual_seed(seed)                  # the reference draws every random tensor on the CPU generator
+        out, loss = R.forward_loss(inp, gt)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in R.model.named_parameters() if p.grad is not None}
     return {k: v.detach().clone() for k, v in out.items()}, float(loss), grads
 
 
-@pytest.mark.parametrize("M,N", [(16, 160), (128, 512)])
-def test_install_on_live_reference_model(M, N):
-    import ref_runner
-    import robir_b200
-    from robir_b200 import _lib, integration, ops
-    sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=M)
-    R = ref_runner.ReferencePBR(sd, M, device="cuda", optimizer=False)
-    R.generate()
-    keys_before = list(R.model.state_dict().keys())
-    inp = synthetic.camera_inputs(synthetic.training_pixels(31, n=N, crop=400))
-    inp.pop("hdr_shift")
-    gt = {"rgb": torch.rand(1, N, 3, generator=torch.Generator().manual_seed(2))}
-    out_ref, loss_ref, g_ref = _iteration(R, inp, gt, 1234)
-    n_hit = int(out_ref["network_object_mask"].sum())
-    assert 0 < n_hit < N
+def _rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
-    robir_b200.install(R.model)
-    try:
-        R.generate()                              # the runner's own call (train_pbr.py:403-407) now builds OUR octree
-        ops.Stats.reset()
-        before = _lib.launch_count
-        out, loss, g = _iteration(R, inp, gt, 1234)
-        launched = _lib.launch_count - before
-    finally:
-        integration.uninstall_modules()
+
+def _compare(R, N, out_ref, loss_ref, g_ref, out, loss, g, launched, n_hit, keys_before, grad_bound):
+    from robir_b200 import ops
     assert launched > 30, "install() did not route the iteration through librobir_b200 (%d launches)" % launched
     assert ops.Stats.total() > 100 * n_hit, "the fused visibility MLP did not run"
     assert list(R.model.state_dict().keys()) == keys_before
@@ -69,11 +55,80 @@ def test_install_on_live_reference_model(M, N):
             continue
         rows = both if v.shape[0] == N else slice(None)
         assert rel_err(out[k][rows], v[rows]) < REL, (k, rel_err(out[k][rows], v[rows]))
+    errs = {}
     if bool((m_ref == m_new).all()):
         assert abs(loss - loss_ref) < 1e-4 * max(1.0, abs(loss_ref))
         trained = [k for k in g_ref if k.startswith("envmap_material_network.") or k.startswith("gamma.")]
         assert len(trained) >= 19
         for k in trained:
-            a, b = g[k].double().cpu(), g_ref[k].double().cpu()
-            e2 = ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
-            assert e2 < 1e-3, ("gradient", k, e2)
+            errs[k] = _rel_l2(g[k], g_ref[k])
+            assert errs[k] < grad_bound, ("gradient", k, errs[k])
+    return errs
+
+
+def _installed_iteration(R, inp, gt, **kw):
+    import robir_b200
+    from robir_b200 import _lib, integration, ops
+    robir_b200.install(R.model)
+    try:
+        R.generate()                              # the runner's own call (train_pbr.py:403-407) now builds OUR octree
+        ops.Stats.reset()
+        before = _lib.launch_count
+        out, loss, g = _iteration(R, inp, gt, **kw)
+        return out, loss, g, _lib.launch_count - before
+    finally:
+        integration.uninstall_modules()
+
+
+def test_install_on_live_reference_model_golden_inputs(golden, synth_sd16):
+    """M = 16, the golden fixture's rays and recorded randoms: three-way comparison.  The golden gradients were produced
+    by the unmodified reference on the CPU; the same unmodified code on the GPU (cuBLAS fp32, different summation
+    order) reproduces them only to ~1e-3 in relative L2 -- borderline ReLU / LeakyReLU units flip between fp32
+    evaluations -- and the installed library must sit within that same band of BOTH."""
+    import ref_runner
+    g = golden("pbr_step")
+    N = g["pix"].shape[0]
+    R = ref_runner.ReferencePBR(synth_sd16, 16, device="cuda", optimizer=False)
+    R.generate()
+    keys_before = list(R.model.state_dict().keys())
+    inp = synthetic.camera_inputs(g["pix"])
+    inp.pop("hdr_shift")
+    gt = {"rgb": g["gt"]}
+    tape = [("r", g["rnd_%d" % i]) for i in range(9)]
+    out_ref, loss_ref, g_ref = _iteration(R, inp, gt, tape=tape)
+    n_hit = int(out_ref["network_object_mask"].sum())
+    out, loss, gr, launched = _installed_iteration(R, inp, gt, tape=tape)
+    _compare(R, N, out_ref, loss_ref, g_ref, out, loss, gr, launched, n_hit, keys_before, grad_bound=5e-3)
+    pre = "envmap_material_network."
+    dec, enc = pre + "spec_brdf_encoder_layer.brdf_decoder_layer.", pre + "spec_brdf_encoder_layer.brdf_encoder_layer."
+    pick = {"g_lgtSGs": lambda d: d[pre + "lgtSGs"], "g_spec": lambda d: d[pre + "specular_reflectance"],
+            "g_adapt": lambda d: d["gamma.hdr_shift.adapt_illum"], "g_dec4_bias": lambda d: d[dec + "4.bias"],
+            "g_dec4_weight": lambda d: d[dec + "4.weight"], "g_enc0_bias": lambda d: d[enc + "0.bias"],
+            "g_enc8_weight_sum": lambda d: d[enc + "8.weight"].sum(0)}
+    print("\nrelative L2 of gradients: reference-GPU vs reference-CPU (golden) | installed vs golden | installed vs reference-GPU")
+    for name, f in pick.items():
+        rr, og, orr = _rel_l2(f(g_ref), g[name]), _rel_l2(f(gr), g[name]), _rel_l2(f(gr), f(g_ref))
+        print("  %-20s %.2e | %.2e | %.2e" % (name, rr, og, orr))
+        assert og < max(3.0 * rr, 1e-3), (name, "installed vs golden", og, "reference vs itself", rr)
+    for k in ("sg_rgb", "indir_rgb", "normals", "roughness", "diffuse_albedo"):
+        assert rel_err(out[k], g["out_" + k]) < REL, k
+
+
+def test_install_on_live_reference_model_m128():
+    """M = 128 light SGs, 512 rays, the reference's own CPU-generator draws under one seed."""
+    import ref_runner
+    M, N = 128, 512
+    sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=M)
+    R = ref_runner.ReferencePBR(sd, M, device="cuda", optimizer=False)
+    R.generate()
+    keys_before = list(R.model.state_dict().keys())
+    inp = synthetic.camera_inputs(synthetic.training_pixels(31, n=N, crop=400))
+    inp.pop("hdr_shift")
+    gt = {"rgb": torch.rand(1, N, 3, generator=torch.Generator().manual_seed(2))}
+    out_ref, loss_ref, g_ref = _iteration(R, inp, gt, seed=1234)
+    n_hit = int(out_ref["network_object_mask"].sum())
+    assert 0 < n_hit < N
+    out, loss, g, launched = _installed_iteration(R, inp, gt, seed=1234)
+    errs = _compare(R, N, out_ref, loss_ref, g_ref, out, loss, g, launched, n_hit, keys_before, grad_bound=5e-3)
+    if errs:
+        print("\ninstalled vs reference-GPU, worst gradient rel L2: %.2e (%s)" % (max(errs.values()), max(errs, key=errs.get)))

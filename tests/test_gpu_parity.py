@@ -144,6 +144,39 @@ def test_vis_mlp_backward_stagewise(synth_sd16, model16, engine, n):
     grad_close(d2.grad, d1.grad, engine=engine)
 
 
+def test_tc1_fast_mode_error_level(synth_sd16, model16):
+    """ENGINE["vis"] = "tc1": single-pass fp16 on the same kernel (one MMA per product instead of three).  NOT the parity
+    mode -- this test pins its error level: visibility within 1e-3 absolute (TF32-class; measured ~1e-4), direction
+    gradient within 10 % relative L2 (borderline ReLU units flip at the 1e-4 level of its pre-activations)."""
+    from robir_b200 import ops, sg_render
+    sd = synth_sd16
+    gen = torch.Generator().manual_seed(14)
+    n, M, S = 300, 16, 32
+    pts = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1) * 0.33
+    nrm = torch.nn.functional.normalize(pts + 0.1 * torch.randn(n, 3, generator=gen), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(M * S, 3, generator=gen), dim=-1)
+    w = torch.rand(M * S, generator=gen) + 0.1
+    gup = torch.randn(n, M, generator=gen)
+    res = {}
+    old = ops.ENGINE["vis"]
+    try:
+        for eng in ("tc", "tc1"):
+            ops.ENGINE["vis"] = eng
+            d2, w2 = dirs.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+            out = ops.diffuse_vis(pts.cuda(), nrm.cuda(), d2, w2, M, S,
+                                  sg_render._weights_of(model16.visibility_network), True)
+            (out * gup.cuda()).sum().backward()
+            res[eng] = (out.detach().cpu(), d2.grad.cpu(), w2.grad.cpu())
+    finally:
+        ops.ENGINE["vis"] = old
+    e_out = (res["tc1"][0] - res["tc"][0]).abs().max().item()
+    e_gd = ((res["tc1"][1] - res["tc"][1]).norm() / res["tc"][1].norm()).item()
+    e_gw = ((res["tc1"][2] - res["tc"][2]).norm() / res["tc"][2].norm()).item()
+    print("\ntc1 (single-pass fp16) vs tc (fp32 parity): light_vis max abs %.2e, d/d dir rel L2 %.2e, d/d w rel L2 %.2e"
+          % (e_out, e_gd, e_gw))
+    assert 0 < e_out < 1e-3 and e_gd < 0.1 and e_gw < 1e-2
+
+
 def test_diffuse_visibility_fwd_bwd(synth_sd16, model16, engine):
     from robir_b200 import rng, sg_render
     sd = synth_sd16
