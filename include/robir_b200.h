@@ -177,6 +177,10 @@ int robir_vis_tc_fwd(const float* tabA, const float* tabB, const int* rowA, cons
 int robir_vis_tc_bwd(const int* rowB, const int* n_tiles, int max_tiles, const void* img, const float* wd,
                      const float* vis, const float* g_vis, const uint32_t* mask, const float* dirs, float* g_dirs,
                      int terms, int sm_count, void* stream);
+/* diagnostics: device buffer [sm_count][8] uint64 that every following vis_tc launch fills with per-CTA stall clocks
+ * (issuer: total / wait weights / wait A operand / wait D drained; epilogue: total / wait accumulators / wait X free;
+ * producer: wait ring slot); NULL = off */
+int robir_tc_debug_buffer(void* buf);
 /* unit-test hook: D[128][256] = A[128][256] . W[256][256]^T through the same pipeline (one layer image) */
 int robir_tc_selftest(const float* A, const void* img, float* D, int terms, void* stream);
 

@@ -108,6 +108,7 @@ _SIGNATURES = {
     "robir_vis_tc_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "robir_tc_selftest": [_P, _P, _P, _I, _P],
+    "robir_tc_debug_buffer": [_P],
     "robir_pack_pad": [_P, _I, _I, _P, _I, _I, _P],
     "robir_mlp_fwd": [POINTER(MlpParams), _I, _P],
     "robir_mlp_bwd": [POINTER(MlpParams), _I, _P],

@@ -103,7 +103,17 @@ struct TcParams {
   const float* g_vis; const float* dirs; float* g_dirs;
   // self-test: plain GEMM D = A . W^T through the same machinery
   const float* test_A; float* test_D;
+  // optional per-CTA stall accounting (robir_tc_debug_buffer): [grid][8] clock counts, see tools/tc_stalls.py
+  unsigned long long* dbg;
 };
+
+__device__ __forceinline__ long long tc_clock() { return clock64(); }
+#define TC_TIMED_WAIT(acc, bar, par)            \
+  do {                                          \
+    const long long _t = tc_clock();            \
+    mbar_wait(bar, par);                        \
+    acc += tc_clock() - _t;                     \
+  } while (0)
 
 template <int MODE, int TERMS>  // MODE 0 = forward, 1 = backward, 2 = self-test (one 256x256 layer)
 __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
@@ -143,6 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   if (warp == 0) {
     // ===================================== weight producer =====================================
     uint32_t it = 0;
+    long long w_empty = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int layer = 0; layer < kLayers; ++layer) {
         const bool last64 = (MODE == 1 && layer == 3);
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         const uint8_t* src = p.img + (size_t)layer * 8 * SB;
         for (int j = 0; j < nst; ++j, ++it) {
           const int st = it % NST;
-          mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
+          TC_TIMED_WAIT(w_empty, &empty_bar[st], ((it / NST) & 1) ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_bar[st], bytes);
             bulk_g2s(ring + (size_t)st * SB, src + (size_t)j * bytes, bytes, &full_bar[st]);
@@ -160,6 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         }
       }
     }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     // The whole warp runs the loop converged and one elected lane issues (elect.sync): tcgen05.mma / commit are
@@ -169,6 +181,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     // previous tile's last epilogues), a_ready[kh] = K-half kh produced by a layer epilogue of the current tile.  They are
     // separate barriers because in the backward the next tile's first operand is ready before this tile's last hand-off.
     uint32_t it = 0, a_phase = 0, tile_it = 0;
+    long long w_full = 0, w_ready = 0, w_dfree = 0;
+    const long long t_begin = tc_clock();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       for (int layer = 0; layer < kLayers; ++layer) {
         uint64_t* ready = layer == 0 ? s_ready : a_ready;
@@ -180,11 +194,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         const int nst = last64 ? 4 : 8;
         for (int j = 0; j < nst; ++j, ++it) {
           const int nh = last64 ? 0 : tc_stage_nh(j), kb = last64 ? j : tc_stage_kb(j);
-          if (j == 0) mbar_wait(&ready[0], ready_par);                           // K-half 0 of A is in TMEM
-          if (j == (last64 ? 2 : 4)) mbar_wait(&ready[1], ready_par);            // K-half 1
-          if (MODE == 0 && layer == 0 && kb == 0) mbar_wait(&d_free[nh], (tile_it & 1) ^ 1);  // D half drained
+          if (j == 0) TC_TIMED_WAIT(w_ready, &ready[0], ready_par);              // K-half 0 of A is in TMEM
+          if (j == (last64 ? 2 : 4)) TC_TIMED_WAIT(w_ready, &ready[1], ready_par);   // K-half 1
+          if (MODE == 0 && layer == 0 && kb == 0) TC_TIMED_WAIT(w_dfree, &d_free[nh], (tile_it & 1) ^ 1);  // D drained
           const int st = it % NST;
-          mbar_wait(&full_bar[st], (it / NST) & 1);
+          TC_TIMED_WAIT(w_full, &full_bar[st], (it / NST) & 1);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint8_t* sb = ring + (size_t)st * SB;
@@ -216,6 +230,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         }
       }
     }
+    if (p.dbg && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 8;
+      d[0] = (unsigned long long)(tc_clock() - t_begin); d[1] = (unsigned long long)w_full;
+      d[2] = (unsigned long long)w_ready; d[3] = (unsigned long long)w_dfree;
+    }
   } else {
     // ===================================== epilogue warps =====================================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
@@ -224,6 +243,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float inv_sw = 1.f / kSW;
     uint32_t d_phase[2] = {0, 0}, x_phase = 0;
+    long long w_dfull = 0, w_xfree = 0;
+    const long long t_begin = tc_clock();
     // per-tile inputs of this row
     int a_idx = 0, b_idx = -1;
     float g0 = 0.f;
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         if (has_next && layer == kXLayer) {
           // next tile's first A operand, K-half 0: X[0, 128) is dead once this layer's 4th stage has completed
           stage0_prefetch(tile_nxt, 0, a_nxt, b_nxt);
-          mbar_wait(&x_free, x_phase & 1);
+          TC_TIMED_WAIT(w_xfree, &x_free, x_phase & 1);
           ++x_phase;
           tc_fence_after();
           stage0_half(tile_nxt, 0, a_nxt, b_nxt);
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           // ---- backward tail (epilogue group 0 only): dPE[0..63] in X[128, 192) -> d dir via the PE jacobian
           // (every epilogue thread observes the phase: a waiter may never fall two phases behind an mbarrier, or the
           // parity test of its next wait aliases)
-          mbar_wait(&d_full[0], d_phase[0] & 1);
+          TC_TIMED_WAIT(w_dfull, &d_full[0], d_phase[0] & 1);
           ++d_phase[0];
           tc_fence_after();
           if (ch == 0) {
@@ -388,7 +409,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&d_full[h], d_phase[h] & 1);
+          TC_TIMED_WAIT(w_dfull, &d_full[h], d_phase[h] & 1);
           ++d_phase[h];
           tc_fence_after();
 #pragma unroll
@@ -452,6 +473,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       if (has_next) stage0_half(tile_nxt, 1, a_nxt, b_nxt);     // X[128, 256): dead since the last layer completed
       a_idx = a_nxt; b_idx = b_nxt; g0 = g_nxt;
     }
+    if (p.dbg && warp == 2 && lane == 0) {
+      unsigned long long* d = p.dbg + blockIdx.x * 8;
+      d[4] = (unsigned long long)(tc_clock() - t_begin); d[5] = (unsigned long long)w_dfull;
+      d[6] = (unsigned long long)w_xfree;
+    }
   }
   // ---- teardown
   tc_fence_before();
@@ -466,8 +492,11 @@ using namespace robir;
 
 static constexpr int kTcSmem = kTcRingBytes + 1024;
 
+static unsigned long long* g_tc_dbg = nullptr;
+
 template <int MODE, int TERMS>
-static int launch_tc(const TcParams& p, int grid, void* stream) {
+static int launch_tc(TcParams p, int grid, void* stream) {
+  p.dbg = g_tc_dbg;
   RB_CHECK_CUDA(cudaFuncSetAttribute(vis_tc_kernel<MODE, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
   vis_tc_kernel<MODE, TERMS><<<grid, kTcThreads, kTcSmem, (cudaStream_t)stream>>>(p);
   RB_CHECK_CUDA(cudaGetLastError());
@@ -520,6 +549,14 @@ int robir_vis_tc_bwd(const int* rowB, const int* n_tiles, int max_tiles, const v
   p.g_vis = g_vis; p.mask = const_cast<uint32_t*>(mask); p.dirs = dirs; p.g_dirs = g_dirs;
   const int grid = max_tiles < sm_count ? max_tiles : sm_count;
   return terms == 3 ? launch_tc<1, 3>(p, grid, stream) : launch_tc<1, 1>(p, grid, stream);
+}
+
+// Diagnostics: device buffer of [sm_count][8] 64-bit clock counts that every following vis_tc launch overwrites
+// (issuer: total, wait weights, wait A operand, wait D drained; epilogue warp 2: total, wait accumulators, wait X free;
+// producer: wait ring slot); NULL switches it off.  tools/tc_stalls.py prints the breakdown.
+int robir_tc_debug_buffer(void* buf) {
+  g_tc_dbg = (unsigned long long*)buf;
+  return 0;
 }
 
 // Self-test of the GEMM machinery: D[128][256] = A[128][256] . W[256][256]^T (img packed with transpose=0, one layer).
