@@ -17,9 +17,9 @@ import robir_b200  # noqa: E402
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    tiles = int(args[0]) if args else 148 * 60
     out_json = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
+    args = [a for a in sys.argv[1:] if not a.startswith("--") and a != out_json]
+    tiles = int(args[0]) if args else 148 * 60
     dev = torch.device("cuda")
     sd = synthetic.synthetic_state_dict(0, num_lgt_sgs=16)
     model = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=16)))
