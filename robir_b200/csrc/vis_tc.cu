@@ -108,14 +108,19 @@ struct TcParams {
 };
 
 __device__ __forceinline__ long long tc_clock() { return clock64(); }
-#define TC_TIMED_WAIT(acc, bar, par)            \
+// wait on an mbarrier; with PROF the waiting time is added to `acc` (tools/tc_microbench.py)
+#define TC_WAIT(acc, bar, par)                  \
   do {                                          \
-    const long long _t = tc_clock();            \
-    mbar_wait(bar, par);                        \
-    acc += tc_clock() - _t;                     \
+    if (PROF) {                                 \
+      const long long _t = tc_clock();          \
+      mbar_wait(bar, par);                      \
+      acc += tc_clock() - _t;                   \
+    } else {                                    \
+      mbar_wait(bar, par);                      \
+    }                                           \
   } while (0)
 
-template <int MODE, int TERMS>  // MODE 0 = forward, 1 = backward, 2 = self-test (one 256x256 layer)
+template <int MODE, int TERMS, bool PROF>  // MODE 0 = forward, 1 = backward, 2 = self-test (one 256x256 layer)
 __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   constexpr int SB = tc_stage_bytes(TERMS, 128);        // bytes of a 128-row stage
   constexpr int SB64 = tc_stage_bytes(TERMS, 64);
@@ -124,7 +129,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   constexpr int kXLayer = 2;                            // the layer during which X's K-half 0 dies (fwd: last, bwd: L2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[NST], empty_bar[NST], s_ready[2], a_ready[2], d_full[2], d_free[2], x_free;
+  // A-operand hand-offs per 64-wide K block: s_ready[kb] = K block kb of a tile's FIRST operand (written one tile
+  // ahead), a_ready[kb] = K block kb produced by a layer epilogue of the current tile (separate barriers: in the
+  // backward the next tile's first operand is ready before this tile's last hand-off).
+  __shared__ uint64_t full_bar[NST], empty_bar[NST], s_ready[4], a_ready[4], d_full[2], d_free[2], x_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[3 * 256];
   __shared__ __align__(16) float s_wd[256];
@@ -134,8 +142,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&a_ready[0], 256); mbar_init(&a_ready[1], 256);
-    mbar_init(&s_ready[0], 256); mbar_init(&s_ready[1], 256);
+    for (int k = 0; k < 4; ++k) { mbar_init(&a_ready[k], 256); mbar_init(&s_ready[k], 256); }
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
     mbar_init(&d_free[0], 256); mbar_init(&d_free[1], 256);
     mbar_init(&x_free, 1);
@@ -152,7 +159,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
 
   if (warp == 0) {
     // ===================================== weight producer =====================================
-    uint32_t it = 0;
+    int st = 0;
+    uint32_t ph = 1;                                     // "slot is free" parity (fresh barriers pass)
     long long w_empty = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int layer = 0; layer < kLayers; ++layer) {
@@ -160,91 +168,113 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         const int nst = last64 ? 4 : 8;
         const uint32_t bytes = last64 ? SB64 : SB;
         const uint8_t* src = p.img + (size_t)layer * 8 * SB;
-        for (int j = 0; j < nst; ++j, ++it) {
-          const int st = it % NST;
-          TC_TIMED_WAIT(w_empty, &empty_bar[st], ((it / NST) & 1) ^ 1);
+        for (int j = 0; j < nst; ++j) {
+          TC_WAIT(w_empty, &empty_bar[st], ph);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_bar[st], bytes);
             bulk_g2s(ring + (size_t)st * SB, src + (size_t)j * bytes, bytes, &full_bar[st]);
           }
           __syncwarp();
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
     }
-    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
+    if (PROF && p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     // The whole warp runs the loop converged and one elected lane issues (elect.sync): tcgen05.mma / commit are
     // warp-uniform instructions, and inside a divergent `if (lane == 0)` ptxas wraps every one of them in an
-    // ELECT / BRA.U.ANY retry loop (~75 issue cycles per MMA).
-    // A-operand hand-offs: s_ready[kh] = K-half kh of a tile's FIRST operand (written one tile ahead, possibly before the
-    // previous tile's last epilogues), a_ready[kh] = K-half kh produced by a layer epilogue of the current tile.  They are
-    // separate barriers because in the backward the next tile's first operand is ready before this tile's last hand-off.
-    uint32_t it = 0, a_phase = 0, tile_it = 0;
+    // ELECT / BRA.U.ANY retry loop (~75 issue cycles per MMA).  The stage loop is fully unrolled so that the (n-half,
+    // k-block) of a stage, the barriers it waits on and the ones it commits are compile-time constants.
+    int st = 0;
+    uint32_t ph = 0, a_phase = 0, tile_it = 0;
     long long w_full = 0, w_ready = 0, w_dfree = 0;
-    const long long t_begin = tc_clock();
+    const long long t_begin = PROF ? tc_clock() : 0;
+    const uint64_t desc0 = smem_desc_sw128(ring);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+#pragma unroll 1
       for (int layer = 0; layer < kLayers; ++layer) {
         uint64_t* ready = layer == 0 ? s_ready : a_ready;
         const uint32_t ready_par = (layer == 0 ? tile_it : a_phase) & 1;
         if (layer > 0) ++a_phase;
         const uint32_t a_half = tmem_base + ((layer & 1) ? 256u : 0u);
         const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
-        const bool last64 = (MODE == 1 && layer == 3);
-        const int nst = last64 ? 4 : 8;
-        for (int j = 0; j < nst; ++j, ++it) {
-          const int nh = last64 ? 0 : tc_stage_nh(j), kb = last64 ? j : tc_stage_kb(j);
-          if (j == 0) TC_TIMED_WAIT(w_ready, &ready[0], ready_par);              // K-half 0 of A is in TMEM
-          if (j == (last64 ? 2 : 4)) TC_TIMED_WAIT(w_ready, &ready[1], ready_par);   // K-half 1
-          if (MODE == 0 && layer == 0 && kb == 0) TC_TIMED_WAIT(w_dfree, &d_free[nh], (tile_it & 1) ^ 1);  // D drained
-          const int st = it % NST;
-          TC_TIMED_WAIT(w_full, &full_bar[st], (it / NST) & 1);
+        if (MODE == 1 && layer == 3) {
+          // ---- backward tail: N = 64 (W0d^T), four 64-row stages; the 64 dPE columns go to X[128, 192)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            TC_WAIT(w_ready, &ready[j], ready_par);
+            TC_WAIT(w_full, &full_bar[st], ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t b_hi = desc0 + (uint64_t)((st * SB) >> 4), b_lo = b_hi + (8192u >> 4);
+              const uint32_t d_addr = tmem_base + 128u;
+#pragma unroll
+              for (int s4 = 0; s4 < 4; ++s4) {
+                const uint32_t a_hi = a_half + 64u * j + 32u * (s4 >> 1) + 8u * (s4 & 1), a_lo = a_hi + 16u;
+                if (j == 0 && s4 == 0) umma_ts<0>(d_addr, a_hi, b_hi + 2u * s4, kIdescN64);
+                else umma_ts<1>(d_addr, a_hi, b_hi + 2u * s4, kIdescN64);
+                if (TERMS == 3) {
+                  umma_ts<1>(d_addr, a_lo, b_hi + 2u * s4, kIdescN64);
+                  umma_ts<1>(d_addr, a_hi, b_lo + 2u * s4, kIdescN64);
+                }
+              }
+              umma_commit(&empty_bar[st]);
+              if (j == 3) umma_commit(&d_full[0]);
+            }
+            __syncwarp();
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          constexpr int kNhOf[8] = {0, 0, 1, 1, 0, 0, 1, 1}, kKbOf[8] = {0, 1, 0, 1, 2, 3, 2, 3};
+          const int nh = kNhOf[j], kb = kKbOf[j];
+          if (nh == 0) TC_WAIT(w_ready, &ready[kb], ready_par);                   // K block kb of A is in TMEM
+          if (MODE == 0 && kb == 0) { if (layer == 0) TC_WAIT(w_dfree, &d_free[nh], (tile_it & 1) ^ 1); }  // D drained
+          TC_WAIT(w_full, &full_bar[st], ph);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint8_t* sb = ring + (size_t)st * SB;
-            const uint64_t b_hi = smem_desc_sw128(sb);
-            const uint64_t b_lo = smem_desc_sw128(sb + (last64 ? 8192 : 16384));
-            // backward tail: the 64 dPE columns go to X[128, 192) -- the columns epilogue group 0 rewrites itself
-            const uint32_t d_addr = last64 ? (tmem_base + 128u) : (d_half + 128u * nh);
-            const uint32_t idesc = last64 ? kIdescN64 : kIdescN128;
+            const uint64_t b_hi = desc0 + (uint64_t)((st * SB) >> 4), b_lo = b_hi + (16384u >> 4);
+            const uint32_t d_addr = d_half + 128u * nh;
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
-              const int s = kb * 4 + s4;                   // k16 step 0..15
-              const uint32_t a_hi = a_half + 32u * (s >> 1) + 8u * (s & 1), a_lo = a_hi + 16u;
-              if (kb == 0 && s4 == 0) umma_ts<0>(d_addr, a_hi, b_hi + 2u * s4, idesc);
-              else umma_ts<1>(d_addr, a_hi, b_hi + 2u * s4, idesc);
+              const uint32_t a_hi = a_half + 64u * kb + 32u * (s4 >> 1) + 8u * (s4 & 1), a_lo = a_hi + 16u;
+              if (kb == 0 && s4 == 0) umma_ts<0>(d_addr, a_hi, b_hi + 2u * s4, kIdescN128);
+              else umma_ts<1>(d_addr, a_hi, b_hi + 2u * s4, kIdescN128);
               if (TERMS == 3) {
-                umma_ts<1>(d_addr, a_lo, b_hi + 2u * s4, idesc);
-                umma_ts<1>(d_addr, a_hi, b_lo + 2u * s4, idesc);
+                umma_ts<1>(d_addr, a_lo, b_hi + 2u * s4, kIdescN128);
+                umma_ts<1>(d_addr, a_hi, b_lo + 2u * s4, kIdescN128);
               }
             }
             umma_commit(&empty_bar[st]);
-            if (last64) { if (j == 3) umma_commit(&d_full[0]); }
-            else {
-              if (j == 5) umma_commit(&d_full[0]);
-              if (j == 7) umma_commit(&d_full[1]);
-              if (MODE <= 1 && layer == kXLayer && j == 3) umma_commit(&x_free);
-            }
+            if (j == 5) umma_commit(&d_full[0]);
+            if (j == 7) umma_commit(&d_full[1]);
+            if (MODE <= 1 && j == 3) { if (layer == kXLayer) umma_commit(&x_free); }
           }
           __syncwarp();
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
     }
-    if (p.dbg && lane == 0) {
+    if (PROF && p.dbg && lane == 0) {
       unsigned long long* d = p.dbg + blockIdx.x * 8;
       d[0] = (unsigned long long)(tc_clock() - t_begin); d[1] = (unsigned long long)w_full;
       d[2] = (unsigned long long)w_ready; d[3] = (unsigned long long)w_dfree;
     }
   } else {
     // ===================================== epilogue warps =====================================
+    // Thread (row, ch): row = its TMEM lane, ch = which 32 of the 64 columns of every K block [64 kb, 64 kb + 64) it
+    // converts: one 32-column chunk per hand-off, four hand-offs per layer.
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int ch = (warp - 2) >> 2;                  // which 64 columns of every 128-column half this thread owns
+    const int ch = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float inv_sw = 1.f / kSW;
     uint32_t d_phase[2] = {0, 0}, x_phase = 0;
     long long w_dfull = 0, w_xfree = 0;
-    const long long t_begin = tc_clock();
+    const long long t_begin = PROF ? tc_clock() : 0;
     // per-tile inputs of this row
     int a_idx = 0, b_idx = -1;
     float g0 = 0.f;
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         tmem_st16(taddr, hi);
       }
     };
-    // ---- first A operand of a tile: K-half kh (columns [128 kh, 128 kh + 128)) of X, this thread's 64 of them
+    // ---- first A operand of a tile, K block kb: this thread's 32 columns [64 kb + 32 ch, +32) of X
     float4 ga[2][4], gb[2][4];
     auto gather = [&](int col, int slot, int a, int b) {      // 16 features of tabA[a] and tabB[b] from column col
       const float4* pa = reinterpret_cast<const float4*>(p.tabA + (size_t)a * 256 + col);
@@ -279,67 +309,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       for (int i = 0; i < 4; ++i) { ga[slot][i] = __ldg(pa + i); gb[slot][i] = __ldg(pb + i); }
     };
     uint32_t mw0[4];                                           // backward: this thread's 4 words of mask slot 3
-    auto stage0_prefetch = [&](int t, int kh, int a, int b) {
-      if (MODE == 0) { gather(128 * kh + 64 * ch, 0, a, b); gather(128 * kh + 64 * ch + 16, 1, a, b); }
-      if (MODE == 1 && kh == 0) {
+    auto stage0_prefetch = [&](int t, int kb, int a, int b) {  // requests what stage0_block(t, kb) consumes
+      if (MODE == 0) { gather(64 * kb + 32 * ch, 0, a, b); gather(64 * kb + 32 * ch + 16, 1, a, b); }
+      if (MODE == 1 && kb == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          mw0[i] = __ldg(p.mask + ((size_t)t * 32 + 3 * 8 + 4 * (i >> 1) + 2 * ch + (i & 1)) * 128 + row);
+        for (int i = 0; i < 4; ++i) mw0[i] = __ldg(p.mask + ((size_t)t * 32 + 3 * 8 + 2 * i + ch) * 128 + row);
       }
     };
-    auto stage0_half = [&](int t, int kh, int a, int b) {
+    // converts K block kb; with `more` the loads of block kb + 1 are requested while this one converts
+    auto stage0_block = [&](int t, int kb, int a, int b, bool more) {
       const bool ok = b >= 0;
-      uint32_t* mtile = (MODE == 0 && p.mask && ok) ? p.mask + (size_t)t * (32 * 128) + row : nullptr;
+      const int col = 64 * kb + 32 * ch;
+      float x[32];
+      if (MODE == 0) {
+        uint32_t m = 0;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col = 128 * kh + 64 * ch + 32 * c;
-        float x[32];
-        if (MODE == 0) {
-          uint32_t m = 0;
+        for (int s = 0; s < 2; ++s) {                          // two 16-feature gathers per 32-column chunk
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {                        // two 16-feature gathers per 32-column chunk
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 va = ga[s][i], vb = gb[s][i];
-              const float v0 = va.x + vb.x, v1 = va.y + vb.y, v2 = va.z + vb.z, v3 = va.w + vb.w;
-              m = __funnelshift_l(__float_as_uint(v0), m, 1);
-              m = __funnelshift_l(__float_as_uint(v1), m, 1);
-              m = __funnelshift_l(__float_as_uint(v2), m, 1);
-              m = __funnelshift_l(__float_as_uint(v3), m, 1);
-              x[16 * s + 4 * i] = fmaxf(v0, 0.f) * kSA; x[16 * s + 4 * i + 1] = fmaxf(v1, 0.f) * kSA;
-              x[16 * s + 4 * i + 2] = fmaxf(v2, 0.f) * kSA; x[16 * s + 4 * i + 3] = fmaxf(v3, 0.f) * kSA;
-            }
-            if (c == 0) gather(col + 32 + 16 * s, s, a, b);    // next chunk's loads fly while this one converts
+          for (int i = 0; i < 4; ++i) {
+            const float4 va = ga[s][i], vb = gb[s][i];
+            const float v0 = va.x + vb.x, v1 = va.y + vb.y, v2 = va.z + vb.z, v3 = va.w + vb.w;
+            m = __funnelshift_l(__float_as_uint(v0), m, 1);
+            m = __funnelshift_l(__float_as_uint(v1), m, 1);
+            m = __funnelshift_l(__float_as_uint(v2), m, 1);
+            m = __funnelshift_l(__float_as_uint(v3), m, 1);
+            x[16 * s + 4 * i] = fmaxf(v0, 0.f) * kSA; x[16 * s + 4 * i + 1] = fmaxf(v1, 0.f) * kSA;
+            x[16 * s + 4 * i + 2] = fmaxf(v2, 0.f) * kSA; x[16 * s + 4 * i + 3] = fmaxf(v3, 0.f) * kSA;
           }
-          if (mtile != nullptr) mtile[(0 * 8 + (col >> 5)) * 128] = ~m;
-        } else if (MODE == 1) {
-          const uint32_t mword = ok ? mw0[2 * kh + c] : 0u;
-          const float4* wp = reinterpret_cast<const float4*>(s_wd + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 w = wp[i];
-            x[4 * i] = ((int)(mword << (4 * i)) < 0) ? kSG * w.x : 0.f;
-            x[4 * i + 1] = ((int)(mword << (4 * i + 1)) < 0) ? kSG * w.y : 0.f;
-            x[4 * i + 2] = ((int)(mword << (4 * i + 2)) < 0) ? kSG * w.z : 0.f;
-            x[4 * i + 3] = ((int)(mword << (4 * i + 3)) < 0) ? kSG * w.w : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = p.test_A[(size_t)row * 256 + col + i] * kSA;
+          if (more) gather(col + 64 + 16 * s, s, a, b);
         }
-        store_a(tmem_base + lane_addr + (uint32_t)col, x);
+        if (p.mask && ok) p.mask[((size_t)t * 32 + (col >> 5)) * 128 + row] = ~m;
+      } else if (MODE == 1) {
+        const uint32_t mword = ok ? mw0[kb] : 0u;
+        const float4* wp = reinterpret_cast<const float4*>(s_wd + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = wp[i];
+          x[4 * i] = ((int)(mword << (4 * i)) < 0) ? kSG * w.x : 0.f;
+          x[4 * i + 1] = ((int)(mword << (4 * i + 1)) < 0) ? kSG * w.y : 0.f;
+          x[4 * i + 2] = ((int)(mword << (4 * i + 2)) < 0) ? kSG * w.z : 0.f;
+          x[4 * i + 3] = ((int)(mword << (4 * i + 3)) < 0) ? kSG * w.w : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = p.test_A[(size_t)row * 256 + col + i] * kSA;
       }
+      store_a(tmem_base + lane_addr + (uint32_t)col, x);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&s_ready[kh]);
+      mbar_arrive(&s_ready[kb]);
     };
 
     if (blockIdx.x < ntiles) {
       if (MODE <= 1) load_row(blockIdx.x, a_idx, b_idx, g0);
       stage0_prefetch(blockIdx.x, 0, a_idx, b_idx);
-      stage0_half(blockIdx.x, 0, a_idx, b_idx);
-      stage0_prefetch(blockIdx.x, 1, a_idx, b_idx);
-      stage0_half(blockIdx.x, 1, a_idx, b_idx);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) stage0_block(blockIdx.x, kb, a_idx, b_idx, kb < 3);
     }
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
@@ -358,108 +383,107 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         const bool fwd_last = (MODE == 0 && layer == 2);
         if (has_next && layer == kXLayer - 1) load_row(tile_nxt, a_nxt, b_nxt, g_nxt);
         if (has_next && layer == kXLayer) {
-          // next tile's first A operand, K-half 0: X[0, 128) is dead once this layer's 4th stage has completed
+          // next tile's first A operand, K blocks 0 and 1: X[0, 128) is dead once this layer's 4th stage has completed
           stage0_prefetch(tile_nxt, 0, a_nxt, b_nxt);
-          TC_TIMED_WAIT(w_xfree, &x_free, x_phase & 1);
+          TC_WAIT(w_xfree, &x_free, x_phase & 1);
           ++x_phase;
           tc_fence_after();
-          stage0_half(tile_nxt, 0, a_nxt, b_nxt);
-          stage0_prefetch(tile_nxt, 1, a_nxt, b_nxt);          // consumed after this tile's last epilogue
+          stage0_block(tile_nxt, 0, a_nxt, b_nxt, true);
+          stage0_block(tile_nxt, 1, a_nxt, b_nxt, false);
         }
         // backward: the 4 mask words of this layer's epilogue (slot 2 - layer), requested before the wait
         uint32_t mw[4] = {0u, 0u, 0u, 0u};
         if (MODE == 1 && layer < 3 && valid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            mw[i] = __ldg(p.mask + ((size_t)tile * 32 + (2 - layer) * 8 + 4 * (i >> 1) + 2 * ch + (i & 1)) * 128 + row);
+            mw[i] = __ldg(p.mask + ((size_t)tile * 32 + (2 - layer) * 8 + 2 * i + ch) * 128 + row);
         }
         if (last64) {
-          // ---- backward tail (epilogue group 0 only): dPE[0..63] in X[128, 192) -> d dir via the PE jacobian
-          // (every epilogue thread observes the phase: a waiter may never fall two phases behind an mbarrier, or the
-          // parity test of its next wait aliases)
-          TC_TIMED_WAIT(w_dfull, &d_full[0], d_phase[0] & 1);
+          // ---- backward tail (epilogue group 0 only): dPE[0..63] in X[128, 192) -> d dir via the PE jacobian.
+          // Every epilogue thread observes the phase (a waiter may never fall two phases behind an mbarrier, or the
+          // parity test of its next wait aliases); group 1 must not overwrite X[160, 192) before group 0 has read it.
+          TC_WAIT(w_dfull, &d_full[0], d_phase[0] & 1);
           ++d_phase[0];
           tc_fence_after();
+          uint32_t r0[32], r1[32];
           if (ch == 0) {
-            uint32_t r0[32], r1[32];
             tmem_ld32(tmem_base + 128u + lane_addr, r0);
             tmem_ld32(tmem_base + 160u + lane_addr, r1);
             tmem_wait_ld();
-            if (valid) {
-              float dpe[64];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (ch == 0 && valid) {
+            float dpe[64];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { dpe[i] = __uint_as_float(r0[i]); dpe[32 + i] = __uint_as_float(r1[i]); }
-              const float gs = g0 * (inv_sw / kSG);            // accumulators carry kSG * kSW * (unit gradient)
+            for (int i = 0; i < 32; ++i) { dpe[i] = __uint_as_float(r0[i]); dpe[32 + i] = __uint_as_float(r1[i]); }
+            const float gs = g0 * (inv_sw / kSG);            // accumulators carry kSG * kSW * (unit gradient)
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const float xin = __ldg(p.dirs + 3 * b_idx + i);
-                float g = dpe[i], f = 1.f;
+            for (int i = 0; i < 3; ++i) {
+              const float xin = __ldg(p.dirs + 3 * b_idx + i);
+              float g = dpe[i], f = 1.f;
 #pragma unroll
-                for (int l = 0; l < 10; ++l) {
-                  float sn, cs;
-                  sincosf(xin * f, &sn, &cs);
-                  g += f * (cs * dpe[3 + 6 * l + i] - sn * dpe[6 + 6 * l + i]);
-                  f *= 2.f;
-                }
-                atomicAdd(p.g_dirs + 3 * b_idx + i, g * gs);
+              for (int l = 0; l < 10; ++l) {
+                float sn, cs;
+                sincosf(xin * f, &sn, &cs);
+                g += f * (cs * dpe[3 + 6 * l + i] - sn * dpe[6 + 6 * l + i]);
+                f *= 2.f;
               }
+              atomicAdd(p.g_dirs + 3 * b_idx + i, g * gs);
             }
           }
           continue;
         }
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          TC_TIMED_WAIT(w_dfull, &d_full[h], d_phase[h] & 1);
-          ++d_phase[h];
-          tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int n0 = 128 * h + 64 * ch + 32 * c;          // first output feature of this chunk
-            const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
-            uint32_t r[32];
-            tmem_ld32(taddr, r);
-            tmem_wait_ld();
-            float x[32];
-            if (MODE == 0) {
-              const float2* bp = reinterpret_cast<const float2*>(s_bias + layer * 256 + n0);
-              uint32_t m = 0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 v = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
-                                       make_float2(inv_sw, inv_sw), bp[i]);
-                m = __funnelshift_l(__float_as_uint(v.x), m, 1);
-                m = __funnelshift_l(__float_as_uint(v.y), m, 1);
-                x[2 * i] = fmaxf(v.x, 0.f); x[2 * i + 1] = fmaxf(v.y, 0.f);
-              }
-              if (mtile != nullptr) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
-            } else if (MODE == 1) {
-              const uint32_t mword = mw[2 * h + c];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) * inv_sw : 0.f;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                p.test_D[(size_t)row * 256 + n0 + i] = __uint_as_float(r[i]) * (inv_sw / kSA);
-            }
-            if (fwd_last) {
-              const float4* wp = reinterpret_cast<const float4*>(s_wd + n0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 w = wp[i];
-                logit = fmaf(w.x, x[4 * i], logit); logit = fmaf(w.y, x[4 * i + 1], logit);
-                logit = fmaf(w.z, x[4 * i + 2], logit); logit = fmaf(w.w, x[4 * i + 3], logit);
-              }
-            } else if (MODE <= 1) {
-              store_a(taddr, x);
-            }
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb == 0 || kb == 2) {                            // D columns [128 h, 128 h + 128) are complete
+            TC_WAIT(w_dfull, &d_full[kb >> 1], d_phase[kb >> 1] & 1);
+            ++d_phase[kb >> 1];
+            tc_fence_after();
           }
-          if (fwd_last) {                                        // this D half may be overwritten by the next tile
-            tc_fence_before();
-            mbar_arrive(&d_free[h]);
+          const int n0 = 64 * kb + 32 * ch;                    // first output feature of this chunk
+          const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
+          uint32_t r[32];
+          tmem_ld32(taddr, r);
+          tmem_wait_ld();
+          float x[32];
+          if (MODE == 0) {
+            const float2* bp = reinterpret_cast<const float2*>(s_bias + layer * 256 + n0);
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 v = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
+                                     make_float2(inv_sw, inv_sw), bp[i]);
+              m = __funnelshift_l(__float_as_uint(v.x), m, 1);
+              m = __funnelshift_l(__float_as_uint(v.y), m, 1);
+              x[2 * i] = fmaxf(v.x, 0.f); x[2 * i + 1] = fmaxf(v.y, 0.f);
+            }
+            if (mtile != nullptr) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
+          } else if (MODE == 1) {
+            const uint32_t mword = mw[kb];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) * inv_sw : 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              p.test_D[(size_t)row * 256 + n0 + i] = __uint_as_float(r[i]) * (inv_sw / kSA);
+          }
+          if (fwd_last) {
+            const float4* wp = reinterpret_cast<const float4*>(s_wd + n0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 w = wp[i];
+              logit = fmaf(w.x, x[4 * i], logit); logit = fmaf(w.y, x[4 * i + 1], logit);
+              logit = fmaf(w.z, x[4 * i + 2], logit); logit = fmaf(w.w, x[4 * i + 3], logit);
+            }
+            if (kb == 1 || kb == 3) {                          // this D half may be overwritten by the next tile
+              tc_fence_before();
+              mbar_arrive(&d_free[kb >> 1]);
+            }
           } else if (MODE <= 1) {
+            store_a(taddr, x);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_ready[h]);
+            mbar_arrive(&a_ready[kb]);
           }
         }
       }
@@ -470,10 +494,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         if (ch == 0)
           p.vis[q0 + row] = valid ? 1.f / (1.f + expf(-((logit + s_part[tile_it & 1][row]) * (1.f / kSA) + p.bd[0]))) : 0.f;
       }
-      if (has_next) stage0_half(tile_nxt, 1, a_nxt, b_nxt);     // X[128, 256): dead since the last layer completed
+      if (has_next) {                                          // X[128, 256): dead since the last layer completed
+        stage0_prefetch(tile_nxt, 2, a_nxt, b_nxt);
+        stage0_block(tile_nxt, 2, a_nxt, b_nxt, true);
+        stage0_block(tile_nxt, 3, a_nxt, b_nxt, false);
+      }
       a_idx = a_nxt; b_idx = b_nxt; g0 = g_nxt;
     }
-    if (p.dbg && warp == 2 && lane == 0) {
+    if (PROF && p.dbg && warp == 2 && lane == 0) {
       unsigned long long* d = p.dbg + blockIdx.x * 8;
       d[4] = (unsigned long long)(tc_clock() - t_begin); d[5] = (unsigned long long)w_dfull;
       d[6] = (unsigned long long)w_xfree;
@@ -497,8 +525,15 @@ static unsigned long long* g_tc_dbg = nullptr;
 template <int MODE, int TERMS>
 static int launch_tc(TcParams p, int grid, void* stream) {
   p.dbg = g_tc_dbg;
-  RB_CHECK_CUDA(cudaFuncSetAttribute(vis_tc_kernel<MODE, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-  vis_tc_kernel<MODE, TERMS><<<grid, kTcThreads, kTcSmem, (cudaStream_t)stream>>>(p);
+  if (g_tc_dbg != nullptr) {          // stall accounting build of the same kernel (clock reads around every wait)
+    RB_CHECK_CUDA(cudaFuncSetAttribute(vis_tc_kernel<MODE, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTcSmem));
+    vis_tc_kernel<MODE, TERMS, true><<<grid, kTcThreads, kTcSmem, (cudaStream_t)stream>>>(p);
+  } else {
+    RB_CHECK_CUDA(cudaFuncSetAttribute(vis_tc_kernel<MODE, TERMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTcSmem));
+    vis_tc_kernel<MODE, TERMS, false><<<grid, kTcThreads, kTcSmem, (cudaStream_t)stream>>>(p);
+  }
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
