@@ -172,6 +172,12 @@ __device__ __forceinline__ void split_pack_f16(float x0, float x1, uint32_t& hi,
   lo = pack_f16(x0 - h.x, x1 - h.y);
 }
 
+// hi = f16_rz(relu(x)) (round toward zero: the residual keeps the sign of x), lo = f16_rn(relu(x - hi)):
+// relu and split of an fp32 pair in 5 instructions (two converts with the relu modifier, two unpacks, one packed
+// subtract); for x < 0 both halves are +0.  RELU = false: plain split (lo = f16_rn(x - hi), any sign).
+template <bool RELU>
+__device__ __forceinline__ void split_pack_f16_rz(float x0, float x1, uint32_t& hi, uint32_t& lo);
+
 // packed fp32 pair FMA (FFMA2 on sm_100)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t ra, rb, rc, rd;
@@ -182,6 +188,23 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
   asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
+}
+
+template <bool RELU>
+__device__ __forceinline__ void split_pack_f16_rz(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  if (RELU) asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  else asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 d = ffma2(h, make_float2(-1.f, -1.f), make_float2(x0, x1));      // exact: hi is x truncated
+  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
+}
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_f16_act(float x0, float x1) {
+  uint32_t r;
+  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
 }
 
 }  // namespace tc

@@ -287,16 +287,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         g = p.g_vis[t * 128 + row] * v * (1.f - v);
       }
     };
-    auto store_a = [&](uint32_t taddr, float (&x)[32]) {      // x (already scaled, >= 0 / masked) -> A operand chunk
+    // v (scaled; forward: pre-activations, relu applied by the converts; backward: masked gradients) -> A operand chunk
+    auto store_a = [&](uint32_t taddr, float (&v)[32]) {
       uint32_t hi[16], lo[16];
       if (TERMS == 3) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) split_pack_f16(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+        for (int i = 0; i < 16; ++i) split_pack_f16_rz<MODE == 0>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
         tmem_st16(taddr, hi);
         tmem_st16(taddr + 16u, lo);
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hi[i] = pack_f16(x[2 * i], x[2 * i + 1]);
+        for (int i = 0; i < 16; ++i) hi[i] = pack_f16_act<MODE == 0>(v[2 * i], v[2 * i + 1]);
         tmem_st16(taddr, hi);
       }
     };
@@ -328,13 +329,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 va = ga[s][i], vb = gb[s][i];
-            const float v0 = va.x + vb.x, v1 = va.y + vb.y, v2 = va.z + vb.z, v3 = va.w + vb.w;
-            m = __funnelshift_l(__float_as_uint(v0), m, 1);
-            m = __funnelshift_l(__float_as_uint(v1), m, 1);
-            m = __funnelshift_l(__float_as_uint(v2), m, 1);
-            m = __funnelshift_l(__float_as_uint(v3), m, 1);
-            x[16 * s + 4 * i] = fmaxf(v0, 0.f) * kSA; x[16 * s + 4 * i + 1] = fmaxf(v1, 0.f) * kSA;
-            x[16 * s + 4 * i + 2] = fmaxf(v2, 0.f) * kSA; x[16 * s + 4 * i + 3] = fmaxf(v3, 0.f) * kSA;
+            const float2 sa2 = make_float2(kSA, kSA);
+            const float2 t0 = ffma2(make_float2(va.x, va.y), sa2, make_float2(vb.x * kSA, vb.y * kSA));
+            const float2 t1 = ffma2(make_float2(va.z, va.w), sa2, make_float2(vb.z * kSA, vb.w * kSA));
+            m = __funnelshift_l(__float_as_uint(t0.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(t0.y), m, 1);
+            m = __funnelshift_l(__float_as_uint(t1.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(t1.y), m, 1);
+            x[16 * s + 4 * i] = t0.x; x[16 * s + 4 * i + 1] = t0.y;
+            x[16 * s + 4 * i + 2] = t1.x; x[16 * s + 4 * i + 3] = t1.y;
           }
           if (more) gather(col + 64 + 16 * s, s, a, b);
         }
@@ -434,56 +437,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           continue;
         }
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          if (kb == 0 || kb == 2) {                            // D columns [128 h, 128 h + 128) are complete
-            TC_WAIT(w_dfull, &d_full[kb >> 1], d_phase[kb >> 1] & 1);
-            ++d_phase[kb >> 1];
-            tc_fence_after();
-          }
-          const int n0 = 64 * kb + 32 * ch;                    // first output feature of this chunk
-          const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
-          uint32_t r[32];
-          tmem_ld32(taddr, r);
+        for (int h = 0; h < 2; ++h) {
+          // D columns [128 h, 128 h + 128) are complete: both of this thread's chunks of the half are requested at once
+          TC_WAIT(w_dfull, &d_full[h], d_phase[h] & 1);
+          ++d_phase[h];
+          tc_fence_after();
+          uint32_t rr[2][32];
+          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 32 * ch), rr[0]);
+          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 64 + 32 * ch), rr[1]);
           tmem_wait_ld();
-          float x[32];
-          if (MODE == 0) {
-            const float2* bp = reinterpret_cast<const float2*>(s_bias + layer * 256 + n0);
-            uint32_t m = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 v = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
-                                     make_float2(inv_sw, inv_sw), bp[i]);
-              m = __funnelshift_l(__float_as_uint(v.x), m, 1);
-              m = __funnelshift_l(__float_as_uint(v.y), m, 1);
-              x[2 * i] = fmaxf(v.x, 0.f); x[2 * i + 1] = fmaxf(v.y, 0.f);
+          for (int c = 0; c < 2; ++c) {
+            const int kb = 2 * h + c;
+            const int n0 = 64 * kb + 32 * ch;                  // first output feature of this chunk
+            const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
+            uint32_t (&r)[32] = rr[c];
+            float x[32];
+            if (MODE == 0) {
+              const float2* bp = reinterpret_cast<const float2*>(s_bias + layer * 256 + n0);
+              uint32_t m = 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 v = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
+                                       make_float2(inv_sw, inv_sw), bp[i]);
+                m = __funnelshift_l(__float_as_uint(v.x), m, 1);
+                m = __funnelshift_l(__float_as_uint(v.y), m, 1);
+                x[2 * i] = v.x; x[2 * i + 1] = v.y;            // relu happens in the converts (store_a) / below
+              }
+              if (mtile != nullptr) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
+            } else if (MODE == 1) {
+              const uint32_t mword = mw[kb];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) * inv_sw : 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                p.test_D[(size_t)row * 256 + n0 + i] = __uint_as_float(r[i]) * (inv_sw / kSA);
             }
-            if (mtile != nullptr) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
-          } else if (MODE == 1) {
-            const uint32_t mword = mw[kb];
+            if (fwd_last) {
+              const float4* wp = reinterpret_cast<const float4*>(s_wd + n0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) * inv_sw : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              p.test_D[(size_t)row * 256 + n0 + i] = __uint_as_float(r[i]) * (inv_sw / kSA);
-          }
-          if (fwd_last) {
-            const float4* wp = reinterpret_cast<const float4*>(s_wd + n0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 w = wp[i];
-              logit = fmaf(w.x, x[4 * i], logit); logit = fmaf(w.y, x[4 * i + 1], logit);
-              logit = fmaf(w.z, x[4 * i + 2], logit); logit = fmaf(w.w, x[4 * i + 3], logit);
-            }
-            if (kb == 1 || kb == 3) {                          // this D half may be overwritten by the next tile
+              for (int i = 0; i < 8; ++i) {
+                const float4 w = wp[i];
+                logit = fmaf(w.x, fmaxf(x[4 * i], 0.f), logit); logit = fmaf(w.y, fmaxf(x[4 * i + 1], 0.f), logit);
+                logit = fmaf(w.z, fmaxf(x[4 * i + 2], 0.f), logit); logit = fmaf(w.w, fmaxf(x[4 * i + 3], 0.f), logit);
+              }
+            } else if (MODE <= 1) {
+              store_a(taddr, x);
+              tmem_wait_st();
               tc_fence_before();
-              mbar_arrive(&d_free[kb >> 1]);
+              mbar_arrive(&a_ready[kb]);
             }
-          } else if (MODE <= 1) {
-            store_a(taddr, x);
-            tmem_wait_st();
+          }
+          if (fwd_last) {                                      // this D half may be overwritten by the next tile
             tc_fence_before();
-            mbar_arrive(&a_ready[kb]);
+            mbar_arrive(&d_free[h]);
           }
         }
       }
