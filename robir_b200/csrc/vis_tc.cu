@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       const int col = 64 * kb + 32 * ch;
       float x[32];
       if (MODE == 0) {
-        uint32_t mq[2] = {0u, 0u};
+        uint32_t m = 0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {                          // two 16-feature gathers per 32-column chunk
 #pragma unroll
@@ -332,16 +332,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
             const float2 sa2 = make_float2(kSA, kSA);
             const float2 t0 = ffma2(make_float2(va.x, va.y), sa2, make_float2(vb.x * kSA, vb.y * kSA));
             const float2 t1 = ffma2(make_float2(va.z, va.w), sa2, make_float2(vb.z * kSA, vb.w * kSA));
-            mq[s] = __funnelshift_l(__float_as_uint(t0.x), mq[s], 1);
-            mq[s] = __funnelshift_l(__float_as_uint(t0.y), mq[s], 1);
-            mq[s] = __funnelshift_l(__float_as_uint(t1.x), mq[s], 1);
-            mq[s] = __funnelshift_l(__float_as_uint(t1.y), mq[s], 1);
+            m = __funnelshift_l(__float_as_uint(t0.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(t0.y), m, 1);
+            m = __funnelshift_l(__float_as_uint(t1.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(t1.y), m, 1);
             x[16 * s + 4 * i] = t0.x; x[16 * s + 4 * i + 1] = t0.y;
             x[16 * s + 4 * i + 2] = t1.x; x[16 * s + 4 * i + 3] = t1.y;
           }
           if (more) gather(col + 64 + 16 * s, s, a, b);
         }
-        if (p.mask && ok) p.mask[((size_t)t * 32 + (col >> 5)) * 128 + row] = ~((mq[0] << 16) | (mq[1] & 0xffffu));
+        if (p.mask && ok) p.mask[((size_t)t * 32 + (col >> 5)) * 128 + row] = ~m;
       } else if (MODE == 1) {
         const uint32_t mword = ok ? mw0[kb] : 0u;
         const float4* wp = reinterpret_cast<const float4*>(s_wd + col);
@@ -438,9 +438,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          // the table rows of the next tile's K block 2 are requested before the last wait of this tile (the last
-          // layer's epilogue keeps few registers live), so that their L2 round trip is off the next tile's critical path
-          if (MODE == 0 && h == 1) { if (fwd_last && has_next) stage0_prefetch(tile_nxt, 2, a_nxt, b_nxt); }
           // D columns [128 h, 128 h + 128) are complete: both of this thread's chunks of the half are requested at once
           TC_WAIT(w_dfull, &d_full[h], d_phase[h] & 1);
           ++d_phase[h];
@@ -458,24 +455,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
             float x[32];
             if (MODE == 0) {
               const float2* bp = reinterpret_cast<const float2*>(s_bias + layer * 256 + n0);
-              uint32_t mq[4] = {0u, 0u, 0u, 0u};                // four independent sign-bit chains (8 features each)
+              uint32_t m = 0;
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float2 v = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
                                        make_float2(inv_sw, inv_sw), bp[i]);
-                mq[i >> 2] = __funnelshift_l(__float_as_uint(v.x), mq[i >> 2], 1);
-                mq[i >> 2] = __funnelshift_l(__float_as_uint(v.y), mq[i >> 2], 1);
+                m = __funnelshift_l(__float_as_uint(v.x), m, 1);
+                m = __funnelshift_l(__float_as_uint(v.y), m, 1);
                 x[2 * i] = v.x; x[2 * i + 1] = v.y;            // relu happens in the converts (store_a) / below
               }
-              const uint32_t m = (mq[0] << 24) | ((mq[1] & 0xffu) << 16) | ((mq[2] & 0xffu) << 8) | (mq[3] & 0xffu);
               if (mtile != nullptr) mtile[((layer + 1) * 8 + (n0 >> 5)) * 128] = ~m;
             } else if (MODE == 1) {
               const uint32_t mword = mw[kb];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {                       // keep = all ones if bit (31 - i) of the mask word is set
-                const uint32_t keep = (uint32_t)((int)(mword << i) >> 31);
-                x[i] = __uint_as_float(r[i] & keep) * inv_sw;
-              }
+              for (int i = 0; i < 32; ++i) x[i] = ((int)(mword << i) < 0) ? __uint_as_float(r[i]) * inv_sw : 0.f;
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -510,7 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           p.vis[q0 + row] = valid ? 1.f / (1.f + expf(-((logit + s_part[tile_it & 1][row]) * (1.f / kSA) + p.bd[0]))) : 0.f;
       }
       if (has_next) {                                          // X[128, 256): dead since the last layer completed
-        if (MODE != 0) stage0_prefetch(tile_nxt, 2, a_nxt, b_nxt);
+        stage0_prefetch(tile_nxt, 2, a_nxt, b_nxt);
         stage0_block(tile_nxt, 2, a_nxt, b_nxt, true);
         stage0_block(tile_nxt, 3, a_nxt, b_nxt, false);
       }
