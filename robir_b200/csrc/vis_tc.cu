@@ -103,6 +103,8 @@ struct TcParams {
   const float* g_vis; const float* dirs; float* g_dirs;
   // self-test: plain GEMM D = A . W^T through the same machinery
   const float* test_A; float* test_D;
+  // dynamic tile scheduler: zero-initialised counter; CTA b starts on tile b and then draws gridDim.x + counter++
+  int* tile_counter;
   // optional per-CTA stall accounting (robir_tc_debug_buffer): [grid][8] clock counts, see tools/tc_stalls.py
   unsigned long long* dbg;
 };
@@ -133,6 +135,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
   // ahead), a_ready[kb] = K block kb produced by a layer epilogue of the current tile (separate barriers: in the
   // backward the next tile's first operand is ready before this tile's last hand-off).
   __shared__ uint64_t full_bar[NST], empty_bar[NST], s_ready[4], a_ready[4], d_full[2], d_free[2], x_free;
+  // tile scheduler: the epilogue's leader thread draws the next tile one tile ahead and publishes it to all roles
+  __shared__ uint64_t t_ready[2];
+  __shared__ int s_tile[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[3 * 256];
   __shared__ __align__(16) float s_wd[256];
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
     mbar_init(&d_free[0], 256); mbar_init(&d_free[1], 256);
     mbar_init(&x_free, 1);
+    mbar_init(&t_ready[0], 1); mbar_init(&t_ready[1], 1);
     fence_barrier_init();
   }
   if (MODE == 0) for (int i = tid; i < 3 * 256; i += kTcThreads) s_bias[i] = p.bias[i] * kSA;
@@ -162,7 +168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     int st = 0;
     uint32_t ph = 1;                                     // "slot is free" parity (fresh barriers pass)
     long long w_empty = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile >= 0 && tile < ntiles; ++tile_it) {
       for (int layer = 0; layer < kLayers; ++layer) {
         const bool last64 = (MODE == 1 && layer == 3);
         const int nst = last64 ? 4 : 8;
@@ -178,6 +185,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
+      if (MODE >= 2) break;
+      mbar_wait(&t_ready[(tile_it + 1) & 1], (tile_it >> 1) & 1);          // next tile of this CTA (or -1)
+      tile = s_tile[(tile_it + 1) & 1];
     }
     if (PROF && p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
   } else if (warp == 1) {
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
     long long w_full = 0, w_ready = 0, w_dfree = 0;
     const long long t_begin = PROF ? tc_clock() : 0;
     const uint64_t desc0 = smem_desc_sw128(ring);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+    for (int tile = blockIdx.x; tile >= 0 && tile < ntiles; ++tile_it) {
 #pragma unroll 1
       for (int layer = 0; layer < kLayers; ++layer) {
         uint64_t* ready = layer == 0 ? s_ready : a_ready;
@@ -257,6 +267,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
+      if (MODE >= 2) break;
+      mbar_wait(&t_ready[(tile_it + 1) & 1], (tile_it >> 1) & 1);
+      tile = s_tile[(tile_it + 1) & 1];
     }
     if (PROF && p.dbg && lane == 0) {
       unsigned long long* d = p.dbg + blockIdx.x * 8;
@@ -370,11 +383,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       for (int kb = 0; kb < 4; ++kb) stage0_block(blockIdx.x, kb, a_idx, b_idx, kb < 3);
     }
     uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+    for (int tile = blockIdx.x; tile >= 0 && tile < ntiles; ++tile_it) {
       const int q0 = tile * 128;
       const bool valid = b_idx >= 0;
-      const int tile_nxt = tile + (int)gridDim.x;
-      const bool has_next = MODE <= 1 && tile_nxt < ntiles;
+      int tile_nxt = -1;
+      bool has_next = false;
       uint32_t* mtile = (MODE == 0 && p.mask && valid) ? p.mask + (size_t)tile * (32 * 128) + row : nullptr;
       int a_nxt = 0, b_nxt = -1;
       float g_nxt = 0.f;
@@ -384,7 +397,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         const uint32_t d_half = tmem_base + ((layer & 1) ? 0u : 256u);
         const bool last64 = (MODE == 1 && layer == 3);
         const bool fwd_last = (MODE == 0 && layer == 2);
-        if (has_next && layer == kXLayer - 1) load_row(tile_nxt, a_nxt, b_nxt, g_nxt);
+        if (MODE <= 1 && layer == kXLayer - 1) {
+          // draw the next tile (one thread), publish it to the producer / issuer / epilogue threads of this CTA
+          if (warp == 2 && lane == 0) {
+            int t = (int)gridDim.x + atomicAdd(p.tile_counter, 1);
+            s_tile[(tile_it + 1) & 1] = t < ntiles ? t : -1;
+            __threadfence_block();
+            mbar_arrive(&t_ready[(tile_it + 1) & 1]);
+          }
+          mbar_wait(&t_ready[(tile_it + 1) & 1], (tile_it >> 1) & 1);
+          tile_nxt = s_tile[(tile_it + 1) & 1];
+          has_next = tile_nxt >= 0;
+          if (has_next) load_row(tile_nxt, a_nxt, b_nxt, g_nxt);
+        }
         if (has_next && layer == kXLayer) {
           // next tile's first A operand, K blocks 0 and 1: X[0, 128) is dead once this layer's 4th stage has completed
           stage0_prefetch(tile_nxt, 0, a_nxt, b_nxt);
@@ -508,6 +533,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
         stage0_block(tile_nxt, 3, a_nxt, b_nxt, false);
       }
       a_idx = a_nxt; b_idx = b_nxt; g0 = g_nxt;
+      if (MODE >= 2) break;
+      tile = tile_nxt;
     }
     if (PROF && p.dbg && warp == 2 && lane == 0) {
       unsigned long long* d = p.dbg + blockIdx.x * 8;
@@ -529,10 +556,16 @@ using namespace robir;
 static constexpr int kTcSmem = kTcRingBytes + 1024;
 
 static unsigned long long* g_tc_dbg = nullptr;
+static int* g_tile_counters = nullptr;       // pool of tile-scheduler counters (one per launch in flight, round robin)
+static unsigned g_tile_counter_next = 0;
+constexpr int kTileCounters = 256;
 
 template <int MODE, int TERMS>
 static int launch_tc(TcParams p, int grid, void* stream) {
   p.dbg = g_tc_dbg;
+  if (g_tile_counters == nullptr) RB_CHECK_CUDA(cudaMalloc(&g_tile_counters, kTileCounters * sizeof(int)));
+  p.tile_counter = g_tile_counters + (g_tile_counter_next++ % kTileCounters);
+  RB_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), (cudaStream_t)stream));
   if (g_tc_dbg != nullptr) {          // stall accounting build of the same kernel (clock reads around every wait)
     RB_CHECK_CUDA(cudaFuncSetAttribute(vis_tc_kernel<MODE, TERMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kTcSmem));

@@ -320,13 +320,21 @@ def _vis_mlp_fwd(W, tabA, tabB, rowA, rowB, n_tiles, max_tiles, need_mask):
     return vis, mask
 
 
+# SMs the big visibility backward leaves free: the backward of the material / indirect networks does not depend on it
+# and runs on other streams at the same time, but its kernels cannot share an SM with a visibility CTA (shared memory);
+# with every SM taken they would queue behind it and then stretch its tail.  The kernel draws tiles from a counter, so
+# a smaller persistent grid only costs its share of the throughput.
+VIS_BWD_RESERVED_SMS = 12
+
+
 def _vis_mlp_bwd(W, rowB, n_tiles, max_tiles, vis, g_vis, mask, dirs, engine):
     g_dirs = _zeros(dirs.shape[0], 3, like=dirs)
     terms = vis_engine_terms(engine)
     if terms:
+        ctas = sm_count() - (VIS_BWD_RESERVED_SMS if max_tiles > 4 * sm_count() else 0)
         with _Timed("vis_mlp_bwd", max_tiles):
             check(lib().robir_vis_tc_bwd(ptr(rowB), ptr(n_tiles), max_tiles, ptr(W["tc_bwd%d" % terms]), ptr(W["wd"]),
-                                         ptr(vis), ptr(g_vis), ptr(mask), ptr(dirs), ptr(g_dirs), terms, sm_count(),
+                                         ptr(vis), ptr(g_vis), ptr(mask), ptr(dirs), ptr(g_dirs), terms, max(ctas, 1),
                                          stream()))
         return g_dirs
     with _Timed("vis_mlp_bwd", max_tiles):
