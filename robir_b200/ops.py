@@ -481,28 +481,9 @@ def spec_prep(normal, view, rough, valid=None):
     return _SpecPrep.apply(normal, view, rough, valid)
 
 
-_vis_streams = {}
-
-
 def diffuse_vis(points, normals, dirs, w, M, S, weights, need_grad, tabB=None):
-    """tabB: optional pre-computed direction table pe_linear(dirs, Wt0d) of the same weights.
-
-    The operator runs on its own stream (forked from / joined into the caller's): autograd replays a node on the stream
-    of its forward, so the ~1 ms visibility backward no longer sits on the main stream in front of the many small
-    backward nodes that do not depend on it (they used to queue behind it, and the network backwards behind them)."""
-    if not points.is_cuda:
-        return _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad, tabB)
-    main = torch.cuda.current_stream()
-    side = _vis_streams.get(points.device)
-    if side is None:
-        side = _vis_streams[points.device] = torch.cuda.Stream(device=points.device)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        out = _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad, tabB)
-    main.wait_stream(side)
-    if not torch.cuda.is_current_stream_capturing():
-        out.record_stream(main)
-    return out
+    """tabB: optional pre-computed direction table pe_linear(dirs, Wt0d) of the same weights."""
+    return _DiffuseVis.apply(points, normals, dirs, w, M, S, weights, need_grad, tabB)
 
 
 def spec_vis(points, normals, dirs, w, S, inv, testing, weights, need_grad):
