@@ -215,11 +215,7 @@ class IDRNetwork(nn.Module):
                 return dirs, w
             W = sg_render._weights_of(self.visibility_network).get()
             return dirs, w, ops.pe_linear(dirs.detach(), W["Wt0d"], None)
-        # (the empty first branch keeps the main stream free: every network runs on a side stream, and so does its
-        # backward -- autograd replays a node on its forward stream -- which lets the indirect-illumination backward
-        # overlap the visibility backward instead of queueing behind it on the main stream)
-        _, (sgs, integ), mat, nrm, presampled = ops.fork_join([
-            lambda: None,
+        (sgs, integ), mat, nrm, presampled = ops.fork_join([
             act(lambda: self.indirect_illum_network(pts, hdr)),
             act(lambda: self.envmap_material_network(pts, train_spec=train_spec)),
             act(lambda: self.get_idr_render(pts, None, normal_only=True)),
