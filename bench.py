@@ -190,11 +190,14 @@ def oracle_step(O, P, tree, sd, step, n_rays, gen, cam):
 
 
 def reference_pbr(device, sd):
-    """The unmodified reference's PBR runner objects (oracle/ref_runner.py), octree built by the reference."""
+    """The unmodified reference's PBR runner objects (oracle/ref_runner.py), octree built by the reference.  The
+    reference prints progress to stdout; this script's stdout carries exactly one JSON line, so it goes to stderr."""
+    import contextlib
     _oracle_paths()
     import ref_runner
-    R = ref_runner.ReferencePBR(sd, M_LOBES, device=device)
-    R.generate()
+    with contextlib.redirect_stdout(sys.stderr):
+        R = ref_runner.ReferencePBR(sd, M_LOBES, device=device)
+        R.generate()
     return R
 
 
