@@ -531,6 +531,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.config in ("c2", "c5"):
         return run_pbr(args)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_configs
     return getattr(bench_configs, "run_" + args.config)(args)
 

@@ -1,0 +1,207 @@
+"""bench.py --config c1 | c3 | c4: the BASELINE.json configurations besides the headline one (c2) and its DTU-sized
+sibling (c5), which live in bench.py itself.  Same JSON contract (one line on rank 0, CUDA-event timing, max over ranks,
+weak scaling over the ranks); these are measured for the record under profiles/, the driver's bench is c2.
+
+    c1  64x64 centre crop (4096 rays, one call), M = 16 light SGs, PBR forward only (no_grad) -- octree tracer (shipped
+        default; headline value) and the IDR sphere tracer with ray_tracer.n_steps = 32 (the "march steps" knob)
+    c3  Vis stage iteration (training/train_visibility.py:286-324): forward('Illum') on 256 primary rays +
+        trace_radiance(nsamp = 512) + IllumLoss + both backwards + both Adam steps; primary and secondary rays/s
+    c4  PBR + CESR iteration (training/train_cesr.py:465-559, explore phase, S = 8, lin_diff), every rank its own batch
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from robir_b200 import synthetic  # noqa: E402
+
+SEED, SDF_RADIUS = 0, 0.87
+
+
+def _setup(M, use_octree=True, n_steps=100):
+    import robir_b200
+    from robir_b200 import dist as rdist, rng
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rng.set_mode("device")
+    sd = synthetic.synthetic_state_dict(SEED, num_lgt_sgs=M, sdf_radius=SDF_RADIUS)
+    conf = dict(envmap_material_network=dict(num_lgt_sgs=M), use_octree=use_octree,
+                ray_tracer=dict(n_steps=n_steps))
+    model = robir_b200.IDRNetwork(conf)
+    model.load_state_dict(sd, strict=True)
+    model.to(dev).train()
+    model.generate()
+    return rank, world, local, dev, sd, model
+
+
+def _timed(fn, warmup, steps, dev, world):
+    from robir_b200 import dist as rdist
+    for s in range(warmup):
+        fn(s)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(warmup, warmup + steps):
+        fn(s)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    return rdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+
+
+def _line(args, metric, value, unit, ms, world, cfg, extra):
+    d = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+         "data": "synthetic", "config": cfg}
+    d.update(extra)
+    print(json.dumps(d))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c1(args):
+    """64x64 crop, 16 SG lobes, PBR forward only."""
+    import bench
+    N, M = 4096, 16
+    out = {}
+    for tracer, use_octree in (("octree", True), ("sphere_tracer_n_steps_32", False)):
+        rank, world, local, dev, sd, model = _setup(M, use_octree=use_octree, n_steps=32)
+        model.eval() if False else None          # the reference times the training-mode forward
+        yy, xx = torch.meshgrid(torch.arange(368, 432), torch.arange(368, 432), indexing="ij")
+        pix = (yy * 800 + xx).reshape(-1)
+        inp = {k: v.to(dev) for k, v in synthetic.camera_inputs(pix).items()}
+        hits = []
+
+        def step(s):
+            with torch.no_grad():
+                o = model(inp, trainstage="Material", train_spec=True)
+            hits.append(o["network_object_mask"].sum())
+        clocks = bench.ClockSampler(local).start()
+        t = _timed(step, args.warmup, args.steps, dev, world)
+        clk = clocks.stop()
+        out[tracer] = dict(rays_per_s=N * args.steps * world / t, ms_per_call=1e3 * t / args.steps,
+                           hit_fraction=float(torch.stack(hits[-args.steps:]).float().mean()) / N, clocks=clk)
+    if rank == 0:
+        cfg = {"workload": "hotdog-synthetic 64x64 centre crop (4096 rays, one call), M=16 light SGs, PBR forward only "
+                           "(no_grad, training-mode networks), stage-2 SDF radius ~0.6", "config": "c1",
+               "rays_per_call": N, "num_lgt_sgs": M, "tracer": "octree"}
+        o = out["octree"]
+        _line(args, "rays/sec (fwd) PBR stage, hotdog 64x64 crop, 16 SG lobes", o["rays_per_s"], "rays/s",
+              o["ms_per_call"], world, cfg, {"clocks": o["clocks"], "tracers": out,
+                                             "e2e": {"value": o["rays_per_s"], "unit": "rays/s",
+                                                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                     "note": "inputs resident; forward-only diagnostic config"}})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c3(args):
+    """Vis stage iteration: 256 primary rays x 512 secondary rays."""
+    import bench
+    from robir_b200.loss import IllumLoss
+    N, NS, M = 256, 512, 128
+    rank, world, local, dev, sd, model = _setup(M)
+    model.indirect_illum_network.train_weights = True
+    illum_loss = IllumLoss()
+    illum_opt = torch.optim.Adam(model.indirect_illum_network.parameters(), lr=5e-4)     # train_visibility.py:99-107
+    vis_opt = torch.optim.Adam(model.visibility_network.parameters(), lr=5e-4)
+    stats = {"sec": 0, "sec_hit": 0, "prim_hit": 0}
+
+    def step(s):
+        pix = synthetic.training_pixels(s * world + rank, n=N)
+        inp = {k: v.to(dev) for k, v in synthetic.camera_inputs(pix).items()}
+        inp["hdr_shift"] = torch.rand(N, 1, device=dev)                                   # :297
+        out = model(inp, trainstage="Illum")
+        tr = model.trace_radiance(out, nsamp=NS)
+        n_hit = int(out["network_object_mask"].sum())
+        if n_hit:
+            rad, vis = illum_loss(out, tr, 0.0)
+            vis_opt.zero_grad()
+            vis.backward(retain_graph=True)
+            vis_opt.step()
+            illum_opt.zero_grad()
+            rad.backward()
+            illum_opt.step()
+        stats["prim_hit"] += n_hit
+        stats["sec"] += n_hit * NS
+        stats["sec_hit"] += int(tr["gt_vis"].sum())
+    clocks = bench.ClockSampler(local).start()
+    for k in stats:
+        stats[k] = 0
+    t = _timed(step, args.warmup, args.steps, dev, world)
+    clk = clocks.stop()
+    tot = args.warmup + args.steps
+    if rank == 0:
+        cfg = {"workload": "lego-synthetic Vis stage: forward('Illum') on 256 random pixels + trace_radiance(nsamp=512) + "
+                           "IllumLoss + both backwards + both Adam steps (train_visibility.py:286-324), eager dynamic "
+                           "shapes, stage-2 SDF radius ~0.6", "config": "c3", "primary_rays_per_step_per_gpu": N,
+               "secondary_per_hit": NS, "primary_hit_fraction": stats["prim_hit"] / float(N * tot),
+               "secondary_hit_fraction": stats["sec_hit"] / float(max(stats["sec"], 1))}
+        sec_per_step = stats["sec"] / float(tot)
+        _line(args, "primary rays/sec Vis stage (256 x 512 secondary), lego 800x800", N * args.steps * world / t,
+              "rays/s", 1e3 * t / args.steps, world, cfg,
+              {"secondary_rays_per_s": sec_per_step * args.steps * world / t, "clocks": clk,
+               "e2e": {"value": N * args.steps * world / t, "unit": "rays/s", "h2d_bytes_per_step": N * 8 + N + 100,
+                       "d2h_bytes_per_step": 8, "note": "the step builds its batch on the host and copies it (dynamic "
+                                                        "shapes sync the host several times per step)"}})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c4(args):
+    """PBR + CESR iteration (explore phase), eager dynamic shapes, every rank its own 1024-ray batch."""
+    import bench
+    from robir_b200 import cesr, dist as rdist, ops
+    from robir_b200.loss import InvLoss
+    N, M = 1024, 128
+    rank, world, local, dev, sd, model = _setup(M)
+    model.static_shapes = False
+    sh, nr = synthetic.cesr_state_dicts(SEED)
+    shadow, normal = cesr.WnMLP(191, 2), cesr.WnMLP(63, 3)
+    shadow.load_state_dict(sh)
+    normal.load_state_dict(nr)
+    hook = cesr.ClusteredAlbedoHook(model, shadow.to(dev), normal.to(dev), cur_iter=600)     # explore phase
+    model.get_sg_render = hook.get_sg_render
+    loss_fn = InvLoss()
+    params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters()) + hook.parameters()
+    opt = torch.optim.Adam(params, lr=5e-4)                                                  # train_cesr.py:111-117
+    reducer = rdist.GradAllReducer(params)
+    pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
+    hits = []
+
+    def step(s):
+        pix = synthetic.training_pixels(s * world + rank, n=N).to(dev)
+        uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None]
+        inp = {"uv": uv, "object_mask": torch.ones(1, N, dtype=torch.bool, device=dev), "pose": pose,
+               "intrinsics": K, "hdr_shift": model.gamma.hdr_shift.as_input().expand(N, 1)}
+        out = model(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss, _ = hook.pbr_step(loss_fn, out, {"rgb": torch.full((1, N, 3), 0.5, device=dev)})
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer()
+        opt.step()
+        hits.append(out["network_object_mask"].sum())
+    clocks = bench.ClockSampler(local).start()
+    t = _timed(step, args.warmup, args.steps, dev, world)
+    clk = clocks.stop()
+    if rank == 0:
+        hf = float(torch.stack(hits[-args.steps:]).float().mean()) / N
+        cfg = {"workload": "truck-synthetic PBR + CESR step: 1024 random pixels/step/GPU, M=128, shadow_net (191->512x8->2 "
+                           "on n_hit x 128 rows) + normal_net, explore phase (iteration 600), S=8, fwd+loss+bwd+Adam over 3 "
+                           "networks, eager dynamic shapes", "config": "c4", "rays_per_step_per_gpu": N, "num_lgt_sgs": M,
+               "hit_fraction": hf, "wn_engine": ops.ENGINE["wn"],
+               "parallelism": "rays x%d (+ NCCL grad all-reduce incl. shadow_net / normal_net)" % world}
+        _line(args, "rays/sec (fwd+bwd) PBR+CESR stage, truck", N * args.steps * world / t, "rays/s",
+              1e3 * t / args.steps, world, cfg,
+              {"clocks": clk, "e2e": {"value": N * args.steps * world / t, "unit": "rays/s",
+                                      "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": 0,
+                                      "note": "pixel indices are drawn on the host and copied every step"}})
+    if world > 1:
+        torch.distributed.destroy_process_group()
