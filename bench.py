@@ -348,7 +348,8 @@ def run_pbr(args):
         loss_fn.static_shapes = True
     if args.mode == "graph":
         from robir_b200.graph import GraphedPBRStep
-        graphed = GraphedPBRStep(model, loss_fn, opt, N_RAYS, pose, K, reducer=reducer if world > 1 else None)
+        graphed = GraphedPBRStep(model, loss_fn, opt, N_RAYS, pose, K, reducer=reducer if world > 1 else None,
+                                 split_reduce=args.split_reduce)
 
         def train_step(uv, om, gt):   # noqa: F811  (replay of the captured step)
             return graphed(uv, om, gt), None
@@ -497,7 +498,9 @@ def run_pbr(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.config, {
-                "parallelism": "rays x%d (+ NCCL grad all-reduce)" % world, "hit_fraction": hit_frac,
+                "parallelism": "rays x%d (+ NCCL grad all-reduce%s)" % (
+                    world, "" if world == 1 else (", eager between two graphs" if args.split_reduce else
+                                                  ", captured inside the step graph")), "hit_fraction": hit_frac,
                 "vis_queries_per_step": pairs_total / float(args.steps), "vis_engine": ops.ENGINE["vis"],
                 "rng": "device", "mode": args.mode}),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -522,6 +525,8 @@ def main():
     ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back replays for the sustained record")
     ap.add_argument("--engine", default=None, help="visibility-MLP engine: tc (default, fp32 parity) | tc1 (single-pass "
                                                    "fast mode) | ffma")
+    ap.add_argument("--split-reduce", action="store_true", help="multi-GPU: issue the gradient all-reduce eagerly between "
+                                                               "two graphs (round-1 arrangement) instead of capturing it")
     ap.add_argument("--mode", default="graph", help="graph: whole step as one CUDA graph (default) | eager | eager-static")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,6 +17,9 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
+        # the gradient all-reduce is captured inside the step's CUDA graph: the process group's watchdog must not poll
+        # (and thereby synchronise with) a stream that is being captured
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
 
@@ -29,13 +32,16 @@ def shard_rays(n_rays, rank, world):
 
 
 class GradAllReducer:
-    """Flat-bucket all-reduce of the gradients of ``params`` (one NCCL call on the current stream).  average=True
-    (weak scaling: every rank steps on its own batch, the reference's DataParallel-free equivalent is the mean of the
-    per-batch gradients) divides by the world size; average=False is the plain sum that strong sharding of ONE batch
-    needs: under ``STRONG_SHARDING`` the loss code normalises every per-ray term by the GLOBAL ray / hit counts
-    (``global_count`` / ``global_mean``), shares the parameter-only terms out over the ranks (``param_only``) and takes
-    the batch means of both KL terms over all ranks (``batch_mean_rows``), so the summed per-rank gradients equal the
-    full-batch gradient (2-rank test: tests/test_dist_cpu.py)."""
+    """Flat-bucket all-reduce of the gradients of ``params``: one gather kernel, ONE NCCL call on the current stream
+    (ReduceOp.AVG does the division inside the collective), one multi-tensor scatter.  Everything is stream-ordered
+    device work with static shapes, so ``GraphedPBRStep`` captures it INSIDE the step's CUDA graph between the backward
+    and the optimizer update (no second graph launch, no host round trip between them).  average=True (weak scaling:
+    every rank steps on its own batch; the mean of the per-batch gradients is what a K-times larger batch would give);
+    average=False is the plain sum that strong sharding of ONE batch needs: under ``STRONG_SHARDING`` the loss code
+    normalises every per-ray term by the GLOBAL ray / hit counts (``global_count`` / ``global_mean``), shares the
+    parameter-only terms out over the ranks (``param_only``) and takes the batch means of both KL terms over all ranks
+    (``batch_mean_rows``), so the summed per-rank gradients equal the full-batch gradient (2-rank test:
+    tests/test_dist_cpu.py)."""
 
     def __init__(self, params, average=True):
         self.params = [p for p in params if p.requires_grad]
@@ -50,9 +56,12 @@ class GradAllReducer:
             return
         grads = [p.grad for p in ps]
         flat = torch.cat([g.reshape(-1) for g in grads])              # one gather kernel
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        if self.average:
-            flat.div_(dist.get_world_size())
+        if self.average and dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if self.average:
+                flat.div_(dist.get_world_size())
         views, off = [], 0
         for g in grads:
             views.append(flat[off:off + g.numel()].view_as(g))

@@ -11,11 +11,13 @@ from .loss import pbr_step_loss
 class GraphedPBRStep:
     """step(uv [1,N,2], object_mask [1,N] bool, rgb_gt [1,N,3]) -> loss (0-d device tensor, valid until the next call).
 
-    With ``reducer`` (multi-GPU gradient all-reduce) the step is split into two graphs -- forward+backward and the
-    optimizer update -- with the NCCL collective issued eagerly in between."""
+    With ``reducer`` (multi-GPU gradient all-reduce, ``dist.GradAllReducer``) the NCCL collective is captured inside the
+    same graph, between the backward and the optimizer update: one graph launch per step on every rank.
+    ``split_reduce=True`` restores the round-1 arrangement (two graphs with the collective issued eagerly in between) for
+    comparison or for back ends whose collectives cannot be captured."""
 
     def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3,
-                 record_randoms=False):
+                 record_randoms=False, split_reduce=False):
         """record_randoms: keep references to the random tensors drawn inside the captured step (``self.random_tape``, in
         draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes)."""
         if rng._mode != "device":
@@ -29,13 +31,14 @@ class GraphedPBRStep:
         self.gt = torch.zeros(1, n_rays, 3, device=dev)
         self.pose, self.K, self.n = pose, intrinsics, n_rays
         self.hits = None
-        split = reducer is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        multi = reducer is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        split = multi and split_reduce
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._fwd_bwd()
-                if split:
+                if multi:
                     reducer()
                 self.opt.step()
                 ops.invalidate_packed_weights()   # optimizers with fused multi-tensor kernels do not bump versions
@@ -50,6 +53,8 @@ class GraphedPBRStep:
             with torch.cuda.graph(self.g1):
                 self.loss = self._fwd_bwd()
                 if not split:
+                    if multi:
+                        reducer()                  # NCCL all-reduce as a node of this graph
                     self.opt.step()
         self.random_tape = list(tape) if record_randoms else None
         self.launches_per_step = _lib.launch_count - before    # kernels of the C-ABI library inside one replay
