@@ -525,8 +525,9 @@ def main():
     ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back replays for the sustained record")
     ap.add_argument("--engine", default=None, help="visibility-MLP engine: tc (default, fp32 parity) | tc1 (single-pass "
                                                    "fast mode) | ffma")
-    ap.add_argument("--split-reduce", action="store_true", help="multi-GPU: issue the gradient all-reduce eagerly between "
-                                                               "two graphs (round-1 arrangement) instead of capturing it")
+    ap.add_argument("--capture-reduce", dest="split_reduce", action="store_false",
+                    help="multi-GPU: capture the gradient all-reduce inside the step graph instead of issuing it eagerly "
+                         "between the forward/backward graph and the optimizer graph (same speed, see graph.py)")
     ap.add_argument("--mode", default="graph", help="graph: whole step as one CUDA graph (default) | eager | eager-static")
     args = ap.parse_args()
     if args.impl == "reference":

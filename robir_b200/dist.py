@@ -17,9 +17,6 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
-        # the gradient all-reduce is captured inside the step's CUDA graph: the process group's watchdog must not poll
-        # (and thereby synchronise with) a stream that is being captured
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
 
@@ -34,8 +31,7 @@ def shard_rays(n_rays, rank, world):
 class GradAllReducer:
     """Flat-bucket all-reduce of the gradients of ``params``: one gather kernel, ONE NCCL call on the current stream
     (ReduceOp.AVG does the division inside the collective), one multi-tensor scatter.  Everything is stream-ordered
-    device work with static shapes, so ``GraphedPBRStep`` captures it INSIDE the step's CUDA graph between the backward
-    and the optimizer update (no second graph launch, no host round trip between them).  average=True (weak scaling:
+    device work with static shapes (``GraphedPBRStep`` can capture it inside the step's CUDA graph).  average=True (weak scaling:
     every rank steps on its own batch; the mean of the per-batch gradients is what a K-times larger batch would give);
     average=False is the plain sum that strong sharding of ONE batch needs: under ``STRONG_SHARDING`` the loss code
     normalises every per-ray term by the GLOBAL ray / hit counts (``global_count`` / ``global_mean``), shares the

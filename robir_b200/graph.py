@@ -11,13 +11,15 @@ from .loss import pbr_step_loss
 class GraphedPBRStep:
     """step(uv [1,N,2], object_mask [1,N] bool, rgb_gt [1,N,3]) -> loss (0-d device tensor, valid until the next call).
 
-    With ``reducer`` (multi-GPU gradient all-reduce, ``dist.GradAllReducer``) the NCCL collective is captured inside the
-    same graph, between the backward and the optimizer update: one graph launch per step on every rank.
-    ``split_reduce=True`` restores the round-1 arrangement (two graphs with the collective issued eagerly in between) for
-    comparison or for back ends whose collectives cannot be captured."""
+    With ``reducer`` (multi-GPU gradient all-reduce, ``dist.GradAllReducer``) the step is two graphs -- forward+backward
+    and the optimizer update -- with the NCCL collective issued eagerly in between (``split_reduce=True``, default), or
+    ONE graph with the collective captured between the backward and the optimizer update (``split_reduce=False``).
+    Measured on 2 B200s (profiles/r2_v15_*): 3.80 vs 3.82 ms/step -- the ~0.1 ms over the single-GPU step is the
+    collective's own serial device time (gather + 3.4 MB all-reduce + scatter after the last gradient), not host
+    latency, so capturing it buys nothing; only bucketing it under the visibility backward would."""
 
     def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3,
-                 record_randoms=False, split_reduce=False):
+                 record_randoms=False, split_reduce=True):
         """record_randoms: keep references to the random tensors drawn inside the captured step (``self.random_tape``, in
         draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes)."""
         if rng._mode != "device":
