@@ -184,6 +184,22 @@ int robir_tc_debug_buffer(void* buf);
 /* unit-test hook: D[128][256] = A[128][256] . W[256][256]^T through the same pipeline (one layer image) */
 int robir_tc_selftest(const float* A, const void* img, float* D, int terms, void* stream);
 
+/* ---- 8f rank 4: stage-1 NeuS volume renderer, forward path (neus/volume_render/sdf_render.py) -- the per-ray parts
+ * around the network evaluations (robir_sdf_eval + the fused colour chain): up_sample / sample_pdf (:5-82), the sorted
+ * merge of cat_z_vals (:85-99), the section midpoints and the alpha compositing of render_core (:141-233) incl. the
+ * per-ray depth / accumulation of render_neus (:333-341).  One warp per ray, <= 256 depths per ray.
+ * eik_acc [2] (zero-initialised): sum of relax_inside * (|grad| - 1)^2 and of relax_inside. */
+int robir_neus_upsample(int B, int n, int n_imp, const float* rays_o, const float* rays_d, const float* z,
+                        const float* sdf, float inv_s, float radius, float* new_z, void* stream);
+int robir_neus_merge(int B, int n, int m, const float* z, const float* sdf, const float* new_z, const float* new_sdf,
+                     float* out_z, float* out_sdf, void* stream);
+int robir_neus_midpoints(int B, int n, float sample_dist, const float* rays_o, const float* rays_d, const float* z,
+                         float* mid_z, float* pts, void* stream);
+int robir_neus_composite(int B, int n, float sample_dist, float inv_s, float cos_anneal, float radius, int white_bkgd,
+                         const float* rays_o, const float* rays_d, const float* z, const float* sdf, const float* grad,
+                         const float* color, const float* near, const float* far, float* rgb, float* weights,
+                         float* acc, float* dist, float* eik_acc, void* stream);
+
 /* ---- a10/a11: weighted per-lobe / per-point means (model/sg_render.py:180-183, :283-294) -------------------------- */
 int robir_diffuse_reduce_fwd(int n, int M, int S, const uint32_t* bits, const int* lobe_off, const int* start,
                              const float* vis, const float* w, float* light_vis /*[n][M]*/, void* stream);

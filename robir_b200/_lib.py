@@ -109,6 +109,10 @@ _SIGNATURES = {
     "robir_vis_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "robir_tc_selftest": [_P, _P, _P, _I, _P],
     "robir_tc_debug_buffer": [_P],
+    "robir_neus_upsample": [_I, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P],
+    "robir_neus_merge": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "robir_neus_midpoints": [_I, _I, _F, _P, _P, _P, _P, _P, _P],
+    "robir_neus_composite": [_I, _I, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_pack_pad": [_P, _I, _I, _P, _I, _I, _P],
     "robir_mlp_fwd": [POINTER(MlpParams), _I, _P],
     "robir_mlp_bwd": [POINTER(MlpParams), _I, _P],

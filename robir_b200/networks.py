@@ -121,7 +121,7 @@ class ImplicitNetworkMy(nn.Module):
         return sdf, grad
 
     # ---- NeuS-coordinate evaluation used by the secondary-ray radiance (neus_model.py:745-752, 828-884) ----------------
-    def neus_forward(self, pts_neus, dirs):
+    def neus_forward(self, pts_neus, dirs, return_grad=False):
         """NeuSModel.forward: colour(x, grad sdf(x), dirs, feat) and sdf at NeuS-coordinate points (no autograd)."""
         sdf, grad, feat = ops.sdf_eval(self._w, pts_neus, in_scale=1.0, sdf_scale=1.0, feat_scale=1.0, want_grad=True,
                                        want_feat=True)
@@ -130,7 +130,10 @@ class ImplicitNetworkMy(nn.Module):
             self.__dict__["_color_chain"] = ops.MlpChain.from_weightnorm([getattr(net, "lin%d" % l) for l in range(5)],
                                                                           "relu", "raw")
         x = torch.cat([pts_neus, positional_encoding(dirs, 4), grad, feat], -1)
-        return torch.sigmoid(ops.fused_mlp(self.__dict__["_color_chain"], x)), sdf[:, None]
+        color = torch.sigmoid(ops.fused_mlp(self.__dict__["_color_chain"], x))
+        if return_grad:
+            return color, sdf[:, None], grad
+        return color, sdf[:, None]
 
     def borrow_color(self, points, view_dirs):
         """16-sample NeuS micro volume render around a surface point (neus_model.py:828-869)."""

@@ -1018,3 +1018,45 @@ def test_cesr_warmup_phase(model128):
         assert all(torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in shadow.parameters())
     finally:
         model128.get_sg_render, model128.static_shapes = old_hook, old_static
+
+
+def test_neus_stage1_render_vs_golden(model16, synth_sd16):
+    """the stage-1 NeuS renderer (render_neus: 64 + 4 x 16 hierarchical depths, render_core
+    compositing) on the CUDA kernels vs the unmodified reference's golden outputs (float64 run of
+    neus/volume_render/sdf_render.py, tests/golden/make_golden.py) -- evaluation mode and the training-time sampler's
+    jittered depths.  Composited quantities agree to the fp32 floor; the individual depths / weights pass through the
+    inverse-CDF sampler, which amplifies evaluation-order noise (the fp32 oracle itself sits at 3.5e-4 there)."""
+    import neus_stage1 as N1
+    from robir_b200 import neus_stage1 as R1
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "neus_stage1.npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    net = model16.implicit_network
+    c = lambda k: g[k].float().cuda()
+    with torch.no_grad():
+        ev = R1.render_neus(net, c("rays_o"), c("rays_d"), c("near"), c("far"), None, 0.3)
+        tr = R1.render_neus(net, c("rays_o"), c("rays_d"), c("near"), c("far"), c("t_rand"), 0.3)
+    for k in ("rgb", "dist", "acc"):
+        assert rel_err(ev[k], g["eval_" + k].float()) < REL, ("eval", k, rel_err(ev[k], g["eval_" + k].float()))
+        assert rel_err(tr[k], g["out_" + k].float()) < REL, ("jittered", k)
+    assert abs(float(tr["sim_or_grad"]) - float(g["out_sim_or_grad"])) < REL
+    assert tr["weights"].shape == (32, 128) and tr["means"].shape == (32, 128)
+    assert (tr["weights"].cpu() - g["out_weights"].float()).abs().max() < 2e-3
+    assert (tr["means"].cpu() - g["out_means"].float()).abs().max() < 2e-3
+    # the sampler's invariants at a larger size: depths sorted, weights a sub-probability, accumulation = their sum
+    gen = torch.Generator().manual_seed(3)
+    B = 777
+    o = torch.nn.functional.normalize(torch.randn(B, 3, generator=gen), dim=-1) * 3.0
+    d = torch.nn.functional.normalize(-o + 0.4 * torch.randn(B, 3, generator=gen), dim=-1)
+    near, far = torch.full((B, 1), 1.0), torch.full((B, 1), 5.0)
+    with torch.no_grad():
+        big = R1.render_neus(net, o.cuda(), d.cuda(), near.cuda(), far.cuda(), torch.rand(B, 1, generator=gen).cuda(), 1.0)
+        ref = N1.render_neus({k: v for k, v in synth_sd16.items() if k.startswith("implicit_network.")}, o[:64], d[:64],
+                             near[:64], far[:64], None, 1.0, training=False)
+        sub = R1.render_neus(net, o[:64].cuda(), d[:64].cuda(), near[:64].cuda(), far[:64].cuda(), None, 1.0)
+    assert (big["means"][:, 1:] >= big["means"][:, :-1]).all()
+    assert (big["weights"] >= 0).all() and (big["acc"] <= 1.0 + 1e-4).all()
+    assert rel_err(big["weights"].sum(-1), big["acc"]) < 1e-5
+    for k in ("rgb", "dist", "acc"):
+        assert rel_err(sub[k], ref[k]) < REL, ("oracle", k, rel_err(sub[k], ref[k]))
+    with pytest.raises(Exception):
+        R1.render_neus(net, o[:4].cuda(), d[:4].cuda(), near[:4].cuda(), far[:4].cuda())     # autograd on: refused
