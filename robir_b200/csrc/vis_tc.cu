@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int k = 0; k < 4; ++k) { mbar_init(&a_ready[k], 256); mbar_init(&s_ready[k], 256); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&a_ready[k], 8); mbar_init(&s_ready[k], 8); }   // one arrival per epilogue warp
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
-    mbar_init(&d_free[0], 256); mbar_init(&d_free[1], 256);
+    mbar_init(&d_free[0], 8); mbar_init(&d_free[1], 8);
     mbar_init(&x_free, 1);
     mbar_init(&t_ready[0], 1); mbar_init(&t_ready[1], 1);
     fence_barrier_init();
@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
       store_a(tmem_base + lane_addr + (uint32_t)col, x);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&s_ready[kb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_ready[kb]);
     };
 
     if (blockIdx.x < ntiles) {
@@ -467,15 +468,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
           TC_WAIT(w_dfull, &d_full[h], d_phase[h] & 1);
           ++d_phase[h];
           tc_fence_after();
+          // software pipeline over the two chunks of the half: the second chunk's accumulators are requested right
+          // after the first chunk's have arrived and travel while the first chunk converts (TMEM reads are 64 B/clk:
+          // requesting both up front doubles the time to the first hand-off)
           uint32_t rr[2][32];
           tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 32 * ch), rr[0]);
-          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 64 + 32 * ch), rr[1]);
           tmem_wait_ld();
+          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 64 + 32 * ch), rr[1]);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int kb = 2 * h + c;
             const int n0 = 64 * kb + 32 * ch;                  // first output feature of this chunk
             const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
+            if (c == 1) tmem_wait_ld();
             uint32_t (&r)[32] = rr[c];
             float x[32];
             if (MODE == 0) {
@@ -511,12 +516,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) vis_tc_kernel(TcParams p) {
               store_a(taddr, x);
               tmem_wait_st();
               tc_fence_before();
-              mbar_arrive(&a_ready[kb]);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[kb]);
             }
           }
           if (fwd_last) {                                      // this D half may be overwritten by the next tile
             tc_fence_before();
-            mbar_arrive(&d_free[h]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_free[h]);
           }
         }
       }
