@@ -3,6 +3,7 @@
 // lift), utils/octree.py:421-438,459-471,493-585, model/octree_tracing.py:43-60.
 // Compiled with -fmad=false: every product/sum is rounded separately like the reference's elementwise ops.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "octree_walk.h"
@@ -56,8 +57,17 @@ struct OctCastParams {
 constexpr int kMaxIter = 4096;
 // counters[kMaxIter + 0] = node visits (low), +1 micro samples, +2 iterations executed
 
-__global__ void __launch_bounds__(256) octree_cast_kernel(OctCastParams p) {
+// CLUSTER = false: cooperative grid of any size, lock-step through grid.sync() and global live counters.
+// CLUSTER = true : ONE thread-block cluster (<= 16 CTAs x 1024 threads) holds every ray of the call: the per-iteration
+// barrier is the hardware cluster barrier and the live count is summed through distributed shared memory -- the
+// reference's multi_samp depends on that count every iteration (utils/octree.py:547-548), so the iterations cannot be
+// decoupled, only the barrier made cheap.  Same per-ray arithmetic in the same order: bit-identical results.
+template <bool CLUSTER>
+__global__ void __launch_bounds__(CLUSTER ? 1024 : 256) octree_cast_kernel(OctCastParams p) {
   cg::grid_group grid = cg::this_grid();
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned s_live[3];
+  if (CLUSTER && threadIdx.x < 3) s_live[threadIdx.x] = 0;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -85,14 +95,29 @@ __global__ void __launch_bounds__(256) octree_cast_kernel(OctCastParams p) {
       live_cnt += s.live ? 1u : 0u;
     }
     live_cnt = __reduce_add_sync(0xffffffffu, live_cnt);
-    if (lane == 0 && live_cnt) atomicAdd(&p.counters[0], live_cnt);
+    if (CLUSTER) {
+      __syncthreads();                                   // s_live zeroed
+      if (lane == 0 && live_cnt) atomicAdd(&s_live[0], live_cnt);
+    } else if (lane == 0 && live_cnt) {
+      atomicAdd(&p.counters[0], live_cnt);
+    }
   }
-  grid.sync();
+  if (CLUSTER) cluster.sync(); else grid.sync();
 
   // state_ptr encoding: >= 0 live in node ptr;  -1 dead outside;  <= -2 finished (hit) in node (-2 - v)
   int it = 0;
   for (;; ++it) {
-    const unsigned live = *((volatile unsigned*)&p.counters[it]);
+    unsigned live;
+    if (CLUSTER) {
+      // sum of every CTA's count of rays alive after iteration it - 1 (slot it % 3 of each CTA's shared memory)
+      unsigned part = 0;
+      if (lane < (int)cluster.num_blocks()) part = *cluster.map_shared_rank(&s_live[it % 3], lane);
+      live = __reduce_add_sync(0xffffffffu, part);
+      if (threadIdx.x == 0) s_live[(it + 2) % 3] = 0;     // read by everyone one iteration ago, next filled in it + 1
+      if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[it] = live;   // statistics only
+    } else {
+      live = *((volatile unsigned*)&p.counters[it]);
+    }
     if (live == 0 || it >= kMaxIter - 1) break;
     if (secondary && it > p.max_iter) break;
     float step = 0.001f;
@@ -152,9 +177,18 @@ __global__ void __launch_bounds__(256) octree_cast_kernel(OctCastParams p) {
         live_next += alive ? 1u : 0u;
       }
     }
-    if (lane == 0 && live_next) atomicAdd(&p.counters[it + 1], live_next);
-    grid.sync();
+    if (CLUSTER) {
+      if (lane == 0 && live_next) atomicAdd(&s_live[(it + 1) % 3], live_next);
+      cluster.sync();
+    } else {
+      if (lane == 0 && live_next) atomicAdd(&p.counters[it + 1], live_next);
+      grid.sync();
+    }
   }
+
+  // a CTA must not exit (and release its shared memory) while a slower CTA of the cluster may still be reading its
+  // live count for the iteration that ended the loop
+  if (CLUSTER) cluster.sync();
 
   // ---- finish: hit test + first-order refinement
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.K; r += gridDim.x * blockDim.x) {
@@ -206,15 +240,46 @@ int robir_octree_counters_len() { return kMaxIter + 8; }
 int robir_octree_cast(const OctCastParams* p, int sm_count, void* stream) {
   if (p->K == 0) return 0;
   RB_REQUIRE(p->o_div >= 1, "octree_cast: o_div must be >= 1");
+  OctCastParams params = *p;
+  // ---- small calls (a training batch of primary rays): one thread-block cluster, hardware barrier per iteration
+  static int cluster_ctas = -1;                           // largest cluster of 1024-thread CTAs this device schedules
+  if (cluster_ctas < 0) {
+    cluster_ctas = 0;
+    if (cudaFuncSetAttribute(octree_cast_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      for (int c = 16; c >= 8 && cluster_ctas == 0; c -= 8) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(c); cfg.blockDim = dim3(1024);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, octree_cast_kernel<true>, &cfg) == cudaSuccess && n >= 1) cluster_ctas = c;
+      }
+    }
+    (void)cudaGetLastError();
+  }
+  const int rays_per_warp = 4;
+  if (cluster_ctas > 0 && p->K <= cluster_ctas * 32 * rays_per_warp && !getenv("ROBIR_OCTREE_COOPERATIVE")) {
+    int ctas = (p->K + 31) / 32;                            // one warp per ray while the rays fit, then up to 4 per warp
+    ctas = ctas > cluster_ctas ? cluster_ctas : (ctas < 1 ? 1 : ctas);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(1024); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, octree_cast_kernel<true>, params));
+    return 0;
+  }
   int per_sm = 0;
-  RB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octree_cast_kernel, 256, 0));
+  RB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octree_cast_kernel<false>, 256, 0));
   RB_REQUIRE(per_sm >= 1, "octree_cast: kernel does not fit on an SM");
   long long want = ((long long)p->K * 32 + 255) / 256;   // one warp per ray
   int grid = (int)(want < (long long)per_sm * sm_count ? want : (long long)per_sm * sm_count);
   if (grid < 1) grid = 1;
-  OctCastParams params = *p;
   void* args[] = {&params};
-  RB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)octree_cast_kernel, dim3(grid), dim3(256), args, 0,
+  RB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)octree_cast_kernel<false>, dim3(grid), dim3(256), args, 0,
                                             (cudaStream_t)stream));
   return 0;
 }

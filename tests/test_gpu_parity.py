@@ -1060,3 +1060,32 @@ def test_neus_stage1_render_vs_golden(model16, synth_sd16):
         assert rel_err(sub[k], ref[k]) < REL, ("oracle", k, rel_err(sub[k], ref[k]))
     with pytest.raises(Exception):
         R1.render_neus(net, o[:4].cuda(), d[:4].cuda(), near[:4].cuda(), far[:4].cuda())     # autograd on: refused
+
+
+@pytest.mark.parametrize("K,max_iter", [(1024, -1), (700, -1), (33, -1), (1500, 32)])
+def test_octree_cluster_walk_matches_cooperative_walk(model16, K, max_iter):
+    """Calls of up to a few thousand rays run as ONE thread-block cluster (hardware barrier + distributed-shared-memory
+    live count per lock-step iteration) instead of the cooperative grid: same per-ray arithmetic, bit-identical
+    distances / hit points / masks / iteration counts."""
+    from robir_b200 import ops
+    model16.generate()
+    tree = model16.ray_tracer.sdf_octree
+    gen = torch.Generator().manual_seed(K)
+    o = (torch.nn.functional.normalize(torch.randn(K, 3, generator=gen), dim=-1) * (0.9 if max_iter > 0 else 2.0)).cuda()
+    d = torch.nn.functional.normalize(-o.cpu() + 0.3 * torch.randn(K, 3, generator=gen), dim=-1).cuda()
+    res = {}
+    for mode in ("cluster", "cooperative"):
+        if mode == "cooperative":
+            os.environ["ROBIR_OCTREE_COOPERATIVE"] = "1"
+        try:
+            x, hit, t, cnt = ops.octree_cast(tree, o, d, max_iter=max_iter, o_div=1, return_stats=True)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("ROBIR_OCTREE_COOPERATIVE", None)
+        res[mode] = (x.cpu(), hit.cpu(), t.cpu(), cnt.cpu())
+    a, b = res["cluster"], res["cooperative"]
+    assert torch.equal(a[1], b[1]) and 0 < int(a[1].sum()) < K
+    assert torch.equal(a[2].nan_to_num(-7.0), b[2].nan_to_num(-7.0)) and torch.equal(a[0].nan_to_num(-7.0), b[0].nan_to_num(-7.0))
+    n_it = int(a[3][-6])                                          # counters[kMaxIter + 2] = iterations executed
+    assert n_it == int(b[3][-6]) and n_it > 3
+    assert torch.equal(a[3][:n_it], b[3][:n_it])                  # live count per iteration
