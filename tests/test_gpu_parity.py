@@ -1064,9 +1064,9 @@ def test_neus_stage1_render_vs_golden(model16, synth_sd16):
 
 @pytest.mark.parametrize("K,max_iter", [(1024, -1), (700, -1), (33, -1), (1500, 32)])
 def test_octree_cluster_walk_matches_cooperative_walk(model16, K, max_iter):
-    """Calls of up to a few thousand rays run as ONE thread-block cluster (hardware barrier + distributed-shared-memory
-    live count per lock-step iteration) instead of the cooperative grid: same per-ray arithmetic, bit-identical
-    distances / hit points / masks / iteration counts."""
+    """The single-cluster variant of the walk (ROBIR_OCTREE_CLUSTER=1: hardware cluster barrier + distributed-shared-
+    memory live count per lock-step iteration; slower than the cooperative grid on this part, see csrc/trace.cu) against
+    the cooperative grid: same per-ray arithmetic, bit-identical distances / hit points / masks / iteration counts."""
     from robir_b200 import ops
     model16.generate()
     tree = model16.ray_tracer.sdf_octree
@@ -1075,13 +1075,13 @@ def test_octree_cluster_walk_matches_cooperative_walk(model16, K, max_iter):
     d = torch.nn.functional.normalize(-o.cpu() + 0.3 * torch.randn(K, 3, generator=gen), dim=-1).cuda()
     res = {}
     for mode in ("cluster", "cooperative"):
-        if mode == "cooperative":
-            os.environ["ROBIR_OCTREE_COOPERATIVE"] = "1"
+        if mode == "cluster":
+            os.environ["ROBIR_OCTREE_CLUSTER"] = "1"
         try:
             x, hit, t, cnt = ops.octree_cast(tree, o, d, max_iter=max_iter, o_div=1, return_stats=True)
             torch.cuda.synchronize()
         finally:
-            os.environ.pop("ROBIR_OCTREE_COOPERATIVE", None)
+            os.environ.pop("ROBIR_OCTREE_CLUSTER", None)
         res[mode] = (x.cpu(), hit.cpu(), t.cpu(), cnt.cpu())
     a, b = res["cluster"], res["cooperative"]
     assert torch.equal(a[1], b[1]) and 0 < int(a[1].sum()) < K
