@@ -494,7 +494,8 @@ def run_pbr(args):
     if rank == 0:
         hit_frac = n_hits_all / float(N_RAYS * args.steps * world)
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.config == "c2" else "rays/sec (fwd+bwd) PBR stage, dtu 1600x1200",
+            "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.config, {
