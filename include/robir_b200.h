@@ -52,6 +52,24 @@ typedef struct {
 } robir_sdf_params;
 int robir_sdf_eval(const robir_sdf_params* p, int sm_count, void* stream);
 
+/* The same network on the tensor cores (tcgen05 / TMEM, scaled fp16 hi/lo 3-term products = fp32 parity): persistent
+ * kernel, 128-row tiles (32 points x value + 3 tangent rows, or 128 points without the normal), activations in TMEM,
+ * Softplus(100) and its derivative applied by the epilogue (csrc/sdf_tc.cu).  img: 8 layer images (9 with features) of
+ * robir_tc_pack_layer(Wt_l, 256, 256, 64 | 256, transpose = 1, n_halves = 2, terms = 3) built from the folded transposed
+ * weights above, layer 4 pre-multiplied by 1/sqrt(2) (the skip concat's scale); bias [8][256].  Points at or beyond
+ * *n_active are not evaluated (the caller zero-fills). */
+typedef struct {
+  const float* pts; int n;
+  float in_scale, sdf_scale, feat_scale;
+  const void* img;
+  const float* bias;                /* [8][256] */
+  const float* w8_sdf;              /* [256] */
+  const float* b8;                  /* [257] */
+  float* sdf; float* grad; float* feat;
+  const int* n_active;
+} robir_sdf_tc_params;
+int robir_sdf_tc(const robir_sdf_tc_params* p, int sm_count, void* stream);
+
 /* ---- a2: camera rays: rend_util.get_camera_params + lift (utils/rend_util.py:51-97), one 4x4 pose ----------------- */
 int robir_camera_rays(int N, const float* uv /*[N][2]*/, const float* pose /*[4][4]*/, const float* K /*[3][3]*/,
                       float* dirs /*[N][3]*/, void* stream);

@@ -34,6 +34,12 @@ class SdfParams(Structure):
                 ("n_active", c_void_p)]
 
 
+class SdfTcParams(Structure):
+    _fields_ = [("pts", c_void_p), ("n", c_int), ("in_scale", c_float), ("sdf_scale", c_float),
+                ("feat_scale", c_float), ("img", c_void_p), ("bias", c_void_p), ("w8_sdf", c_void_p), ("b8", c_void_p),
+                ("sdf", c_void_p), ("grad", c_void_p), ("feat", c_void_p), ("n_active", c_void_p)]
+
+
 class SdfNet(Structure):
     _fields_ = [("Wt", c_void_p * 8), ("bias", c_void_p * 8), ("w8_sdf", c_void_p), ("b8", c_void_p)]
 
@@ -125,6 +131,7 @@ _SIGNATURES = {
     "robir_sg_render_fwd": [POINTER(SgParams), _P],
     "robir_sg_render_bwd": [POINTER(SgParams), _P],
     "robir_sdf_eval": [POINTER(SdfParams), _I, _P],
+    "robir_sdf_tc": [POINTER(SdfTcParams), _I, _P],
     "robir_camera_rays": [_I, _P, _P, _P, _P, _P],
     "robir_octree_cast": [POINTER(OctCastParams), _I, _P],
     "robir_octree_counters_len": [],

@@ -25,6 +25,7 @@ obj sphere_trace.cu build/sphere_trace.o "-Xptxas -v" & pids+=($!)
 obj loss.cu build/loss.o "" & pids+=($!)
 obj tc_mlp.cu build/tc_mlp.o "-Xptxas -v" & pids+=($!)
 obj neus.cu build/neus.o "" & pids+=($!)
+obj sdf_tc.cu build/sdf_tc.o "-Xptxas -v" & pids+=($!)
 for pid in "${pids[@]}"; do wait "$pid" || { echo "build.sh: a compile job failed" >&2; exit 1; }; done
-$NVCC $ARCH -shared -o ../librobir_b200.so build/capi.o build/vis.o build/sg.o build/sdf.o build/trace.o build/vis_tc.o build/mlp.o build/sphere_trace.o build/loss.o build/tc_mlp.o build/neus.o -lcudart_static -lpthread -ldl -lrt
+$NVCC $ARCH -shared -o ../librobir_b200.so build/capi.o build/vis.o build/sg.o build/sdf.o build/trace.o build/vis_tc.o build/mlp.o build/sphere_trace.o build/loss.o build/tc_mlp.o build/neus.o build/sdf_tc.o -lcudart_static -lpthread -ldl -lrt
 echo "built $(cd .. && pwd)/librobir_b200.so"

@@ -7,7 +7,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SgParams, SphereTraceParams, TlParams, check, f32, lib, ptr,
+from ._lib import (MlpParams, OctCastParams, OctreeView, SdfParams, SdfTcParams, SgParams, SphereTraceParams, TlParams, check, f32, lib, ptr,
                    sm_count, stream)
 
 TINY = 1e-6
@@ -277,7 +277,8 @@ class active_rows:
 # vis: "tc": tcgen05, scaled fp16 hi/lo 3-term split (fp32 parity, default) | "tc1": tcgen05 single-pass fp16 (fast mode,
 # ~1e-4: NOT the parity mode) | "ffma": exact-fp32 CUDA cores.  mlp: "tc" (bf16 hi/lo layer engine) | "ffma"
 # wn: the CESR stage's weight-normed 512-wide chains (shadow_net / normal_net): "tc" | "torch" (cuBLAS cross-check)
-ENGINE = {"vis": "tc", "mlp": "tc", "wn": "tc"}
+# sdf: the NeuS SDF network (value / normal / features): "tc" (tcgen05, csrc/sdf_tc.cu) | "ffma" (csrc/sdf.cu)
+ENGINE = {"vis": "tc", "mlp": "tc", "wn": "tc", "sdf": "tc"}
 PROFILE = None             # when a list: (name, start_event, end_event, max_tiles) per hot-kernel launch (bench.py)
 
 
@@ -680,6 +681,16 @@ class SdfWeights:
             check(lib().robir_pack_wn_row(ptr(f32(v8)), ptr(f32(g8)), 256, 0, ptr(w8), stream()))
             d["w8_sdf"] = w8
             d["b8"] = f32(lins[8].bias)
+            # tensor-core engine (csrc/sdf_tc.cu): scaled fp16 hi/lo images of the nine 256-wide layers in streaming
+            # order; the 1/sqrt(2) of the skip concat is folded into layer 4
+            sb = lib().robir_tc_image_bytes(1, 0, 3)
+            img = torch.zeros(9 * sb, dtype=torch.uint8, device=w8.device)
+            for l in range(8):
+                Wt = d["Wt%d" % l] if l != 4 else (d["Wt4"] * (1.0 / math.sqrt(2.0))).contiguous()
+                tc_pack_layer(Wt, 256, 256, 64 if l == 0 else 256, True, 2, img[l * sb:], 3)
+            tc_pack_layer(d["Wt8_feat"], 256, 256, 256, True, 2, img[8 * sb:], 3)
+            d["tc_img"] = img
+            d["bias8"] = torch.stack([d["b%d" % l] for l in range(8)]).contiguous()
             return d
         return self.cache.get(tensors, build)
 
@@ -689,6 +700,8 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     W = weights.get()
     pts = f32(pts)
     n = pts.shape[0]
+    if ENGINE["sdf"] == "tc" and n > 0:
+        return _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat)
     sdf = _empty(n, like=pts)
     grad = _empty(n, 3, like=pts) if want_grad else None
     feat = _empty(n, 256, like=pts) if want_feat else None
@@ -701,6 +714,21 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     p.sdf, p.grad, p.feat = ptr(sdf), ptr(grad), ptr(feat)
     p.n_active = ptr(active_rows.current)
     check(lib().robir_sdf_eval(ctypes.byref(p), sm_count(), stream()))
+    return sdf, grad, feat
+
+
+def _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat):
+    n = pts.shape[0]
+    alloc = _zeros if active_rows.current is not None else _empty      # inactive rows must read as 0
+    sdf = alloc(n, like=pts)
+    grad = alloc(n, 3, like=pts) if want_grad else None
+    feat = alloc(n, 256, like=pts) if want_feat else None
+    p = SdfTcParams()
+    p.pts, p.n, p.in_scale, p.sdf_scale, p.feat_scale = ptr(pts), n, in_scale, sdf_scale, feat_scale
+    p.img, p.bias, p.w8_sdf, p.b8 = ptr(W["tc_img"]), ptr(W["bias8"]), ptr(W["w8_sdf"]), ptr(W["b8"])
+    p.sdf, p.grad, p.feat = ptr(sdf), ptr(grad), ptr(feat)
+    p.n_active = ptr(active_rows.current)
+    check(lib().robir_sdf_tc(ctypes.byref(p), sm_count(), stream()))
     return sdf, grad, feat
 
 

@@ -1089,3 +1089,40 @@ def test_octree_cluster_walk_matches_cooperative_walk(model16, K, max_iter):
     n_it = int(a[3][-6])                                          # counters[kMaxIter + 2] = iterations executed
     assert n_it == int(b[3][-6]) and n_it > 3
     assert torch.equal(a[3][:n_it], b[3][:n_it])                  # live count per iteration
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 129, 5000])
+def test_sdf_tensor_core_engine_vs_ffma_and_oracle(synth_sd16, model16, n):
+    """ENGINE["sdf"] = "tc" (csrc/sdf_tc.cu: the SDF network as a persistent tcgen05 kernel, value + forward-mode normal
+    + features) against the FFMA kernel and the oracle: ragged sizes (tile = 32 points with the normal, 128 without),
+    both coordinate conventions, the fixed-capacity active-row count."""
+    from robir_b200 import ops
+    gen = torch.Generator().manual_seed(100 + n)
+    pts = (torch.rand(n, 3, generator=gen) * 2 - 1) * 0.7
+    w = model16.implicit_network._w
+    ref = O.implicit_forward(synth_sd16, pts[:64])
+    ref_g = O.implicit_gradient(synth_sd16, pts[:64])[:, 0, :]
+    out = {}
+    old = ops.ENGINE["sdf"]
+    try:
+        for eng in ("ffma", "tc"):
+            ops.ENGINE["sdf"] = eng
+            a = ops.sdf_eval(w, pts.cuda(), want_grad=True, want_feat=True)
+            b = ops.sdf_eval(w, pts.cuda())
+            c = ops.sdf_eval(w, pts.cuda(), in_scale=1.0, sdf_scale=1.0, feat_scale=1.0, want_feat=True)
+            n_act = torch.tensor([max(n // 2, 0)], dtype=torch.int32, device="cuda")
+            with ops.active_rows(n_act):
+                d = ops.sdf_eval(w, pts.cuda(), want_grad=True)
+            out[eng] = (a, b, c, d)
+    finally:
+        ops.ENGINE["sdf"] = old
+    (s, g, f), (s2, _, _), (s3, _, f3), (s4, g4, _) = out["tc"]
+    (s_f, g_f, f_f), (s2_f, _, _), (s3_f, _, f3_f), (s4_f, g4_f, _) = out["ffma"]
+    m = min(n, 64)
+    assert rel_err(s[:m], ref[:m, 0]) < REL and rel_err(f[:m], ref[:m, 1:]) < REL and rel_err(g[:m], ref_g[:m]) < REL
+    for a, b in ((s, s_f), (g, g_f), (f, f_f), (s2, s2_f), (s3, s3_f), (f3, f3_f)):
+        assert a.shape == b.shape and rel_err(a, b) < 2e-5, rel_err(a, b)
+    assert torch.equal(s2, s)                       # value-only tiles (128 points) give the same numbers as jet tiles
+    k = n // 2
+    assert rel_err(s4[:k], s_f[:k]) < 2e-5 and rel_err(g4[:k], g_f[:k]) < 2e-5
+    assert float(s4[k:].abs().sum()) == 0.0 and float(g4[k:].abs().sum()) == 0.0
