@@ -1124,5 +1124,6 @@ def test_sdf_tensor_core_engine_vs_ffma_and_oracle(synth_sd16, model16, n):
         assert a.shape == b.shape and rel_err(a, b) < 2e-5, rel_err(a, b)
     assert torch.equal(s2, s)                       # value-only tiles (128 points) give the same numbers as jet tiles
     k = n // 2
-    assert rel_err(s4[:k], s_f[:k]) < 2e-5 and rel_err(g4[:k], g_f[:k]) < 2e-5
+    if k:
+        assert rel_err(s4[:k], s_f[:k]) < 2e-5 and rel_err(g4[:k], g_f[:k]) < 2e-5
     assert float(s4[k:].abs().sum()) == 0.0 and float(g4[k:].abs().sum()) == 0.0
