@@ -121,7 +121,17 @@ class OctreeTracing(nn.Module):
                     y = sdf_fn(xx)
                     g = torch.autograd.grad(y, xx, torch.ones_like(y))[0]
                 return y.detach(), g.detach()
-        self.sdf_octree = build_octree(both, [box_min, box_max], device)
+        # The tree is built with the exact-fp32 FFMA evaluation of the SDF network: a node splits when
+        # |sdf(centre)| < 0.5 |size| (utils/octree.py:381-385), so values that differ in the last bits move a few
+        # borderline nodes and, through them, individual hit points by up to one march step (1e-3).  The FFMA kernel
+        # reproduces the reference's tree (node count within 64, golden masks identical); the build is a one-off
+        # outside the hot path, so it keeps that kernel whatever engine evaluates the network per step.
+        old_engine = ops.ENGINE.get("sdf")
+        ops.ENGINE["sdf"] = "ffma"
+        try:
+            self.sdf_octree = build_octree(both, [box_min, box_max], device)
+        finally:
+            ops.ENGINE["sdf"] = old_engine
         self.sdf_octree.max_iter = self.max_iter
         return self.sdf_octree
 
