@@ -192,17 +192,14 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sdf_tc_kernel(SdfTcParams p) {
           mbar_wait(&d_full[h], d_phase[h] & 1);
           ++d_phase[h];
           tc_fence_after();
-          uint32_t rr[2][32];
-          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 32 * ch), rr[0]);
-          tmem_wait_ld();
-          tmem_ld32(d_half + lane_addr + (uint32_t)(128 * h + 64 + 32 * ch), rr[1]);
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             const int kb = 2 * h + c;
             const int n0 = 64 * kb + 32 * ch;                  // first output column of this chunk
             const uint32_t taddr = d_half + lane_addr + (uint32_t)n0;
-            if (c == 1) tmem_wait_ld();
-            uint32_t (&r)[32] = rr[c];
+            uint32_t r[32];                                    // one chunk at a time: the softplus-jet epilogue needs
+            tmem_ld32(taddr, r);                               // the registers (no spills) more than the overlap
+            tmem_wait_ld();
             float v[32];
             if (layer < 8) {
               // Softplus(100) on the value rows, its derivative (of the VALUE row, same column) on the tangent rows

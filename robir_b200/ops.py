@@ -700,7 +700,10 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     W = weights.get()
     pts = f32(pts)
     n = pts.shape[0]
-    if ENGINE["sdf"] == "tc" and n > 0:
+    # the persistent tensor-core kernel streams the whole 2 MB weight image per 128-row tile: it wins once every SM has
+    # a tile (measured: 1.9x / 5.5x over the FFMA kernel at 740 k points with / without the normal), while a batch of a
+    # few hundred points is latency-bound either way and slightly faster on the FFMA kernel's 32-row tiles
+    if ENGINE["sdf"] == "tc" and n * (4 if want_grad else 1) >= SDF_TC_MIN_ROWS:
         return _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat)
     sdf = _empty(n, like=pts)
     grad = _empty(n, 3, like=pts) if want_grad else None
@@ -715,6 +718,9 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     p.n_active = ptr(active_rows.current)
     check(lib().robir_sdf_eval(ctypes.byref(p), sm_count(), stream()))
     return sdf, grad, feat
+
+
+SDF_TC_MIN_ROWS = 128 * 148          # one 128-row tile per SM
 
 
 def _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat):

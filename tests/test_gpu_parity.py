@@ -1103,7 +1103,8 @@ def test_sdf_tensor_core_engine_vs_ffma_and_oracle(synth_sd16, model16, n):
     ref = O.implicit_forward(synth_sd16, pts[:64])
     ref_g = O.implicit_gradient(synth_sd16, pts[:64])[:, 0, :]
     out = {}
-    old = ops.ENGINE["sdf"]
+    old, old_min = ops.ENGINE["sdf"], ops.SDF_TC_MIN_ROWS
+    ops.SDF_TC_MIN_ROWS = 1                       # force the tensor-core kernel at every size
     try:
         for eng in ("ffma", "tc"):
             ops.ENGINE["sdf"] = eng
@@ -1115,7 +1116,7 @@ def test_sdf_tensor_core_engine_vs_ffma_and_oracle(synth_sd16, model16, n):
                 d = ops.sdf_eval(w, pts.cuda(), want_grad=True)
             out[eng] = (a, b, c, d)
     finally:
-        ops.ENGINE["sdf"] = old
+        ops.ENGINE["sdf"], ops.SDF_TC_MIN_ROWS = old, old_min
     (s, g, f), (s2, _, _), (s3, _, f3), (s4, g4, _) = out["tc"]
     (s_f, g_f, f_f), (s2_f, _, _), (s3_f, _, f3_f), (s4_f, g4_f, _) = out["ffma"]
     m = min(n, 64)
