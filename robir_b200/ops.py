@@ -700,9 +700,9 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     W = weights.get()
     pts = f32(pts)
     n = pts.shape[0]
-    # the persistent tensor-core kernel streams the whole 2 MB weight image per 128-row tile: it wins once every SM has
-    # a tile (measured: 1.9x / 5.5x over the FFMA kernel at 740 k points with / without the normal), while a batch of a
-    # few hundred points is latency-bound either way and slightly faster on the FFMA kernel's 32-row tiles
+    # measured against the FFMA kernel (tools/c3_profile.py): 3.3x / 6.0x at 740 k points with / without the normal and
+    # features (158 / 241 TFLOP/s algorithmic), 1.2x at the 550 hit points of a training batch; below a few tiles both
+    # are latency-bound and the FFMA kernel's 32-row tiles spread better
     if ENGINE["sdf"] == "tc" and n * (4 if want_grad else 1) >= SDF_TC_MIN_ROWS:
         return _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat)
     sdf = _empty(n, like=pts)
@@ -720,7 +720,7 @@ def sdf_eval(weights, pts, in_scale=2.0, sdf_scale=0.5, feat_scale=0.5, want_gra
     return sdf, grad, feat
 
 
-SDF_TC_MIN_ROWS = 128 * 148          # one 128-row tile per SM
+SDF_TC_MIN_ROWS = 128 * 8
 
 
 def _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat):
