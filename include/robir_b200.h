@@ -316,6 +316,16 @@ int robir_tl_pack_weight(const float* W, int ldw, int N, int K, int transpose, i
 int robir_tl_pack_rows(const float* X, int ldx, int n, int K, const float* ref, int ld_ref, int act, int nkb, void* img,
                        void* stream);
 int robir_tl_layer(const robir_tl_params* p, void* stream);
+/* weight gradients of one layer on the tensor cores, for row counts where robir_mlp_wgrad's fp32 FFMA GEMM dominates
+ * (the CESR chains: n_hit x 128 rows).  dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums of G (db may be NULL);
+ * work holds robir_tl_wgrad_workspace(n, N, K, sm_count) bytes.  G and A are transposed into bf16 hi/lo images whose
+ * contraction index (the row) is K-major, a split-K tcgen05 GEMM (3-term hi/lo, fp32 accumulation) fills one 128 x 128
+ * tile per CTA and split, and a fixed-order reduction sums the splits: bitwise reproducible.  Replaces, for those
+ * shapes, what autograd does for lin.weight / lin.bias of model/neus_model.py:385-417 under training/train_cesr.py:533. */
+long long robir_tl_wgrad_workspace(int n, int N, int K, int sm_count);
+int robir_tl_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K,
+                   const int* n_active /* device row count of a fixed-capacity batch (rows beyond it are zero), or NULL */,
+                   void* work, float* dW, float* db, int sm_count, void* stream);
 /* ---- a1: hit compaction of a fixed-capacity ray batch (device-side counterpart of the boolean indexing at
  * implicit_differentiable_renderer.py:341-347): hits first (stable), misses after; pos / order int64 [N], n_act [1],
  * valid [N] (slot < n_act), pts [N][3] = hit points in slot order (0 for misses), view [N][3] = -dirs in slot order */

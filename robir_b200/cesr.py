@@ -64,9 +64,10 @@ def _layers(net):
     return [getattr(net, "lin%d" % l) for l in range(n_lin)], tuple(net.skip_in)
 
 
-def wn_mlp(net, x):
+def wn_mlp(net, x, n_active=None):
     """Forward of a WnMLP / reference SDFNetwork(multires=0) on rows x [R, d_in] (the reference evaluates the same rows
-    in 1024-row chunks, neus_model.py:397-415)."""
+    in 1024-row chunks, neus_model.py:397-415).  n_active (device int32 [1], fixed-capacity batches): only the leading
+    n_active rows carry data; the tensor-core engine skips the row tiles beyond them (see ops.wn_chain)."""
     lins, skip = _layers(net)
     if getattr(net, "embed_fn_fine", None) is not None or getattr(net, "scale", 1) != 1:
         raise RobirError("wn_mlp: only the multires = 0, scale = 1 form of SDFNetwork (CESR shadow_net / normal_net)")
@@ -77,7 +78,7 @@ def wn_mlp(net, x):
         raise RobirError("robir_b200.cesr needs CUDA tensors (there is no CPU path)")
     ops.lib()                                   # fail loudly when the extension is missing, whichever engine is selected
     if ops.ENGINE.get("wn", "tc") == "tc" and x.shape[0] >= 128:
-        return ops.wn_chain(x, Ws, bs, skip)
+        return ops.wn_chain(x, Ws, bs, skip, n_active=n_active)
     return _wn_rows_torch(Ws, bs, skip, x)
 
 
@@ -155,6 +156,11 @@ class ClusteredAlbedoHook:
             return "warmup" if self.cur_iter <= 500 else "project"
         return "explore"
 
+    def phase_key(self):
+        """Everything of the schedule that changes the step's control flow (what a captured CUDA graph bakes in)."""
+        return (self.prefit_option(), self.cur_iter > 1000, self.cur_iter > 500, bool(self.is_training),
+                bool(self.train_spec))
+
     def parameters(self):
         return list(self.shadow_net.parameters()) + list(self.normal_net.parameters())
 
@@ -209,6 +215,60 @@ class ClusteredAlbedoHook:
                     'random_xi_diffuse_albedo': mat['random_xi_diffuse_albedo']})
         return ret
 
+    # ---- the same hook for the fixed-capacity forward (IDRNetwork._forward_static; CUDA-graph mode, graph.GraphedPBRStep
+    # with hook=): rows are the whole ray batch, hits compacted to the front, `valid` marks them, `n_act` counts them on
+    # the device.  Batch statistics (the two supervise means) run over the valid rows; the two extra networks skip the
+    # row tiles beyond n_act.
+    def get_sg_render_static(self, points, view_dirs, indir_lgtSGs, lin_diff=False, train_spec=False,
+                             indir_integral=None, valid=None, n_act=None, precomputed=None, diffuse_presampled=None):
+        model = self.model
+        view_dirs = view_dirs / (torch.norm(view_dirs, dim=-1, keepdim=True) + 1e-6)
+        normals = precomputed[0]
+        normals = normals / torch.clamp(torch.norm(normals, dim=-1, keepdim=True), 1e-4)
+        normals = torch.where(valid[:, None], normals, torch.zeros_like(normals))
+        ret = {'normals': normals}
+        assert train_spec == self.train_spec
+        mat = precomputed[1]
+        lgtSGs = mat['sg_lgtSGs']
+        M = lgtSGs.shape[0]
+        if M != 128:
+            raise RobirError("the CESR hook is written for 128 light lobes (train_cesr.py:492-493), got %d" % M)
+        indir_integral = indir_integral * 2 * np.pi
+        diffuse_albedo, roughness = mat['sg_diffuse_albedo'], mat['sg_roughness']
+        zero3 = torch.zeros_like(normals)
+        normal_map = torch.where(valid[:, None], mat['sg_normal_map'].detach(), zero3)
+        emb = self.shadow_embed(points.detach())
+        with torch.set_grad_enabled(self.is_training and torch.is_grad_enabled()):
+            diffuse_vis = shadow_logits(self.shadow_net, emb, M, n_active=n_act)
+            normal_new = wn_mlp(self.normal_net, emb, n_active=n_act)
+        normal_new = normal_new / torch.clamp(normal_new.norm(dim=-1, keepdim=True), 1e-4)
+        normal_new = torch.where(valid[:, None], normal_new, zero3)
+        diffuse_vis = torch.softmax(diffuse_vis, -1)[..., 1]
+        prefit = self.prefit_option()
+        sg = sg_render.render_with_all_sg(points=points.detach(),
+                                          normal=normal_new if self.cur_iter > 1000 else normal_map,
+                                          viewdirs=view_dirs, lgtSGs=lgtSGs, indir_integral=indir_integral,
+                                          specular_reflectance=mat['sg_specular_reflectance'].abs(),
+                                          roughness=roughness, diffuse_albedo=diffuse_albedo,
+                                          indir_lgtSGs=indir_lgtSGs, VisModel=model.visibility_network, fun_spec=False,
+                                          lin_diff=True, testing=not self.is_training, metallic=None,
+                                          diffuse_vis=diffuse_vis, prefit=prefit, argmax_vis=False, valid=valid,
+                                          diffuse_presampled=diffuse_presampled)
+        sg["sg_rgb"] = sg["sg_diffuse_rgb"] * diffuse_albedo / np.pi + sg["sg_specular_rgb"]
+        sg["indir_rgb"] = sg["indir_diffuse_rgb"] * diffuse_albedo / np.pi + sg["indir_specular_rgb"]
+        supervise = sg['supervise']
+        if self.white_light and prefit != "warmup":
+            supervise = supervise + white_loss(lgtSGs)
+        count = valid.sum().clamp(min=1) * 3
+        supervise = supervise + ((normal_map - normal_new) ** 2).sum() / count          # both are 0 on the other rows
+        ret.update(sg)
+        ret.update({'diffuse_albedo': diffuse_albedo, 'roughness': roughness, 'metallic': mat['sg_metallic'],
+                    'normal_map': normal_new, 'gradient_error': supervise,
+                    'random_xi_roughness': mat['random_xi_roughness'],
+                    'random_xi_metallic': mat['random_xi_metallic'],
+                    'random_xi_diffuse_albedo': mat['random_xi_diffuse_albedo']})
+        return ret
+
     # ---- the step loss (train_cesr.py:387-430); loss_fn is an InvLoss
     def pbr_step(self, loss_fn, model_outputs, ground_truth):
         loss = 0.
@@ -221,8 +281,9 @@ class ClusteredAlbedoHook:
         return loss + model_outputs["gradient_error"], out
 
 
-def shadow_logits(net, emb, M=128):
-    """shadow_net on every (point, lobe) pair: rows [PE10(x_i) | onehot(m)], i-major (train_cesr.py:492-501)."""
+def shadow_logits(net, emb, M=128, n_active=None):
+    """shadow_net on every (point, lobe) pair: rows [PE10(x_i) | onehot(m)], i-major (train_cesr.py:492-501).
+    n_active: device int32 [1] count of leading POINTS that carry data (fixed-capacity mode)."""
     n = emb.shape[0]
     x = torch.cat([emb[:, None, :].expand(-1, M, -1), torch.eye(M, device=emb.device)[None].expand(n, -1, -1)], -1)
-    return wn_mlp(net, x.reshape(n * M, -1))
+    return wn_mlp(net, x.reshape(n * M, -1), n_active=None if n_active is None else n_active * M)

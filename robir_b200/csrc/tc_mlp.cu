@@ -10,7 +10,8 @@
 // is hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (fp32 parity, like vis_tc.cu).  The epilogue (one thread per
 // row) applies bias / activation (or the activation derivative), writes the fp32 rows that the backward and the weight
 // gradients need, and emits the hi/lo image of its 128 output columns = two k-blocks of the next layer's A operand.
-// Warp roles: warp 0 producer, warp 1 MMA issuer (elect.sync lane), warps 2-5 epilogue.
+// Warp roles: warp 0 producer, warp 1 MMA issuer (elect.sync lane), warps 2-9 epilogue (TMEM lane quarter warp % 4,
+// column half (warp - 2) / 4).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -20,7 +21,7 @@ using namespace tc;
 constexpr int kTlStages = 3;
 constexpr int kTlStageBytes = 65536;     // A k-block (32 KB) + W k-block (32 KB)
 constexpr int kTlBlockBytes = 32768;     // one 128 x 64 hi|lo k-block
-constexpr int kTlThreads = 192;
+constexpr int kTlThreads = 320;       // producer, MMA issuer, 8 epilogue warps (two per scheduler: 64 columns each)
 constexpr uint32_t kTlIdesc = idesc_bf16(128, 128);
 constexpr int kTlSmem = kTlStages * kTlStageBytes + 1024;
 
@@ -44,14 +45,16 @@ struct TcLayerParams {
 __device__ __forceinline__ float tl_act(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
-  if (act == ACT_SOFTPLUS100) return softplus100(x);
+  // softplus(beta = 100) as max(x, 0) + log(1 + e^(-100 |x|)) / 100: two MUFU ops, absolute error < 1e-8 (the log's
+  // argument is in [1, 2]); agrees with common.cuh's thresholded log1p(exp) form to that bound
+  if (act == ACT_SOFTPLUS100) return fmaxf(x, 0.f) + 0.01f * __logf(1.f + __expf(-100.f * fabsf(x)));
   return x;
 }
 __device__ __forceinline__ float tl_dact(float y, int act) {
   if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == ACT_LEAKY02) return y > 0.f ? 1.f : 0.2f;
   // softplus(beta = 100): y = log(1 + e^(100 x)) / 100  =>  sigmoid(100 x) = 1 - e^(-100 y)
-  if (act == ACT_SOFTPLUS100) return -expm1f(-100.f * y);
+  if (act == ACT_SOFTPLUS100) return 1.f - __expf(-100.f * y);          // absolute error <= 1 ulp of 1
   return 1.f;
 }
 
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
     uint8_t* img_tile = p.out_img ? p.out_img + (size_t)tile * p.nkb_out * kTlBlockBytes : nullptr;
     mbar_wait(&d_full, 0);
     tc_fence_after();
+    const int half = (warp - 2) >> 2;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * half; c < 2 * half + 2; ++c) {
       const int col0 = col_base + 32 * c;
       uint32_t acc[32];
       tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
@@ -287,6 +291,192 @@ __global__ void tl_pack_rows_kernel(const float* __restrict__ X, int ldx, int n,
   *reinterpret_cast<uint4*>(b + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// weight gradients on the tensor cores: dW [N][K] = G^T A (contraction over the n rows), db = column sums of G
+// ------------------------------------------------------------------------------------------------------------------
+// Both operands become images of their TRANSPOSES (image row = column of the fp32 matrix, k = its row), so that the
+// contraction index is the K-major one and the GEMM below is the same two-bulk-copies-per-stage SS pipeline as
+// tc_layer_kernel.  One CTA transposes a 64-row x 128-column fp32 tile through shared memory: coalesced loads, full
+// 128-byte image rows out.  With colsum != null it also emits the tile's column sums (db partials, summed in a fixed
+// order by tl_wgrad_reduce_kernel).
+__global__ void __launch_bounds__(256) tl_pack_rows_t_kernel(const float* __restrict__ X, int ldx, int n, int C, int nkb,
+                                                             uint8_t* __restrict__ img, float* __restrict__ colsum,
+                                                             int ld_colsum, const int* __restrict__ n_active) {
+  __shared__ float t[64][129];
+  const int kb = blockIdx.x, ct = blockIdx.y, tid = threadIdx.x;
+  const int r0 = kb * 64, c0 = ct * 128;
+  if (n_active != nullptr) {                  // rows >= *n_active are zero by contract: their k-blocks are never read
+    n = min(n, __ldg(n_active));
+    if (r0 >= n) return;
+  }
+  const bool vec = (ldx & 3) == 0 && c0 + 128 <= C && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (vec) {
+    for (int i = tid; i < 64 * 32; i += 256) {
+      const int r = i >> 5, c4 = (i & 31) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < n) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(r0 + r) * ldx + c0 + c4));
+      t[r][c4] = v.x; t[r][c4 + 1] = v.y; t[r][c4 + 2] = v.z; t[r][c4 + 3] = v.w;
+    }
+  } else {
+    for (int i = tid; i < 64 * 128; i += 256) {
+      const int r = i >> 7, c = i & 127;
+      t[r][c] = (r0 + r < n && c0 + c < C) ? __ldg(X + (size_t)(r0 + r) * ldx + c0 + c) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (colsum != nullptr && tid < 128) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) s += t[r][tid];
+    colsum[(size_t)kb * ld_colsum + c0 + tid] = s;
+  }
+  uint8_t* blk = img + ((size_t)ct * nkb + kb) * kTlBlockBytes;
+  for (int i = tid; i < 128 * 8; i += 256) {
+    const int chunk = i & 7, c = i >> 3;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_pack(t[chunk * 8 + 2 * e][c], t[chunk * 8 + 2 * e + 1][c], hi[e], lo[e]);
+    const int off = c * 128 + ((chunk ^ (c & 7)) << 4);
+    *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+struct TlWgradParams {
+  const uint8_t* g_img;      // image of G^T: [row_tiles][nkb][32 KB]   (row = output feature)
+  const uint8_t* a_img;      // image of A^T: [col_blocks][nkb][32 KB]  (row = input feature)
+  int nkb, kb_per_split;     // k-blocks (64 rows of G / A each) in total / per CTA
+  int row_tiles, col_blocks;
+  float* partial;            // [splits][row_tiles * 128][col_blocks * 128]
+  const int* n_active;       // device row count (rows beyond it are zero and skipped), or null
+};
+
+// grid (row_tiles * col_blocks, splits): one 128 x 128 tile of dW over k-blocks [split * kb_per_split, ...)
+__global__ void __launch_bounds__(192, 1) tl_wgrad_kernel(TlWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kTlStages], empty_bar[kTlStages], d_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x / p.col_blocks, cb = blockIdx.x % p.col_blocks;
+  int nkb_eff = p.nkb, kps = p.kb_per_split;
+  if (p.n_active != nullptr) {                // the active k-blocks are re-divided over the launched splits
+    nkb_eff = min(p.nkb, (max(__ldg(p.n_active), 0) + 63) >> 6);
+    kps = (nkb_eff + (int)gridDim.y - 1) / (int)gridDim.y;
+  }
+  const int kb0 = blockIdx.y * kps, nk = min(nkb_eff - kb0, kps);     // <= 0: this split has no rows, partial = 0
+
+  if (tid == 0) {
+    for (int s = 0; s < kTlStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    const uint8_t* g_src = p.g_img + ((size_t)tile * p.nkb + kb0) * kTlBlockBytes;
+    const uint8_t* a_src = p.a_img + ((size_t)cb * p.nkb + kb0) * kTlBlockBytes;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int st = kb % kTlStages;
+      mbar_wait(&empty_bar[st], ((kb / kTlStages) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full_bar[st], kTlStageBytes);
+        bulk_g2s(ring + (size_t)st * kTlStageBytes, g_src + (size_t)kb * kTlBlockBytes, kTlBlockBytes, &full_bar[st]);
+        bulk_g2s(ring + (size_t)st * kTlStageBytes + kTlBlockBytes, a_src + (size_t)kb * kTlBlockBytes, kTlBlockBytes,
+                 &full_bar[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    for (int kb = 0; kb < nk; ++kb) {
+      const int st = kb % kTlStages;
+      mbar_wait(&full_bar[st], (kb / kTlStages) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint8_t* sa = ring + (size_t)st * kTlStageBytes;
+        const uint8_t* sb = sa + kTlBlockBytes;
+        const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + 16384);
+        const uint64_t b_hi = smem_desc_sw128(sb), b_lo = smem_desc_sw128(sb + 16384);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (kb == 0 && q == 0) umma_ss<0>(tmem_base, a_hi + 2u * q, b_hi + 2u * q, kTlIdesc);
+          else umma_ss<1>(tmem_base, a_hi + 2u * q, b_hi + 2u * q, kTlIdesc);
+          umma_ss<1>(tmem_base, a_lo + 2u * q, b_hi + 2u * q, kTlIdesc);
+          umma_ss<1>(tmem_base, a_hi + 2u * q, b_lo + 2u * q, kTlIdesc);
+        }
+        umma_commit(&empty_bar[st]);
+        if (kb == nk - 1) umma_commit(&d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int ld = p.col_blocks * 128;
+    float* dst = p.partial + ((size_t)blockIdx.y * p.row_tiles * 128 + tile * 128 + r) * ld + cb * 128;
+    if (nk > 0) {
+      mbar_wait(&d_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t acc[32];
+      if (nk > 0) {
+        tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst + 32 * c)[i] =
+            make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                        __uint_as_float(acc[4 * i + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// dW[nn][kk] = sum over splits (fixed order).  The last blocks of the grid sum the db partials instead: 8 columns x 32
+// k-block lanes per block, lane j takes k-blocks j, j + 32, ..., then a fixed-order tree over the lanes.
+__global__ void __launch_bounds__(256) tl_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad,
+                                                              int ld, int N, int K, float* __restrict__ dW,
+                                                              const float* __restrict__ colsum, int nkb, int ld_colsum,
+                                                              float* __restrict__ db, int dw_blocks,
+                                                              const int* __restrict__ n_active) {
+  if ((int)blockIdx.x < dw_blocks) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * K) return;
+    const int nn = (int)(idx / K), kk = (int)(idx % K);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * rows_pad + nn) * ld + kk];
+    dW[idx] = s;
+    return;
+  }
+  __shared__ float red[32][9];
+  if (n_active != nullptr) nkb = min(nkb, (max(__ldg(n_active), 0) + 63) >> 6);
+  const int c = threadIdx.x & 7, j = threadIdx.x >> 3;
+  const int nn = ((int)blockIdx.x - dw_blocks) * 8 + c;
+  float s = 0.f;
+  if (nn < N)
+    for (int kb = j; kb < nkb; kb += 32) s += colsum[(size_t)kb * ld_colsum + nn];
+  red[j][c] = s;
+  __syncthreads();
+  for (int w = 16; w >= 1; w >>= 1) {
+    if (j < w) red[j][c] += red[j + w][c];
+    __syncthreads();
+  }
+  if (j == 0 && nn < N) db[nn] = red[0][c];
+}
+
 }  // namespace robir
 
 using namespace robir;
@@ -324,6 +514,55 @@ int robir_tl_layer(const TcLayerParams* p, void* stream) {
   RB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTlSmem));
   dim3 grid((p->n + 127) / 128, (p->N + 127) / 128);
   tc_layer_kernel<<<grid, kTlThreads, kTlSmem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Weight gradients of one layer on the tensor cores (large row counts: the CESR shadow / normal networks).
+//   G [n][ldg] (columns < N), A [n][lda] (columns < K), fp32  ->  dW [N][K] = G^T A, db [N] = column sums of G
+// work: robir_tl_wgrad_workspace(n, N, K, sm_count) bytes (transposed hi/lo images of G and A, split partials, db
+// partials).  Sums run in a fixed order: results are bitwise reproducible.  n_active (device, or null): rows at and
+// beyond *n_active are zero (fixed-capacity batches) -- they are skipped, not read.
+static void tl_wgrad_shape(int n, int N, int K, int sm_count, int* nkb, int* rt, int* cb, int* kps, int* splits) {
+  *nkb = (n + 63) / 64;
+  *rt = (N + 127) / 128;
+  *cb = (K + 127) / 128;
+  int want = sm_count / (*rt * *cb);
+  if (want < 1) want = 1;
+  if (want > *nkb) want = *nkb;
+  *kps = (*nkb + want - 1) / want;
+  *splits = (*nkb + *kps - 1) / *kps;
+}
+
+long long robir_tl_wgrad_workspace(int n, int N, int K, int sm_count) {
+  int nkb, rt, cb, kps, splits;
+  tl_wgrad_shape(n, N, K, sm_count, &nkb, &rt, &cb, &kps, &splits);
+  return (long long)(rt + cb) * nkb * kTlBlockBytes + (long long)splits * rt * 128 * cb * 128 * 4 +
+         (long long)nkb * rt * 128 * 4;
+}
+
+int robir_tl_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K, const int* n_active,
+                   void* work, float* dW, float* db, int sm_count, void* stream) {
+  RB_REQUIRE(n >= 1 && N >= 1 && K >= 1 && work != nullptr && dW != nullptr, "tl_wgrad: empty problem or no workspace");
+  int nkb, rt, cb, kps, splits;
+  tl_wgrad_shape(n, N, K, sm_count, &nkb, &rt, &cb, &kps, &splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* g_img = (uint8_t*)work;
+  uint8_t* a_img = g_img + (size_t)rt * nkb * kTlBlockBytes;
+  float* partial = (float*)(a_img + (size_t)cb * nkb * kTlBlockBytes);
+  float* colsum = partial + (size_t)splits * rt * 128 * cb * 128;
+  tl_pack_rows_t_kernel<<<dim3(nkb, rt), 256, 0, st>>>(G, ldg, n, N, nkb, g_img, db ? colsum : nullptr, rt * 128,
+                                                       n_active);
+  tl_pack_rows_t_kernel<<<dim3(nkb, cb), 256, 0, st>>>(A, lda, n, K, nkb, a_img, nullptr, 0, n_active);
+  TlWgradParams p;
+  p.g_img = g_img; p.a_img = a_img; p.nkb = nkb; p.kb_per_split = kps; p.row_tiles = rt; p.col_blocks = cb;
+  p.partial = partial;
+  p.n_active = n_active;
+  RB_CHECK_CUDA(cudaFuncSetAttribute(tl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTlSmem));
+  tl_wgrad_kernel<<<dim3(rt * cb, splits), 192, kTlSmem, st>>>(p);
+  const int dw_blocks = (int)(((long long)N * K + 255) / 256), db_blocks = db ? (N + 7) / 8 : 0;
+  tl_wgrad_reduce_kernel<<<dw_blocks + db_blocks, 256, 0, st>>>(partial, splits, rt * 128, cb * 128, N, K, dW, colsum, nkb,
+                                                                rt * 128, db, dw_blocks, n_active);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -19,51 +19,77 @@ class GraphedPBRStep:
     latency, so capturing it buys nothing; only bucketing it under the visibility backward would."""
 
     def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3,
-                 record_randoms=False, split_reduce=True):
+                 record_randoms=False, split_reduce=True, hook=None):
         """record_randoms: keep references to the random tensors drawn inside the captured step (``self.random_tape``, in
-        draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes)."""
+        draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes).
+
+        hook: a ``cesr.ClusteredAlbedoHook`` already bound to ``model.get_sg_render`` -- the step is then the CESR stage's
+        (train_cesr.py:465-559,387-430: shadow_net / normal_net, supervise term, explore / project loss weights).  The
+        hook's schedule (warm-up / explore / project, the normal switch at iteration 1000) is host-side control flow:
+        one graph is captured per phase, lazily, when ``hook.phase_key()`` changes."""
         if rng._mode != "device":
             raise RuntimeError("GraphedPBRStep needs robir_b200.rng.set_mode('device')")
         model.static_shapes = True
         loss_fn.static_shapes = True
         dev = pose.device
-        self.model, self.loss_fn, self.opt, self.reducer = model, loss_fn, optimizer, reducer
+        self.model, self.loss_fn, self.opt, self.reducer, self.hook = model, loss_fn, optimizer, reducer, hook
         self.uv = torch.zeros(1, n_rays, 2, device=dev)
         self.om = torch.ones(1, n_rays, dtype=torch.bool, device=dev)
         self.gt = torch.zeros(1, n_rays, 3, device=dev)
         self.pose, self.K, self.n = pose, intrinsics, n_rays
         self.hits = None
-        multi = reducer is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-        split = multi and split_reduce
+        self.multi = reducer is not None and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        self.split = self.multi and split_reduce
+        self.record_randoms = record_randoms
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._fwd_bwd()
-                if multi:
+                if self.multi:
                     reducer()
                 self.opt.step()
                 ops.invalidate_packed_weights()   # optimizers with fused multi-tensor kernels do not bump versions
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
-        self.g1 = torch.cuda.CUDAGraph()
-        self.g2 = None
-        before = _lib.launch_count
+        self._graphs = {}
+        self._capture(self._phase())
+
+    def _phase(self):
+        return self.hook.phase_key() if self.hook is not None else None
+
+    def _capture(self, key):
         import contextlib
-        with (rng.record(on_device=True) if record_randoms else contextlib.nullcontext()) as tape:
-            with torch.cuda.graph(self.g1):
-                self.loss = self._fwd_bwd()
-                if not split:
-                    if multi:
-                        reducer()                  # NCCL all-reduce as a node of this graph
+        from . import _lib
+        g1, g2 = torch.cuda.CUDAGraph(), None
+        before = _lib.launch_count
+        with (rng.record(on_device=True) if self.record_randoms else contextlib.nullcontext()) as tape:
+            with torch.cuda.graph(g1):
+                loss = self._fwd_bwd()
+                if not self.split:
+                    if self.multi:
+                        self.reducer()             # NCCL all-reduce as a node of this graph
                     self.opt.step()
-        self.random_tape = list(tape) if record_randoms else None
-        self.launches_per_step = _lib.launch_count - before    # kernels of the C-ABI library inside one replay
-        if split:
-            self.g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g2):
+        launches = _lib.launch_count - before      # kernels of the C-ABI library inside one replay
+        if self.split:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
                 self.opt.step()
+        # the gradient tensors this capture allocated (its backward writes them, its optimizer update and the eager
+        # all-reduce of the split mode read them): p.grad is pointed back at them whenever this graph is selected
+        grads = [(p, p.grad) for g in self.opt.param_groups for p in g["params"]]
+        self._graphs[key] = dict(g1=g1, g2=g2, loss=loss, hits=self.hits, launches=launches, grads=grads,
+                                 tape=list(tape) if self.record_randoms else None)
+        self._select(key)
+
+    def _select(self, key):
+        g = self._graphs[key]
+        self.g1, self.g2, self.loss, self.hits = g["g1"], g["g2"], g["loss"], g["hits"]
+        self.launches_per_step, self.random_tape = g["launches"], g["tape"]
+        for p, gr in g["grads"]:
+            p.grad = gr
+        self._key = key
 
     def _fwd_bwd(self):
         m = self.model
@@ -71,13 +97,22 @@ class GraphedPBRStep:
         inp = {"uv": self.uv, "object_mask": self.om, "pose": self.pose, "intrinsics": self.K,
                "hdr_shift": m.gamma.hdr_shift.as_input().expand(self.n, 1)}
         out = m(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
-        loss, _ = pbr_step_loss(m, self.loss_fn, out, {"rgb": self.gt})
+        if self.hook is not None:
+            loss, _ = self.hook.pbr_step(self.loss_fn, out, {"rgb": self.gt})
+        else:
+            loss, _ = pbr_step_loss(m, self.loss_fn, out, {"rgb": self.gt})
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.hits = out["network_object_mask"].sum()
         return loss.detach()
 
     def __call__(self, uv, object_mask, rgb_gt):
+        key = self._phase()
+        if key != self._key:
+            if key in self._graphs:
+                self._select(key)
+            else:
+                self._capture(key)
         self.uv.copy_(uv, non_blocking=True)
         self.om.copy_(object_mask, non_blocking=True)
         self.gt.copy_(rgb_gt, non_blocking=True)

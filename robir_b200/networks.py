@@ -301,7 +301,7 @@ class EnvmapMaterialNetwork(nn.Module):
                 # order = random-draw order of the reference: BRDF latent noise, then normal input noise)
                 head, (nm, nm_r, _) = ops.fork_join([
                     lambda: self.spec_brdf_encoder_layer.brdf_points(points.detach(), train=None if train_spec else False),
-                    lambda: self.normal_decoder_layer.forward_points(points.detach(), "ipe10")])
+                    lambda: self.normal_decoder_layer.forward_points(points.detach(), "ipe10")], tag="mat")
                 self._last_spec_latent = head.pop("z")   # reused by the KL term of the loss (same points, same encoder)
                 if train_spec is False:
                     head = {k: v.detach() for k, v in head.items()}
@@ -353,7 +353,7 @@ class IndirctIllumNetwork(nn.Module):
             out, (_, env_r, _) = ops.fork_join([
                 lambda: ops.fused_mlp(self._lobe_chain, pts, extra=hdr_shift, want_param_grad=train),
                 lambda: self.integral_layer.forward_points(pts, "pe10_extra", extra=hdr_shift, train=train,
-                                                           noisy_only=True)])
+                                                           noisy_only=True)], tag="indir")
             out = out.reshape(pts.shape[0], self.num_lgt_sgs, 6)
             return ops.decode_lobes(out), torch.abs(env_r)
         x = torch.cat([positional_encoding(points, 10), hdr_shift], -1)

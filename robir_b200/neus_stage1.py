@@ -63,9 +63,10 @@ def render_core(net, rays_o, rays_d, z_vals, sample_dist, near, far, white_bkgd=
     rgb, weights = torch.empty(B, 3, device=dev), torch.empty(B, n, device=dev)
     acc, dist = torch.empty(B, device=dev), torch.empty(B, device=dev)
     eik = torch.zeros(2, device=dev)
+    sdf_c, grad_c, color_c = f32(sdf).reshape(-1), f32(grad), f32(color)     # named: copies must outlive the launch
     check(lib().robir_neus_composite(B, n, float(sample_dist), inv_s, float(cos_anneal_ratio), RADIUS, int(white_bkgd),
-                                     ptr(rays_o), ptr(rays_d), ptr(z_vals), ptr(f32(sdf).reshape(-1)), ptr(f32(grad)),
-                                     ptr(f32(color)), ptr(near), ptr(far), ptr(rgb), ptr(weights), ptr(acc), ptr(dist),
+                                     ptr(rays_o), ptr(rays_d), ptr(z_vals), ptr(sdf_c), ptr(grad_c),
+                                     ptr(color_c), ptr(near), ptr(far), ptr(rgb), ptr(weights), ptr(acc), ptr(dist),
                                      ptr(eik), stream()))
     return dict(color=rgb, weights=weights, mid_z_vals=mid_z, acc=acc, dist=dist,
                 gradient_error=eik[0] / (eik[1] + 1e-5), sdf=sdf, gradients=grad.reshape(B, n, 3))

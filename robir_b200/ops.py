@@ -587,7 +587,8 @@ class _LatentPair(torch.autograd.Function):
     def backward(ctx, g):
         z, = ctx.saved_tensors
         g_z = _empty(*z.shape, like=z)
-        check(lib().robir_latent_pair_bwd(z.shape[0], ptr(z), ptr(f32(g)), ptr(g_z), stream()))
+        g = f32(g)                  # a contiguous copy (if one is made) must outlive the launch: bind it to a name
+        check(lib().robir_latent_pair_bwd(z.shape[0], ptr(z), ptr(g), ptr(g_z), stream()))
         return g_z, None
 
 
@@ -608,8 +609,11 @@ class _BrdfHead(torch.autograd.Function):
     def backward(ctx, *gs):
         y2, = ctx.saved_tensors
         g_y2 = _empty(*y2.shape, like=y2)
-        check(lib().robir_brdf_head_bwd(y2.shape[0] // 2, ptr(y2), *[ptr(f32(g)) if g is not None else None for g in gs],
-                                        ptr(g_y2), stream()))
+        # upstream gradients may be strided views (slices of a concatenated gradient): f32() then makes contiguous
+        # copies, and ALL of them have to stay alive until the launch -- a temporary that dies inside the argument list
+        # hands its block to the next copy, and two gradients end up at the same address
+        gs = [f32(g) if g is not None else None for g in gs]
+        check(lib().robir_brdf_head_bwd(y2.shape[0] // 2, ptr(y2), *[ptr(g) for g in gs], ptr(g_y2), stream()))
         return g_y2
 
 
@@ -637,7 +641,8 @@ class _DecodeLobes(torch.autograd.Function):
     def backward(ctx, g):
         raw, = ctx.saved_tensors
         g_raw = _empty(*raw.shape, like=raw)
-        check(lib().robir_decode_lobes_bwd(raw.shape[0] * raw.shape[1], ptr(raw), ptr(f32(g)), ptr(g_raw), stream()))
+        g = f32(g)
+        check(lib().robir_decode_lobes_bwd(raw.shape[0] * raw.shape[1], ptr(raw), ptr(g), ptr(g_raw), stream()))
         return g_raw
 
 
@@ -677,8 +682,9 @@ class SdfWeights:
             if tuple(v8.shape) != (257, 256):
                 raise _lib.RobirError("SDFNetwork last layer must be 256 -> 257")
             d["Wt8_feat"] = pack_wn_transpose(v8, g8, 1, 256, 256, 256)
-            w8 = _empty(256, like=f32(v8))
-            check(lib().robir_pack_wn_row(ptr(f32(v8)), ptr(f32(g8)), 256, 0, ptr(w8), stream()))
+            v8c, g8c = f32(v8), f32(g8)
+            w8 = _empty(256, like=v8c)
+            check(lib().robir_pack_wn_row(ptr(v8c), ptr(g8c), 256, 0, ptr(w8), stream()))
             d["w8_sdf"] = w8
             d["b8"] = f32(lins[8].bias)
             # tensor-core engine (csrc/sdf_tc.cu): scaled fp16 hi/lo images of the nine 256-wide layers in streaming
@@ -1042,6 +1048,11 @@ def _tl_backward(chain, packed, tc, n, g_out, saves, Gs, g_x, n_active, segments
 # ----------------------------------------------------------------------------------------------------------------------
 # weight-normed softplus chains with a skip concat (CESR shadow_net / normal_net) on the tensor-core layer engine
 # ----------------------------------------------------------------------------------------------------------------------
+# rows from which the CESR chains' weight gradients run on the tensor cores (robir_tl_wgrad); below it the fp32 FFMA
+# kernel of csrc/mlp.cu is launch-bound anyway.  Tests lower it to cover the kernel at small sizes.
+WN_TC_WGRAD_MIN_ROWS = 4096
+
+
 def _tl_weight_images(W, rows_bw):
     """Forward image of W [N,K] and backward image of W^T restricted to its first rows_bw rows (the columns of W that
     lead back to the previous layer; the rest belongs to the skip input, which needs no gradient)."""
@@ -1069,10 +1080,11 @@ class _WnChain(torch.autograd.Function):
     """y = lin_{L-1}( ... softplus100(lin_l(a_l)) ... ), a_l = cat([h_{l-1}, x]) / sqrt(2) at the skip layers
     (SDFNetwork.forward with multires = 0, model/neus_model.py:397-415), one csrc/tc_mlp.cu launch per layer.
     The 1/sqrt(2) is folded into the skip layer's weight; the concat is a 512-column buffer that the previous layer
-    writes its columns into.  backward: input-gradient chain on the same engine, dW / db by robir_mlp_wgrad."""
+    writes its columns into.  backward: input-gradient chain on the same engine, dW / db by robir_tl_wgrad (tensor cores,
+    R >= WN_TC_WGRAD_MIN_ROWS) or robir_mlp_wgrad."""
 
     @staticmethod
-    def forward(ctx, x, skip, L, *wb):
+    def forward(ctx, x, skip, L, n_active, *wb):
         Ws, bs = wb[:L], wb[L:]
         if x.requires_grad:
             raise _lib.RobirError("wn_chain: gradients with respect to the input rows are not produced")
@@ -1105,12 +1117,13 @@ class _WnChain(torch.autograd.Function):
             nkb_out = 0 if (last or next_skip) else (N + 63) // 64
             nxt = _tl_image(tiles, nkb_out, x) if nkb_out else None
             q = _tl_params(img, fw, bias, R, N, (K + 63) // 64, 0, 0 if last else SOFTPLUS, None, out, nxt, nkb_out,
-                           None, 0)
+                           n_active, 0)
             check(lib().robir_tl_layer(ctypes.byref(q), stream()))
             a = out
             img = _tl_rows_image(out, N + d_in) if next_skip else nxt
         ctx.meta = (R, d_in, L, tuple(skip))
         ctx.imgs = imgs
+        ctx.n_active = n_active
         ctx.save_for_backward(*a_rows, *We)
         return out
 
@@ -1120,6 +1133,7 @@ class _WnChain(torch.autograd.Function):
         a_rows, We = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
         tiles = (R + 127) // 128
         SOFTPLUS = ACT["softplus100"]
+        n_active = ctx.n_active
         G = f32(g_out)
         img = _tl_rows_image(G, G.shape[1])
         gW, gb = [None] * L, [None] * L
@@ -1128,12 +1142,18 @@ class _WnChain(torch.autograd.Function):
             A = a_rows[l]
             # ---- dW_l = G_l^T A_l, db_l = column sums of G_l
             dW, db = _empty(N, K, like=G), _empty(N, like=G)
-            wt = ((N + 63) // 64) * ((K + 63) // 64)
-            splits = max(1, min(64, (4 * sm_count()) // wt, (R + 63) // 64))
-            part = _empty(splits * wt * 4160, like=G) if splits > 1 else None
-            tickets = _zeros(wt, dtype=torch.int32, like=G)
-            check(lib().robir_mlp_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, None, 0, splits, ptr(part),
-                                        ptr(tickets), ptr(dW), ptr(db), stream()))
+            if R >= WN_TC_WGRAD_MIN_ROWS:
+                # split-K tcgen05 GEMM over transposed hi/lo images (csrc/tc_mlp.cu tl_wgrad_kernel)
+                work = torch.empty(lib().robir_tl_wgrad_workspace(R, N, K, sm_count()), dtype=torch.uint8, device=G.device)
+                check(lib().robir_tl_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, ptr(n_active), ptr(work),
+                                           ptr(dW), ptr(db), sm_count(), stream()))
+            else:
+                wt = ((N + 63) // 64) * ((K + 63) // 64)
+                splits = max(1, min(64, (4 * sm_count()) // wt, (R + 63) // 64))
+                part = _empty(splits * wt * 4160, like=G) if splits > 1 else None
+                tickets = _zeros(wt, dtype=torch.int32, like=G)
+                check(lib().robir_mlp_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, None, 0, splits, ptr(part),
+                                            ptr(tickets), ptr(dW), ptr(db), stream()))
             gW[l] = dW * (1.0 / math.sqrt(2.0)) if l in skip else dW
             gb[l] = db
             if l == 0:
@@ -1143,15 +1163,18 @@ class _WnChain(torch.autograd.Function):
             Gp = _empty(R, Np, like=G)
             nkb_out = (Np + 63) // 64
             nxt = _tl_image(tiles, nkb_out, G)
-            q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, None, 0)
+            q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, n_active, 0)
             check(lib().robir_tl_layer(ctypes.byref(q), stream()))
             G, img = Gp, nxt
-        return (None, None, None, *gW, *gb)
+        return (None, None, None, None, *gW, *gb)
 
 
-def wn_chain(x, Ws, bs, skip=(4,)):
-    """x [R, d_in] (no gradient), Ws[l] [N_l, K_l] the folded weight-norm weights, bs[l] [N_l] -> [R, N_last]."""
-    return _WnChain.apply(x, tuple(skip), len(Ws), *Ws, *bs)
+def wn_chain(x, Ws, bs, skip=(4,), n_active=None):
+    """x [R, d_in] (no gradient), Ws[l] [N_l, K_l] the folded weight-norm weights, bs[l] [N_l] -> [R, N_last].
+    n_active: optional device int32 [1], the number of leading rows that carry data (fixed-capacity batches, CUDA-graph
+    mode): row tiles entirely beyond it are neither computed nor differentiated (outputs 0); the caller must feed zero
+    upstream gradients for rows >= n_active."""
+    return _WnChain.apply(x, tuple(skip), len(Ws), n_active, *Ws, *bs)
 
 
 class _FusedMLP(torch.autograd.Function):
@@ -1234,7 +1257,7 @@ class _FusedMLP(torch.autograd.Function):
                 return gw, gb
             if chain.wgrad_streams is None:
                 chain.wgrad_streams = [torch.cuda.Stream() for _ in range(len(packed) - 1)]
-            for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))], chain.wgrad_streams):
+            for gw, gb in fork_join([(lambda l=l: layer_grads(l)) for l in range(len(packed))], chain.wgrad_streams, tag="wgrad"):
                 grads.append(gw)
                 grads.append(gb)
         gx = g_x[:, :packed[0]["K"]] if chain.in_mode == 0 else None
@@ -1267,14 +1290,21 @@ def _tensors_in(obj):
 
 
 _fork_state = {"depth": 0, "next": 0}
+# debugging aids: ROBIR_FORK_SERIAL=1 runs every branch on the caller's stream, ROBIR_FORK_SERIAL_TAGS=nets,wgrad,...
+# only the call sites with those tags (bisecting a suspected cross-stream hazard)
+import os as _os
+_FORK_SERIAL = _os.environ.get("ROBIR_FORK_SERIAL", "0") == "1"
+_FORK_SERIAL_TAGS = set(_os.environ.get("ROBIR_FORK_SERIAL_TAGS", "").split(",")) - {""}
 
 
-def fork_join(fns, streams=None):
+def fork_join(fns, streams=None, tag=""):
     """Run the callables concurrently: fns[0] on the current stream, the others on side streams that fork from and join
     back into it.  Host-side call order (hence the order of random draws) stays sequential.  Calls nest: every branch
     of one outermost call gets its own pooled stream, so sibling sub-branches never queue behind each other.
     streams: caller-owned side streams instead of the pool (autograd backward nodes, whose joins must not wait on
     unrelated work queued on the forward's pool streams)."""
+    if _FORK_SERIAL or tag in _FORK_SERIAL_TAGS:
+        return [fn() for fn in fns]
     main = torch.cuda.current_stream()
     st = _fork_state
     base = st["next"]

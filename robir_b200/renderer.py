@@ -84,11 +84,14 @@ class IDRNetwork(nn.Module):
         if fun_spec:
             raise RobirError("fun_spec=True is not on the accelerated path")
         if self.static_shapes and trainstage != 'Illum' and "intrinsics" in input and 'hdr_shift' in input:
+            hook = None
             if getattr(self.get_sg_render, "__func__", None) is not IDRNetwork.get_sg_render:
-                raise RobirError("the fixed-capacity forward (static_shapes = True) implements the PBR runner's hook only; "
-                                 "a re-bound get_sg_render (e.g. robir_b200.cesr.ClusteredAlbedoHook) needs "
-                                 "static_shapes = False")
-            return self._forward_static(input, lin_diff=lin_diff, train_spec=train_spec)
+                hook = getattr(self.get_sg_render, "__self__", None)
+                if not hasattr(hook, "get_sg_render_static"):
+                    raise RobirError("the fixed-capacity forward (static_shapes = True) implements the PBR runner's hook "
+                                     "and robir_b200.cesr.ClusteredAlbedoHook; any other re-bound get_sg_render needs "
+                                     "static_shapes = False")
+            return self._forward_static(input, lin_diff=lin_diff, train_spec=train_spec, hook=hook)
         if "intrinsics" in input:
             object_mask = input["object_mask"].reshape(-1)
             ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
@@ -168,7 +171,7 @@ class IDRNetwork(nn.Module):
         ret.update(buf)
         return ret
 
-    def _forward_static(self, input, lin_diff=False, train_spec=False):
+    def _forward_static(self, input, lin_diff=False, train_spec=False, hook=None):
         object_mask = input["object_mask"].reshape(-1)
         ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
         batch_size, num_pixels, _ = ray_dirs.shape
@@ -176,7 +179,7 @@ class IDRNetwork(nn.Module):
             with torch.no_grad():
                 return self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
         # packed copies of the weights that are being trained are rebuilt while the tracer walks the octree
-        (_, mask, dists), _ = ops.fork_join([trace, self.prepack])
+        (_, mask, dists), _ = ops.fork_join([trace, self.prepack], tag="trace")
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
         ray_dirs = ray_dirs.reshape(-1, 3)
         total, dev = points.shape[0], points.device
@@ -210,7 +213,8 @@ class IDRNetwork(nn.Module):
             if mnet.upper_hemi:
                 lgt = torch.cat((lgt[..., :1], torch.abs(lgt[..., 1:2]), lgt[..., 2:]), dim=-1)
             lobes, lambdas = sg_render.light_lobes(lgt)
-            dirs, w = sg_render.sample_diffuse_dirs(lobes, lambdas, 32, dev)
+            # 32 samples per lobe; 8 when the CESR shadow_net stands in for the average (sg_render.py:388-391)
+            dirs, w = sg_render.sample_diffuse_dirs(lobes, lambdas, 32 if hook is None else 8, dev)
             if not ops.vis_engine_terms():
                 return dirs, w
             W = sg_render._weights_of(self.visibility_network).get()
@@ -219,12 +223,16 @@ class IDRNetwork(nn.Module):
             act(lambda: self.indirect_illum_network(pts, hdr)),
             act(lambda: self.envmap_material_network(pts, train_spec=train_spec)),
             act(lambda: self.get_idr_render(pts, None, normal_only=True)),
-            diffuse_samples])
+            diffuse_samples], tag="nets")
         self.envmap_material_network._last_latent_valid = valid
         ret = {'points': points, 'sdf_output': sdf_output, 'network_object_mask': mask, 'object_mask': object_mask,
                'ray_dirs': ray_dirs, 'hdr_shift': input['hdr_shift']}
-        r = pbr_get_sg_render(self, pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
-                              valid=valid, precomputed=(nrm, mat), diffuse_presampled=presampled)
+        if hook is None:
+            r = pbr_get_sg_render(self, pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
+                                  valid=valid, precomputed=(nrm, mat), diffuse_presampled=presampled)
+        else:
+            r = hook.get_sg_render_static(pts, view, sgs, lin_diff=lin_diff, train_spec=train_spec, indir_integral=integ,
+                                          valid=valid, n_act=n_act, precomputed=(nrm, mat), diffuse_presampled=presampled)
         # back to ray order, 1.0 for the rays that missed (implicit_differentiable_renderer.py:365-385): one gather over
         # the column-concatenated outputs instead of one per tensor
         keys = ('sg_rgb', 'indir_rgb', 'sg_diffuse_rgb', 'sg_specular_rgb', 'indir_diffuse_rgb', 'indir_specular_rgb',
@@ -254,7 +262,8 @@ class IDRNetwork(nn.Module):
         main.wait_stream(aux)
         if not torch.cuda.is_current_stream_capturing():
             sdf_output.record_stream(main)
-        ret.update({'final_t': torch.ones(total, 1, device=dev), 'gradient_error': torch.zeros((), device=dev),
+        ret.update({'final_t': torch.ones(total, 1, device=dev),
+                    'gradient_error': r['gradient_error'] if 'gradient_error' in r else torch.zeros((), device=dev),
                     'acc': torch.ones(total, 1, device=dev), 'bg_rgb': torch.ones(total, 3, device=dev),
                     'surface_mask': mask})
         return ret

@@ -125,18 +125,19 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
                          "accelerated path")
     if lgtSGs.dim() != 2:
         raise RobirError("render_with_all_sg expects the shared light SGs as [M,7]")
-    if normal.requires_grad and valid is not None:
-        raise RobirError("render_with_all_sg: a normal that carries a gradient (CESR after iteration 1000, "
-                         "train_cesr.py:508) is not supported in the fixed-capacity mode")
     with ops.point_table_scope():
         return _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, roughness, diffuse_albedo,
                                    indir_integral, indir_lgtSGs, VisModel, lin_diff, testing, valid, diffuse_presampled,
                                    diffuse_vis, prefit)
 
 
-def kl_divergence(x, mu=0.05):
-    """utils/utils.py:14-17 (the batch mean spans all ranks under dist.STRONG_SHARDING)."""
-    rho_hat = rdist.batch_mean_rows(x)
+def kl_divergence(x, mu=0.05, valid=None):
+    """utils/utils.py:14-17 (the batch mean spans all ranks under dist.STRONG_SHARDING).  valid [n] bool (fixed-capacity
+    mode): the batch mean runs over those rows only."""
+    if valid is not None:
+        rho_hat = torch.where(valid[:, None], x, torch.zeros_like(x)).sum(0) / valid.sum().clamp(min=1)
+    else:
+        rho_hat = rdist.batch_mean_rows(x)
     rho = torch.full_like(rho_hat, mu)
     return torch.mean(rho * torch.log(rho / (rho_hat + 1e-4)) + (1 - rho) * torch.log((1 - rho) / (1 - rho_hat + 1e-4)))
 
@@ -155,14 +156,13 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
                                        testing=testing, presampled=diffuse_presampled).permute(1, 0)
     supervise = torch.zeros((), device=points.device)
     if diffuse_vis is not None:
-        if valid is not None:
-            raise RobirError("render_with_all_sg: diffuse_vis is not supported in the fixed-capacity mode")
         light_vis_gt, light_vis = light_vis, diffuse_vis.reshape(-1, M)
         if prefit == "warmup":                                                          # sg_render.py:397-399
-            supervise = kl_divergence((light_vis_gt.detach() - light_vis).abs(), 0.01) * 0.1
+            supervise = kl_divergence((light_vis_gt.detach() - light_vis).abs(), 0.01, valid) * 0.1
             light_vis = light_vis_gt
         else:                                                                           # :400-403
-            supervise = kl_divergence((light_vis_gt - light_vis).abs(), 0.01) * (0.2 if prefit == "project" else 1.0)
+            supervise = kl_divergence((light_vis_gt - light_vis).abs(), 0.01, valid) * \
+                (0.2 if prefit == "project" else 1.0)
     # ---- BRDF-lobe visibility, direct then indirect (draw order of SURVEY.md A.4)
     bv_ind = None
     normal_grad = normal.requires_grad and torch.is_grad_enabled() and not testing
@@ -175,10 +175,10 @@ def _render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, 
         # render differentiate on the device (robir_sample_dirs_bwd, robir_sg_render_bwd with g_normal)
         wl, wlam = _spec_warp(normal, viewdirs, roughness)
         bv_dir = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
-                                         inv=False)
+                                         inv=False, valid=valid)
         if indir_lgtSGs is not None:
             bv_ind = get_specular_visibility(points, normal, viewdirs, VisModel, wl, wlam, nsamp=8, testing=testing,
-                                             inv=True)
+                                             inv=True, valid=valid)
     elif indir_lgtSGs is not None:
         # both get_specular_visibility calls (inv = False / True) share their sampling inputs: one prep kernel, one
         # launch chain over 2n "points" (rows [0, n) direct, [n, 2n) indirect)

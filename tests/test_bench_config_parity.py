@@ -233,3 +233,112 @@ def test_eager_forward_after_graph_replays_uses_current_weights(bench_setup):
     # and the weights did move (otherwise the test proves nothing)
     moved = (model.envmap_material_network.lgtSGs.detach().cpu() - sd["envmap_material_network.lgtSGs"]).abs().max()
     assert float(moved) > 1e-4
+
+
+@pytest.mark.parametrize("cur_iter", [300, 600, 1200])
+def test_cesr_graph_step_matches_eager_dynamic(bench_setup, cur_iter):
+    """bench.py --config c4: the CESR step (train_cesr.py:465-559,387-430) as ONE CUDA graph over the fixed-capacity batch
+    (IDRNetwork._forward_static -> ClusteredAlbedoHook.get_sg_render_static; shadow_net / normal_net skip the row tiles
+    beyond the device-side hit count, the two supervise means run over the valid rows) against the eager dynamic-shape
+    step -- the one pinned to the reference's goldens in test_cesr_step_vs_golden -- ON THE SAME RANDOMS: loss and the
+    gradients of all trained tensors (19 PBR + 2 x 27 of the weight-normed networks), in the warm-up (300), explore (600)
+    and project (1200: the render loss trains normal_net through d render / d normal) phases."""
+    from robir_b200 import cesr, graph, ops, rng
+    from robir_b200.loss import InvLoss
+    sd, model, inp, gt = bench_setup
+    dev = torch.device("cuda")
+    _load(model, sd)
+    sh, nr = synthetic.cesr_state_dicts(SEED)
+    shadow, normal = cesr.WnMLP(191, 2), cesr.WnMLP(63, 3)
+    shadow.load_state_dict(sh)
+    normal.load_state_dict(nr)
+    hook = cesr.ClusteredAlbedoHook(model, shadow.to(dev), normal.to(dev), cur_iter=cur_iter)
+    old_hook = model.__dict__.get("get_sg_render")
+    model.get_sg_render = hook.get_sg_render
+    params = trained_params(model) + hook.parameters()
+    names = trained_names(model) + ["shadow_net." + k for k, _ in hook.shadow_net.named_parameters()] + \
+        ["normal_net." + k for k, _ in hook.normal_net.named_parameters()]
+
+    def reload():
+        _load(model, sd)
+        with torch.no_grad():
+            for net, ref in ((hook.shadow_net, sh), (hook.normal_net, nr)):
+                cur = net.state_dict()
+                for k, v in ref.items():
+                    cur[k].copy_(v)
+
+    try:
+        rng.set_mode("device")
+        loss_fn = InvLoss()
+        opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=True)
+        step = graph.GraphedPBRStep(model, loss_fn, opt, N_RAYS, synthetic.camera_pose().to(dev),
+                                    synthetic.camera_intrinsics().to(dev), record_randoms=True, hook=hook)
+        reload()
+        loss_c = float(step(inp["uv"].to(dev), inp["object_mask"].to(dev), gt.to(dev)))
+        torch.cuda.synchronize()
+        grads_c = [None if p.grad is None else p.grad.detach().clone() for p in params]
+        tape = [t.detach().cpu().clone() for t in step.random_tape]
+        n_hit = int(step.hits)
+        assert 0.3 * N_RAYS < n_hit < 0.8 * N_RAYS, n_hit
+        assert step.launches_per_step > 60
+        # ------------------------------------------------------------ eager dynamic-shape step on the same randoms
+        N = N_RAYS
+        if cur_iter > 1000:                      # normal-gradient branch: two get_specular_visibility calls
+            assert len(tape) == 9, [tuple(t.shape) for t in tape]
+            host_tape = [tape[0][:n_hit], tape[1][:n_hit], tape[2][:n_hit], tape[3], tape[4]] + \
+                [t[:n_hit] for t in tape[5:]]
+        else:
+            host_tape = _static_tape_to_host_order(tape, n_hit)
+        reload()
+        model.static_shapes, loss_fn.static_shapes = False, False
+        dinp = {k: v.to(dev) for k, v in inp.items()}
+        dinp["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+        for p in params:
+            p.grad = None
+        with rng.replay(host_tape):
+            out_a = model(dinp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss_a, _ = hook.pbr_step(InvLoss(), out_a, {"rgb": gt.to(dev)})
+        loss_a.backward()
+        assert int(out_a["network_object_mask"].sum()) == n_hit
+        grads_a = [None if p.grad is None else p.grad.detach().clone() for p in params]
+        # ------------------------------------------------------------ eager fixed-capacity step, same randoms
+        reload()
+        model.static_shapes, loss_fn.static_shapes = True, True
+        dinp["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+        if cur_iter > 1000:
+            static_tape = [t.clone() for t in tape]
+        else:
+            static_tape = _static_tape_for_replay(tape)
+        for p in params:
+            p.grad = None
+        with rng.replay(static_tape):
+            out_b = model(dinp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        loss_b, _ = hook.pbr_step(loss_fn, out_b, {"rgb": gt.to(dev)})
+        loss_b.backward()
+        grads_b = [None if p.grad is None else p.grad.detach().clone() for p in params]
+        print("\nCESR step @%d: loss graph %.8f eager-static %.8f eager-dynamic %.8f" %
+              (cur_iter, loss_c, float(loss_b), float(loss_a)))
+        rows, checked = [], 0
+        for k, ga, gb, gc in zip(names, grads_a, grads_b, grads_c):
+            if ga is None or float(ga.abs().max()) == 0.0:
+                assert gc is None or float(gc.abs().max()) == 0.0, k
+                assert gb is None or float(gb.abs().max()) == 0.0, k
+                continue
+            rows.append((k, grad_err(gc, gb), grad_err(gb, ga)))
+            checked += 1
+        for k, (c2, ci), (b2, bi) in rows:
+            if max(c2, b2) > 2e-5:
+                print("  %-75s graph/static %.1e %.1e   static/dynamic %.1e %.1e" % (k, c2, ci, b2, bi))
+        assert abs(float(loss_b) - loss_c) < 2e-6 * max(1.0, abs(loss_c)), (float(loss_b), loss_c)
+        assert abs(float(loss_a) - loss_c) < 1e-5 * max(1.0, abs(loss_c)), (float(loss_a), loss_c)
+        for k, (c2, ci), (b2, bi) in rows:
+            assert c2 < 2e-5 and ci < 2e-4, ("graph vs eager-static", cur_iter, k, c2, ci)
+            assert b2 < 1e-4 and bi < 1e-3, ("eager-static vs dynamic", cur_iter, k, b2, bi)
+        assert checked >= (54 if cur_iter <= 500 else 19 + 27), checked
+    finally:
+        rng.set_mode("cpu")
+        model.static_shapes = False
+        if old_hook is None:
+            model.__dict__.pop("get_sg_render", None)
+        else:
+            model.get_sg_render = old_hook

@@ -114,12 +114,23 @@ class _EmulatedEngine:
         db.copy_(G[:n, :N].sum(0))
         return 0
 
+    def robir_tl_wgrad_workspace(self, n, N, K, sm_count):
+        return 1024
 
-@pytest.mark.parametrize("d_in,d_out,rows", [(191, 2, 256), (191, 2, 200), (63, 3, 130)])
-def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows):
+    def robir_tl_wgrad(self, G, ldg, A, lda, n, N, K, n_active, work, dW, db, sm_count, stream):
+        assert G.shape[1] == ldg and A.shape[1] == lda and work.numel() >= 1024 and n_active is None
+        self.tc_wgrads = getattr(self, "tc_wgrads", 0) + 1
+        dW.copy_(G[:n, :N].t() @ A[:n, :K])
+        db.copy_(G[:n, :N].sum(0))
+        return 0
+
+
+@pytest.mark.parametrize("d_in,d_out,rows,tc_wgrad", [(191, 2, 256, False), (191, 2, 200, True), (63, 3, 130, False)])
+def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows, tc_wgrad):
     import types
     from robir_b200 import ops
     eng = _EmulatedEngine()
+    monkeypatch.setattr(ops, "WN_TC_WGRAD_MIN_ROWS", 128 if tc_wgrad else 1 << 30)
 
     def params(a_img, w_img, bias, n, N, nkb, mode, act, ref, out, out_img, nkb_out, n_active, seg):
         return types.SimpleNamespace(a_img=a_img, w_img=w_img, bias=bias, n=n, N=N, nkb=nkb, mode=mode, act=act, ref=ref,
@@ -152,6 +163,7 @@ def test_wn_chain_host_logic_with_emulated_engine(monkeypatch, d_in, d_out, rows
     assert torch.equal(o3, o1) and not o3.requires_grad
     assert (o1 - o2).abs().max().item() < 1e-5 * max(1.0, o2.abs().max().item())
     assert set(g1) == set(g2) and len(g1) == 27
+    assert getattr(eng, "tc_wgrads", 0) == (9 if tc_wgrad else 0)      # one launch chain per layer on the selected engine
     for k in g2:
         assert (g1[k] - g2[k]).abs().max().item() < 2e-4 * max(1e-6, g2[k].abs().max().item()), k
 
@@ -183,22 +195,47 @@ def test_hook_binds_to_a_live_runner_and_follows_its_counters():
     assert own.cur_iter == 900 and own.prefit_option() == "explore"
 
 
-def test_fixed_capacity_forward_refuses_a_rebound_hook():
-    """The fixed-capacity (CUDA-graph) forward inlines the PBR hook; with the CESR hook bound it must refuse instead of
-    silently rendering the PBR stage."""
+def test_fixed_capacity_forward_dispatches_on_the_bound_hook():
+    """The fixed-capacity (CUDA-graph) forward inlines the PBR hook and knows the CESR hook's fixed-capacity form; any
+    other re-bound get_sg_render must be refused instead of silently rendering the PBR stage."""
     import robir_b200
     model = robir_b200.IDRNetwork(dict(envmap_material_network=dict(num_lgt_sgs=128)))
     hook = cesr.ClusteredAlbedoHook(model, object(), object(), cur_iter=600)
     inp = {"intrinsics": None, "hdr_shift": None, "uv": None, "pose": None, "object_mask": None}
     model.static_shapes = True
     default = model.get_sg_render
+    seen = {}
+    model._forward_static = lambda input, lin_diff=False, train_spec=False, hook=None: seen.setdefault("hook", hook)
     model.get_sg_render = hook.get_sg_render
+    model(inp, trainstage="Material", train_spec=True)
+    assert seen.pop("hook") is hook                     # CESR: the hook's get_sg_render_static is what will run
+    model.get_sg_render = default                       # restoring the default bound method is not a re-binding
+    model(inp, trainstage="Material", train_spec=True)
+    assert "hook" in seen and seen.pop("hook") is None
+    model.get_sg_render = lambda *a, **k: {}            # anything else
     with pytest.raises(RobirError, match="static_shapes"):
         model(inp, trainstage="Material", train_spec=True)
-    model.get_sg_render = default                       # restoring the default bound method is not a re-binding
-    with pytest.raises(Exception) as e:
+
+    class Other:
+        def get_sg_render(self, *a, **k):
+            return {}
+    model.get_sg_render = Other().get_sg_render
+    with pytest.raises(RobirError, match="static_shapes"):
         model(inp, trainstage="Material", train_spec=True)
-    assert "static_shapes = False" not in str(e.value)
+
+
+def test_phase_key_follows_the_schedule():
+    """One CUDA graph per phase: the key changes exactly where the step's control flow does (train_cesr.py:546-559, :508)."""
+    hook = cesr.ClusteredAlbedoHook(object(), object(), object(), cur_iter=0)
+    keys = {}
+    for it in (0, 300, 500, 501, 600, 1000, 1001, 1500):
+        hook.cur_iter = it
+        keys[it] = hook.phase_key()
+    assert keys[0] == keys[300] == keys[500]
+    assert keys[501] == keys[600] == keys[1000] != keys[500]
+    assert keys[1001] == keys[1500] != keys[1000]
+    hook.is_training = False
+    assert hook.phase_key() != keys[1500]
 
 
 def test_shadow_net_rank_structure_of_the_one_hot_input():

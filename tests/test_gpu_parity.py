@@ -905,7 +905,47 @@ def _cesr_nets():
     return shadow.cuda(), normal.cuda(), sh, nr
 
 
-@pytest.mark.parametrize("which,rows", [("shadow", 1024), ("shadow", 1000), ("normal", 333)])
+@pytest.mark.parametrize("n,N,K", [(5000, 512, 512), (4097, 321, 191), (70, 2, 512), (64, 512, 63), (9000, 3, 512),
+                                   (1, 130, 129)])
+def test_tl_wgrad_vs_fp64(n, N, K):
+    """Tensor-core weight gradients (robir_tl_wgrad: transposed hi/lo images + split-K tcgen05 GEMM + fixed-order
+    reduction) against an fp64 matmul: dW = G^T A and db = column sums, ragged rows / columns, strided inputs; two
+    launches agree bit for bit."""
+    import ctypes
+    from robir_b200 import ops
+    from robir_b200._lib import lib, check
+    gen = torch.Generator().manual_seed(n + N + K)
+    Gf = torch.randn(n, N + 5, generator=gen).cuda() * torch.logspace(-6, 0, N + 5).cuda()      # wide dynamic range
+    Af = torch.randn(n, K + 3, generator=gen).cuda()
+    def run(G, A, rows, n_active=None):
+        dW, db = torch.full((N, K), float("nan"), device="cuda"), torch.full((N,), float("nan"), device="cuda")
+        work = torch.empty(lib().robir_tl_wgrad_workspace(rows, N, K, ops.sm_count()), dtype=torch.uint8, device="cuda")
+        check(lib().robir_tl_wgrad(G.data_ptr(), G.shape[1], A.data_ptr(), A.shape[1], rows, N, K,
+                                   n_active.data_ptr() if n_active is not None else None, work.data_ptr(),
+                                   dW.data_ptr(), db.data_ptr(), ops.sm_count(), ops.stream()))
+        return dW, db
+    dW, db = run(Gf, Af, n)
+    dW2, db2 = run(Gf, Af, n)
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)
+    ref = Gf[:, :N].double().T @ Af[:, :K].double()
+    refb = Gf[:, :N].double().sum(0)
+    # per-row tolerance: every row of dW has its own scale (the logspace above)
+    err = ((dW.double() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-300)).max().item()
+    errb = ((db.double() - refb).abs() / Gf[:, :N].double().abs().sum(0)).max().item()
+    assert err < 2e-5, err
+    assert errb < 1e-6, errb
+    # fixed-capacity form: the same rows at the front of a larger batch whose tail holds garbage that must not be read
+    cap = n + 777
+    Gc = torch.full((cap, Gf.shape[1]), float("nan"), device="cuda")
+    Ac = torch.full((cap, Af.shape[1]), float("nan"), device="cuda")
+    Gc[:n], Ac[:n] = Gf, Af
+    dW3, db3 = run(Gc, Ac, cap, torch.tensor([n], dtype=torch.int32, device="cuda"))
+    err3 = ((dW3.double() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-300)).max().item()
+    assert err3 < 2e-5 and torch.isfinite(db3).all(), err3
+    assert ((db3.double() - refb).abs() / Gf[:, :N].double().abs().sum(0)).max().item() < 1e-6
+
+
+@pytest.mark.parametrize("which,rows", [("shadow", 1024), ("shadow", 1000), ("normal", 333), ("shadow", 4500)])
 def test_wn_chain_vs_oracle(which, rows, wn_engine):
     """shadow_net / normal_net (weight-normed, softplus(100), skip concat at layer 4) forward + every parameter
     gradient against the oracle's wn_mlp (neus_model.py:385-417) on CPU, ragged row counts included."""

@@ -6,7 +6,8 @@ weak scaling over the ranks); these are measured for the record under profiles/,
         default; headline value) and the IDR sphere tracer with ray_tracer.n_steps = 32 (the "march steps" knob)
     c3  Vis stage iteration (training/train_visibility.py:286-324): forward('Illum') on 256 primary rays +
         trace_radiance(nsamp = 512) + IllumLoss + both backwards + both Adam steps; primary and secondary rays/s
-    c4  PBR + CESR iteration (training/train_cesr.py:465-559, explore phase, S = 8, lin_diff), every rank its own batch
+    c4  PBR + CESR iteration (training/train_cesr.py:465-559, explore phase, S = 8, lin_diff), every rank its own batch,
+        one CUDA graph per step (--mode eager: the dynamic-shape eager step)
 """
 import json
 import os
@@ -158,9 +159,11 @@ def run_c3(args):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def run_c4(args):
-    """PBR + CESR iteration (explore phase), eager dynamic shapes, every rank its own 1024-ray batch."""
+    """PBR + CESR iteration (explore phase), every rank its own 1024-ray batch.  --mode graph (default): fixed-capacity
+    batch, the whole step (forward + CESR hook + loss + backward + Adam over 3 networks) as one CUDA graph;
+    --mode eager: the dynamic-shape eager step (what round 1 measured)."""
     import bench
-    from robir_b200 import cesr, dist as rdist, ops
+    from robir_b200 import cesr, dist as rdist, graph, ops
     from robir_b200.loss import InvLoss
     N, M = 1024, 128
     rank, world, local, dev, sd, model = _setup(M)
@@ -173,24 +176,34 @@ def run_c4(args):
     model.get_sg_render = hook.get_sg_render
     loss_fn = InvLoss()
     params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters()) + hook.parameters()
-    opt = torch.optim.Adam(params, lr=5e-4)                                                  # train_cesr.py:111-117
+    graphed = args.mode == "graph"
+    opt = torch.optim.Adam(params, lr=5e-4, capturable=graphed, fused=graphed)               # train_cesr.py:111-117
     reducer = rdist.GradAllReducer(params)
     pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
     hits = []
     host = [synthetic.training_pixels(s * world + rank, n=N) for s in range(args.warmup + args.steps)]
+    om = torch.ones(1, N, dtype=torch.bool, device=dev)
+    gt = torch.full((1, N, 3), 0.5, device=dev)
+    if graphed:
+        host_uv = [torch.stack([(p % 800).float(), (p // 800).float()], -1)[None].pin_memory() for p in host]
+        gstep = graph.GraphedPBRStep(model, loss_fn, opt, N, pose, K, reducer=reducer if world > 1 else None, hook=hook)
 
-    def step(s):
-        pix = host[s].to(dev, non_blocking=True)
-        uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None]
-        inp = {"uv": uv, "object_mask": torch.ones(1, N, dtype=torch.bool, device=dev), "pose": pose,
-               "intrinsics": K, "hdr_shift": model.gamma.hdr_shift.as_input().expand(N, 1)}
-        out = model(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
-        loss, _ = hook.pbr_step(loss_fn, out, {"rgb": torch.full((1, N, 3), 0.5, device=dev)})
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        reducer()
-        opt.step()
-        hits.append(out["network_object_mask"].sum())
+        def step(s):
+            gstep(host_uv[s].to(dev, non_blocking=True), om, gt)
+            hits.append(gstep.hits.clone())
+    else:
+        def step(s):
+            pix = host[s].to(dev, non_blocking=True)
+            uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None]
+            inp = {"uv": uv, "object_mask": om, "pose": pose,
+                   "intrinsics": K, "hdr_shift": model.gamma.hdr_shift.as_input().expand(N, 1)}
+            out = model(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+            loss, _ = hook.pbr_step(loss_fn, out, {"rgb": gt})
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            reducer()
+            opt.step()
+            hits.append(out["network_object_mask"].sum())
     clocks = bench.ClockSampler(local).start()
     t = _timed(step, args.warmup, args.steps, dev, world)
     clk = clocks.stop()
@@ -198,13 +211,15 @@ def run_c4(args):
         hf = float(torch.stack(hits[-args.steps:]).float().mean()) / N
         cfg = {"workload": "truck-synthetic PBR + CESR step: 1024 random pixels/step/GPU, M=128, shadow_net (191->512x8->2 "
                            "on n_hit x 128 rows) + normal_net, explore phase (iteration 600), S=8, fwd+loss+bwd+Adam over 3 "
-                           "networks, eager dynamic shapes", "config": "c4", "rays_per_step_per_gpu": N, "num_lgt_sgs": M,
+                           "networks", "config": "c4", "rays_per_step_per_gpu": N, "num_lgt_sgs": M,
+               "mode": "one CUDA graph per step (fixed-capacity batch)" if graphed else "eager dynamic shapes",
+               "launches_per_step": gstep.launches_per_step if graphed else None,
                "hit_fraction": hf, "wn_engine": ops.ENGINE["wn"],
                "parallelism": "rays x%d (+ NCCL grad all-reduce incl. shadow_net / normal_net)" % world}
         _line(args, "rays/sec (fwd+bwd) PBR+CESR stage, truck", N * args.steps * world / t, "rays/s",
               1e3 * t / args.steps, world, cfg,
               {"clocks": clk, "e2e": {"value": N * args.steps * world / t, "unit": "rays/s",
                                       "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": 0,
-                                      "note": "pixel indices are drawn on the host and copied every step"}})
+                                      "note": "pixel coordinates are drawn on the host and copied every step"}})
     if world > 1:
         torch.distributed.destroy_process_group()
