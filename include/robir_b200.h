@@ -316,6 +316,9 @@ int robir_tl_pack_weight(const float* W, int ldw, int N, int K, int transpose, i
 int robir_tl_pack_rows(const float* X, int ldx, int n, int K, const float* ref, int ld_ref, int act, int nkb, void* img,
                        void* stream);
 int robir_tl_layer(const robir_tl_params* p, void* stream);
+/* the same layer as persistent CTAs over 128 x 256 output tiles with two TMEM accumulators (the epilogue of one tile runs
+ * under the MMAs of the next) -- identical results, for row counts of several waves (the CESR chains) */
+int robir_tl_layer_big(const robir_tl_params* p, int sm_count, void* stream);
 /* weight gradients of one layer on the tensor cores, for row counts where robir_mlp_wgrad's fp32 FFMA GEMM dominates
  * (the CESR chains: n_hit x 128 rows).  dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums of G (db may be NULL);
  * work holds robir_tl_wgrad_workspace(n, N, K, sm_count) bytes.  G and A are transposed into bf16 hi/lo images whose

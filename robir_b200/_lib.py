@@ -149,6 +149,7 @@ _SIGNATURES = {
     "robir_tl_pack_weight": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "robir_tl_pack_rows": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P],
     "robir_tl_layer": [POINTER(TlParams), _P],
+    "robir_tl_layer_big": [POINTER(TlParams), _I, _P],
     "robir_tl_wgrad_workspace": [_I, _I, _I, _I],
     "robir_tl_wgrad": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "robir_mlp_encode": [POINTER(MlpParams), _I, _P],

@@ -75,6 +75,96 @@ __device__ __forceinline__ void tl_store_image(uint8_t* img_tile, int nkb_out, i
   }
 }
 
+// activation / activation derivative of 32 values with the activation as a compile-time constant: straight-line code
+// whose 32 independent MUFU / FMA chains interleave (a per-element switch on p.act serialises them)
+template <int ACT>
+__device__ __forceinline__ void tl_act32(float (&x)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = tl_act(x[i], ACT);
+}
+template <int ACT>
+__device__ __forceinline__ void tl_dact32(float (&d)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) d[i] = tl_dact(d[i], ACT);
+}
+
+// one 32-column chunk of the epilogue: accumulator columns at taddr (this warp's lane quarter) -> bias / activation
+// (forward) or activation derivative (backward) -> fp32 rows and / or the hi|lo image of the next layer's A operand
+__device__ __forceinline__ void tl_epilogue_chunk(const TcLayerParams& p, uint32_t taddr, int row, int r, int col0,
+                                                  uint8_t* img_tile) {
+  uint32_t acc[32];
+  tmem_ld32(taddr, acc);
+  float x[32];
+  const bool full = col0 + 32 <= p.N;               // whole chunk inside the valid columns (the common case)
+  if (p.mode == 0) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);   // zero padded to 128
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = 0.f;
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] += __uint_as_float(acc[i]);
+    switch (p.act) {
+      case ACT_RELU: tl_act32<ACT_RELU>(x); break;
+      case ACT_LEAKY02: tl_act32<ACT_LEAKY02>(x); break;
+      case ACT_SOFTPLUS100: tl_act32<ACT_SOFTPLUS100>(x); break;
+      default: break;
+    }
+    if (!full) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i >= p.N) x[i] = 0.f;
+    }
+  } else {
+    const bool have_ref = p.ref != nullptr && row < p.n;
+    if (have_ref && full && (p.ld_ref & 3) == 0) {
+      const float4* rp = reinterpret_cast<const float4*>(p.ref + (size_t)row * p.ld_ref + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(rp + i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+    } else if (have_ref) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = col0 + i < p.N ? __ldg(p.ref + (size_t)row * p.ld_ref + col0 + i) : 0.f;
+    }
+    if (have_ref) {
+      switch (p.act) {
+        case ACT_RELU: tl_dact32<ACT_RELU>(x); break;
+        case ACT_LEAKY02: tl_dact32<ACT_LEAKY02>(x); break;
+        case ACT_SOFTPLUS100: tl_dact32<ACT_SOFTPLUS100>(x); break;
+        default: tl_dact32<0>(x); break;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = 1.f;
+    }
+    tmem_wait_ld();
+    const bool row_ok = row < p.n;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = (row_ok && (full || col0 + i < p.N)) ? __uint_as_float(acc[i]) * x[i] : 0.f;
+  }
+  if (p.out != nullptr && row < p.n) {
+    float* dst = p.out + (size_t)row * p.ld_out + col0;
+    if (full && (p.ld_out & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) dst[i] = x[i];
+    }
+  }
+  if (img_tile != nullptr) tl_store_image(img_tile, p.nkb_out, r, col0, x);
+}
+
 __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,68 +253,176 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
     tc_fence_after();
     const int half = (warp - 2) >> 2;
 #pragma unroll 1
-    for (int c = 2 * half; c < 2 * half + 2; ++c) {
-      const int col0 = col_base + 32 * c;
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
-      float x[32];
-      const bool full = col0 + 32 <= p.N;               // whole chunk inside the valid columns (the common case)
-      if (p.mode == 0) {
-        float b[32];
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);   // zero padded to 128
-            b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) b[i] = 0.f;
-        }
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          x[i] = (full || col0 + i < p.N) ? tl_act(__uint_as_float(acc[i]) + b[i], p.act) : 0.f;
-      } else {
-        float d[32];
-        if (p.ref != nullptr && row < p.n && full && (p.ld_ref & 3) == 0) {
-          const float4* rp = reinterpret_cast<const float4*>(p.ref + (size_t)row * p.ld_ref + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(rp + i);
-            d[4 * i] = tl_dact(v.x, p.act); d[4 * i + 1] = tl_dact(v.y, p.act);
-            d[4 * i + 2] = tl_dact(v.z, p.act); d[4 * i + 3] = tl_dact(v.w, p.act);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            d[i] = (p.ref != nullptr && row < p.n && col0 + i < p.N)
-                       ? tl_dact(__ldg(p.ref + (size_t)row * p.ld_ref + col0 + i), p.act) : 1.f;
-        }
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = (col0 + i < p.N && row < p.n) ? __uint_as_float(acc[i]) * d[i] : 0.f;
-      }
-      if (p.out != nullptr && row < p.n) {
-        float* dst = p.out + (size_t)row * p.ld_out + col0;
-        if (col0 + 32 <= p.N && (p.ld_out & 3) == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) dst[i] = x[i];
-        }
-      }
-      if (img_tile != nullptr) tl_store_image(img_tile, p.nkb_out, r, col0, x);
-    }
+    for (int c = 2 * half; c < 2 * half + 2; ++c)
+      tl_epilogue_chunk(p, tmem_base + lane_addr + 32u * c, row, r, col_base + 32 * c, img_tile);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// the same layer for large row counts (the CESR chains: n_hit x 128 rows): persistent CTAs, 128 x 256 output tiles
+// (N = 256 MMAs: half the A-operand traffic of 128 x 128 tiles), two TMEM accumulators so that the epilogue of tile i
+// runs under the MMAs of tile i + 1.  Stage = A k-block (hi 16 KB | lo 16 KB) + W k-blocks of the two 128-column
+// blocks (hi 32 KB | lo 32 KB) = 96 KB, two stages.  Tiles are scheduled column-tile fastest: the CTAs that share a row
+// tile's A image read it back to back (L2), the 1 MB weight image stays L2-resident.  A tile whose second column block
+// does not exist (N <= 128 mod 256) runs N = 128 MMAs.  Inactive row tiles (see tc_layer_kernel) are zero-filled by
+// the epilogue warps and skipped by the producer / MMA warps.
+constexpr int kTbStages = 2;
+constexpr int kTbStageBytes = 98304;
+constexpr int kTbSmem = kTbStages * kTbStageBytes + 1024;
+constexpr uint32_t kTbIdesc256 = idesc_bf16(128, 256);
+
+__device__ __forceinline__ bool tb_tile_active(const TcLayerParams& p, int row0) {
+  const int sg = p.seg > 0 ? p.seg : (p.n > 0 ? p.n : 1);
+  const int n_act = p.n_active ? min(__ldg(p.n_active), sg) : sg;
+  const int o = row0 % sg;
+  return !(o >= n_act && o + 128 <= sg);
+}
+
+__global__ void __launch_bounds__(kTlThreads, 1) tc_layer_big_kernel(TcLayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kTbStages], empty_bar[kTbStages], acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col_blocks = (p.N + 127) >> 7, col_tiles = (col_blocks + 1) >> 1, row_tiles = (p.n + 127) >> 7;
+  const int n_tiles = row_tiles * col_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTbStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================================== producer =====================================
+    int it = 0;                                             // k-block counter over this CTA's active tiles
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int tile = t / col_tiles, ct = t % col_tiles;
+      if (!tb_tile_active(p, tile * 128)) continue;
+      const int ncb = min(2, col_blocks - 2 * ct);
+      const uint8_t* a_src = p.a_img + (size_t)tile * p.nkb * kTlBlockBytes;
+      const uint8_t* w_src = p.w_img + (size_t)(2 * ct) * p.nkb * kTlBlockBytes;
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int st = it % kTbStages;
+        mbar_wait(&empty_bar[st], ((it / kTbStages) & 1) ^ 1);
+        if (elect_one_sync()) {
+          uint8_t* sa = ring + (size_t)st * kTbStageBytes;
+          mbar_arrive_expect_tx(&full_bar[st], kTlBlockBytes * (1 + ncb));
+          bulk_g2s(sa, a_src + (size_t)kb * kTlBlockBytes, kTlBlockBytes, &full_bar[st]);
+          for (int j = 0; j < ncb; ++j) {
+            const uint8_t* wb = w_src + ((size_t)j * p.nkb + kb) * kTlBlockBytes;
+            bulk_g2s(sa + 32768 + j * 16384, wb, 16384, &full_bar[st]);                    // hi rows 128 j ..
+            bulk_g2s(sa + 65536 + j * 16384, wb + 16384, 16384, &full_bar[st]);            // lo rows 128 j ..
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    int it = 0, j = 0;                                      // k-block / active-tile counters
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int tile = t / col_tiles, ct = t % col_tiles;
+      if (!tb_tile_active(p, tile * 128)) continue;
+      const int ncb = min(2, col_blocks - 2 * ct);
+      const uint32_t idesc = ncb == 2 ? kTbIdesc256 : kTlIdesc;
+      const int buf = j & 1;
+      mbar_wait(&acc_free[buf], ((j >> 1) & 1) ^ 1);        // the epilogue of the tile before last has drained it
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + 256u * buf;
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int st = it % kTbStages;
+        mbar_wait(&full_bar[st], (it / kTbStages) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint8_t* sa = ring + (size_t)st * kTbStageBytes;
+          const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + 16384);
+          const uint64_t b_hi = smem_desc_sw128(sa + 32768), b_lo = smem_desc_sw128(sa + 65536);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (kb == 0 && q == 0) umma_ss<0>(d_tmem, a_hi + 2u * q, b_hi + 2u * q, idesc);
+            else umma_ss<1>(d_tmem, a_hi + 2u * q, b_hi + 2u * q, idesc);
+            umma_ss<1>(d_tmem, a_lo + 2u * q, b_hi + 2u * q, idesc);
+            umma_ss<1>(d_tmem, a_hi + 2u * q, b_lo + 2u * q, idesc);
+          }
+          umma_commit(&empty_bar[st]);
+          if (kb == p.nkb - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+      ++j;
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int j = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int tile = t / col_tiles, ct = t % col_tiles;
+      const int row0 = tile * 128, row = row0 + r;
+      const int ncb = min(2, col_blocks - 2 * ct);
+      uint8_t* img_tile = p.out_img ? p.out_img + (size_t)tile * p.nkb_out * kTlBlockBytes : nullptr;
+      if (!tb_tile_active(p, row0)) {
+        // zero outputs of an inactive row tile: this warp's 32 rows x its 128-column block, coalesced
+        if (half < ncb) {
+          const int col_base = (2 * ct + half) * 128;
+          if (p.out != nullptr) {
+            const bool vec = (p.ld_out & 3) == 0 && col_base + 128 <= p.N;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int orow = row0 + q * 32 + rr;
+              if (orow >= p.n) break;
+              float* d = p.out + (size_t)orow * p.ld_out + col_base;
+              if (vec) {
+                reinterpret_cast<float4*>(d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+                for (int c = lane; c < 128 && col_base + c < p.N; c += 32) d[c] = 0.f;
+              }
+            }
+          }
+          if (img_tile != nullptr)
+            for (int kb = 2 * (2 * ct + half); kb < 2 * (2 * ct + half) + 2 && kb < p.nkb_out; ++kb) {
+              uint8_t* blk = img_tile + (size_t)kb * kTlBlockBytes + q * 4096;       // rows 32 q .. of the hi half
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                *reinterpret_cast<uint4*>(blk + (i * 32 + lane) * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(blk + 16384 + (i * 32 + lane) * 16) = make_uint4(0, 0, 0, 0);
+              }
+            }
+        }
+        continue;
+      }
+      const int buf = j & 1;
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      if (half < ncb) {
+        const int col_base = (2 * ct + half) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c)
+          tl_epilogue_chunk(p, tmem_base + lane_addr + 256u * buf + 128u * half + 32u * c, row, r, col_base + 32 * c,
+                            img_tile);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[buf]);
+      ++j;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // images
@@ -514,6 +712,18 @@ int robir_tl_layer(const TcLayerParams* p, void* stream) {
   RB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTlSmem));
   dim3 grid((p->n + 127) / 128, (p->N + 127) / 128);
   tc_layer_kernel<<<grid, kTlThreads, kTlSmem, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// the persistent 128 x 256-tile form of the same layer (same parameters, same results bit for bit: the k order of the
+// accumulation is unchanged); pays off from a few waves of row tiles on
+int robir_tl_layer_big(const TcLayerParams* p, int sm_count, void* stream) {
+  if (p->n == 0) return 0;
+  RB_REQUIRE(p->nkb >= 1 && p->nkb <= 8 && p->N >= 1, "tl_layer_big: 1..8 k-blocks (K <= 512)");
+  RB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTbSmem));
+  const int col_tiles = ((p->N + 127) / 128 + 1) / 2, tiles = ((p->n + 127) / 128) * col_tiles;
+  tc_layer_big_kernel<<<tiles < sm_count ? tiles : sm_count, kTlThreads, kTbSmem, (cudaStream_t)stream>>>(*p);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1051,6 +1051,16 @@ def _tl_backward(chain, packed, tc, n, g_out, saves, Gs, g_x, n_active, segments
 # rows from which the CESR chains' weight gradients run on the tensor cores (robir_tl_wgrad); below it the fp32 FFMA
 # kernel of csrc/mlp.cu is launch-bound anyway.  Tests lower it to cover the kernel at small sizes.
 WN_TC_WGRAD_MIN_ROWS = 4096
+# rows from which a layer runs as persistent CTAs over 128 x 256 tiles (robir_tl_layer_big) instead of one CTA per
+# 128 x 128 tile (robir_tl_layer): identical results
+TL_BIG_MIN_ROWS = 4096
+
+
+def _tl_layer(q, rows):
+    if rows >= TL_BIG_MIN_ROWS:
+        check(lib().robir_tl_layer_big(ctypes.byref(q), sm_count(), stream()))
+    else:
+        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
 
 
 def _tl_weight_images(W, rows_bw):
@@ -1118,7 +1128,7 @@ class _WnChain(torch.autograd.Function):
             nxt = _tl_image(tiles, nkb_out, x) if nkb_out else None
             q = _tl_params(img, fw, bias, R, N, (K + 63) // 64, 0, 0 if last else SOFTPLUS, None, out, nxt, nkb_out,
                            n_active, 0)
-            check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+            _tl_layer(q, R)
             a = out
             img = _tl_rows_image(out, N + d_in) if next_skip else nxt
         ctx.meta = (R, d_in, L, tuple(skip))
@@ -1164,7 +1174,7 @@ class _WnChain(torch.autograd.Function):
             nkb_out = (Np + 63) // 64
             nxt = _tl_image(tiles, nkb_out, G)
             q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, n_active, 0)
-            check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+            _tl_layer(q, R)
             G, img = Gp, nxt
         return (None, None, None, None, *gW, *gb)
 

@@ -945,6 +945,42 @@ def test_tl_wgrad_vs_fp64(n, N, K):
     assert ((db3.double() - refb).abs() / Gf[:, :N].double().abs().sum(0)).max().item() < 1e-6
 
 
+@pytest.mark.parametrize("n_active", [None, 1536, 0])
+def test_tl_layer_big_equals_tile_kernel(n_active):
+    """The persistent 128 x 256-tile layer kernel (robir_tl_layer_big: two TMEM accumulators, N = 256 MMAs) against the
+    one-CTA-per-tile kernel on the shadow_net chain (K = 191 / 512 / 512 + skip, N = 512 / 321 / 2): outputs and all
+    parameter gradients bit for bit, with and without a device-side active-row count (fixed-capacity batches)."""
+    from robir_b200 import cesr, ops
+    shadow, _, sh, _ = _cesr_nets()
+    rows = 4500
+    gen = torch.Generator().manual_seed(31)
+    x = (torch.randn(rows, 191, generator=gen) * 0.4).cuda()
+    gup = torch.randn(rows, 2, generator=gen).cuda()
+    na = None if n_active is None else torch.tensor([n_active], dtype=torch.int32, device="cuda")
+    if n_active is not None:
+        gup[n_active:] = 0                      # contract of the fixed-capacity form
+    res = []
+    old = ops.TL_BIG_MIN_ROWS, ops.ENGINE["wn"]
+    ops.ENGINE["wn"] = "tc"
+    try:
+        for thr in (1 << 30, 128):
+            ops.TL_BIG_MIN_ROWS = thr
+            shadow.zero_grad()
+            out = cesr.wn_mlp(shadow, x, n_active=na)
+            (out * gup).sum().backward()
+            res.append((out.detach().clone(), [p.grad.clone() for p in shadow.parameters()]))
+    finally:
+        ops.TL_BIG_MIN_ROWS, ops.ENGINE["wn"] = old
+    (o1, g1), (o2, g2) = res
+    assert torch.isfinite(o2).all()
+    assert torch.equal(o1, o2)
+    if n_active is not None:
+        first_inactive = ((n_active + 127) // 128) * 128          # whole row tiles beyond the count are zero-filled
+        assert float(o2[first_inactive:(rows // 128) * 128].abs().max()) == 0.0
+    for a, b in zip(g1, g2):
+        assert torch.isfinite(b).all() and torch.equal(a, b)
+
+
 @pytest.mark.parametrize("which,rows", [("shadow", 1024), ("shadow", 1000), ("normal", 333), ("shadow", 4500)])
 def test_wn_chain_vs_oracle(which, rows, wn_engine):
     """shadow_net / normal_net (weight-normed, softplus(100), skip concat at layer 4) forward + every parameter

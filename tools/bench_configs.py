@@ -207,6 +207,15 @@ def run_c4(args):
     clocks = bench.ClockSampler(local).start()
     t = _timed(step, args.warmup, args.steps, dev, world)
     clk = clocks.stop()
+    prof_path = os.environ.get("ROBIR_C4_PROFILE")
+    if prof_path and rank == 0:                 # per-kernel table of two more steps (diagnostic, after the timed region)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for s in range(2):
+                step(args.warmup + args.steps - 1 - s)
+            torch.cuda.synchronize()
+        with open(prof_path, "w") as f:
+            f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=90))
     if rank == 0:
         hf = float(torch.stack(hits[-args.steps:]).float().mean()) / N
         cfg = {"workload": "truck-synthetic PBR + CESR step: 1024 random pixels/step/GPU, M=128, shadow_net (191->512x8->2 "

@@ -1,6 +1,7 @@
-"""One forward layer of the CESR shadow_net chain on the tensor-core layer engine (512x512, Softplus(100), rows = 542 hit
-points x 128 lobes as in tools/cesr_bench.py) and the weight-gradient launch of the same layer, inside a
-cudaProfilerStart/Stop range so that `ncu --profile-from-start off` captures exactly these two kernels:
+"""One forward and one backward layer of the CESR shadow_net chain on the tensor-core layer engine (512x512, Softplus(100),
+rows = 542 hit points x 128 lobes as in tools/cesr_bench.py; persistent 128x256-tile kernel) and the tensor-core
+weight-gradient launches of the same layer, inside a cudaProfilerStart/Stop range so that
+`ncu --profile-from-start off` captures exactly these kernels:
 
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/cesr_kernels \\
         python tools/cesr_kernels_probe.py
@@ -41,12 +42,29 @@ def main():
     tickets = torch.zeros(wt, dtype=torch.int32, device=dev)
     dW, db = torch.empty(N, K, device=dev), torch.empty(N, device=dev)
 
+    Gp = torch.empty(R, K, device=dev)
+    bw = ops._tl_weight_images(W, K)[1]
+    gimg = ops._tl_rows_image(G, N)
+    nxt_b = ops._tl_image(tiles, K // 64, x)
+    qb = ops._tl_params(gimg, bw, None, R, K, N // 64, 1, 3, out, Gp, nxt_b, K // 64, None, 0)
+    work = torch.empty(lib().robir_tl_wgrad_workspace(R, N, K, ops.sm_count()), dtype=torch.uint8, device=dev)
+
     def layer():
+        check(lib().robir_tl_layer_big(ctypes.byref(q), ops.sm_count(), stream()))
+
+    def layer_tile():
         check(lib().robir_tl_layer(ctypes.byref(q), stream()))
 
-    def wgrad():
+    def layer_bwd():
+        check(lib().robir_tl_layer_big(ctypes.byref(qb), ops.sm_count(), stream()))
+
+    def wgrad_ffma():
         check(lib().robir_mlp_wgrad(ptr(G), N, ptr(x), K, R, N, K, None, 0, splits, ptr(part), ptr(tickets), ptr(dW),
                                     ptr(db), stream()))
+
+    def wgrad():
+        check(lib().robir_tl_wgrad(ptr(G), N, ptr(x), K, R, N, K, None, ptr(work), ptr(dW), ptr(db), ops.sm_count(),
+                                   stream()))
 
     def timed(fn, reps=10):
         fn()
@@ -59,16 +77,19 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    t_layer, t_wgrad = timed(layer), timed(wgrad)
+    t_layer, t_tile, t_bwd, t_wgrad, t_ffma = timed(layer), timed(layer_tile), timed(layer_bwd), timed(wgrad), \
+        timed(wgrad_ffma)
     flop = 2.0 * R * N * K
-    print("tc_layer fwd 512x512 on %d rows: %.3f ms = %.1f TFLOP/s algorithmic (x3 executed); wgrad: %.3f ms = %.1f TFLOP/s"
-          % (R, t_layer, flop / t_layer / 1e9, t_wgrad, flop / t_wgrad / 1e9))
+    print("rows %d, 512x512: layer fwd %.3f ms = %.1f TFLOP/s algorithmic (x3 executed) [one CTA per 128x128 tile: %.3f ms]; "
+          "layer bwd %.3f ms; wgrad (tensor cores, 4 launches) %.3f ms = %.1f TFLOP/s [fp32 FFMA: %.3f ms]"
+          % (R, t_layer, flop / t_layer / 1e9, t_tile, t_bwd, t_wgrad, flop / t_wgrad / 1e9, t_ffma))
     ref = torch.nn.functional.softplus(x @ W.t(), beta=100)
     print("max |layer - torch| = %.3e, max |dW - torch| rel = %.3e"
           % ((out - ref).abs().max().item(), ((dW - G.t() @ x).abs().max() / (G.t() @ x).abs().max()).item()))
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     layer()
+    layer_bwd()
     wgrad()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
