@@ -23,7 +23,7 @@ constexpr int kTlStageBytes = 65536;     // A k-block (32 KB) + W k-block (32 KB
 constexpr int kTlBlockBytes = 32768;     // one 128 x 64 hi|lo k-block
 constexpr int kTlThreads = 320;       // producer, MMA issuer, 8 epilogue warps (two per scheduler: 64 columns each)
 constexpr uint32_t kTlIdesc = idesc_bf16(128, 128);
-constexpr int kTlSmem = kTlStages * kTlStageBytes + 1024;
+constexpr int kTlSmem = kTlStages * kTlStageBytes + 1024 + 8 * 4096;      // ring + alignment + epilogue staging
 
 struct TcLayerParams {
   const uint8_t* a_img;      // [row_tiles][nkb][32 KB]
@@ -58,21 +58,57 @@ __device__ __forceinline__ float tl_dact(float y, int act) {
   return 1.f;
 }
 
-// hi / lo words of 32 consecutive columns of row r -> image k-block(s); col0 % 32 == 0
-__device__ __forceinline__ void tl_store_image(uint8_t* img_tile, int nkb_out, int r, int col0, const float (&x)[32]) {
+// Epilogue stores go through a per-warp 4 KB staging buffer in shared memory: a thread owns one accumulator row, so a
+// direct store instruction would touch 32 different 128-byte lines with 16 bytes each (32 LSU wavefronts, half-written
+// sectors); after the transposition each instruction writes whole lines (fp32 rows: 4 lines per instruction) or whole
+// 64-byte halves of image rows (8 per instruction).
+constexpr int kTlStageWarpBytes = 4096;
+
+// hi / lo words of 32 consecutive columns of this warp's 32 rows (thread = row q * 32 + lane) -> image k-block;
+// col0 % 32 == 0; warp-collective
+__device__ __forceinline__ void tl_store_image(uint8_t* img_tile, int nkb_out, int r, int lane, int col0,
+                                               const float (&x)[32], uint8_t* stage) {
   const int kb = col0 >> 6;
   if (kb >= nkb_out) return;
-  uint8_t* blk = img_tile + (size_t)kb * kTlBlockBytes + r * 128;
   const int c16_0 = (col0 & 63) >> 3;                 // first 16-byte chunk (8 bf16) of this 32-column group
+  const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_pack(x[8 * j + 2 * e], x[8 * j + 2 * e + 1], hi[e], lo[e]);
-    const int off = ((c16_0 + j) ^ (r & 7)) << 4;
-    *reinterpret_cast<uint4*>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(blk + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const int off = lane * 64 + ((j ^ sw) << 4);
+    *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(stage + 2048 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+  __syncwarp();
+  uint8_t* blk = img_tile + (size_t)kb * kTlBlockBytes + (r - lane) * 128;      // this warp's first row
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), j = lane & 3;
+    const int src = rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4);
+    const int dst = rr * 128 + (((c16_0 + j) ^ (rr & 7)) << 4);                  // (r - lane) % 8 == 0
+    *reinterpret_cast<uint4*>(blk + dst) = *reinterpret_cast<const uint4*>(stage + src);
+    *reinterpret_cast<uint4*>(blk + 16384 + dst) = *reinterpret_cast<const uint4*>(stage + 2048 + src);
+  }
+  __syncwarp();
+}
+
+// 32 fp32 columns of this warp's 32 rows -> out rows (whole 128-byte lines per instruction); warp-collective
+__device__ __forceinline__ void tl_store_rows(float* dst_w0 /* row of lane 0, column col0 */, int ld_out, int rows_valid,
+                                              int lane, const float (&x)[32], uint8_t* stage) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3), pc = lane & 7;
+    const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((pc ^ (rr & 7)) << 4));
+    if (rr < rows_valid) *reinterpret_cast<float4*>(dst_w0 + (size_t)rr * ld_out + pc * 4) = v;
+  }
+  __syncwarp();
 }
 
 // activation / activation derivative of 32 values with the activation as a compile-time constant: straight-line code
@@ -90,8 +126,8 @@ __device__ __forceinline__ void tl_dact32(float (&d)[32]) {
 
 // one 32-column chunk of the epilogue: accumulator columns at taddr (this warp's lane quarter) -> bias / activation
 // (forward) or activation derivative (backward) -> fp32 rows and / or the hi|lo image of the next layer's A operand
-__device__ __forceinline__ void tl_epilogue_chunk(const TcLayerParams& p, uint32_t taddr, int row, int r, int col0,
-                                                  uint8_t* img_tile) {
+__device__ __forceinline__ void tl_epilogue_chunk(const TcLayerParams& p, uint32_t taddr, int row, int r, int lane,
+                                                  int col0, uint8_t* img_tile, uint8_t* stage) {
   uint32_t acc[32];
   tmem_ld32(taddr, acc);
   float x[32];
@@ -150,19 +186,17 @@ __device__ __forceinline__ void tl_epilogue_chunk(const TcLayerParams& p, uint32
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = (row_ok && (full || col0 + i < p.N)) ? __uint_as_float(acc[i]) * x[i] : 0.f;
   }
-  if (p.out != nullptr && row < p.n) {
-    float* dst = p.out + (size_t)row * p.ld_out + col0;
+  if (p.out != nullptr) {
     if (full && (p.ld_out & 3) == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-    } else {
+      tl_store_rows(p.out + (size_t)(row - lane) * p.ld_out + col0, p.ld_out, p.n - (row - lane), lane, x, stage);
+    } else if (row < p.n) {
+      float* dst = p.out + (size_t)row * p.ld_out + col0;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < p.N) dst[i] = x[i];
     }
   }
-  if (img_tile != nullptr) tl_store_image(img_tile, p.nkb_out, r, col0, x);
+  if (img_tile != nullptr) tl_store_image(img_tile, p.nkb_out, r, lane, col0, x, stage);
 }
 
 __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p) {
@@ -253,8 +287,9 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
     tc_fence_after();
     const int half = (warp - 2) >> 2;
 #pragma unroll 1
+    uint8_t* stage = ring + kTlStages * kTlStageBytes + (warp - 2) * kTlStageWarpBytes;
     for (int c = 2 * half; c < 2 * half + 2; ++c)
-      tl_epilogue_chunk(p, tmem_base + lane_addr + 32u * c, row, r, col_base + 32 * c, img_tile);
+      tl_epilogue_chunk(p, tmem_base + lane_addr + 32u * c, row, r, lane, col_base + 32 * c, img_tile, stage);
   }
   tc_fence_before();
   __syncthreads();
@@ -272,7 +307,7 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
 // the epilogue warps and skipped by the producer / MMA warps.
 constexpr int kTbStages = 2;
 constexpr int kTbStageBytes = 98304;
-constexpr int kTbSmem = kTbStages * kTbStageBytes + 1024;
+constexpr int kTbSmem = kTbStages * kTbStageBytes + 1024 + 8 * 4096;
 constexpr uint32_t kTbIdesc256 = idesc_bf16(128, 256);
 
 __device__ __forceinline__ bool tb_tile_active(const TcLayerParams& p, int row0) {
@@ -366,6 +401,7 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_big_kernel(TcLayerPara
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* stage = ring + kTbStages * kTbStageBytes + (warp - 2) * kTlStageWarpBytes;
     int j = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int tile = t / col_tiles, ct = t % col_tiles;
@@ -408,8 +444,8 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_big_kernel(TcLayerPara
         const int col_base = (2 * ct + half) * 128;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c)
-          tl_epilogue_chunk(p, tmem_base + lane_addr + 256u * buf + 128u * half + 32u * c, row, r, col_base + 32 * c,
-                            img_tile);
+          tl_epilogue_chunk(p, tmem_base + lane_addr + 256u * buf + 128u * half + 32u * c, row, r, lane,
+                            col_base + 32 * c, img_tile, stage);
       }
       tc_fence_before();
       __syncwarp();
