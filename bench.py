@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- rays/s of RobIR's per-ray rendering hot path on synthetic inputs of BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5] [--impl reference|reference-cuda]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5|c2e] [--impl reference|reference-cuda]
 
 Default = BASELINE config 2 (the configuration the metric is quoted on): each step = one training iteration of the
 reference's PBR stage (training/train_pbr.py:431-460): 1024 random pixels of one 800x800 view, M=128 light SGs, S=32
@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="robir_b200")
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c2e"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-baseline", action="store_true")
     ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back replays for the sustained record")

@@ -6,6 +6,8 @@ weak scaling over the ranks); these are measured for the record under profiles/,
         default; headline value) and the IDR sphere tracer with ray_tracer.n_steps = 32 (the "march steps" knob)
     c3  Vis stage iteration (training/train_visibility.py:286-324): forward('Illum') on 256 primary rays +
         trace_radiance(nsamp = 512) + IllumLoss + both backwards + both Adam steps; primary and secondary rays/s
+    c2e full 800x800 image of config 2's model in evaluation mode (PBRTrainRunner.plot_to_disk, training/train_pbr.py:235-311):
+        forward only, the reference's 1024-pixel chunks and 16 384-pixel chunks; a "step" is one whole image
     c4  PBR + CESR iteration (training/train_cesr.py:465-559, explore phase, S = 8, lin_diff), every rank its own batch,
         one CUDA graph per step (--mode eager: the dynamic-shape eager step)
 """
@@ -155,6 +157,62 @@ def run_c3(args):
                "e2e": {"value": N * args.steps * world / t, "unit": "rays/s", "h2d_bytes_per_step": N * 8 + N + 100,
                        "d2h_bytes_per_step": 8, "note": "the step builds its batch on the host and copies it (dynamic "
                                                         "shapes sync the host several times per step)"}})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c2e(args):
+    """Whole 800x800 image, evaluation mode (train_pbr.py:235-311: model.eval(), is_training = False, split_input chunks,
+    hdr2ldr of sg_rgb + indir_rgb), forward only.  One step = one image; the image is read back to the host (e2e)."""
+    import bench
+    H = W = 800
+    M = 128
+    rank, world, local, dev, sd, model = _setup(M)
+    model.eval()
+    model.is_training = False
+    model.static_shapes = False
+    pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
+    pix = torch.arange(H * W, device=dev)
+    uv_all = torch.stack([(pix % W).float(), (pix // W).float()], -1)[None]
+    host_img = torch.empty(H * W, 3).pin_memory()
+    out = {}
+    for chunk in (1024, 16384):
+        img = torch.empty(H * W, 3, device=dev)
+        hits = torch.zeros((), device=dev)
+        om = torch.ones(1, chunk, dtype=torch.bool, device=dev)
+
+        def step(s, chunk=chunk, img=img, om=om):
+            hits.zero_()
+            with torch.no_grad():
+                shift = model.gamma.hdr_shift.as_input()
+                for lo in range(0, H * W, chunk):
+                    hi = min(lo + chunk, H * W)
+                    inp = {"uv": uv_all[:, lo:hi], "object_mask": om[:, :hi - lo], "pose": pose, "intrinsics": K,
+                           "hdr_shift": shift.expand(hi - lo, 1)}
+                    o = model(inp, trainstage="Material", lin_diff=False, fun_spec=False, train_spec=True)
+                    img[lo:hi] = model.gamma.hdr_shift.hdr2ldr(o["sg_rgb"] + o["indir_rgb"])
+                    hits.add_(o["network_object_mask"].sum())
+                host_img.copy_(img, non_blocking=True)
+        clocks = bench.ClockSampler(local).start()
+        t = _timed(step, 1, args.steps, dev, world)
+        clk = clocks.stop()
+        torch.cuda.synchronize()
+        out["chunk_%d" % chunk] = dict(rays_per_s=H * W * args.steps * world / t, s_per_image=t / args.steps,
+                                       hit_fraction=float(hits) / (H * W), clocks=clk,
+                                       finite=bool(torch.isfinite(host_img).all()))
+    if rank == 0:
+        best = out["chunk_16384"]
+        cfg = {"workload": "hotdog-synthetic full 800x800 image, evaluation mode (plot_to_disk path: model.eval(), testing "
+                           "visibility, hdr2ldr), M=128, S=32, forward only, eager dynamic shapes; headline = 16 384-pixel "
+                           "chunks, the reference's 1024-pixel chunking beside it", "config": "c2e",
+               "rays_per_image": H * W, "num_lgt_sgs": M, "chunks": out}
+        _line(args, "rays/sec (fwd, eval) PBR stage full image, hotdog 800x800", best["rays_per_s"], "rays/s",
+              1e3 * best["s_per_image"], world, cfg,
+              {"clocks": best["clocks"], "e2e": {"value": best["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0,
+                                                 "d2h_bytes_per_step": H * W * 12,
+                                                 "note": "pixel grid resident, rendered image copied to pinned host memory "
+                                                         "inside the timed region"}})
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
