@@ -37,14 +37,20 @@ def main():
             step(uv, om, gt)
         torch.cuda.synchronize()
     rows = []
-    for ev in prof.events():
-        if ev.device_type == torch.autograd.DeviceType.CUDA:
-            rows.append((ev.time_range.start, ev.time_range.end - ev.time_range.start, ev.name))
+    try:                                     # kineto events carry the stream id (device_resource_id)
+        for ev in prof.profiler.kineto_results.events():
+            if ev.device_type() == torch.autograd.DeviceType.CUDA:
+                rows.append((ev.start_ns() / 1e3, ev.duration_ns() / 1e3, ev.name(), ev.device_resource_id()))
+    except Exception:
+        rows = []
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                rows.append((ev.time_range.start, ev.time_range.end - ev.time_range.start, ev.name, -1))
     rows.sort()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "timeline.csv"), "w") as f:
-        for s, d, n in rows:
-            f.write("%.3f,%.3f,%s\n" % (s, d, n.replace(",", ";")[:120]))
+        for s, d, n, st in rows:
+            f.write("%.3f,%.3f,%s,%d\n" % (s, d, n.replace(",", ";")[:120], st))
     print("kernels:", len(rows))
 
 
