@@ -941,6 +941,56 @@ class MlpChain:
             return out
         return self.__dict__["_tc_cache"].get(self.params(), build)
 
+    def eval_tc_ok(self, n, x):
+        """Evaluation-only forward of a raw-input chain on the layer engine: large batches outside autograd (the colour
+        network of borrow_color, 131 072 rows per call) -- weight-normed chains included, the weight norm is folded into
+        the images."""
+        if ENGINE["mlp"] != "tc" or self.in_mode != 0 or n < TL_BIG_MIN_ROWS or torch.is_grad_enabled():
+            return False
+        dims = [tuple((l.weight_v if self.weightnorm else l.weight).shape) for l in self.linears]
+        return x.shape[1] == dims[0][1] and max(d[0] for d in dims) >= 256 and all(d[0] <= 512 and d[1] <= 512 for d in dims)
+
+    def packed_eval_tc(self):
+        """Forward images of the (folded) weights + zero-padded biases, cached on the parameters."""
+        if "_tc_eval_cache" not in self.__dict__:
+            self.__dict__["_tc_eval_cache"] = _PackCache()
+
+        def build():
+            out = []
+            for lin in self.linears:
+                if self.weightnorm:
+                    v, g = f32(lin.weight_v), f32(lin.weight_g)
+                    W = (g * v / v.norm(dim=1, keepdim=True)).contiguous()
+                else:
+                    W = f32(lin.weight)
+                N, K = W.shape
+                cbn, nkb = (N + 127) // 128, (K + 63) // 64
+                fw = torch.empty(cbn * nkb * 32768, dtype=torch.uint8, device=W.device)
+                check(lib().robir_tl_pack_weight(ptr(W), K, N, K, 0, cbn, nkb, ptr(fw), stream()))
+                bias = torch.zeros(cbn * 128, device=W.device)
+                bias[:N] = f32(lin.bias)
+                out.append(dict(fw=fw, bias=bias, N=N, K=K, nkb=nkb))
+            return out
+        return self.__dict__["_tc_eval_cache"].get(self.params(), build)
+
+    def eval_tc(self, x):
+        """x [n, K0] -> [n, N_last]: one layer-engine launch per Linear, hidden activations only as hi/lo images."""
+        x = f32(x)
+        n = x.shape[0]
+        layers = self.packed_eval_tc()
+        tiles = (n + 127) // 128
+        img = _tl_rows_image(x, layers[0]["K"])
+        out = None
+        for l, d in enumerate(layers):
+            last = l == len(layers) - 1
+            out = _empty(n, d["N"], like=x) if last else None
+            nkb_out = 0 if last else (d["N"] + 63) // 64
+            nxt = _tl_image(tiles, nkb_out, x) if nkb_out else None
+            q = _tl_params(img, d["fw"], d["bias"], n, d["N"], d["nkb"], 0, self.acts[l], None, out, nxt, nkb_out, None, 0)
+            _tl_layer(q, n)
+            img = nxt
+        return out
+
     def wgrad_tickets(self, layer, tiles, like):
         """Persistent zero-initialised ticket counters of robir_mlp_wgrad's in-kernel split reduction (it re-zeroes them)."""
         t = self.__dict__.setdefault("_tickets", {})
@@ -1018,7 +1068,7 @@ def _tl_forward(chain, packed, tc, p, n, x0, saves, out, n_active, segments):
         nxt = _tl_image(tiles, nkb_out, x0) if not last else None
         q = _tl_params(img, tc[l]["fw"], d["bias"], n, d["N"], tc[l]["nkb_fw"], 0, chain.acts[l], None, dst, nxt, nkb_out,
                        na, seg)
-        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+        _tl_layer(q, n)
         img = nxt
 
 
@@ -1041,7 +1091,7 @@ def _tl_backward(chain, packed, tc, n, g_out, saves, Gs, g_x, n_active, segments
         nxt = _tl_image(tiles, nkb_out, g_out) if not first else None
         q = _tl_params(img, tc[l]["bw"], None, n, d["K"], tc[l]["nkb_bw"], 1, chain.acts[l - 1] if not first else 0,
                        saves[l - 1] if not first else None, dst, nxt, nkb_out, na, seg)
-        check(lib().robir_tl_layer(ctypes.byref(q), stream()))
+        _tl_layer(q, n)
         img = nxt
 
 
@@ -1258,6 +1308,14 @@ class _FusedMLP(torch.autograd.Function):
                 d = packed[l]
                 gw, gb = _empty(d["N"], d["K"], like=x), _empty(d["N"], like=x)
                 seg = n // ctx.segments
+                if n >= WN_TC_WGRAD_MIN_ROWS and ENGINE["mlp"] == "tc":
+                    # large batches (the Vis stage trains VisNetwork on n_hit x 512 rows): split-K tcgen05 GEMM
+                    work = torch.empty(lib().robir_tl_wgrad_workspace(n, d["N"], d["K"], sm_count()), dtype=torch.uint8,
+                                       device=x.device)
+                    check(lib().robir_tl_wgrad(ptr(Gs[l]), Gs[l].shape[1], ptr(prevs[l]), prevs[l].shape[1], n, d["N"],
+                                               d["K"], ptr(n_active) if ctx.segments == 1 else None, ptr(work), ptr(gw),
+                                               ptr(gb), sm_count(), stream()))
+                    return gw, gb
                 tiles = ((d["N"] + 63) // 64) * ((d["K"] + 63) // 64)
                 splits = max(1, min(32, 160 // tiles, (n + 63) // 64))      # ~one wave of CTAs per layer
                 part = _empty(splits * tiles * 4160, like=x) if splits > 1 else None
@@ -1278,6 +1336,9 @@ class _FusedMLP(torch.autograd.Function):
 def fused_mlp(chain, x, extra=None, noise=None, noise_scale=0.02, want_param_grad=False, segments=1):
     """x: [n,K] (raw mode) or points [n,3]; extra: [n,1] appended column (pe10_extra); noise: [n,K] in embedding space;
     segments: the batch is a concatenation of that many equally ordered copies (matters under ops.active_rows)."""
+    if extra is None and noise is None and not want_param_grad and active_rows.current is None and \
+            chain.eval_tc_ok(x.shape[0], x):
+        return chain.eval_tc(x)
     params = chain.params() if want_param_grad else []
     return _FusedMLP.apply(chain, x, extra, noise, noise_scale, want_param_grad, segments, *params)
 
