@@ -309,6 +309,8 @@ typedef struct {
   int nkb_out;
   const int* n_active;      /* as robir_mlp_params */
   int seg;
+  int no_fill;              /* 1: leave the outputs of inactive row tiles unwritten instead of zero-filling them (only when
+                               every consumer honours the same n_active: the hidden layers of a fixed-capacity chain) */
 } robir_tl_params;
 int robir_tl_block_bytes(void);
 int robir_tl_pack_weight(const float* W, int ldw, int N, int K, int transpose, int col_blocks, int nkb, void* img,

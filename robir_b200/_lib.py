@@ -56,7 +56,8 @@ class SphereTraceParams(Structure):
 class TlParams(Structure):
     _fields_ = [("a_img", c_void_p), ("w_img", c_void_p), ("bias", c_void_p), ("n", c_int), ("N", c_int), ("nkb", c_int),
                 ("mode", c_int), ("act", c_int), ("ref", c_void_p), ("ld_ref", c_int), ("out", c_void_p),
-                ("ld_out", c_int), ("out_img", c_void_p), ("nkb_out", c_int), ("n_active", c_void_p), ("seg", c_int)]
+                ("ld_out", c_int), ("out_img", c_void_p), ("nkb_out", c_int), ("n_active", c_void_p), ("seg", c_int),
+                ("no_fill", c_int)]
 
 
 class LossParams(Structure):

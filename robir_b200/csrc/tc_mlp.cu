@@ -40,6 +40,7 @@ struct TcLayerParams {
   int nkb_out;
   const int* n_active;       // see MlpParams (mlp.cu)
   int seg;
+  int no_fill;               // 1: outputs of inactive row tiles are left unwritten (every consumer skips those rows too)
 };
 
 __device__ __forceinline__ float tl_act(float x, int act) {
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_kernel(TcLayerParams p
     const int n_act = p.n_active ? min(__ldg(p.n_active), sg) : sg;
     const int o = row0 % sg;
     if (o >= n_act && o + 128 <= sg) {
+      if (p.no_fill) return;
       if (p.out != nullptr)
         for (int i = tid; i < 128 * 128; i += kTlThreads) {
           const int r = row0 + (i >> 7), c = col_base + (i & 127);
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kTlThreads, 1) tc_layer_big_kernel(TcLayerPara
       uint8_t* img_tile = p.out_img ? p.out_img + (size_t)tile * p.nkb_out * kTlBlockBytes : nullptr;
       if (!tb_tile_active(p, row0)) {
         // zero outputs of an inactive row tile: this warp's 32 rows x its 128-column block, coalesced
-        if (half < ncb) {
+        if (half < ncb && !p.no_fill) {
           const int col_base = (2 * ct + half) * 128;
           if (p.out != nullptr) {
             const bool vec = (p.ld_out & 3) == 0 && col_base + 128 <= p.N;

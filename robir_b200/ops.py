@@ -1178,6 +1178,9 @@ class _WnChain(torch.autograd.Function):
             nxt = _tl_image(tiles, nkb_out, x) if nkb_out else None
             q = _tl_params(img, fw, bias, R, N, (K + 63) // 64, 0, 0 if last else SOFTPLUS, None, out, nxt, nkb_out,
                            n_active, 0)
+            # hidden layers of a fixed-capacity batch: every consumer of these rows (next layer, backward, tensor-core
+            # weight gradients) skips the row tiles beyond n_active, so they are not zero-filled (189 MB per layer)
+            q.no_fill = int(n_active is not None and not last and R >= max(TL_BIG_MIN_ROWS, WN_TC_WGRAD_MIN_ROWS))
             _tl_layer(q, R)
             a = out
             img = _tl_rows_image(out, N + d_in) if next_skip else nxt
@@ -1224,6 +1227,7 @@ class _WnChain(torch.autograd.Function):
             nkb_out = (Np + 63) // 64
             nxt = _tl_image(tiles, nkb_out, G)
             q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, n_active, 0)
+            q.no_fill = int(n_active is not None and R >= max(TL_BIG_MIN_ROWS, WN_TC_WGRAD_MIN_ROWS))
             _tl_layer(q, R)
             G, img = Gp, nxt
         return (None, None, None, None, *gW, *gb)
