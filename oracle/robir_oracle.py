@@ -520,12 +520,35 @@ def render_with_all_sg(points, normal, viewdirs, lgtSGs, specular_reflectance, r
 # ----------------------------------------------------------------------------------------------------------------------
 # camera (utils/rend_util.py:51-97,141-163)
 # ----------------------------------------------------------------------------------------------------------------------
+def quat_to_rot(q):
+    """utils/rend_util.py:100-117: rotation matrix of the normalised quaternion (r, i, j, k)."""
+    q = F.normalize(q, dim=1)
+    qr, qi, qj, qk = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.ones(q.shape[0], 3, 3)
+    R[:, 0, 0] = 1 - 2 * (qj ** 2 + qk ** 2)
+    R[:, 0, 1] = 2 * (qj * qi - qk * qr)
+    R[:, 0, 2] = 2 * (qi * qk + qr * qj)
+    R[:, 1, 0] = 2 * (qj * qi + qk * qr)
+    R[:, 1, 1] = 1 - 2 * (qi ** 2 + qk ** 2)
+    R[:, 1, 2] = 2 * (qj * qk - qi * qr)
+    R[:, 2, 0] = 2 * (qk * qi - qj * qr)
+    R[:, 2, 1] = 2 * (qj * qk + qi * qr)
+    R[:, 2, 2] = 1 - 2 * (qi ** 2 + qj ** 2)
+    return R
+
+
 def camera_rays(uv, pose, intrinsics):
-    """get_camera_params + lift for 4x4 pose matrices. uv [B,N,2], pose [B,4,4], K [B,3,3] -> dirs [B,N,3], cam [B,3]."""
-    cam_loc = pose[:, :3, 3]
+    """get_camera_params + lift (utils/rend_util.py:51-97). uv [B,N,2], pose [B,4,4] or [B,7] (quaternion + position),
+    K [B,3,3] -> dirs [B,N,3], cam [B,3]."""
     B, N, _ = uv.shape
     p = torch.eye(4).repeat(B, 1, 1)
-    p[:, :3, :4] = pose[:, :3, :4]
+    if pose.shape[1] == 7:
+        cam_loc = pose[:, 4:]
+        p[:, :3, :3] = quat_to_rot(pose[:, :4])
+        p[:, :3, 3] = cam_loc
+    else:
+        cam_loc = pose[:, :3, 3]
+        p[:, :3, :4] = pose[:, :3, :4]
     fx, fy = intrinsics[:, 0, 0], intrinsics[:, 1, 1]
     cx, cy, sk = intrinsics[:, 0, 2], intrinsics[:, 1, 2], intrinsics[:, 0, 1]
     x, y = uv[:, :, 0], uv[:, :, 1]

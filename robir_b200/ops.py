@@ -747,10 +747,28 @@ def _sdf_eval_tc(W, pts, in_scale, sdf_scale, feat_scale, want_grad, want_feat):
 # ----------------------------------------------------------------------------------------------------------------------
 # camera rays / octree
 # ----------------------------------------------------------------------------------------------------------------------
+def _pose_from_quaternion(pose7):
+    """[1,7] = unit-normalised quaternion (r, i, j, k) + camera position -> [1,4,4] camera-to-world matrix
+    (utils/rend_util.py:52-57,100-117: the Hamilton-convention rotation matrix of the normalised quaternion)."""
+    q = torch.nn.functional.normalize(pose7[:, :4].float(), dim=1)
+    r, i, j, k = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    rows = [1 - 2 * (j * j + k * k), 2 * (j * i - k * r), 2 * (i * k + r * j),
+            2 * (j * i + k * r), 1 - 2 * (i * i + k * k), 2 * (j * k - i * r),
+            2 * (k * i - j * r), 2 * (j * k + i * r), 1 - 2 * (i * i + j * j)]
+    p = torch.eye(4, device=pose7.device, dtype=torch.float32).repeat(pose7.shape[0], 1, 1)
+    p[:, :3, :3] = torch.stack(rows, -1).reshape(-1, 3, 3)
+    p[:, :3, 3] = pose7[:, 4:].float()
+    return p
+
+
 def camera_rays(uv, pose, intrinsics):
-    """uv [1,N,2], pose [1,4,4], intrinsics [1,3,3] -> ray_dirs [1,N,3], cam_loc [1,3]  (utils/rend_util.py:51-97)."""
+    """uv [1,N,2], pose [1,4,4] (or [1,7]: quaternion + position), intrinsics [1,3,3] (focal lengths, principal point,
+    skew) -> ray_dirs [1,N,3], cam_loc [1,3]  (utils/rend_util.py:51-97)."""
+    if pose.dim() == 2 and pose.shape[1] == 7:
+        pose = _pose_from_quaternion(pose)
     if uv.shape[0] != 1 or pose.shape[1:] != (4, 4):
-        raise _lib.RobirError("camera_rays supports one 4x4 pose per call (the reference's training/eval usage)")
+        raise _lib.RobirError("camera_rays supports one pose (4x4 matrix or 7-vector) per call (the reference's "
+                              "training/eval usage)")
     uv, pose, K = f32(uv), f32(pose), f32(intrinsics)
     N = uv.shape[1]
     dirs = _empty(1, N, 3, like=uv)

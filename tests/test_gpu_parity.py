@@ -630,6 +630,29 @@ def _trace_agreement(got, ref, tol=2e-4, frac=0.98):
     return agree
 
 
+def test_camera_rays_skew_and_quaternion_pose():
+    """Row a2, directly: robir_camera_rays against the oracle's get_camera_params + lift (utils/rend_util.py:51-97, pinned to
+    the reference in tests/test_oracle_vs_reference.py) with non-zero skew, an off-centre principal point, DTU-sized
+    intrinsics, a 4x4 pose and the 7-vector (quaternion + position) pose; ragged and empty batches."""
+    from robir_b200 import ops
+    gen = torch.Generator().manual_seed(77)
+    uv = torch.rand(1, 300, 2, generator=gen) * torch.tensor([1600.0, 1200.0])
+    K = torch.eye(3)[None].clone()
+    K[0, 0, 0], K[0, 1, 1], K[0, 0, 2], K[0, 1, 2], K[0, 0, 1] = 2892.0, 2883.0, 823.2, 619.1, 7.5
+    pose7 = torch.tensor([[0.31, -0.62, 0.48, 0.53, 1.3, -0.4, 2.2]])
+    for pose in (pose7, synthetic.camera_pose()):
+        rd_o, cl_o = O.camera_rays(uv, pose, K)
+        for n in (300, 1, 0, 37):
+            rd, cl = ops.camera_rays(uv[:, :n].cuda(), pose.cuda(), K.cuda())
+            assert rd.shape == (1, n, 3) and cl.shape == (1, 3)
+            assert (cl.cpu() - cl_o).abs().max().item() < 1e-6
+            if n:
+                assert (rd.cpu() - rd_o[:, :n]).abs().max().item() < 1e-6
+                assert (rd.norm(dim=-1) - 1).abs().max().item() < 1e-6
+    with pytest.raises(Exception):
+        ops.camera_rays(uv.cuda(), torch.zeros(1, 5).cuda(), K.cuda())
+
+
 def test_sphere_tracer_vs_golden(golden, synth_sd16, model16):
     """Row a3: persistent march kernels (csrc/sphere_trace.cu) vs the reference's RayTracing outputs (eval and training
     mode, n_steps = 32, hotdog.conf tracer settings)."""

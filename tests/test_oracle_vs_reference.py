@@ -74,6 +74,31 @@ def test_pbr_step_matches_reference(ref_model):
     assert checked >= 19  # lgtSGs, specular_reflectance, spec-BRDF AE (16), adapt_illum
 
 
+def _camera_cases():
+    gen = torch.Generator().manual_seed(77)
+    uv = torch.rand(1, 300, 2, generator=gen) * torch.tensor([1600.0, 1200.0])
+    K = torch.eye(3)[None].clone()
+    K[0, 0, 0], K[0, 1, 1], K[0, 0, 2], K[0, 1, 2], K[0, 0, 1] = 2892.0, 2883.0, 823.2, 619.1, 7.5      # skew != 0
+    q = torch.tensor([[0.31, -0.62, 0.48, 0.53]])                                                      # not normalised
+    pos = torch.tensor([[1.3, -0.4, 2.2]])
+    pose7 = torch.cat([q, pos], 1)
+    pose44 = synthetic.camera_pose().clone()
+    return uv, K, pose7, pose44
+
+
+def test_camera_rays_with_skew_and_quaternion_pose_match_reference():
+    """utils/rend_util.py:51-97 get_camera_params + lift: non-zero skew, off-centre principal point, the 7-vector
+    (quaternion + position) pose branch and the 4x4 branch."""
+    import importlib
+    ref_shim.install()
+    rend_util = importlib.import_module("utils.rend_util")
+    uv, K, pose7, pose44 = _camera_cases()
+    for pose in (pose7, pose44):
+        rd_ref, cl_ref = rend_util.get_camera_params(uv, pose, K)
+        rd, cl = O.camera_rays(uv, pose, K)
+        assert (rd - rd_ref).abs().max().item() < 1e-6 and (cl - cl_ref).abs().max().item() == 0.0
+
+
 def test_sphere_tracer_matches_reference():
     sdn = ref_shim.reference_neus_state_dict(0)
     model = ref_shim.build_reference_model(sdn, num_lgt_sgs=16, use_octree=False, n_steps=32)
