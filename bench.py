@@ -487,6 +487,38 @@ def run_pbr(args):
                                "share_of_step": t_bwd / prof_steps / (t_res / args.steps)},
                 "share_of_step": t_fwd / prof_steps / (t_res / args.steps)}
 
+    # ---- (3b) the octree walk (32 B per node visit), timed alone with CUDA events on the bench batch
+    octree = None
+    try:
+        uv0 = dev_batches[args.warmup][0]
+        rd, cl = ops.camera_rays(uv0, pose, K)
+        tracer = model.ray_tracer
+        tr = lambda: tracer(sdf=None, cam_loc=cl, object_mask=None, ray_directions=rd)
+        for _ in range(3):
+            tr()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            tr()
+        e1.record()
+        torch.cuda.synchronize()
+        cnt = tracer.last_counters.cpu().tolist()
+        visits, samples, iters = cnt[-8], cnt[-7], cnt[-6]        # [kMaxIter + 0 / 1 / 2] of kMaxIter + 8 counters
+        t_oct = e0.elapsed_time(e1) * 1e-3 / 10
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        octree = {"kernel": "octree_cast_kernel", "bound": "latency", "ms": 1e3 * t_oct, "rays": int(rd.shape[1]),
+                  "lockstep_iterations": iters, "node_visits": visits, "micro_march_samples": samples,
+                  "algorithmic_bytes": 32 * visits, "achieved_GBps": 32 * visits / t_oct / 1e9,
+                  "frac_of_hbm_peak": 32 * visits / t_oct / 1e9 / hbm,
+                  "us_per_iteration": 1e6 * t_oct / max(iters, 1),
+                  "note": "one warp per ray, lock-step iterations (the reference's batch-level sample count depends on the "
+                          "number of live rays every iteration): each iteration is a grid barrier plus a chain of "
+                          "dependent 32-byte node fetches (L2-resident tree), so the bound is latency per iteration, not "
+                          "bytes"}
+    except Exception as exc:            # diagnostic only
+        octree = {"error": str(exc)[:200]}
+
     # ---- (4) baselines on rank 0 at N=1: the reference's CPU path on a bounded sample, and the reference eagerly on
     # this GPU (what RobIR's users run today)
     cpu = cuda_ref = None
@@ -527,7 +559,7 @@ def run_pbr(args):
                     "ms_per_step": 1e3 * t_e2e / args.steps,
                     "note": "per step: H2D of uv / mask / rgb from pinned memory, the step, D2H of its loss into pinned "
                             "memory; the host reads each loss one step later (no device stall on .item())"},
-            "hit_rays_per_s": value * hit_frac, "sustained": sustained,
+            "hit_rays_per_s": value * hit_frac, "sustained": sustained, "octree": octree,
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "cuda_baseline": cuda_ref, "final_loss": losses[-1] if losses else None}))
     if world > 1:
