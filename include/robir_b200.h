@@ -328,6 +328,13 @@ int robir_tl_layer_big(const robir_tl_params* p, int sm_count, void* stream);
  * tile per CTA and split, and a fixed-order reduction sums the splits: bitwise reproducible.  Replaces, for those
  * shapes, what autograd does for lin.weight / lin.bias of model/neus_model.py:385-417 under training/train_cesr.py:533. */
 long long robir_tl_wgrad_workspace(int n, int N, int K, int sm_count);
+/* the same weight gradients taken directly from the layer engine's images (no transposing pack): a K-major SWIZZLE_128B
+ * block of 128 rows x 64 features is read as an MN-major operand when the contraction runs over the rows.  g_img / a_img:
+ * images of G [n][N] and A [n][K] as robir_tl_pack_rows / robir_tl_layer write them (nkb_g / nkb_a k-blocks per row tile);
+ * image rows of G at and beyond *n_active (or n) must be zero. */
+long long robir_tl_wgrad_mn_workspace(int n, int N, int K, int sm_count);
+int robir_tl_wgrad_mn(const void* g_img, int nkb_g, const void* a_img, int nkb_a, int n, int N, int K,
+                      const int* n_active, void* work, float* dW, float* db, int sm_count, void* stream);
 int robir_tl_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K,
                    const int* n_active /* device row count of a fixed-capacity batch (rows beyond it are zero), or NULL */,
                    void* work, float* dW, float* db, int sm_count, void* stream);

@@ -152,6 +152,8 @@ _SIGNATURES = {
     "robir_tl_layer": [POINTER(TlParams), _P],
     "robir_tl_layer_big": [POINTER(TlParams), _I, _P],
     "robir_tl_wgrad_workspace": [_I, _I, _I, _I],
+    "robir_tl_wgrad_mn_workspace": [_I, _I, _I, _I],
+    "robir_tl_wgrad_mn": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "robir_tl_wgrad": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "robir_mlp_encode": [POINTER(MlpParams), _I, _P],
     "robir_pbr_loss": [POINTER(LossParams), _P],
@@ -165,6 +167,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ["robir_last_error"])
 _KERNELS_PER_CALL = {"robir_diffuse_rows": 3, "robir_sphere_trace": 7, "robir_sphere_trace_launches": 0, "robir_octree_counters_len": 0, "robir_device_info": 0,
                      "robir_tc_image_bytes": 0, "robir_tl_block_bytes": 0,
                      "robir_tl_wgrad_workspace": 0, "robir_tl_wgrad": 4,
+                     "robir_tl_wgrad_mn_workspace": 0, "robir_tl_wgrad_mn": 2,
                      "robir_abi_version": 0, "robir_last_error": 0}
 launch_count = 0
 
@@ -199,7 +202,7 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_longlong if name == "robir_tl_wgrad_workspace" else c_int
+            fn.restype = ctypes.c_longlong if name.endswith("_workspace") else c_int
         handle.robir_last_error.restype = c_char_p
         handle.robir_last_error.argtypes = []
         _lib = _Counting(handle)

@@ -681,6 +681,161 @@ __global__ void __launch_bounds__(192, 1) tl_wgrad_kernel(TlWgradParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// weight gradients straight from the layer engine's own images (no transposing pack): the K-major SWIZZLE_128B block of
+// 128 rows x 64 features IS the MN-major SWIZZLE_128B atom sequence the MMA wants when the contraction runs over the
+// rows -- 64 contiguous features (128 bytes) per row, eight rows per 1024-byte swizzle atom, the XOR on the row index.
+// So dW[n][k] = sum_r G[r][n] A[r][k] takes both operands MN-major (instruction descriptor bits 15 / 16) from the image
+// of G (the backward chain's input image of this layer) and the image of A (the forward chain's input image).
+// Stage = 64 rows: G features [128 tn, +128) as two 64-feature pieces (hi 8 KB each | lo 8 KB each) + the same for A
+// features [128 tk, +128) = 64 KB; LBO = 8 KB (next 64 features), SBO = 1 KB (next 8 rows), +2 KB per 16-row k-step.
+// db rides along: CTAs with tk == 0 multiply G by a tile of ones (N = 16) into 16 more TMEM columns.
+struct TlWgradMnParams {
+  const uint8_t* g_img;      // [row_tiles][nkb_g][32 KB] image of G (rows x N)
+  const uint8_t* a_img;      // [row_tiles][nkb_a][32 KB] image of A (rows x K)
+  int nkb_g, nkb_a, row_tiles;
+  int n;                     // rows
+  int tiles_n, tiles_k;      // 128-feature tiles of N / K
+  float* partial;            // [splits][tiles_n * 128][tiles_k * 128]
+  float* db_part;            // [splits][tiles_n * 128] or null
+  const int* n_active;
+};
+
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N, int a_mn, int b_mn) {
+  return idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(const void* base, uint32_t lbo_bytes) {
+  const uint64_t addr = (uint64_t)((smem_u32(base) & 0x3FFFF) >> 4);
+  return addr | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192, 1) tl_wgrad_mn_kernel(TlWgradMnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kTlStages], empty_bar[kTlStages], d_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tn = blockIdx.x / p.tiles_k, tk = blockIdx.x % p.tiles_k;
+  const bool with_db = p.db_part != nullptr && tk == 0;
+  uint8_t* ones = ring + kTlStages * kTlStageBytes;                  // 2 KB of bf16 1.0 (16 rows x 128 B)
+
+  int rows = p.n;
+  if (p.n_active != nullptr) rows = min(rows, max(__ldg(p.n_active), 0));
+  const int tiles_eff = min(p.row_tiles, (rows + 127) >> 7);
+  const int per = (tiles_eff + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int t0 = blockIdx.y * per, t1 = min(tiles_eff, t0 + per);
+  const int nsteps = max(t1 - t0, 0) * 2;                            // 64-row steps
+  // feature pieces that exist in the images (the others stay unwritten in shared memory: they only feed output rows /
+  // columns beyond N / K, which are not stored)
+  const int g_pieces = min(2, p.nkb_g - 2 * tn), a_pieces = min(2, p.nkb_a - 2 * tk);
+
+  if (tid == 0) {
+    for (int s = 0; s < kTlStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&d_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2048 / 4; i += 192) reinterpret_cast<uint32_t*>(ones)[i] = 0x3f803f80u;
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    for (int it = 0; it < nsteps; ++it) {
+      const int st = it % kTlStages;
+      mbar_wait(&empty_bar[st], ((it / kTlStages) & 1) ^ 1);
+      if (elect_one_sync()) {
+        const int tile = t0 + (it >> 1), half = it & 1;
+        uint8_t* sg = ring + (size_t)st * kTlStageBytes;
+        uint8_t* sa = sg + 32768;
+        mbar_arrive_expect_tx(&full_bar[st], 16384u * (g_pieces + a_pieces));
+        for (int c = 0; c < g_pieces; ++c) {
+          const uint8_t* blk = p.g_img + ((size_t)tile * p.nkb_g + 2 * tn + c) * kTlBlockBytes + half * 8192;
+          bulk_g2s(sg + c * 8192, blk, 8192, &full_bar[st]);                  // hi, rows 64 half ..
+          bulk_g2s(sg + 16384 + c * 8192, blk + 16384, 8192, &full_bar[st]);  // lo
+        }
+        for (int c = 0; c < a_pieces; ++c) {
+          const uint8_t* blk = p.a_img + ((size_t)tile * p.nkb_a + 2 * tk + c) * kTlBlockBytes + half * 8192;
+          bulk_g2s(sa + c * 8192, blk, 8192, &full_bar[st]);
+          bulk_g2s(sa + 16384 + c * 8192, blk + 16384, 8192, &full_bar[st]);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kIdesc = idesc_bf16_mn(128, 128, 1, 1);
+    constexpr uint32_t kIdescOnes = idesc_bf16_mn(128, 16, 1, 0);
+    const uint64_t ones_desc = smem_desc_sw128(ones);
+    for (int it = 0; it < nsteps; ++it) {
+      const int st = it % kTlStages;
+      mbar_wait(&full_bar[st], (it / kTlStages) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint8_t* sg = ring + (size_t)st * kTlStageBytes;
+        const uint8_t* sa = sg + 32768;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                       // 16 rows per k-step = 2 KB
+          const uint64_t g_hi = smem_desc_sw128_mn(sg + q * 2048, 8192), g_lo = smem_desc_sw128_mn(sg + 16384 + q * 2048, 8192);
+          const uint64_t a_hi = smem_desc_sw128_mn(sa + q * 2048, 8192), a_lo = smem_desc_sw128_mn(sa + 16384 + q * 2048, 8192);
+          if (it == 0 && q == 0) umma_ss<0>(tmem_base, g_hi, a_hi, kIdesc);
+          else umma_ss<1>(tmem_base, g_hi, a_hi, kIdesc);
+          umma_ss<1>(tmem_base, g_lo, a_hi, kIdesc);
+          umma_ss<1>(tmem_base, g_hi, a_lo, kIdesc);
+          if (with_db) {
+            if (it == 0 && q == 0) umma_ss<0>(tmem_base + 128u, g_hi, ones_desc, kIdescOnes);
+            else umma_ss<1>(tmem_base + 128u, g_hi, ones_desc, kIdescOnes);
+            umma_ss<1>(tmem_base + 128u, g_lo, ones_desc, kIdescOnes);
+          }
+        }
+        umma_commit(&empty_bar[st]);
+        if (it == nsteps - 1) umma_commit(&d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int ld = p.tiles_k * 128;
+    float* dst = p.partial + ((size_t)blockIdx.y * p.tiles_n * 128 + tn * 128 + r) * ld + tk * 128;
+    if (nsteps > 0) {
+      mbar_wait(&d_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t acc[32];
+      if (nsteps > 0) {
+        tmem_ld32(tmem_base + lane_addr + 32u * c, acc);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst + 32 * c)[i] =
+            make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                        __uint_as_float(acc[4 * i + 3]));
+    }
+    if (with_db) {
+      uint32_t acc[32];
+      float v = 0.f;
+      if (nsteps > 0) {
+        tmem_ld32(tmem_base + lane_addr + 128u, acc);          // 16 valid columns (all equal: every column of the ones tile)
+        tmem_wait_ld();
+        v = __uint_as_float(acc[0]);
+      }
+      p.db_part[(size_t)blockIdx.y * p.tiles_n * 128 + tn * 128 + r] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // dW[nn][kk] = sum over splits (fixed order).  The last blocks of the grid sum the db partials instead: 8 columns x 32
 // k-block lanes per block, lane j takes k-blocks j, j + 32, ..., then a fixed-order tree over the lanes.
 __global__ void __launch_bounds__(256) tl_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad,
@@ -811,6 +966,47 @@ int robir_tl_wgrad(const float* G, int ldg, const float* A, int lda, int n, int 
   const int dw_blocks = (int)(((long long)N * K + 255) / 256), db_blocks = db ? (N + 7) / 8 : 0;
   tl_wgrad_reduce_kernel<<<dw_blocks + db_blocks, 256, 0, st>>>(partial, splits, rt * 128, cb * 128, N, K, dW, colsum, nkb,
                                                                 rt * 128, db, dw_blocks, n_active);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// The same weight gradients from the layer engine's images (see tl_wgrad_mn_kernel): g_img = image of G [n][N] (nkb_g
+// k-blocks per row tile), a_img = image of A [n][K]; rows of G at and beyond *n_active (or n) must be zero in the image.
+// work: robir_tl_wgrad_mn_workspace(N, K, sm_count) bytes.
+static void tl_wgrad_mn_shape(int n, int N, int K, int sm_count, int* tn, int* tk, int* splits) {
+  *tn = (N + 127) / 128;
+  *tk = (K + 127) / 128;
+  const int tiles = (n + 127) / 128;
+  int want = sm_count / (*tn * *tk);
+  if (want < 1) want = 1;
+  *splits = want < tiles ? want : tiles;
+}
+
+long long robir_tl_wgrad_mn_workspace(int n, int N, int K, int sm_count) {
+  int tn, tk, splits;
+  tl_wgrad_mn_shape(n, N, K, sm_count, &tn, &tk, &splits);
+  return (long long)splits * tn * 128 * tk * 128 * 4 + (long long)splits * tn * 128 * 4;
+}
+
+int robir_tl_wgrad_mn(const void* g_img, int nkb_g, const void* a_img, int nkb_a, int n, int N, int K,
+                      const int* n_active, void* work, float* dW, float* db, int sm_count, void* stream) {
+  RB_REQUIRE(n >= 1 && N >= 1 && K >= 1 && work != nullptr && dW != nullptr, "tl_wgrad_mn: empty problem or no workspace");
+  RB_REQUIRE(nkb_g * 64 >= N && nkb_a * 64 >= K, "tl_wgrad_mn: images narrower than the matrices");
+  int tn, tk, splits;
+  tl_wgrad_mn_shape(n, N, K, sm_count, &tn, &tk, &splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  TlWgradMnParams p;
+  p.g_img = (const uint8_t*)g_img; p.a_img = (const uint8_t*)a_img; p.nkb_g = nkb_g; p.nkb_a = nkb_a;
+  p.row_tiles = (n + 127) / 128; p.n = n; p.tiles_n = tn; p.tiles_k = tk;
+  p.partial = (float*)work;
+  p.db_part = db ? p.partial + (size_t)splits * tn * 128 * tk * 128 : nullptr;
+  p.n_active = n_active;
+  const int smem = kTlStages * kTlStageBytes + 1024 + 2048;
+  RB_CHECK_CUDA(cudaFuncSetAttribute(tl_wgrad_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tl_wgrad_mn_kernel<<<dim3(tn * tk, splits), 192, smem, st>>>(p);
+  const int dw_blocks = (int)(((long long)N * K + 255) / 256), db_blocks = db ? (N + 7) / 8 : 0;
+  tl_wgrad_reduce_kernel<<<dw_blocks + db_blocks, 256, 0, st>>>(p.partial, splits, tn * 128, tk * 128, N, K, dW, p.db_part,
+                                                                splits, tn * 128, db, dw_blocks, nullptr);
   RB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1171,7 +1171,7 @@ class _WnChain(torch.autograd.Function):
         tiles = (R + 127) // 128
         SOFTPLUS = ACT["softplus100"]
         need_bwd = any(ctx.needs_input_grad)      # evaluation (plots, testing=True): keep nothing, free layer by layer
-        We, imgs, a_rows = [], [], []
+        We, imgs, a_rows, a_imgs = [], [], [], []
         a, img = x, _tl_rows_image(x, d_in)
         out = None
         for l in range(L):
@@ -1184,6 +1184,8 @@ class _WnChain(torch.autograd.Function):
                 We.append(W)
                 imgs.append((fw, bw))
                 a_rows.append(a)
+                if R >= WN_TC_WGRAD_MIN_ROWS:
+                    a_imgs.append(img)          # the layer's input image doubles as the weight-gradient GEMM's operand
             bias = _zeros(((N + 127) // 128) * 128, like=x)
             bias[:N] = f32(bs[l])
             last, next_skip = l == L - 1, (l + 1) in skip
@@ -1204,6 +1206,7 @@ class _WnChain(torch.autograd.Function):
             img = _tl_rows_image(out, N + d_in) if next_skip else nxt
         ctx.meta = (R, d_in, L, tuple(skip))
         ctx.imgs = imgs
+        ctx.a_imgs = a_imgs
         ctx.n_active = n_active
         ctx.save_for_backward(*a_rows, *We)
         return out
@@ -1223,7 +1226,14 @@ class _WnChain(torch.autograd.Function):
             A = a_rows[l]
             # ---- dW_l = G_l^T A_l, db_l = column sums of G_l
             dW, db = _empty(N, K, like=G), _empty(N, like=G)
-            if R >= WN_TC_WGRAD_MIN_ROWS:
+            if R >= WN_TC_WGRAD_MIN_ROWS and ctx.a_imgs:
+                # split-K tcgen05 GEMM straight from the chain's own images (csrc/tc_mlp.cu tl_wgrad_mn_kernel): `img` is
+                # the image of G_l (this layer's backward input), a_imgs[l] the image of its forward input
+                work = torch.empty(lib().robir_tl_wgrad_mn_workspace(R, N, K, sm_count()), dtype=torch.uint8,
+                                   device=G.device)
+                check(lib().robir_tl_wgrad_mn(ptr(img), (N + 63) // 64, ptr(ctx.a_imgs[l]), (K + 63) // 64, R, N, K,
+                                              ptr(n_active), ptr(work), ptr(dW), ptr(db), sm_count(), stream()))
+            elif R >= WN_TC_WGRAD_MIN_ROWS:
                 # split-K tcgen05 GEMM over transposed hi/lo images (csrc/tc_mlp.cu tl_wgrad_kernel)
                 work = torch.empty(lib().robir_tl_wgrad_workspace(R, N, K, sm_count()), dtype=torch.uint8, device=G.device)
                 check(lib().robir_tl_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, ptr(n_active), ptr(work),

@@ -117,6 +117,18 @@ class _EmulatedEngine:
     def robir_tl_wgrad_workspace(self, n, N, K, sm_count):
         return 1024
 
+    def robir_tl_wgrad_mn_workspace(self, n, N, K, sm_count):
+        return 1024
+
+    def robir_tl_wgrad_mn(self, g_img, nkb_g, a_img, nkb_a, n, N, K, n_active, work, dW, db, sm_count, stream):
+        (G, kg), (A, ka) = self.mats[id(g_img)], self.mats[id(a_img)]
+        assert kg == nkb_g == (N + 63) // 64 and ka == nkb_a == (K + 63) // 64 and n_active is None
+        assert G.shape == (n, N) and A.shape == (n, K) and work.numel() >= 1024
+        self.tc_wgrads = getattr(self, "tc_wgrads", 0) + 1
+        dW.copy_(G.t() @ A)
+        db.copy_(G.sum(0))
+        return 0
+
     def robir_tl_wgrad(self, G, ldg, A, lda, n, N, K, n_active, work, dW, db, sm_count, stream):
         assert G.shape[1] == ldg and A.shape[1] == lda and work.numel() >= 1024 and n_active is None
         self.tc_wgrads = getattr(self, "tc_wgrads", 0) + 1

@@ -1077,6 +1077,45 @@ def test_tl_layer_big_equals_tile_kernel(n_active):
         assert torch.isfinite(b).all() and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n,N,K", [(5000, 512, 512), (4097, 321, 191), (300, 2, 512), (128, 512, 63), (9000, 3, 512),
+                                   (1, 130, 129)])
+def test_tl_wgrad_mn_vs_fp64(n, N, K):
+    """Weight gradients straight from the layer engine's images (robir_tl_wgrad_mn: the K-major SWIZZLE_128B image blocks
+    read as MN-major tcgen05 operands, contraction over the rows, db through a tile of ones) against fp64, on images
+    written by robir_tl_pack_rows; ragged shapes, bitwise repeatability, the fixed-capacity form."""
+    from robir_b200 import ops
+    from robir_b200._lib import lib, check
+    gen = torch.Generator().manual_seed(n + N + K + 1)
+    Gf = (torch.randn(n, N, generator=gen) * torch.logspace(-6, 0, N)).cuda()
+    Af = torch.randn(n, K, generator=gen).cuda()
+
+    def run(G, A, n_active=None):
+        rows = G.shape[0]
+        gi, ai = ops._tl_rows_image(G, N), ops._tl_rows_image(A, K)
+        dW, db = torch.full((N, K), float("nan"), device="cuda"), torch.full((N,), float("nan"), device="cuda")
+        work = torch.empty(lib().robir_tl_wgrad_mn_workspace(rows, N, K, ops.sm_count()), dtype=torch.uint8, device="cuda")
+        check(lib().robir_tl_wgrad_mn(gi.data_ptr(), (N + 63) // 64, ai.data_ptr(), (K + 63) // 64, rows, N, K,
+                                      n_active.data_ptr() if n_active is not None else None, work.data_ptr(),
+                                      dW.data_ptr(), db.data_ptr(), ops.sm_count(), ops.stream()))
+        return dW, db
+    dW, db = run(Gf, Af)
+    dW2, db2 = run(Gf, Af)
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)
+    ref = Gf.double().T @ Af.double()
+    refb = Gf.double().sum(0)
+    err = ((dW.double() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-300)).max().item()
+    errb = ((db.double() - refb).abs() / Gf.double().abs().sum(0).clamp_min(1e-300)).max().item()
+    assert err < 2e-5, err
+    assert errb < 2e-5, errb                   # db passes through the bf16 hi/lo split as well
+    cap = n + 777                              # fixed-capacity form: zero G rows beyond the count, anything in A
+    Gc = torch.zeros(cap, N, device="cuda")
+    Ac = torch.randn(cap, K, generator=gen).cuda()
+    Gc[:n], Ac[:n] = Gf, Af
+    dW3, db3 = run(Gc, Ac, torch.tensor([n], dtype=torch.int32, device="cuda"))
+    err3 = ((dW3.double() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-300)).max().item()
+    assert err3 < 2e-5 and torch.isfinite(db3).all(), err3
+
+
 @pytest.mark.parametrize("which,rows", [("shadow", 1024), ("shadow", 1000), ("normal", 333), ("shadow", 4500)])
 def test_wn_chain_vs_oracle(which, rows, wn_engine):
     """shadow_net / normal_net (weight-normed, softplus(100), skip concat at layer 4) forward + every parameter
