@@ -1218,31 +1218,31 @@ class _WnChain(torch.autograd.Function):
         tiles = (R + 127) // 128
         SOFTPLUS = ACT["softplus100"]
         n_active = ctx.n_active
-        G = f32(g_out)
+        G = g0 = f32(g_out)              # g0: device / dtype reference for allocations (G may become None below)
         img = _tl_rows_image(G, G.shape[1])
         gW, gb = [None] * L, [None] * L
         for l in range(L - 1, -1, -1):
             N, K = We[l].shape
             A = a_rows[l]
             # ---- dW_l = G_l^T A_l, db_l = column sums of G_l
-            dW, db = _empty(N, K, like=G), _empty(N, like=G)
+            dW, db = _empty(N, K, like=g0), _empty(N, like=g0)
             if R >= WN_TC_WGRAD_MIN_ROWS and ctx.a_imgs:
                 # split-K tcgen05 GEMM straight from the chain's own images (csrc/tc_mlp.cu tl_wgrad_mn_kernel): `img` is
                 # the image of G_l (this layer's backward input), a_imgs[l] the image of its forward input
                 work = torch.empty(lib().robir_tl_wgrad_mn_workspace(R, N, K, sm_count()), dtype=torch.uint8,
-                                   device=G.device)
+                                   device=g0.device)
                 check(lib().robir_tl_wgrad_mn(ptr(img), (N + 63) // 64, ptr(ctx.a_imgs[l]), (K + 63) // 64, R, N, K,
                                               ptr(n_active), ptr(work), ptr(dW), ptr(db), sm_count(), stream()))
             elif R >= WN_TC_WGRAD_MIN_ROWS:
                 # split-K tcgen05 GEMM over transposed hi/lo images (csrc/tc_mlp.cu tl_wgrad_kernel)
-                work = torch.empty(lib().robir_tl_wgrad_workspace(R, N, K, sm_count()), dtype=torch.uint8, device=G.device)
+                work = torch.empty(lib().robir_tl_wgrad_workspace(R, N, K, sm_count()), dtype=torch.uint8, device=g0.device)
                 check(lib().robir_tl_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, ptr(n_active), ptr(work),
                                            ptr(dW), ptr(db), sm_count(), stream()))
             else:
                 wt = ((N + 63) // 64) * ((K + 63) // 64)
                 splits = max(1, min(64, (4 * sm_count()) // wt, (R + 63) // 64))
-                part = _empty(splits * wt * 4160, like=G) if splits > 1 else None
-                tickets = _zeros(wt, dtype=torch.int32, like=G)
+                part = _empty(splits * wt * 4160, like=g0) if splits > 1 else None
+                tickets = _zeros(wt, dtype=torch.int32, like=g0)
                 check(lib().robir_mlp_wgrad(ptr(G), G.shape[1], ptr(A), A.shape[1], R, N, K, None, 0, splits, ptr(part),
                                             ptr(tickets), ptr(dW), ptr(db), stream()))
             gW[l] = dW * (1.0 / math.sqrt(2.0)) if l in skip else dW
@@ -1251,9 +1251,10 @@ class _WnChain(torch.autograd.Function):
                 break
             # ---- G_{l-1} = (G_l W_l)[:, :N_{l-1}] * softplus'(h_{l-1}); h_{l-1} = the first N_{l-1} columns of A_l
             Np = K - d_in if l in skip else K
-            Gp = _empty(R, Np, like=G)
+            # the fp32 copy of the hidden gradient is only read by the fp32-row weight-gradient kernels
+            Gp = None if (R >= WN_TC_WGRAD_MIN_ROWS and ctx.a_imgs) else _empty(R, Np, like=g0)
             nkb_out = (Np + 63) // 64
-            nxt = _tl_image(tiles, nkb_out, G)
+            nxt = _tl_image(tiles, nkb_out, g0)
             q = _tl_params(img, ctx.imgs[l][1], None, R, Np, (N + 63) // 64, 1, SOFTPLUS, A, Gp, nxt, nkb_out, n_active, 0)
             q.no_fill = int(n_active is not None and R >= max(TL_BIG_MIN_ROWS, WN_TC_WGRAD_MIN_ROWS))
             _tl_layer(q, R)
