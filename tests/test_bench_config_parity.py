@@ -353,3 +353,58 @@ def test_cesr_graph_step_matches_eager_dynamic(bench_setup, cur_iter):
             model.__dict__.pop("get_sg_render", None)
         else:
             model.get_sg_render = old_hook
+
+
+def test_evaluation_mode_forward_vs_oracle(bench_setup):
+    """bench.py --config c2e: the plot_to_disk path (training/train_pbr.py:235-311) -- model.eval(), is_training = False
+    (visibility evaluated in testing mode, sg_render.py:148-160,231-243), forward only, tone-mapped prediction -- at the
+    benchmarked model size (M = 128, S = 32) on a 1024-pixel chunk of raster-ordered pixels, against the oracle on the
+    same randoms."""
+    from robir_b200 import rng
+    sd, model, inp, gt = bench_setup
+    dev = torch.device("cuda")
+    _load(model, sd)
+    rng.set_mode("cpu")
+    model.static_shapes = False
+    N = 1024
+    pix = torch.arange(N) + 800 * 380 + 100            # a raster chunk through the middle of the image (split_input order)
+    einp = synthetic.camera_inputs(pix)
+    dinp = {k: v.to(dev) for k, v in einp.items()}
+    model.eval()
+    model.is_training = False
+    try:
+        torch.manual_seed(77)
+        with rng.record() as tape, torch.no_grad():
+            dinp["hdr_shift"] = model.gamma.hdr_shift.as_input().expand(N, 1)
+            out = model(dinp, trainstage="Material", lin_diff=False, fun_spec=False, train_spec=True)
+            ldr = model.gamma.hdr_shift.hdr2ldr(out["sg_rgb"] + out["indir_rgb"])
+    finally:
+        model.train()
+        model.is_training = True
+    n_hit = int(out["network_object_mask"].sum())
+    assert 0.2 * N < n_hit < N, n_hit
+    torch.set_num_threads(max(1, min(32, torch.get_num_threads() * 4)))
+    tree = T.OctreeOracle.__new__(T.OctreeOracle)
+    for k, v in model.ray_tracer.sdf_octree.host_arrays().items():
+        setattr(tree, k, v)
+    tree.max_iter = -1
+    sdo = {k: v.detach().clone() for k, v in sd.items()}
+    oinp = dict(einp)
+    oinp["hdr_shift"] = O.hdr_shift_as_input(sdo).expand(N, 1)
+    with torch.no_grad():
+        ref = P.idr_forward(sdo, oinp, lambda c, m, d: tree.trace(c, d), P.tape_to_rnd([("r", t) for t in tape]),
+                            is_training=False)
+    assert torch.equal(ref["network_object_mask"], out["network_object_mask"].cpu())
+    worst = {}
+    for k, v in ref.items():
+        if v.dtype == torch.bool or k not in out:
+            continue
+        if k == "vis_shadow":                      # hard culling predicate: see the training-mode test above
+            d = (out[k].float().cpu() - v).abs().amax(-1)
+            assert int((d > REL).sum()) <= 3 and float(d.max()) < 2e-3
+            continue
+        worst[k] = rel_err(out[k], v)
+        assert worst[k] < REL, ("evaluation forward vs oracle", k, worst[k])
+    ldr_ref = O.hdr2ldr(ref["sg_rgb"] + ref["indir_rgb"], O.hdr_shift_as_input(sdo))       # model/loss.py:61-64
+    assert rel_err(ldr, ldr_ref) < REL
+    print("\nevaluation-mode forward vs oracle (worst rel):", max(worst.values()), max(worst, key=worst.get))
