@@ -26,6 +26,9 @@ def __getattr__(name):
     if name == "invalidate_packed_weights":
         from .ops import invalidate_packed_weights
         return invalidate_packed_weights
+    if name == "render_image":
+        from .render import render_image
+        return render_image
     if name in ("InvLoss", "pbr_step_loss"):
         from . import loss
         return getattr(loss, name)

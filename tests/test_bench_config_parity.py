@@ -408,3 +408,35 @@ def test_evaluation_mode_forward_vs_oracle(bench_setup):
     ldr_ref = O.hdr2ldr(ref["sg_rgb"] + ref["indir_rgb"], O.hdr_shift_as_input(sdo))       # model/loss.py:61-64
     assert rel_err(ldr, ldr_ref) < REL
     print("\nevaluation-mode forward vs oracle (worst rel):", max(worst.values()), max(worst, key=worst.get))
+
+
+def test_render_image_public_entry_point(bench_setup):
+    """robir_b200.render_image (the plot_to_disk compute path as a library call): chunking does not change what is rendered
+    -- the traced mask and the per-point material maps (no random draws) are identical for 1024- and 4096-pixel chunks, the
+    shaded images agree up to the Monte-Carlo noise of the visibility samples -- and the model's mode flags are restored."""
+    import robir_b200
+    sd, model, inp, gt = bench_setup
+    dev = torch.device("cuda")
+    _load(model, sd)
+    from robir_b200 import rng
+    rng.set_mode("device")
+    H = W = 96
+    pose = synthetic.camera_pose().to(dev)
+    K = synthetic.camera_intrinsics(H, W, 1111.1 * H / 800.0).to(dev)
+    model.train()
+    try:
+        a = robir_b200.render_image(model, pose, K, H, W, chunk=1024)
+        a = {k: v.clone() for k, v in a.items()}
+        b = robir_b200.render_image(model, pose, K, H, W, chunk=4096)
+    finally:
+        rng.set_mode("cpu")
+    assert model.training and model.is_training and not model.static_shapes
+    assert set(a) == {"pred_rgb", "sg_rgb", "indir_rgb", "diffuse_albedo", "roughness", "vis_shadow", "network_object_mask"}
+    m = a["network_object_mask"]
+    assert torch.equal(m, b["network_object_mask"]) and 0.2 < float(m.float().mean()) < 0.95
+    for k in ("diffuse_albedo", "roughness"):       # batch size selects the engine of a chain (FFMA / layer engine): 1e-4
+        assert a[k].shape == (H * W, 3) and rel_err(a[k], b[k]) < REL, k
+    for k in ("pred_rgb", "sg_rgb", "vis_shadow"):
+        assert torch.isfinite(a[k]).all() and torch.isfinite(b[k]).all()
+        assert float((a[k] - b[k]).abs().mean()) < 0.02, (k, float((a[k] - b[k]).abs().mean()))
+    assert float(a["pred_rgb"][~m].min()) >= 0.0        # rays that miss: the reference's fill value through the tone-mapper

@@ -167,37 +167,25 @@ def run_c2e(args):
     H = W = 800
     M = 128
     rank, world, local, dev, sd, model = _setup(M)
-    model.eval()
-    model.is_training = False
-    model.static_shapes = False
+    import robir_b200
     pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
-    pix = torch.arange(H * W, device=dev)
-    uv_all = torch.stack([(pix % W).float(), (pix // W).float()], -1)[None]
     host_img = torch.empty(H * W, 3).pin_memory()
+    bufs = None
     out = {}
     for chunk in (1024, 16384):
-        img = torch.empty(H * W, 3, device=dev)
-        hits = torch.zeros((), device=dev)
-        om = torch.ones(1, chunk, dtype=torch.bool, device=dev)
+        state = {}
 
-        def step(s, chunk=chunk, img=img, om=om):
-            hits.zero_()
-            with torch.no_grad():
-                shift = model.gamma.hdr_shift.as_input()
-                for lo in range(0, H * W, chunk):
-                    hi = min(lo + chunk, H * W)
-                    inp = {"uv": uv_all[:, lo:hi], "object_mask": om[:, :hi - lo], "pose": pose, "intrinsics": K,
-                           "hdr_shift": shift.expand(hi - lo, 1)}
-                    o = model(inp, trainstage="Material", lin_diff=False, fun_spec=False, train_spec=True)
-                    img[lo:hi] = model.gamma.hdr_shift.hdr2ldr(o["sg_rgb"] + o["indir_rgb"])
-                    hits.add_(o["network_object_mask"].sum())
-                host_img.copy_(img, non_blocking=True)
+        def step(s, chunk=chunk):
+            nonlocal bufs
+            bufs = robir_b200.render_image(model, pose, K, H, W, chunk=chunk, out=bufs)      # the public entry point
+            host_img.copy_(bufs["pred_rgb"], non_blocking=True)
+            state["hits"] = bufs["network_object_mask"].sum()
         clocks = bench.ClockSampler(local).start()
         t = _timed(step, 1, args.steps, dev, world)
         clk = clocks.stop()
         torch.cuda.synchronize()
         out["chunk_%d" % chunk] = dict(rays_per_s=H * W * args.steps * world / t, s_per_image=t / args.steps,
-                                       hit_fraction=float(hits) / (H * W), clocks=clk,
+                                       hit_fraction=float(state["hits"]) / (H * W), clocks=clk,
                                        finite=bool(torch.isfinite(host_img).all()))
     if rank == 0:
         best = out["chunk_16384"]
