@@ -22,7 +22,9 @@ def init_from_env(backend=None):
 
 
 def shard_rays(n_rays, rank, world):
-    """Contiguous slice [lo, hi) of the ray axis owned by ``rank`` (uv order)."""
+    """Contiguous slice [lo, hi) of the ray axis owned by ``rank`` (uv order).  For exact strong
+    sharding pass the whole batch to ``IDRNetwork.forward`` with ``input["shard"] = shard_rays(...)``: every rank then walks
+    the full batch through the octree (its lock-step sample count is a batch-level quantity) and shades its slice."""
     per = (n_rays + world - 1) // world
     lo = min(rank * per, n_rays)
     return lo, min(lo + per, n_rays)

@@ -98,6 +98,19 @@ class IDRNetwork(nn.Module):
             batch_size, num_pixels, _ = ray_dirs.shape
             with torch.no_grad():
                 points, network_object_mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+            shard = input.get("shard")
+            if shard is not None:
+                # strong sharding of ONE batch over ranks (dist.STRONG_SHARDING): `uv` / `object_mask` / `hdr_shift` hold
+                # the WHOLE batch and every rank walks all of it -- the octree walk's per-iteration sample count depends
+                # on the number of live rays of the whole batch (utils/octree.py:542-548), and the walk is latency-bound,
+                # so the replicated trace costs what the sharded one would -- then shades rays [lo, hi) only
+                lo, hi = int(shard[0]), int(shard[1])
+                object_mask, network_object_mask, dists = object_mask[lo:hi], network_object_mask[lo:hi], dists[lo:hi]
+                ray_dirs, num_pixels = ray_dirs[:, lo:hi], hi - lo
+                input = dict(input)
+                for k in ("hdr_shift", "albedo_ratio"):
+                    if k in input and input[k] is not None and input[k].shape[0] == points.shape[0]:
+                        input[k] = input[k][lo:hi]
         else:
             cam_loc = input["points"].reshape(-1, 3)
             ray_dirs = input["dirs"].reshape(-1, 1, 3)

@@ -428,6 +428,37 @@ def test_static_shape_mode_matches_compacted_mode(model16):
             assert int(bad.sum()) <= 2 and float(d.max()) < 5e-3, (k, int(bad.sum()), float(d.max()))
 
 
+def test_strong_sharding_replicated_walk_is_exact(model16):
+    """dist.STRONG_SHARDING with input["shard"]: every rank walks the WHOLE batch through the octree (the walk's sample
+    count per lock-step iteration depends on the live rays of the whole batch, utils/octree.py:542-548) and shades its
+    slice -- the traced quantities of the slices are bit-identical to the single-rank forward of the full batch, which a
+    rank tracing only its own rays does not guarantee.  (The loss / gradient side of strong sharding is covered by the
+    2-rank gloo tests in tests/test_dist_cpu.py.)"""
+    from robir_b200 import dist as rdist, rng
+    model16.generate()
+    N = 600
+    inp = {k: v.cuda() for k, v in synthetic.camera_inputs(synthetic.training_pixels(21, n=N, crop=520)).items()}
+    inp["hdr_shift"] = torch.full((N, 1), 0.5).cuda()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        full = model16(inp, trainstage="Material", train_spec=True)
+    parts = []
+    for rank in range(3):
+        lo, hi = rdist.shard_rays(N, rank, 3)
+        torch.manual_seed(5 + rank)
+        with torch.no_grad():
+            parts.append(model16(dict(inp, shard=(lo, hi)), trainstage="Material", train_spec=True))
+        assert parts[-1]["network_object_mask"].shape[0] == hi - lo
+    for k in ("network_object_mask", "object_mask", "points", "ray_dirs", "sdf_output", "normals", "diffuse_albedo"):
+        cat = torch.cat([p[k] for p in parts], 0)
+        assert cat.shape == full[k].shape, k
+        if k in ("sdf_output", "normals", "diffuse_albedo"):        # per-point networks: batch size picks the engine
+            assert rel_err(cat, full[k]) < REL, k
+        else:
+            assert torch.equal(cat, full[k]), k
+    assert 0 < int(full["network_object_mask"].sum()) < N
+
+
 def test_graphed_step_runs_and_trains(synth_sd16):
     """CUDA-graph capture of the whole PBR training step: the loss goes down, and the captured graph re-packs the
     trained weights on every replay whatever optimizer implementation updates them (torch's fused Adam does not bump
