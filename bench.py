@@ -349,9 +349,11 @@ def run_pbr(args):
     if args.mode == "graph":
         from robir_b200.graph import GraphedPBRStep
         graphed = GraphedPBRStep(model, loss_fn, opt, N_RAYS, pose, K, reducer=reducer if world > 1 else None,
-                                 split_reduce=args.split_reduce)
+                                 split_reduce=args.split_reduce, pipeline_trace=args.pipeline_trace)
 
-        def train_step(uv, om, gt):   # noqa: F811  (replay of the captured step)
+        def train_step(uv, om, gt, nxt=None):   # noqa: F811  (replay of the captured step)
+            if args.pipeline_trace:             # nxt = (uv, object_mask) of the batch of the NEXT step
+                return graphed(uv, om, gt, nxt[0], nxt[1]), None
             return graphed(uv, om, gt), None
 
     total = args.warmup + args.steps
@@ -378,8 +380,13 @@ def run_pbr(args):
     ops.Stats.reset()
     _lib.launch_count = 0
 
+    pipelined = graphed is not None and args.pipeline_trace
+
     def step_resident(s):
-        loss, m = train_step(*dev_batches[s % total])
+        if pipelined:
+            loss, m = train_step(*dev_batches[s % total], nxt=dev_batches[(s + 1) % total][:2])
+        else:
+            loss, m = train_step(*dev_batches[s % total])
         hits.append(graphed.hits.clone() if graphed is not None else m.sum())
 
     for s in range(args.warmup):
@@ -415,19 +422,32 @@ def run_pbr(args):
             loss_done[j].synchronize()
             losses.append(float(loss_host[j]))
 
+    def prime(s):                # pipelined mode: the trace buffers must hold batch s before a loop starts at s
+        if pipelined:
+            graphed.prime(*dev_batches[s % total][:2])
+
     def step_e2e(s):
-        uv, om, gt = (t.to(dev, non_blocking=True) for t in batches[s])
-        loss, _ = train_step(uv, om, gt)
+        if pipelined:
+            # this step's ground truth and the NEXT step's pixels / mask travel now (the walk of batch s + 1 runs under
+            # this step's backward); the current batch's pixels were uploaded one step earlier
+            gt = batches[s][2].to(dev, non_blocking=True)
+            uv_n, om_n = (t.to(dev, non_blocking=True) for t in batches[(s + 1) % total][:2])
+            loss, _ = train_step(dev_batches[s][0], dev_batches[s][1], gt, nxt=(uv_n, om_n))
+        else:
+            uv, om, gt = (t.to(dev, non_blocking=True) for t in batches[s])
+            loss, _ = train_step(uv, om, gt)
         j = s & 1
         loss_host[j].copy_(loss.detach().reshape(()), non_blocking=True)     # device -> host copy of the step's result
         loss_done[j].record()
         read_pending()                                                      # host read of the previous step's loss
         pending.append(j)
 
+    prime(0)
     for s in range(min(args.warmup, 3)):
         step_e2e(s)
     read_pending()
     losses.clear()
+    prime(args.warmup)
     t_e2e = timed(step_e2e, args.warmup, total)
     read_pending()
     e2e = rdist.sum_over_ranks(N_RAYS * args.steps, dev) / t_e2e
@@ -438,6 +458,7 @@ def run_pbr(args):
     if args.sustain > 0:
         n_sus = int(max(50, args.sustain / max(t_res / args.steps, 1e-4)))
         clocks = ClockSampler(local, period=0.05).start()
+        prime(0)
         t_sus = timed(step_resident, 0, n_sus)
         clk_sus = clocks.stop()
         sustained = {"value": rdist.sum_over_ranks(N_RAYS * n_sus, dev) / t_sus, "unit": "rays/s", "steps": n_sus,
@@ -554,7 +575,9 @@ def run_pbr(args):
                     world, "" if world == 1 else (", eager between two graphs" if args.split_reduce else
                                                   ", captured inside the step graph")), "hit_fraction": hit_frac,
                 "vis_queries_per_step": pairs_total / float(args.steps), "vis_engine": ops.ENGINE["vis"],
-                "rng": "device", "mode": args.mode}),
+                "rng": "device", "mode": args.mode,
+                "pipeline_trace": bool(pipelined) and "octree walk of batch i+1 runs inside step i's graph, under its "
+                                                      "loss / backward (frozen SDF: nothing trained feeds the tracer)"}),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * t_e2e / args.steps,
                     "note": "per step: H2D of uv / mask / rgb from pinned memory, the step, D2H of its loss into pinned "
@@ -582,6 +605,10 @@ def main():
     ap.add_argument("--capture-reduce", dest="split_reduce", action="store_false",
                     help="multi-GPU: capture the gradient all-reduce inside the step graph instead of issuing it eagerly "
                          "between the forward/backward graph and the optimizer graph (same speed, see graph.py)")
+    ap.add_argument("--no-pipeline-trace", dest="pipeline_trace", action="store_false",
+                    help="graph mode: trace every batch at the start of its own step instead of walking the NEXT batch "
+                         "through the octree under the current step's loss / backward (GraphedPBRStep(pipeline_trace=True), "
+                         "the default here: same numbers, the latency-bound walk leaves the critical path)")
     ap.add_argument("--mode", default="graph", help="graph: whole step as one CUDA graph (default) | eager | eager-static")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,14 +19,20 @@ class GraphedPBRStep:
     latency, so capturing it buys nothing; only bucketing it under the visibility backward would."""
 
     def __init__(self, model, loss_fn, optimizer, n_rays, pose, intrinsics, reducer=None, warmup=3,
-                 record_randoms=False, split_reduce=True, hook=None):
+                 record_randoms=False, split_reduce=True, hook=None, pipeline_trace=False):
         """record_randoms: keep references to the random tensors drawn inside the captured step (``self.random_tape``, in
         draw order); after a replay they hold the numbers that replay used (test hook: nothing in the graph changes).
 
         hook: a ``cesr.ClusteredAlbedoHook`` already bound to ``model.get_sg_render`` -- the step is then the CESR stage's
         (train_cesr.py:465-559,387-430: shadow_net / normal_net, supervise term, explore / project loss weights).  The
         hook's schedule (warm-up / explore / project, the normal switch at iteration 1000) is host-side control flow:
-        one graph is captured per phase, lazily, when ``hook.phase_key()`` changes."""
+        one graph is captured per phase, lazily, when ``hook.phase_key()`` changes.
+
+        pipeline_trace: software-pipeline the surface trace across steps.  The octree walk is latency-bound (65 lock-step
+        iterations, 0.6 % of the HBM peak) and depends on nothing that is trained, so step i's graph walks batch i + 1 on a
+        side branch under its own loss / backward and step i + 1 starts from the finished trace.  Call ``prime(uv, om)``
+        once with the first batch, then ``step(uv_i, om_i, gt_i, uv_next, om_next)``; ``uv_i`` / ``om_i`` must be what the
+        previous call passed as next (they are only used by ``prime``).  Same numbers as the plain step."""
         if rng._mode != "device":
             raise RuntimeError("GraphedPBRStep needs robir_b200.rng.set_mode('device')")
         model.static_shapes = True
@@ -38,6 +44,14 @@ class GraphedPBRStep:
         self.gt = torch.zeros(1, n_rays, 3, device=dev)
         self.pose, self.K, self.n = pose, intrinsics, n_rays
         self.hits = None
+        self.pipeline_trace = pipeline_trace
+        if pipeline_trace:
+            self.uv_next, self.om_next = torch.zeros_like(self.uv), torch.ones_like(self.om)
+            self.cur = [torch.zeros(1, n_rays, 3, device=dev), torch.zeros(1, 3, device=dev),
+                        torch.zeros(n_rays, dtype=torch.bool, device=dev), torch.zeros(n_rays, device=dev)]
+            self.nxt = [torch.zeros_like(t) for t in self.cur]
+            self.trace_stream = torch.cuda.Stream()
+            self._primed = False
         self.multi = reducer is not None and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1
         self.split = self.multi and split_reduce
@@ -96,7 +110,16 @@ class GraphedPBRStep:
         ops.invalidate_packed_weights()      # the optimizer ran since the last forward: trained weights are re-packed once
         inp = {"uv": self.uv, "object_mask": self.om, "pose": self.pose, "intrinsics": self.K,
                "hdr_shift": m.gamma.hdr_shift.as_input().expand(self.n, 1)}
+        if self.pipeline_trace:
+            inp["traced"] = tuple(self.cur)
         out = m(inp, trainstage="Material", fun_spec=False, lin_diff=False, train_spec=True)
+        if self.pipeline_trace:
+            # the next batch's walk starts when this step's forward is done and runs under the loss and the backward
+            main = torch.cuda.current_stream()
+            self.trace_stream.wait_stream(main)
+            with torch.cuda.stream(self.trace_stream):
+                for dst, src in zip(self.nxt, m.trace_rays(self.uv_next, self.pose, self.K, self.om_next)):
+                    dst.copy_(src)
         if self.hook is not None:
             loss, _ = self.hook.pbr_step(self.loss_fn, out, {"rgb": self.gt})
         else:
@@ -104,9 +127,27 @@ class GraphedPBRStep:
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.hits = out["network_object_mask"].sum()
+        if self.pipeline_trace:
+            torch.cuda.current_stream().wait_stream(self.trace_stream)
+            for dst, src in zip(self.cur, self.nxt):          # every consumer of the current trace is behind us
+                dst.copy_(src)
         return loss.detach()
 
-    def __call__(self, uv, object_mask, rgb_gt):
+    def prime(self, uv, object_mask):
+        """pipeline_trace: trace the first batch (eagerly) into the buffers the next replay starts from."""
+        with torch.no_grad():
+            for dst, src in zip(self.cur, self.model.trace_rays(uv, self.pose, self.K, object_mask)):
+                dst.copy_(src)
+        self._primed = True
+
+    def __call__(self, uv, object_mask, rgb_gt, uv_next=None, om_next=None):
+        if self.pipeline_trace:
+            if uv_next is None or om_next is None:
+                raise RuntimeError("GraphedPBRStep(pipeline_trace=True): pass the next batch's uv / object_mask")
+            if not self._primed:
+                self.prime(uv, object_mask)
+            self.uv_next.copy_(uv_next, non_blocking=True)
+            self.om_next.copy_(om_next, non_blocking=True)
         key = self._phase()
         if key != self._key:
             if key in self._graphs:

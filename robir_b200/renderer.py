@@ -184,15 +184,30 @@ class IDRNetwork(nn.Module):
         ret.update(buf)
         return ret
 
+    def trace_rays(self, uv, pose, intrinsics, object_mask):
+        """Camera rays + surface trace of one batch, outside autograd: (ray_dirs [1,N,3], cam_loc [1,3], mask [N] bool,
+        dists [N]).  Nothing here depends on the parameters the PBR / CESR stages train, which is what lets
+        graph.GraphedPBRStep(pipeline_trace=True) walk the NEXT batch while the current step is in its backward."""
+        ray_dirs, cam_loc = ops.camera_rays(uv, pose, intrinsics)
+        with torch.no_grad():
+            _, mask, dists = self._trace(self.ray_tracer, cam_loc, object_mask.reshape(-1), ray_dirs)
+        return ray_dirs, cam_loc, mask, dists
+
     def _forward_static(self, input, lin_diff=False, train_spec=False, hook=None):
         object_mask = input["object_mask"].reshape(-1)
-        ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
-        batch_size, num_pixels, _ = ray_dirs.shape
-        def trace():
-            with torch.no_grad():
-                return self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
-        # packed copies of the weights that are being trained are rebuilt while the tracer walks the octree
-        (_, mask, dists), _ = ops.fork_join([trace, self.prepack], tag="trace")
+        traced = input.get("traced")
+        if traced is not None:                      # (ray_dirs, cam_loc, mask, dists) of trace_rays for exactly this batch
+            ray_dirs, cam_loc, mask, dists = traced
+            batch_size, num_pixels, _ = ray_dirs.shape
+            self.prepack()
+        else:
+            ray_dirs, cam_loc = ops.camera_rays(input["uv"], input["pose"], input["intrinsics"])
+            batch_size, num_pixels, _ = ray_dirs.shape
+            def trace():
+                with torch.no_grad():
+                    return self._trace(self.ray_tracer, cam_loc, object_mask, ray_dirs)
+            # packed copies of the weights that are being trained are rebuilt while the tracer walks the octree
+            (_, mask, dists), _ = ops.fork_join([trace, self.prepack], tag="trace")
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
         ray_dirs = ray_dirs.reshape(-1, 3)
         total, dev = points.shape[0], points.device

@@ -440,3 +440,55 @@ def test_render_image_public_entry_point(bench_setup):
         assert torch.isfinite(a[k]).all() and torch.isfinite(b[k]).all()
         assert float((a[k] - b[k]).abs().mean()) < 0.02, (k, float((a[k] - b[k]).abs().mean()))
     assert float(a["pred_rgb"][~m].min()) >= 0.0        # rays that miss: the reference's fill value through the tone-mapper
+
+
+def test_pipelined_trace_graph_step_equals_plain_graph_step(bench_setup):
+    """GraphedPBRStep(pipeline_trace=True): step i's graph walks batch i + 1 through the octree under its own loss /
+    backward and step i + 1 starts from the finished trace.  Same seeds, same batches: losses, hit counts and the trained
+    parameters after four steps equal those of the plain graphed step (the tracer depends on nothing that is trained)."""
+    from robir_b200 import graph, rng
+    from robir_b200.loss import InvLoss
+    sd, model, inp, gt = bench_setup
+    dev = torch.device("cuda")
+    params = trained_params(model)
+    batches = []
+    for s in range(5):
+        b = synthetic.camera_inputs(synthetic.training_pixels(900 + s, n=N_RAYS))
+        batches.append((b["uv"].to(dev), b["object_mask"].to(dev),
+                        torch.rand(1, N_RAYS, 3, generator=torch.Generator().manual_seed(s)).to(dev)))
+    rng.set_mode("device")
+    res = {}
+    try:
+        for pipe in (False, True):
+            _load(model, sd)
+            torch.cuda.manual_seed(4711)
+            opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=True)
+            step = graph.GraphedPBRStep(model, InvLoss(), opt, N_RAYS, synthetic.camera_pose().to(dev),
+                                        synthetic.camera_intrinsics().to(dev), pipeline_trace=pipe)
+            _load(model, sd)
+            for st in opt.state.values():                     # the construction trained for a few steps: reset Adam
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            losses, hits = [], []
+            for s in range(4):
+                uv, om, g = batches[s]
+                if pipe:
+                    loss = step(uv, om, g, batches[s + 1][0], batches[s + 1][1])
+                else:
+                    loss = step(uv, om, g)
+                losses.append(float(loss))
+                hits.append(int(step.hits))
+            torch.cuda.synchronize()
+            res[pipe] = (losses, hits, [p.detach().clone() for p in params])
+            del step
+    finally:
+        rng.set_mode("cpu")
+        model.static_shapes = False
+    (l0, h0, p0), (l1, h1, p1) = res[False], res[True]
+    assert h0 == h1, (h0, h1)
+    print("\nplain vs pipelined losses:", l0, l1)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert rel_err(b, a) < 1e-5

@@ -232,10 +232,21 @@ def run_c4(args):
     gt = torch.full((1, N, 3), 0.5, device=dev)
     if graphed:
         host_uv = [torch.stack([(p % 800).float(), (p // 800).float()], -1)[None].pin_memory() for p in host]
-        gstep = graph.GraphedPBRStep(model, loss_fn, opt, N, pose, K, reducer=reducer if world > 1 else None, hook=hook)
+        pipe = getattr(args, "pipeline_trace", True)
+        gstep = graph.GraphedPBRStep(model, loss_fn, opt, N, pose, K, reducer=reducer if world > 1 else None, hook=hook,
+                                     pipeline_trace=pipe)
+        n_b = len(host_uv)
+        if pipe:
+            gstep.prime(host_uv[0].to(dev), om)
+        cur_uv = [host_uv[0].to(dev)]
 
         def step(s):
-            gstep(host_uv[s].to(dev, non_blocking=True), om, gt)
+            if pipe:      # the NEXT batch's pixels travel now: its octree walk runs under this step's backward
+                nxt = host_uv[(s + 1) % n_b].to(dev, non_blocking=True)
+                gstep(cur_uv[0], om, gt, nxt, om)
+                cur_uv[0] = nxt
+            else:
+                gstep(host_uv[s].to(dev, non_blocking=True), om, gt)
             hits.append(gstep.hits.clone())
     else:
         def step(s):
@@ -267,7 +278,8 @@ def run_c4(args):
         cfg = {"workload": "truck-synthetic PBR + CESR step: 1024 random pixels/step/GPU, M=128, shadow_net (191->512x8->2 "
                            "on n_hit x 128 rows) + normal_net, explore phase (iteration 600), S=8, fwd+loss+bwd+Adam over 3 "
                            "networks", "config": "c4", "rays_per_step_per_gpu": N, "num_lgt_sgs": M,
-               "mode": "one CUDA graph per step (fixed-capacity batch)" if graphed else "eager dynamic shapes",
+               "mode": ("one CUDA graph per step (fixed-capacity batch)" + (", next batch's octree walk pipelined under the "
+                        "backward" if getattr(args, "pipeline_trace", True) else "")) if graphed else "eager dynamic shapes",
                "launches_per_step": gstep.launches_per_step if graphed else None,
                "hit_fraction": hf, "wn_engine": ops.ENGINE["wn"],
                "parallelism": "rays x%d (+ NCCL grad all-reduce incl. shadow_net / normal_net)" % world}
