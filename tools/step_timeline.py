@@ -23,18 +23,20 @@ def main():
     params = list(model.gamma.parameters()) + list(model.envmap_material_network.parameters())
     opt = torch.optim.Adam(params, lr=5e-4, capturable=True, fused=True)
     pose, K = synthetic.camera_pose().to(dev), synthetic.camera_intrinsics().to(dev)
-    step = GraphedPBRStep(model, InvLoss(), opt, N, pose, K)
+    pipe = os.environ.get("ROBIR_PIPELINE_TRACE", "1") == "1"       # what bench.py runs by default
+    step = GraphedPBRStep(model, InvLoss(), opt, N, pose, K, pipeline_trace=pipe)
     pix = synthetic.training_pixels(0, n=N)
     uv = torch.stack([(pix % 800).float(), (pix // 800).float()], -1)[None].to(dev)
     om = torch.ones(1, N, dtype=torch.bool, device=dev)
     gt = torch.full((1, N, 3), 0.5, device=dev)
+    args = (uv, om, gt, uv, om) if pipe else (uv, om, gt)
     for _ in range(3):
-        step(uv, om, gt)
+        step(*args)
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(2):
-            step(uv, om, gt)
+            step(*args)
         torch.cuda.synchronize()
     rows = []
     try:                                     # kineto events carry the stream id (device_resource_id)
