@@ -283,6 +283,18 @@ int robir_mlp_encode(const robir_mlp_params* p, int sm_count, void* stream);
 /* weight / bias gradient of one layer of the chain from its pre-activation gradient G (robir_mlp_bwd) and its input A
  * (x0_save or the previous layer's save): dW [N][K] = G[:, :N]^T A[:, :K], db [N] = column sums (db may be NULL).
  * splits > 1 divides the rows over that many CTAs per 64 x 64 tile (deterministic in-kernel reduction of the partials) */
+/* every packed copy of a chain of plain Linear layers (model/sg_envmap_material.py:40-72 nn.Sequential of nn.Linear) in one
+ * launch: Wt [Kp][Np] = W^T, Wb [Nb][Kb] = W, bias [Np] = b, all zero padded */
+typedef struct {
+  const float* W; const float* b;   /* [N][K], [N] */
+  float* Wt; float* Wb; float* bias;
+  int N, K, Kp, Np, Nb, Kb;
+} robir_pack_chain_layer;
+typedef struct {
+  int n_layers;
+  robir_pack_chain_layer L[8];
+} robir_pack_chain_params;
+int robir_pack_chain(const robir_pack_chain_params* p, void* stream);
 int robir_mlp_wgrad(const float* G, int ldg, const float* A, int lda, int n, int N, int K, const int* n_active, int seg,
                     int splits, float* partial /*[splits * tiles * 4160]*/, int* tickets /*[tiles], zero-initialised once*/,
                     float* dW, float* db, void* stream);

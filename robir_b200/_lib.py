@@ -76,6 +76,15 @@ class MlpLayer(Structure):
                 ("Npad", c_int), ("act", c_int), ("save", c_void_p), ("G", c_void_p)]
 
 
+class PackChainLayer(Structure):
+    _fields_ = [("W", c_void_p), ("b", c_void_p), ("Wt", c_void_p), ("Wb", c_void_p), ("bias", c_void_p),
+                ("N", c_int), ("K", c_int), ("Kp", c_int), ("Np", c_int), ("Nb", c_int), ("Kb", c_int)]
+
+
+class PackChainParams(Structure):
+    _fields_ = [("n_layers", c_int), ("L", PackChainLayer * 8)]
+
+
 class MlpParams(Structure):
     _fields_ = [("n", c_int), ("n_layers", c_int), ("in_mode", c_int), ("in_dim", c_int), ("in_pad", c_int),
                 ("x", c_void_p), ("extra", c_void_p), ("noise", c_void_p), ("noise_scale", c_float),
@@ -121,6 +130,7 @@ _SIGNATURES = {
     "robir_neus_midpoints": [_I, _I, _F, _P, _P, _P, _P, _P, _P],
     "robir_neus_composite": [_I, _I, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "robir_pack_pad": [_P, _I, _I, _P, _I, _I, _P],
+    "robir_pack_chain": [POINTER(PackChainParams), _P],
     "robir_mlp_fwd": [POINTER(MlpParams), _I, _P],
     "robir_mlp_bwd": [POINTER(MlpParams), _I, _P],
     "robir_vis_mlp_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],

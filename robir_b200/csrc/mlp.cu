@@ -477,6 +477,36 @@ __global__ void pack_pad_kernel(const float* __restrict__ W, int N, int K, float
   out[idx] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
 }
 
+// every packed copy of a chain of plain Linear layers in ONE launch (the re-pack of the trained chains sits at the head of
+// the step once the octree walk is pipelined away): per layer Wt [Kp][Np] = W^T zero padded, Wb [Nb][Kb] = W zero padded,
+// bias [Np] = b zero padded; blockIdx.y = layer
+struct PackChainLayer {
+  const float* W; const float* b;
+  float* Wt; float* Wb; float* bias;
+  int N, K, Kp, Np, Nb, Kb;
+};
+struct PackChainParams {
+  int n_layers;
+  PackChainLayer L[8];
+};
+__global__ void pack_chain_kernel(PackChainParams p) {
+  const PackChainLayer& l = p.L[blockIdx.y];
+  const int n_wt = l.Kp * l.Np, n_wb = l.Nb * l.Kb;
+  const int total = n_wt + n_wb + l.Np;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    if (idx < n_wt) {
+      const int k = idx / l.Np, n = idx % l.Np;
+      l.Wt[idx] = (k < l.K && n < l.N) ? l.W[(size_t)n * l.K + k] : 0.f;
+    } else if (idx < n_wt + n_wb) {
+      const int j = idx - n_wt, n = j / l.Kb, k = j % l.Kb;
+      l.Wb[j] = (n < l.N && k < l.K) ? l.W[(size_t)n * l.K + k] : 0.f;
+    } else {
+      const int n = idx - n_wt - n_wb;
+      l.bias[n] = n < l.N ? l.b[n] : 0.f;
+    }
+  }
+}
+
 }  // namespace robir
 
 using namespace robir;
@@ -510,6 +540,16 @@ static int mlp_launch(const MlpParams* p, int sm_count, void* stream) {
 }
 
 extern "C" {
+
+int robir_pack_chain(const PackChainParams* p, void* stream) {
+  RB_REQUIRE(p->n_layers >= 1 && p->n_layers <= 8, "pack_chain: 1..8 layers");
+  for (int l = 0; l < p->n_layers; ++l)
+    RB_REQUIRE(p->L[l].Kp >= p->L[l].K && p->L[l].Np >= p->L[l].N && p->L[l].Nb >= p->L[l].N && p->L[l].Kb >= p->L[l].K,
+               "pack_chain: padded shape too small");
+  pack_chain_kernel<<<dim3(64, p->n_layers), 256, 0, (cudaStream_t)stream>>>(*p);
+  RB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int robir_pack_pad(const float* W, int N, int K, float* out, int Np, int Kp, void* stream) {
   RB_REQUIRE(Np >= N && Kp >= K, "pack_pad: padded shape too small");
