@@ -974,24 +974,6 @@ class MlpChain:
             self.__dict__["_tc_eval_cache"] = _PackCache()
 
         def build():
-            if not self.weightnorm and len(self.linears) <= 8:
-                # one launch for all layers (csrc/mlp.cu pack_chain_kernel): the re-pack of a trained chain is on the
-                # critical path of the step once the octree walk is pipelined
-                q = _lib.PackChainParams()
-                q.n_layers = len(self.linears)
-                out, keep = [], []
-                for l, lin in enumerate(self.linears):
-                    W, b = f32(lin.weight), f32(lin.bias)
-                    N, K = W.shape
-                    Kp, Np = _up(K, 16), _up(N, 256)
-                    Wt, Wb, bp = _empty(Kp, Np, like=W), _empty(_up(N, 16), _up(K, 256), like=W), _empty(Np, like=W)
-                    L = q.L[l]
-                    L.W, L.b, L.Wt, L.Wb, L.bias = W.data_ptr(), b.data_ptr(), Wt.data_ptr(), Wb.data_ptr(), bp.data_ptr()
-                    L.N, L.K, L.Kp, L.Np, L.Nb, L.Kb = N, K, Kp, Np, _up(N, 16), _up(K, 256)
-                    keep.append((W, b))
-                    out.append(dict(Wt=Wt, Wb=Wb, bias=bp, K=K, N=N, Kpad=Kp, Npad=Np))
-                check(lib().robir_pack_chain(ctypes.byref(q), stream()))
-                return out
             out = []
             for lin in self.linears:
                 if self.weightnorm:
@@ -1041,6 +1023,24 @@ class MlpChain:
 
     def packed(self):
         def build():
+            if not self.weightnorm and len(self.linears) <= 8:
+                # one launch for all layers (csrc/mlp.cu pack_chain_kernel): the re-pack of a trained chain is on the
+                # critical path of the step once the octree walk is pipelined
+                q = _lib.PackChainParams()
+                q.n_layers = len(self.linears)
+                out, keep = [], []
+                for l, lin in enumerate(self.linears):
+                    W, b = f32(lin.weight), f32(lin.bias)
+                    N, K = W.shape
+                    Kp, Np = _up(K, 16), _up(N, 256)
+                    Wt, Wb, bp = _empty(Kp, Np, like=W), _empty(_up(N, 16), _up(K, 256), like=W), _empty(Np, like=W)
+                    L = q.L[l]
+                    L.W, L.b, L.Wt, L.Wb, L.bias = W.data_ptr(), b.data_ptr(), Wt.data_ptr(), Wb.data_ptr(), bp.data_ptr()
+                    L.N, L.K, L.Kp, L.Np, L.Nb, L.Kb = N, K, Kp, Np, _up(N, 16), _up(K, 256)
+                    keep.append((W, b))
+                    out.append(dict(Wt=Wt, Wb=Wb, bias=bp, K=K, N=N, Kpad=Kp, Npad=Np))
+                check(lib().robir_pack_chain(ctypes.byref(q), stream()))
+                return out
             out = []
             for lin in self.linears:
                 if self.weightnorm:
