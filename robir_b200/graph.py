@@ -154,7 +154,8 @@ class GraphedPBRStep:
                 self._select(key)
             else:
                 self._capture(key)
-        self.uv.copy_(uv, non_blocking=True)
+        if not self.pipeline_trace:          # the pipelined graph starts from the finished trace: it never reads uv
+            self.uv.copy_(uv, non_blocking=True)
         self.om.copy_(object_mask, non_blocking=True)
         self.gt.copy_(rgb_gt, non_blocking=True)
         self.g1.replay()
